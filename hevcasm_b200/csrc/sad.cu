@@ -1,0 +1,534 @@
+// hevcasm_b200 - SAD / SSD kernels for sm_100a.
+//
+// Reference semantics: sad.c:47-60 (hevcasm_sad_c_ref), sad.c:101-121 (hevcasm_sad_multiref_4_c_ref),
+// ssd.c:43-55 (hevcasm_ssd_c_ref) of kupix/hevcasm.  All outputs are exact 32-bit integer sums.
+//
+// Design (not a translation of the x86 psadbw loops):
+//   * motion-estimation sweep: a CTA stages the source tile and the reference search window of that tile in shared
+//     memory once; each thread owns one 8x8 (or 8x4 / 4x8 / 4x4) source CELL in registers and walks the window rows,
+//     feeding every window row to all candidates it belongs to.  64 accumulators (8 dy x 8 dx) live in registers; one
+//     VABSDIFF4.U8.ACC retires 4 absolute differences + the add.  Byte-misaligned candidates cost one funnel shift
+//     per 4-byte window word per misalignment, shared by the two candidates (dx, dx+4) that use it.
+//   * cell sums are composed on chip into the requested PU size(s) (8x8 -> 16x16 -> 32x32 -> 64x64 for the pyramid
+//     entry point), so the frames are read from HBM once for all PU sizes; results leave through a swizzled shared
+//     staging buffer as fully coalesced 128-bit stores.
+//   * SSD: |a-b| per byte (VABSDIFF4) then IDP.4A.U8.U8 of the difference with itself, 4x4 partials composed in
+//     shared memory.
+#include "common.cuh"
+
+namespace hv {
+
+// ------------------------------------------------------------------------------------------------ cell core
+
+template <int CW, int CH>
+struct SadCell {
+    static constexpr int KW = CW / 4;  // words per cell row
+    uint32_t src[CH][KW];
+    uint32_t acc[8][8];  // [dy][dx]
+
+    __device__ __forceinline__ void clear()
+    {
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+#pragma unroll
+            for (int i = 0; i < 8; ++i) acc[j][i] = 0;
+    }
+
+    // s -> word (0, 0) of this cell in the staged source tile
+    __device__ __forceinline__ void load_src(const uint32_t *s, int pitch_words)
+    {
+#pragma unroll
+        for (int r = 0; r < CH; ++r) {
+            if (KW == 2) {
+                const uint2 v = *reinterpret_cast<const uint2 *>(s + r * pitch_words);
+                src[r][0] = v.x;
+                src[r][KW - 1] = v.y;
+            } else {
+                src[r][0] = s[r * pitch_words];
+            }
+        }
+    }
+
+    // win -> the staged window word holding candidate (dx index 0, dy index 0) of this cell, i.e. window row 0 at the
+    // cell's x.  Consumes CH+7 window rows of CW+8 bytes.
+    __device__ __forceinline__ void run(const uint32_t *win, int pitch_words)
+    {
+#pragma unroll
+        for (int r = 0; r < CH + 7; ++r) {
+            uint32_t W[KW + 2];
+            if (KW == 2) {
+                const uint2 a = *reinterpret_cast<const uint2 *>(win + r * pitch_words);
+                const uint2 b = *reinterpret_cast<const uint2 *>(win + r * pitch_words + 2);
+                W[0] = a.x, W[1] = a.y, W[KW] = b.x, W[KW + 1] = b.y;
+            } else {
+#pragma unroll
+                for (int j = 0; j < KW + 2; ++j) W[j] = win[r * pitch_words + j];
+            }
+            uint32_t S[4][KW + 1];
+#pragma unroll
+            for (int j = 0; j <= KW; ++j) {
+                S[0][j] = W[j];
+                S[1][j] = shr_bytes(W[j], W[j + 1], 1);
+                S[2][j] = shr_bytes(W[j], W[j + 1], 2);
+                S[3][j] = shr_bytes(W[j], W[j + 1], 3);
+            }
+#pragma unroll
+            for (int dy = 0; dy < 8; ++dy) {
+                const int sr = r - dy;
+                if (sr < 0 || sr >= CH) continue;
+#pragma unroll
+                for (int dx = 0; dx < 8; ++dx)
+#pragma unroll
+                    for (int k = 0; k < KW; ++k) acc[dy][dx] = sad4(src[sr][k], S[dx & 3][(dx >> 2) + k], acc[dy][dx]);
+            }
+        }
+    }
+};
+
+// swizzled int4 staging of 64 candidates per cell: [cell][16 groups of 4 candidates]
+__device__ __forceinline__ int cb_index(int cell, int g) { return cell * 16 + (g ^ (cell & 15)); }
+
+template <int CW, int CH>
+__device__ __forceinline__ void store_cell(int4 *cb, int cell, const SadCell<CW, CH> &c)
+{
+#pragma unroll
+    for (int g = 0; g < 16; ++g) {
+        const int dy = g >> 1, dx = (g & 1) * 4;
+        cb[cb_index(cell, g)] = make_int4((int)c.acc[dy][dx], (int)c.acc[dy][dx + 1], (int)c.acc[dy][dx + 2], (int)c.acc[dy][dx + 3]);
+    }
+}
+
+__device__ __forceinline__ int4 add4(int4 a, int4 b) { return make_int4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); }
+
+// ------------------------------------------------------------------------------------------------ pyramid sweep
+
+namespace pyr {
+constexpr int TW = 128, TH = 64, CX = TW / 8, CY = TH / 8, NT = CX * CY;  // 128 threads, one 8x8 cell each
+constexpr int WIN_PITCH = (TW + 16) / 4;                                   // words; keeps rows 16-byte aligned
+constexpr int WIN_ROWS = TH + 8;
+constexpr int SRC_PITCH = TW / 4;
+constexpr int STAGE_BYTES = (WIN_PITCH * WIN_ROWS + SRC_PITCH * TH) * 4;  // 18560
+constexpr int CB_BYTES = NT * 64 * 4;                                      // 32768 (aliases the staging area)
+constexpr int L16_BYTES = (CX / 2) * (CY / 2) * 64 * 4;                    // 8192
+constexpr int L32_BYTES = (CX / 4) * (CY / 4) * 64 * 4;                    // 2048
+constexpr int SMEM_BYTES = (CB_BYTES > STAGE_BYTES ? CB_BYTES : STAGE_BYTES) + L16_BYTES + L32_BYTES;
+}  // namespace pyr
+
+struct PyramidParams {
+    const uint8_t *src, *ref;
+    ptrdiff_t ss, sr, fs_src, fs_ref;
+    int width, height, dx0, dy0;
+    int32_t *out[4];  // 8, 16, 32, 64
+};
+
+__global__ void __launch_bounds__(pyr::NT) sad_sweep_pyramid_kernel(PyramidParams p)
+{
+    using namespace pyr;
+    extern __shared__ __align__(16) uint8_t smem[];
+    uint32_t *win = reinterpret_cast<uint32_t *>(smem);
+    uint32_t *srct = win + WIN_PITCH * WIN_ROWS;
+    int4 *cb = reinterpret_cast<int4 *>(smem);
+    int4 *l16 = reinterpret_cast<int4 *>(smem + (CB_BYTES > STAGE_BYTES ? CB_BYTES : STAGE_BYTES));
+    int4 *l32 = l16 + L16_BYTES / 16;
+
+    const int tid = threadIdx.x;
+    const int f = blockIdx.z;
+    const int npx8 = p.width >> 3, npy8 = p.height >> 3;
+    const int cx0 = blockIdx.x * CX, cy0 = blockIdx.y * CY;  // first cell of the tile
+    const int vcx = min(CX, npx8 - cx0), vcy = min(CY, npy8 - cy0);
+    const int x0 = cx0 * 8, y0 = cy0 * 8;
+
+    const uint8_t *src = p.src + f * p.fs_src + (ptrdiff_t)y0 * p.ss + x0;
+    const uint8_t *ref = p.ref + f * p.fs_ref + (ptrdiff_t)(y0 + p.dy0) * p.sr + (x0 + p.dx0);
+    stage_tile_u8(srct, SRC_PITCH, src, p.ss, vcx * 2, vcy * 8, tid, NT);
+    stage_tile_u8(win, WIN_PITCH, ref, p.sr, vcx * 2 + 2, vcy * 8 + 7, tid, NT);
+    __syncthreads();
+
+    const int cx = tid % CX, cy = tid / CX;
+    SadCell<8, 8> cell;
+    cell.clear();
+    if (cx < vcx && cy < vcy) {
+        cell.load_src(srct + cy * 8 * SRC_PITCH + cx * 2, SRC_PITCH);
+        cell.run(win + cy * 8 * WIN_PITCH + cx * 2, WIN_PITCH);
+    }
+    __syncthreads();  // staging area is dead from here on; cb aliases it
+    store_cell(cb, tid, cell);
+    __syncthreads();
+
+    // level 0 (8x8): linear, coalesced copy-out
+    if (p.out[0]) {
+        int4 *o = reinterpret_cast<int4 *>(p.out[0]) + (size_t)f * npy8 * npx8 * 16;
+        for (int i = tid; i < NT * 16; i += NT) {
+            const int c = i >> 4, g = i & 15, ccx = c % CX, ccy = c / CX;
+            if (ccx < vcx && ccy < vcy) o[((size_t)(cy0 + ccy) * npx8 + (cx0 + ccx)) * 16 + g] = cb[cb_index(c, g)];
+        }
+    }
+    // level 1 (16x16) from four cells
+    {
+        const int npx = p.width >> 4, npy = p.height >> 4, px0 = cx0 >> 1, py0 = cy0 >> 1;
+        int4 *o = p.out[1] ? reinterpret_cast<int4 *>(p.out[1]) + (size_t)f * npy * npx * 16 : nullptr;
+        for (int i = tid; i < (CX / 2) * (CY / 2) * 16; i += NT) {
+            const int pu = i >> 4, g = i & 15, px = pu % (CX / 2), py = pu / (CX / 2);
+            const int c00 = (2 * py) * CX + 2 * px;
+            const int4 v = add4(add4(cb[cb_index(c00, g)], cb[cb_index(c00 + 1, g)]), add4(cb[cb_index(c00 + CX, g)], cb[cb_index(c00 + CX + 1, g)]));
+            l16[i] = v;
+            if (o && px0 + px < npx && py0 + py < npy) o[((size_t)(py0 + py) * npx + (px0 + px)) * 16 + g] = v;
+        }
+    }
+    __syncthreads();
+    // level 2 (32x32) from four 16x16
+    {
+        const int npx = p.width >> 5, npy = p.height >> 5, px0 = cx0 >> 2, py0 = cy0 >> 2;
+        int4 *o = p.out[2] ? reinterpret_cast<int4 *>(p.out[2]) + (size_t)f * npy * npx * 16 : nullptr;
+        for (int i = tid; i < (CX / 4) * (CY / 4) * 16; i += NT) {
+            const int pu = i >> 4, g = i & 15, px = pu % (CX / 4), py = pu / (CX / 4);
+            const int q00 = ((2 * py) * (CX / 2) + 2 * px) * 16 + g;
+            const int4 v = add4(add4(l16[q00], l16[q00 + 16]), add4(l16[q00 + (CX / 2) * 16], l16[q00 + (CX / 2) * 16 + 16]));
+            l32[i] = v;
+            if (o && px0 + px < npx && py0 + py < npy) o[((size_t)(py0 + py) * npx + (px0 + px)) * 16 + g] = v;
+        }
+    }
+    __syncthreads();
+    // level 3 (64x64) from four 32x32
+    if (p.out[3]) {
+        const int npx = p.width >> 6, npy = p.height >> 6, px0 = cx0 >> 3, py0 = cy0 >> 3;
+        int4 *o = reinterpret_cast<int4 *>(p.out[3]) + (size_t)f * npy * npx * 16;
+        for (int i = tid; i < (CX / 8) * (CY / 8) * 16; i += NT) {
+            const int pu = i >> 4, g = i & 15, px = pu % (CX / 8), py = pu / (CX / 8);
+            const int q00 = ((2 * py) * (CX / 4) + 2 * px) * 16 + g;
+            const int4 v = add4(add4(l32[q00], l32[q00 + 16]), add4(l32[q00 + (CX / 4) * 16], l32[q00 + (CX / 4) * 16 + 16]));
+            if (px0 + px < npx && py0 + py < npy) o[((size_t)(py0 + py) * npx + (px0 + px)) * 16 + g] = v;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ single-size sweep
+//
+// Any PU size w x h (multiples of 4, <= 64), any dense candidate window, processed in tiles of 8 x 8 candidates.
+// A CTA owns TPX x TPY whole PUs (<= 16 x 8 cells) and loops over the window tiles.
+
+struct SweepParams {
+    const uint8_t *src, *ref;
+    ptrdiff_t ss, sr, fs_src, fs_ref;
+    int w, h, npx, npy;       // PU size, PU grid per frame
+    int tpx, tpy;             // PUs per CTA tile
+    int dx0, dy0, ncx, ncy;   // candidate window
+    int32_t *out;
+};
+
+constexpr int SWEEP_NT = 128;
+constexpr int SWEEP_WIN_PITCH = 36, SWEEP_WIN_ROWS = 72, SWEEP_SRC_PITCH = 32, SWEEP_SRC_ROWS = 64;
+constexpr int SWEEP_STAGE_BYTES = (SWEEP_WIN_PITCH * SWEEP_WIN_ROWS + SWEEP_SRC_PITCH * SWEEP_SRC_ROWS) * 4;
+constexpr int SWEEP_CB_BYTES = SWEEP_NT * 64 * 4;
+constexpr int SWEEP_SMEM_BYTES = SWEEP_STAGE_BYTES + SWEEP_CB_BYTES;
+
+template <int CW, int CH>
+__global__ void __launch_bounds__(SWEEP_NT) sad_sweep_kernel(SweepParams p)
+{
+    extern __shared__ __align__(16) uint8_t smem[];
+    uint32_t *win = reinterpret_cast<uint32_t *>(smem);
+    uint32_t *srct = win + SWEEP_WIN_PITCH * SWEEP_WIN_ROWS;
+    int4 *cb = reinterpret_cast<int4 *>(smem + SWEEP_STAGE_BYTES);
+
+    const int tid = threadIdx.x, f = blockIdx.z;
+    const int mx = p.w / CW, my = p.h / CH;                   // cells per PU
+    const int pu_x0 = blockIdx.x * p.tpx, pu_y0 = blockIdx.y * p.tpy;
+    const int vpx = min(p.tpx, p.npx - pu_x0), vpy = min(p.tpy, p.npy - pu_y0);
+    const int ncellx = vpx * mx, ncelly = vpy * my;           // valid cells of this tile (<= 16 x 8)
+    const int x0 = pu_x0 * p.w, y0 = pu_y0 * p.h;
+    const int tile_w = vpx * p.w, tile_h = vpy * p.h;
+    const int nc = p.ncx * p.ncy;
+
+    const uint8_t *src = p.src + f * p.fs_src + (ptrdiff_t)y0 * p.ss + x0;
+    stage_tile_u8(srct, SWEEP_SRC_PITCH, src, p.ss, tile_w / 4, tile_h, tid, SWEEP_NT);
+
+    const int cx = tid % 16, cy = tid / 16;
+    const bool active = cx < ncellx && cy < ncelly;
+    SadCell<CW, CH> cell;
+    bool src_loaded = false;
+
+    for (int wy = 0; wy < p.ncy; wy += 8)
+        for (int wx = 0; wx < p.ncx; wx += 8) {
+            const int nvx = min(8, p.ncx - wx), nvy = min(8, p.ncy - wy);  // valid candidates of this window tile
+            const uint8_t *ref = p.ref + f * p.fs_ref + (ptrdiff_t)(y0 + p.dy0 + wy) * p.sr + (x0 + p.dx0 + wx);
+            __syncthreads();  // previous iteration's readers of win / cb are done
+            stage_tile_u8(win, SWEEP_WIN_PITCH, ref, p.sr, (tile_w + nvx - 1 + 3) / 4, tile_h + nvy - 1, tid, SWEEP_NT);
+            __syncthreads();
+            cell.clear();
+            if (active) {
+                if (!src_loaded) {
+                    cell.load_src(srct + cy * CH * SWEEP_SRC_PITCH + cx * (CW / 4), SWEEP_SRC_PITCH);
+                    src_loaded = true;
+                }
+                cell.run(win + cy * CH * SWEEP_WIN_PITCH + cx * (CW / 4), SWEEP_WIN_PITCH);
+            }
+            store_cell(cb, tid, cell);
+            __syncthreads();
+            // compose cells into PUs and write the valid candidates
+            for (int i = tid; i < vpx * vpy * 16; i += SWEEP_NT) {
+                const int pu = i >> 4, g = i & 15, px = pu % vpx, py = pu / vpx;
+                int4 v = make_int4(0, 0, 0, 0);
+                for (int b = 0; b < my; ++b)
+                    for (int a = 0; a < mx; ++a) v = add4(v, cb[cb_index((py * my + b) * 16 + px * mx + a, g)]);
+                const int dyi = g >> 1, dxi = (g & 1) * 4;
+                if (dyi < nvy) {
+                    int32_t *o = p.out + (((size_t)f * p.npy + (pu_y0 + py)) * p.npx + (pu_x0 + px)) * nc + (wy + dyi) * p.ncx + wx + dxi;
+                    if (dxi + 0 < nvx) o[0] = v.x;
+                    if (dxi + 1 < nvx) o[1] = v.y;
+                    if (dxi + 2 < nvx) o[2] = v.z;
+                    if (dxi + 3 < nvx) o[3] = v.w;
+                }
+            }
+        }
+}
+
+// ------------------------------------------------------------------------------------------------ list forms
+
+__device__ __forceinline__ uint32_t ldg_word_unaligned(const uint8_t *p)
+{
+    const int a = (int)((uintptr_t)p & 3);
+    const uint32_t *pa = reinterpret_cast<const uint32_t *>(p - a);
+    uint32_t lo = __ldg(pa);
+    if (a) lo = shr_bytes(lo, __ldg(pa + 1), a);
+    return lo;
+}
+
+// one warp per (PU, candidate).  per_pu_mv: cand holds one vector per PU (n_cand == 1) or may be null.
+__global__ void __launch_bounds__(256) sad_list_kernel(const uint8_t *__restrict__ src, ptrdiff_t ss, const uint8_t *__restrict__ ref,
+                                                       ptrdiff_t sr, int w, int h, const int16_t *__restrict__ pu_xy, int n_pu,
+                                                       const int16_t *__restrict__ cand, int n_cand, int per_pu_mv,
+                                                       int32_t *__restrict__ out)
+{
+    const long long gw = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (gw >= (long long)n_pu * n_cand) return;
+    const int i = (int)(gw / n_cand), c = (int)(gw - (long long)i * n_cand);
+    const int x = pu_xy[2 * i], y = pu_xy[2 * i + 1];
+    int dx = 0, dy = 0;
+    if (cand) {
+        const int ci = per_pu_mv ? i : c;
+        dx = cand[2 * ci], dy = cand[2 * ci + 1];
+    }
+    const uint8_t *s = src + (ptrdiff_t)y * ss + x;
+    const uint8_t *r = ref + (ptrdiff_t)(y + dy) * sr + (x + dx);
+    const int wpr = w >> 2, total = wpr * h;
+    uint32_t acc = 0;
+    for (int idx = lane; idx < total; idx += 32) {
+        const int row = idx / wpr, k = idx - row * wpr;
+        acc = sad4(ldg_word_unaligned(s + (ptrdiff_t)row * ss + 4 * k), ldg_word_unaligned(r + (ptrdiff_t)row * sr + 4 * k), acc);
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) out[gw] = (int32_t)acc;
+}
+
+// ------------------------------------------------------------------------------------------------ SSD
+
+// one warp per listed block
+__global__ void __launch_bounds__(256) ssd_list_kernel(const uint8_t *__restrict__ a, ptrdiff_t sa, const uint8_t *__restrict__ b,
+                                                       ptrdiff_t sb, int n_size, const int16_t *__restrict__ blk_xy, int n,
+                                                       int32_t *__restrict__ out)
+{
+    const int gw = (int)(((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
+    if (gw >= n) return;
+    const int x = blk_xy[2 * gw], y = blk_xy[2 * gw + 1];
+    const uint8_t *pa = a + (ptrdiff_t)y * sa + x, *pb = b + (ptrdiff_t)y * sb + x;
+    const int wpr = n_size >> 2, total = wpr * n_size;
+    uint32_t acc = 0;
+    for (int idx = lane; idx < total; idx += 32) {
+        const int row = idx / wpr, k = idx - row * wpr;
+        const uint32_t d = __vabsdiffu4(ldg_word_unaligned(pa + (ptrdiff_t)row * sa + 4 * k), ldg_word_unaligned(pb + (ptrdiff_t)row * sb + 4 * k));
+        acc = dp4a_uu(d, d, acc);
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) out[gw] = (int32_t)acc;
+}
+
+// Regular grid.  CTA tile = 128 x 32 samples, 64 threads... each thread owns a 16-byte x 4-row patch, i.e. four 4x4
+// partial sums; partials are composed into N x N blocks through shared memory.
+namespace ssdk {
+constexpr int TW = 256, TH = 32, NT = (TW / 16) * (TH / 4);  // 128 threads
+constexpr int PX = TW / 4, PY = TH / 4;                       // 64 x 8 partials
+}  // namespace ssdk
+
+struct SsdParams {
+    const uint8_t *a, *b;
+    ptrdiff_t sa, sb, fs_a, fs_b;
+    int log2, nbx, nby;  // block size, block grid per frame
+    int32_t *out;
+};
+
+template <bool ALIGNED>
+__global__ void __launch_bounds__(ssdk::NT) ssd_frames_kernel(SsdParams p)
+{
+    using namespace ssdk;
+    __shared__ __align__(16) uint32_t part[PY][PX + 4];
+    const int tid = threadIdx.x, f = blockIdx.z;
+    const int N = 1 << p.log2;
+    const int TH_EFF = N > TH ? N : TH;              // a 64x64 block needs two 32-row passes
+    const int x0 = blockIdx.x * TW, y0 = blockIdx.y * TH_EFF;
+    const int vw = min(TW, p.nbx * N - x0), vh = min(TH_EFF, p.nby * N - y0);  // valid samples of this tile
+    const int tx = tid % (TW / 16), ty = tid / (TW / 16);
+    const uint8_t *a = p.a + f * p.fs_a + (ptrdiff_t)y0 * p.sa + x0;
+    const uint8_t *b = p.b + f * p.fs_b + (ptrdiff_t)y0 * p.sb + x0;
+
+    for (int pass = 0; pass < TH_EFF / TH; ++pass) {
+        uint32_t acc[4] = {0, 0, 0, 0};
+        const int yy = pass * TH + ty * 4;
+        if (tx * 16 < vw && yy < vh) {
+            uint32_t wa[4][4], wb[4][4];
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                const uint8_t *ra = a + (ptrdiff_t)(yy + r) * p.sa + tx * 16, *rb = b + (ptrdiff_t)(yy + r) * p.sb + tx * 16;
+                if (ALIGNED) {
+                    const int4 va = ldg_stream(reinterpret_cast<const int4 *>(ra)), vb = ldg_stream(reinterpret_cast<const int4 *>(rb));
+                    wa[r][0] = va.x, wa[r][1] = va.y, wa[r][2] = va.z, wa[r][3] = va.w;
+                    wb[r][0] = vb.x, wb[r][1] = vb.y, wb[r][2] = vb.z, wb[r][3] = vb.w;
+                } else {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const bool in = tx * 16 + 4 * k < vw;  // never touch words right of the last valid block
+                        wa[r][k] = in ? ldg_word_unaligned(ra + 4 * k) : 0;
+                        wb[r][k] = in ? ldg_word_unaligned(rb + 4 * k) : 0;
+                    }
+                }
+            }
+#pragma unroll
+            for (int r = 0; r < 4; ++r)
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const uint32_t d = __vabsdiffu4(wa[r][k], wb[r][k]);
+                    acc[k] = dp4a_uu(d, d, acc[k]);
+                }
+        }
+        __syncthreads();
+        *reinterpret_cast<uint4 *>(&part[ty][tx * 4]) = make_uint4(acc[0], acc[1], acc[2], acc[3]);
+        __syncthreads();
+        // compose (N/4)^2 partials per block.  Blocks taller than the tile accumulate over passes in `carry`.
+        const int m = N >> 2;                           // partials per block side
+        const int mrows = min(m, PY);                   // partial rows available per pass
+        const int bpr = PX / m, bpc = PY / mrows;       // blocks per tile row / column (per pass)
+        for (int i = tid; i < bpr * bpc; i += NT) {
+            const int bx = i % bpr, by = i / bpr;
+            uint32_t s = 0;
+            for (int r = 0; r < mrows; ++r)
+                for (int c = 0; c < m; ++c) s += part[by * mrows + r][bx * m + c];
+            const int gx = blockIdx.x * bpr + bx;
+            const int gy = N > TH ? blockIdx.y : blockIdx.y * bpc + by;
+            if (gx < p.nbx && gy < p.nby) {
+                int32_t *o = p.out + ((size_t)f * p.nby + gy) * p.nbx + gx;
+                if (N > TH && pass > 0) *o += (int32_t)s;  // same thread wrote pass 0
+                else *o = (int32_t)s;
+            }
+        }
+    }
+}
+
+}  // namespace hv
+
+// ================================================================================================ C ABI
+
+using namespace hv;
+
+static bool rect_ok(uint32_t rect, int &w, int &h)
+{
+    w = (int)(rect >> 8), h = (int)(rect & 0xff);
+    return w >= 4 && h >= 4 && w <= 64 && h <= 64 && (w & 3) == 0 && (h & 3) == 0;
+}
+
+extern "C" int hevcasm_sad_multiref_batch(const uint8_t *src, ptrdiff_t ss, const uint8_t *ref, ptrdiff_t sr, uint32_t rect,
+                                          const int16_t *pu_xy, int n_pu, const int16_t *cand, int n_cand, int32_t *sad, void *stream)
+{
+    int w, h;
+    if (!rect_ok(rect, w, h) || n_pu < 0 || n_cand < 1 || !cand) return HEVCASM_ERR_ARGUMENT;
+    if (n_pu == 0) return 0;
+    const long long warps = (long long)n_pu * n_cand;
+    const unsigned grid = (unsigned)((warps + 7) / 8);
+    HV_LAUNCH(sad_list_kernel, grid, 256, 0, stream, src, ss, ref, sr, w, h, pu_xy, n_pu, cand, n_cand, 0, sad);
+    return 0;
+}
+
+extern "C" int hevcasm_sad_batch(const uint8_t *src, ptrdiff_t ss, const uint8_t *ref, ptrdiff_t sr, uint32_t rect, const int16_t *pu_xy,
+                                 const int16_t *mv_xy, int n_pu, int32_t *sad, void *stream)
+{
+    int w, h;
+    if (!rect_ok(rect, w, h) || n_pu < 0) return HEVCASM_ERR_ARGUMENT;
+    if (n_pu == 0) return 0;
+    const unsigned grid = (unsigned)((n_pu + 7) / 8);
+    HV_LAUNCH(sad_list_kernel, grid, 256, 0, stream, src, ss, ref, sr, w, h, pu_xy, n_pu, mv_xy, 1, 1, sad);
+    return 0;
+}
+
+extern "C" int hevcasm_sad_sweep_frames(const uint8_t *src, ptrdiff_t ss, const uint8_t *ref, ptrdiff_t sr, int width, int height,
+                                        uint32_t rect, int dx0, int dy0, int ncx, int ncy, int n_frames, ptrdiff_t fs_src,
+                                        ptrdiff_t fs_ref, int32_t *sad, void *stream)
+{
+    int w, h;
+    if (!rect_ok(rect, w, h) || ncx < 1 || ncy < 1 || n_frames < 0 || width < 0 || height < 0) return HEVCASM_ERR_ARGUMENT;
+    SweepParams p;
+    p.src = src, p.ref = ref, p.ss = ss, p.sr = sr, p.fs_src = fs_src, p.fs_ref = fs_ref;
+    p.w = w, p.h = h, p.npx = width / w, p.npy = height / h;
+    p.dx0 = dx0, p.dy0 = dy0, p.ncx = ncx, p.ncy = ncy, p.out = sad;
+    if (p.npx == 0 || p.npy == 0 || n_frames == 0) return 0;
+    const int cw = (w & 7) ? 4 : 8, ch = (h & 7) ? 4 : 8;
+    p.tpx = (16 * cw) / w > 0 ? (16 * cw) / w : 1;
+    p.tpy = (8 * ch) / h > 0 ? (8 * ch) / h : 1;
+    const dim3 grid((p.npx + p.tpx - 1) / p.tpx, (p.npy + p.tpy - 1) / p.tpy, n_frames);
+#define HV_SWEEP(CW_, CH_)                                                        \
+    do {                                                                          \
+        auto kern = sad_sweep_kernel<CW_, CH_>;                                   \
+        HV_CUDA((cudaError_t)set_max_smem(kern, SWEEP_SMEM_BYTES));               \
+        HV_LAUNCH(kern, grid, SWEEP_NT, SWEEP_SMEM_BYTES, stream, p);             \
+    } while (0)
+    if (cw == 8 && ch == 8) HV_SWEEP(8, 8);
+    else if (cw == 8) HV_SWEEP(8, 4);
+    else if (ch == 8) HV_SWEEP(4, 8);
+    else HV_SWEEP(4, 4);
+#undef HV_SWEEP
+    return 0;
+}
+
+extern "C" int hevcasm_sad_sweep_pyramid_frames(const uint8_t *src, ptrdiff_t ss, const uint8_t *ref, ptrdiff_t sr, int width, int height,
+                                                int dx0, int dy0, int n_frames, ptrdiff_t fs_src, ptrdiff_t fs_ref, int32_t *sad8,
+                                                int32_t *sad16, int32_t *sad32, int32_t *sad64, void *stream)
+{
+    if (width < 8 || height < 8 || n_frames < 0) return HEVCASM_ERR_ARGUMENT;
+    if (n_frames == 0) return 0;
+    PyramidParams p;
+    p.src = src, p.ref = ref, p.ss = ss, p.sr = sr, p.fs_src = fs_src, p.fs_ref = fs_ref;
+    p.width = width, p.height = height, p.dx0 = dx0, p.dy0 = dy0;
+    p.out[0] = sad8, p.out[1] = sad16, p.out[2] = sad32, p.out[3] = sad64;
+    const int npx8 = width >> 3, npy8 = height >> 3;
+    const dim3 grid((npx8 + pyr::CX - 1) / pyr::CX, (npy8 + pyr::CY - 1) / pyr::CY, n_frames);
+    HV_CUDA((cudaError_t)set_max_smem(sad_sweep_pyramid_kernel, pyr::SMEM_BYTES));
+    HV_LAUNCH(sad_sweep_pyramid_kernel, grid, pyr::NT, pyr::SMEM_BYTES, stream, p);
+    return 0;
+}
+
+extern "C" int hevcasm_ssd_batch(const uint8_t *a, ptrdiff_t sa, const uint8_t *b, ptrdiff_t sb, int log2size, const int16_t *blk_xy, int n,
+                                 int32_t *ssd, void *stream)
+{
+    if (log2size < 2 || log2size > 6 || n < 0) return HEVCASM_ERR_ARGUMENT;
+    if (n == 0) return 0;
+    HV_LAUNCH(ssd_list_kernel, (unsigned)((n + 7) / 8), 256, 0, stream, a, sa, b, sb, 1 << log2size, blk_xy, n, ssd);
+    return 0;
+}
+
+extern "C" int hevcasm_ssd_frames(const uint8_t *a, ptrdiff_t sa, const uint8_t *b, ptrdiff_t sb, int width, int height, int log2size,
+                                  int n_frames, ptrdiff_t fs_a, ptrdiff_t fs_b, int32_t *ssd, void *stream)
+{
+    if (log2size < 2 || log2size > 6 || n_frames < 0 || width < 0 || height < 0) return HEVCASM_ERR_ARGUMENT;
+    SsdParams p;
+    p.a = a, p.b = b, p.sa = sa, p.sb = sb, p.fs_a = fs_a, p.fs_b = fs_b, p.log2 = log2size;
+    p.nbx = width >> log2size, p.nby = height >> log2size, p.out = ssd;
+    if (p.nbx == 0 || p.nby == 0 || n_frames == 0) return 0;
+    const int N = 1 << log2size, th = N > ssdk::TH ? N : ssdk::TH;
+    const dim3 grid((p.nbx * N + ssdk::TW - 1) / ssdk::TW, (p.nby * N + th - 1) / th, n_frames);
+    // the 128-bit path needs 16-byte aligned rows and a block grid that ends on a 16-sample boundary (no over-read)
+    const bool aligned = (((uintptr_t)a | (uintptr_t)b | (uintptr_t)sa | (uintptr_t)sb | (uintptr_t)fs_a | (uintptr_t)fs_b |
+                           (uintptr_t)(p.nbx * (1 << log2size))) & 15) == 0;
+    if (aligned) HV_LAUNCH(ssd_frames_kernel<true>, grid, ssdk::NT, 0, stream, p);
+    else HV_LAUNCH(ssd_frames_kernel<false>, grid, ssdk::NT, 0, stream, p);
+    return 0;
+}

@@ -1,0 +1,177 @@
+/*
+ * hevcasm_b200 - batched, stream-aware GPU entry points (the extension SURVEY.md section 8(b) asks for).
+ *
+ * One block per call cannot feed a GPU, so every per-block function type of the reference's function-select
+ * API gets batched siblings here.  The semantics of EACH batch element are exactly those of the per-block
+ * reference function cited next to the entry point; outputs are bit-exact with the reference's C path.
+ *
+ * Conventions (all entry points):
+ *   - C linkage, plain pointers and sizes; every data pointer is a DEVICE pointer (cudaMalloc'ed or
+ *     otherwise device-accessible); strides are in ELEMENTS of the pointed-to type, like the reference's;
+ *   - `stream` is a cudaStream_t passed as void* (NULL = the legacy default stream); work is only enqueued -
+ *     the call returns before it runs; the library allocates nothing and keeps no pointer;
+ *   - the return value is 0 on success, otherwise a cudaError_t value (hevcasm_cuda_error_string()) or
+ *     HEVCASM_ERR_ARGUMENT for a shape the entry point does not serve.  (The reference's kernels cannot fail;
+ *     a launch can.)
+ *   - "_batch" variants take an explicit list of block positions, "_frames" variants process every block of
+ *     a regular grid over `n_frames` planes laid out `frame stride` elements apart (one launch for the lot -
+ *     that is how a 4K/8K batch reaches HBM speed);
+ *   - frames must be padded like the reference's test buffers (reference pred_inter.c:468-471): interpolation
+ *     reads taps/2-1 samples left/above and taps/2 right/below the block, the SAD entry points read the
+ *     candidate window around each PU;
+ *   - position lists are int16_t pairs {x, y} (an 8K plane fits), candidate / motion vectors int16_t {dx, dy}.
+ *
+ * Host-memory convenience forms (host pointers, H2D/D2H inside) live behind hevcasm_cuda_context at the end.
+ */
+#ifndef INCLUDED_hevcasm_batch_h
+#define INCLUDED_hevcasm_batch_h
+
+#include "hevcasm.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HEVCASM_ERR_ARGUMENT (-1)
+
+const char HEVCASM_API *hevcasm_cuda_error_string(int code);
+/* number of kernels this library has launched in the calling process (bench.py's gpu_launches) */
+unsigned long long HEVCASM_API hevcasm_cuda_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------------ SAD
+ * element semantics: reference sad.h:50 / sad.c:47-60 (hevcasm_sad) and sad.h:95 / sad.c:101-121
+ * (hevcasm_sad_multiref, 4 references per call).  rect = HEVCASM_RECT(w, h), w and h multiples of 4, <= 64. */
+
+/* sad[i][c] = SAD(src block at pu_xy[i], ref block at pu_xy[i] + cand_dxdy[c]);  i < n_pu, c < n_cand */
+int HEVCASM_API hevcasm_sad_multiref_batch(const uint8_t *src, ptrdiff_t stride_src, const uint8_t *ref, ptrdiff_t stride_ref,
+                                           uint32_t rect, const int16_t *pu_xy, int n_pu, const int16_t *cand_dxdy, int n_cand,
+                                           int32_t *sad, void *stream);
+
+/* sad[i] = SAD(src block at pu_xy[i], ref block at pu_xy[i] + mv_xy[i]); mv_xy may be NULL (co-located) */
+int HEVCASM_API hevcasm_sad_batch(const uint8_t *src, ptrdiff_t stride_src, const uint8_t *ref, ptrdiff_t stride_ref, uint32_t rect,
+                                  const int16_t *pu_xy, const int16_t *mv_xy, int n_pu, int32_t *sad, void *stream);
+
+/* Motion-estimation sweep: the floor(width/w) x floor(height/h) non-overlapping PUs of every frame, each against
+ * the dense candidate window dx in [dx0, dx0+ncx), dy in [dy0, dy0+ncy).
+ * sad[frame][py][px][(dy-dy0)*ncx + (dx-dx0)].  ncx*ncy <= 256. */
+int HEVCASM_API hevcasm_sad_sweep_frames(const uint8_t *src, ptrdiff_t stride_src, const uint8_t *ref, ptrdiff_t stride_ref,
+                                         int width, int height, uint32_t rect, int dx0, int dy0, int ncx, int ncy, int n_frames,
+                                         ptrdiff_t frame_stride_src, ptrdiff_t frame_stride_ref, int32_t *sad, void *stream);
+
+/* The same sweep for the four square PU sizes 8, 16, 32, 64 in ONE pass over the frames (the 8x8 partial sums are
+ * composed on chip into the larger PUs).  Window fixed at 8 x 8 candidates: dx in [dx0, dx0+8), dy in [dy0, dy0+8).
+ * width and height must be multiples of 64.  Any of the four outputs may be NULL.  Each output has the layout
+ * hevcasm_sad_sweep_frames would produce for that size. */
+int HEVCASM_API hevcasm_sad_sweep_pyramid_frames(const uint8_t *src, ptrdiff_t stride_src, const uint8_t *ref, ptrdiff_t stride_ref,
+                                                 int width, int height, int dx0, int dy0, int n_frames,
+                                                 ptrdiff_t frame_stride_src, ptrdiff_t frame_stride_ref, int32_t *sad8,
+                                                 int32_t *sad16, int32_t *sad32, int32_t *sad64, void *stream);
+
+/* ------------------------------------------------------------------------------------------------ SSD
+ * element semantics: reference ssd.h:53 / ssd.c:43-55, square blocks of size 1<<log2size (2..6) */
+int HEVCASM_API hevcasm_ssd_batch(const uint8_t *srcA, ptrdiff_t stride_srcA, const uint8_t *srcB, ptrdiff_t stride_srcB,
+                                  int log2size, const int16_t *blk_xy, int n, int32_t *ssd, void *stream);
+/* ssd[frame][by][bx] over the regular grid of floor(width/N) x floor(height/N) blocks */
+int HEVCASM_API hevcasm_ssd_frames(const uint8_t *srcA, ptrdiff_t stride_srcA, const uint8_t *srcB, ptrdiff_t stride_srcB, int width,
+                                   int height, int log2size, int n_frames, ptrdiff_t frame_stride_srcA,
+                                   ptrdiff_t frame_stride_srcB, int32_t *ssd, void *stream);
+
+/* ------------------------------------------------------------------------------------------------ inter prediction
+ * element semantics: reference pred_inter.h:56 (hevcasm_pred_uni_8to8; C path pred_inter.c:90-228) and
+ * pred_inter.h:76 (hevcasm_pred_bi_8to8; pred_inter.c:490-530).  taps = 8 (luma, fractions 0..3) or 4 (chroma, 0..7). */
+
+/* whole planes with one fractional position: dst(x, y) = prediction from ref(x, y), 0 <= x < width, 0 <= y < height */
+int HEVCASM_API hevcasm_pred_uni_frames(uint8_t *dst, ptrdiff_t stride_dst, const uint8_t *ref, ptrdiff_t stride_ref, int width,
+                                        int height, int taps, int xFrac, int yFrac, int n_frames, ptrdiff_t frame_stride_dst,
+                                        ptrdiff_t frame_stride_ref, void *stream);
+int HEVCASM_API hevcasm_pred_bi_frames(uint8_t *dst, ptrdiff_t stride_dst, const uint8_t *ref0, const uint8_t *ref1,
+                                       ptrdiff_t stride_ref, int width, int height, int taps, int xFrac0, int yFrac0, int xFrac1,
+                                       int yFrac1, int n_frames, ptrdiff_t frame_stride_dst, ptrdiff_t frame_stride_ref,
+                                       void *stream);
+
+/* prediction-unit lists.  Uni descriptor = 6 x int16 {x, y, w, h, mvx, mvy}; bi descriptor = 8 x int16
+ * {x, y, w, h, mvx0, mvy0, mvx1, mvy1}.  Motion vectors are in 1/4 (taps 8) or 1/8 (taps 4) sample units:
+ * integer part mv >> 2 (>> 3), fraction mv & 3 (& 7).  w, h <= 64.  Unlike the reference (pred_inter.h:42) nothing is
+ * written outside the w x h block, so neighbouring PUs may be processed in one launch. */
+int HEVCASM_API hevcasm_pred_uni_batch(uint8_t *dst, ptrdiff_t stride_dst, const uint8_t *ref, ptrdiff_t stride_ref, int taps,
+                                       const int16_t *pus, int n_pu, void *stream);
+int HEVCASM_API hevcasm_pred_bi_batch(uint8_t *dst, ptrdiff_t stride_dst, const uint8_t *ref0, const uint8_t *ref1,
+                                      ptrdiff_t stride_ref, int taps, const int16_t *pus, int n_pu, void *stream);
+
+/* ------------------------------------------------------------------------------------------------ transforms
+ * element semantics: reference residual_decode.h:82 (hevcasm_transform; residual_decode.c:592-893) and
+ * residual_decode.h:54 (hevcasm_inverse_transform_add; residual_decode.c:69-413).  log2size 2..5; trType 1 selects
+ * the 4x4 DST (log2size must be 2).  Coefficients of block i are N*N contiguous int16 at coeffs + i*N*N. */
+int HEVCASM_API hevcasm_transform_batch(int16_t *coeffs, const int16_t *residual, ptrdiff_t stride, int log2size, int trType,
+                                        const int16_t *blk_xy, int n, void *stream);
+/* coeffs[frame][by][bx][N*N] over the regular grid of floor(width/N) x floor(height/N) blocks */
+int HEVCASM_API hevcasm_transform_frames(int16_t *coeffs, const int16_t *residual, ptrdiff_t stride, int width, int height,
+                                         int log2size, int trType, int n_frames, ptrdiff_t frame_stride_residual, void *stream);
+int HEVCASM_API hevcasm_inverse_transform_add_batch(uint8_t *dst, ptrdiff_t stride_dst, const uint8_t *pred, ptrdiff_t stride_pred,
+                                                    const int16_t *coeffs, int log2size, int trType, const int16_t *blk_xy, int n,
+                                                    void *stream);
+int HEVCASM_API hevcasm_inverse_transform_add_frames(uint8_t *dst, ptrdiff_t stride_dst, const uint8_t *pred, ptrdiff_t stride_pred,
+                                                     const int16_t *coeffs, int width, int height, int log2size, int trType,
+                                                     int n_frames, ptrdiff_t frame_stride_dst, ptrdiff_t frame_stride_pred,
+                                                     void *stream);
+
+/* ------------------------------------------------------------------------------------------------ quantisation
+ * element semantics: reference quantize.h:78 / quantize.c:160-186 (quantize), quantize.h:57 / quantize.c:53-62
+ * (quantize_inverse), quantize.h:99 / quantize.c:292-302 (quantize_reconstruct). */
+
+/* n_blocks runs of n_per_block coefficients (a power of two, 16..1024); cbf[i] = OR of block i's outputs, the
+ * reference's return value; cbf may be NULL.  dst, src 16-byte aligned. */
+int HEVCASM_API hevcasm_quantize_batch(int16_t *dst, const int16_t *src, int scale, int shift, int offset, int n_per_block,
+                                       int n_blocks, int32_t *cbf, void *stream);
+int HEVCASM_API hevcasm_quantize_inverse_batch(int16_t *dst, const int16_t *src, int scale, int shift, long long n_total,
+                                               void *stream);
+int HEVCASM_API hevcasm_quantize_reconstruct_batch(uint8_t *rec, ptrdiff_t stride_rec, const uint8_t *pred, ptrdiff_t stride_pred,
+                                                   const int16_t *res, int log2size, const int16_t *blk_xy, int n, void *stream);
+int HEVCASM_API hevcasm_quantize_reconstruct_frames(uint8_t *rec, ptrdiff_t stride_rec, const uint8_t *pred, ptrdiff_t stride_pred,
+                                                    const int16_t *res, int width, int height, int log2size, int n_frames,
+                                                    ptrdiff_t frame_stride_rec, ptrdiff_t frame_stride_pred, void *stream);
+
+/* ------------------------------------------------------------------------------------------------ fused residual pipeline
+ * forward transform -> quantize -> (levels written) -> quantize_inverse -> inverse transform -> add to pred,
+ * one pass over HBM.  Element semantics = the composition of the four reference
+ * functions above, bit for bit.  levels[frame][by][bx][N*N]; cbf[frame][by][bx] (may be NULL). */
+int HEVCASM_API hevcasm_residual_pipeline_frames(uint8_t *rec, ptrdiff_t stride_rec, int16_t *levels, int32_t *cbf,
+                                                 const int16_t *residual, ptrdiff_t stride_residual, const uint8_t *pred,
+                                                 ptrdiff_t stride_pred, int width, int height, int log2size, int trType,
+                                                 int q_scale, int q_shift, int q_offset, int iq_scale, int iq_shift, int n_frames,
+                                                 ptrdiff_t frame_stride_rec, ptrdiff_t frame_stride_residual,
+                                                 ptrdiff_t frame_stride_pred, void *stream);
+
+/* ------------------------------------------------------------------------------------------------ host-memory forms
+ * A context owns one CUDA stream and a device staging arena on one device.  The *_host entry points take HOST
+ * pointers with the same meaning as the device forms, copy inputs in, run, copy results out and synchronise
+ * before returning - this is what the per-block slots of the function-select tables and bench.py's e2e
+ * measurement use. */
+typedef struct hevcasm_cuda_context hevcasm_cuda_context;
+
+hevcasm_cuda_context HEVCASM_API *hevcasm_cuda_context_create(int device, size_t arena_bytes);
+void HEVCASM_API hevcasm_cuda_context_destroy(hevcasm_cuda_context *ctx);
+void HEVCASM_API *hevcasm_cuda_context_stream(hevcasm_cuda_context *ctx);
+
+/* plane-level host forms: each frame is a tightly described plane {pointer to sample (0,0), stride}; `pad` = the number
+ * of valid samples around the width x height area that must travel with it (>= candidate range / filter reach). */
+int HEVCASM_API hevcasm_sad_sweep_pyramid_frames_host(hevcasm_cuda_context *ctx, const uint8_t *src, ptrdiff_t stride_src,
+                                                      const uint8_t *ref, ptrdiff_t stride_ref, int width, int height, int pad,
+                                                      int dx0, int dy0, int n_frames, ptrdiff_t frame_stride_src,
+                                                      ptrdiff_t frame_stride_ref, int32_t *sad8, int32_t *sad16, int32_t *sad32,
+                                                      int32_t *sad64);
+int HEVCASM_API hevcasm_pred_uni_frames_host(hevcasm_cuda_context *ctx, uint8_t *dst, ptrdiff_t stride_dst, const uint8_t *ref,
+                                             ptrdiff_t stride_ref, int width, int height, int pad, int taps, int xFrac, int yFrac,
+                                             int n_frames, ptrdiff_t frame_stride_dst, ptrdiff_t frame_stride_ref);
+int HEVCASM_API hevcasm_residual_pipeline_frames_host(hevcasm_cuda_context *ctx, uint8_t *rec, ptrdiff_t stride_rec, int16_t *levels,
+                                                      int32_t *cbf, const int16_t *residual, ptrdiff_t stride_residual,
+                                                      const uint8_t *pred, ptrdiff_t stride_pred, int width, int height,
+                                                      int log2size, int trType, int q_scale, int q_shift, int q_offset,
+                                                      int iq_scale, int iq_shift, int n_frames, ptrdiff_t frame_stride_rec,
+                                                      ptrdiff_t frame_stride_residual, ptrdiff_t frame_stride_pred);
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif
