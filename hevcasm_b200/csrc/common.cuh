@@ -22,6 +22,15 @@ void count_launch();  // abi.cu
         if (hv_e_ != cudaSuccess) return (int)hv_e_;                                        \
     } while (0)
 
+// function form for template kernels (a template-id with commas cannot go through the macro)
+template <class K, class... A>
+inline int launch(K kernel, dim3 grid, dim3 block, size_t smem, void *stream, A... args)
+{
+    kernel<<<grid, block, smem, (cudaStream_t)stream>>>(args...);
+    count_launch();
+    return (int)cudaGetLastError();
+}
+
 #define HV_CUDA(call)                                       \
     do {                                                    \
         cudaError_t hv_e_ = (call);                         \

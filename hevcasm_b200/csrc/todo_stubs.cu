@@ -6,9 +6,5 @@ int hevcasm_pred_uni_frames(uint8_t *, ptrdiff_t, const uint8_t *, ptrdiff_t, in
 int hevcasm_pred_bi_frames(uint8_t *, ptrdiff_t, const uint8_t *, const uint8_t *, ptrdiff_t, int, int, int, int, int, int, int, int, ptrdiff_t, ptrdiff_t, void *) { NOT_YET; }
 int hevcasm_pred_uni_batch(uint8_t *, ptrdiff_t, const uint8_t *, ptrdiff_t, int, const int16_t *, int, void *) { NOT_YET; }
 int hevcasm_pred_bi_batch(uint8_t *, ptrdiff_t, const uint8_t *, const uint8_t *, ptrdiff_t, int, const int16_t *, int, void *) { NOT_YET; }
-int hevcasm_transform_batch(int16_t *, const int16_t *, ptrdiff_t, int, int, const int16_t *, int, void *) { NOT_YET; }
-int hevcasm_transform_frames(int16_t *, const int16_t *, ptrdiff_t, int, int, int, int, int, ptrdiff_t, void *) { NOT_YET; }
-int hevcasm_inverse_transform_add_batch(uint8_t *, ptrdiff_t, const uint8_t *, ptrdiff_t, const int16_t *, int, int, const int16_t *, int, void *) { NOT_YET; }
-int hevcasm_inverse_transform_add_frames(uint8_t *, ptrdiff_t, const uint8_t *, ptrdiff_t, const int16_t *, int, int, int, int, int, ptrdiff_t, ptrdiff_t, void *) { NOT_YET; }
 int hevcasm_residual_pipeline_frames(uint8_t *, ptrdiff_t, int16_t *, int32_t *, const int16_t *, ptrdiff_t, const uint8_t *, ptrdiff_t, int, int, int, int, int, int, int, int, int, int, ptrdiff_t, ptrdiff_t, ptrdiff_t, void *) { NOT_YET; }
 }

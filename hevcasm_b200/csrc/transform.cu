@@ -1,0 +1,388 @@
+// hevcasm_b200 - forward transforms and inverse transform + add, 4x4 (DCT, DST) .. 32x32, for sm_100a.
+//
+// Reference semantics (kupix/hevcasm): hevcasm_transform = residual_decode.c:855-892 over the stages :592-852;
+// hevcasm_inverse_transform_add = residual_decode.c:371-413 over the stages :69-347 and hevcasm_add_residual :359-368.
+// Arithmetic building blocks and the exactness argument are in transform.cuh.
+//
+// Kernel shapes:
+//   * 4x4 and 8x8: one thread owns a whole block in registers (both stages and the transpose between them are
+//     register renaming); consecutive lanes take consecutive blocks of a block row, so plane accesses coalesce.
+//   * 16x16 and 32x32: a warp owns 64 block columns (4 resp. 2 blocks).  Each lane runs two 1-D transforms per stage
+//     on int16 pairs; the stage-to-stage transpose goes through a conflict-free padded shared-memory tile private to
+//     the warp (only __syncwarp, no CTA barrier).
+// The second inverse stage skips the reference's clip to int16: |value| <= 23040 there, so the clip can never bind,
+// and for the same reason the int16 truncation inside hevcasm_clip (:350-356) is the identity.
+#include "transform.cuh"
+
+namespace hv {
+using namespace tr;
+
+// where block i of a batch lives: explicit list, or raster order over a regular grid of n_frames planes
+struct BlockGrid {
+    const int16_t *blk_xy;
+    int nbx, nby;
+    long long n;
+    __device__ __forceinline__ void locate(long long i, int log2, int &x, int &y, int &f) const
+    {
+        if (blk_xy) {
+            x = blk_xy[2 * i], y = blk_xy[2 * i + 1], f = 0;
+        } else {
+            const long long per = (long long)nbx * nby;
+            f = (int)(i / per);
+            const int r = (int)(i - f * per);
+            y = (r / nbx) << log2, x = (r % nbx) << log2;
+        }
+    }
+};
+
+// ---- alignment-agnostic row access (NW 32-bit words) ---------------------------------------------------
+template <int NW>
+__device__ __forceinline__ void load_words(const void *ptr, uint32_t *w)
+{
+    const uintptr_t a = (uintptr_t)ptr;
+    if (NW % 4 == 0 && (a & 15) == 0) {
+#pragma unroll
+        for (int i = 0; i < NW / 4; ++i) {
+            const uint4 v = __ldg(reinterpret_cast<const uint4 *>(ptr) + i);
+            w[4 * i] = v.x, w[4 * i + 1] = v.y, w[4 * i + 2] = v.z, w[4 * i + 3] = v.w;
+        }
+    } else if (NW % 2 == 0 && (a & 7) == 0) {
+#pragma unroll
+        for (int i = 0; i < NW / 2; ++i) {
+            const uint2 v = __ldg(reinterpret_cast<const uint2 *>(ptr) + i);
+            w[2 * i] = v.x, w[2 * i + 1] = v.y;
+        }
+    } else if ((a & 3) == 0) {
+#pragma unroll
+        for (int i = 0; i < NW; ++i) w[i] = __ldg(reinterpret_cast<const uint32_t *>(ptr) + i);
+    } else if ((a & 1) == 0) {
+        const uint16_t *p = reinterpret_cast<const uint16_t *>(ptr);
+#pragma unroll
+        for (int i = 0; i < NW; ++i) w[i] = (uint32_t)__ldg(p + 2 * i) | ((uint32_t)__ldg(p + 2 * i + 1) << 16);
+    } else {
+        const uint8_t *p = reinterpret_cast<const uint8_t *>(ptr);
+#pragma unroll
+        for (int i = 0; i < NW; ++i)
+            w[i] = (uint32_t)__ldg(p + 4 * i) | ((uint32_t)__ldg(p + 4 * i + 1) << 8) | ((uint32_t)__ldg(p + 4 * i + 2) << 16) |
+                   ((uint32_t)__ldg(p + 4 * i + 3) << 24);
+    }
+}
+
+template <int NW>
+__device__ __forceinline__ void store_words(void *ptr, const uint32_t *w)
+{
+    const uintptr_t a = (uintptr_t)ptr;
+    if (NW % 4 == 0 && (a & 15) == 0) {
+#pragma unroll
+        for (int i = 0; i < NW / 4; ++i) reinterpret_cast<uint4 *>(ptr)[i] = make_uint4(w[4 * i], w[4 * i + 1], w[4 * i + 2], w[4 * i + 3]);
+    } else if (NW % 2 == 0 && (a & 7) == 0) {
+#pragma unroll
+        for (int i = 0; i < NW / 2; ++i) reinterpret_cast<uint2 *>(ptr)[i] = make_uint2(w[2 * i], w[2 * i + 1]);
+    } else if ((a & 3) == 0) {
+#pragma unroll
+        for (int i = 0; i < NW; ++i) reinterpret_cast<uint32_t *>(ptr)[i] = w[i];
+    } else if ((a & 1) == 0) {
+        uint16_t *p = reinterpret_cast<uint16_t *>(ptr);
+#pragma unroll
+        for (int i = 0; i < NW; ++i) p[2 * i] = (uint16_t)w[i], p[2 * i + 1] = (uint16_t)(w[i] >> 16);
+    } else {
+        uint8_t *p = reinterpret_cast<uint8_t *>(ptr);
+#pragma unroll
+        for (int i = 0; i < NW; ++i)
+            p[4 * i] = (uint8_t)w[i], p[4 * i + 1] = (uint8_t)(w[i] >> 8), p[4 * i + 2] = (uint8_t)(w[i] >> 16), p[4 * i + 3] = (uint8_t)(w[i] >> 24);
+    }
+}
+
+// four reconstructed samples: clip8(pred byte + (r >> 12)), packed
+__device__ __forceinline__ uint32_t recon_word(uint32_t pw, const int *r)
+{
+    return pack_sat_u8((int)(pw & 0xff) + (r[0] >> 12), (int)((pw >> 8) & 0xff) + (r[1] >> 12), (int)((pw >> 16) & 0xff) + (r[2] >> 12),
+                       (int)(pw >> 24) + (r[3] >> 12));
+}
+
+// ================================================================================================ 4x4 / 8x8
+
+constexpr int SMALL_NT = 128;
+
+template <int LOG2, bool DST>
+__global__ void __launch_bounds__(SMALL_NT) small_fwd_kernel(int16_t *__restrict__ coeffs, const int16_t *__restrict__ res, ptrdiff_t stride,
+                                                             ptrdiff_t fs, BlockGrid g)
+{
+    constexpr int N = 1 << LOG2, HW = N / 2, S1 = fwd_shift1(LOG2), S2 = fwd_shift2(LOG2);
+    const long long i = (long long)blockIdx.x * SMALL_NT + threadIdx.x;
+    if (i >= g.n) return;
+    int x, y, f;
+    g.locate(i, LOG2, x, y, f);
+    const int16_t *src = res + f * fs + (ptrdiff_t)y * stride + x;
+
+    uint32_t X[N][HW];
+#pragma unroll
+    for (int r = 0; r < N; ++r) load_words<HW>(src + (ptrdiff_t)r * stride, X[r]);
+
+    // stage 1 (along x): A[u][y]; kept as vertical pairs Aw[u][y/2] = (A[u][y], A[u][y+1]), the operand order stage 2 needs
+    uint32_t Aw[N][HW];
+#pragma unroll
+    for (int r = 0; r < N; r += 2) {
+        int a0[N], a1[N];
+        fwd_matrix<N, DST>(X[r], a0, 1 << (S1 - 1));
+        fwd_matrix<N, DST>(X[r + 1], a1, 1 << (S1 - 1));
+#pragma unroll
+        for (int u = 0; u < N; ++u) Aw[u][r / 2] = lolo((uint32_t)(a0[u] >> S1), (uint32_t)(a1[u] >> S1));  // truncating, residual_decode.c:674-682
+    }
+    // stage 2 (along y): Y[v][u], emitted as horizontal pairs (Y[v][u], Y[v][u+1]) = the memory order of coeffs[v*N+u]
+    uint32_t Yw[N][HW];
+#pragma unroll
+    for (int u = 0; u < N; u += 2) {
+        int b0[N], b1[N];
+        fwd_matrix<N, DST>(Aw[u], b0, 1 << (S2 - 1));
+        fwd_matrix<N, DST>(Aw[u + 1], b1, 1 << (S2 - 1));
+#pragma unroll
+        for (int v = 0; v < N; ++v) Yw[v][u / 2] = lolo((uint32_t)(b0[v] >> S2), (uint32_t)(b1[v] >> S2));
+    }
+    int16_t *out = coeffs + i * (N * N);
+#pragma unroll
+    for (int v = 0; v < N; ++v) store_words<HW>(out + v * N, Yw[v]);
+}
+
+template <int LOG2, bool DST>
+__global__ void __launch_bounds__(SMALL_NT) small_inv_kernel(uint8_t *__restrict__ dst, ptrdiff_t sd, const uint8_t *__restrict__ pred, ptrdiff_t sp,
+                                                             ptrdiff_t fs_dst, ptrdiff_t fs_pred, const int16_t *__restrict__ coeffs, BlockGrid g)
+{
+    constexpr int N = 1 << LOG2, HW = N / 2;
+    const long long i = (long long)blockIdx.x * SMALL_NT + threadIdx.x;
+    if (i >= g.n) return;
+    int x, y, f;
+    g.locate(i, LOG2, x, y, f);
+
+    uint32_t Cw[N][HW];
+    const int16_t *c = coeffs + i * (N * N);
+#pragma unroll
+    for (int v = 0; v < N; ++v) load_words<HW>(c + v * N, Cw[v]);
+
+    // stage 1 (along v, shift 7, clip16): B[u][y]
+    int B[N][N];
+#pragma unroll
+    for (int j = 0; j < HW; ++j) {
+        uint32_t pl[HW], ph[HW];
+        static_for<0, HW>([&](auto kk) {
+            constexpr int k = HV_V(kk), r0 = DST ? 2 * k : pair_row(N, k, 0), r1 = DST ? 2 * k + 1 : pair_row(N, k, 1);
+            pl[k] = lolo(Cw[r0][j], Cw[r1][j]);
+            ph[k] = hihi(Cw[r0][j], Cw[r1][j]);
+        });
+        if (DST) {
+            inv_dst4(pl, B[2 * j], 64);
+            inv_dst4(ph, B[2 * j + 1], 64);
+        } else {
+            InvBfly<N>::run(pl, B[2 * j], 64);
+            InvBfly<N>::run(ph, B[2 * j + 1], 64);
+        }
+    }
+    // stage 2 (along u, shift 12) + add to the predictor
+    const uint8_t *pp = pred + f * fs_pred + (ptrdiff_t)y * sp + x;
+    uint8_t *dp = dst + f * fs_dst + (ptrdiff_t)y * sd + x;
+#pragma unroll
+    for (int r = 0; r < N; ++r) {
+        uint32_t p[HW];
+        static_for<0, HW>([&](auto kk) {
+            constexpr int k = HV_V(kk), r0 = DST ? 2 * k : pair_row(N, k, 0), r1 = DST ? 2 * k + 1 : pair_row(N, k, 1);
+            p[k] = pack_sat_s16(B[r0][r] >> 7, B[r1][r] >> 7);  // the clip to int16 of residual_decode.c stage 1
+        });
+        int o[N];
+        if (DST) inv_dst4(p, o, 2048);
+        else InvBfly<N>::run(p, o, 2048);
+        uint32_t pw[N / 4], ow[N / 4];
+        load_words<N / 4>(pp + (ptrdiff_t)r * sp, pw);
+#pragma unroll
+        for (int k = 0; k < N / 4; ++k) ow[k] = recon_word(pw[k], o + 4 * k);
+        store_words<N / 4>(dp + (ptrdiff_t)r * sd, ow);
+    }
+}
+
+// ================================================================================================ 16x16 / 32x32
+
+constexpr int BIG_NT = 128;
+
+template <int LOG2>
+struct BigGeom {
+    static constexpr int N = 1 << LOG2, HW = N / 2, WB = 64 / N;   // words per row, blocks per warp
+    static constexpr int PITCH = HW + 4;                           // 20 / 12 words: conflict-free 128-bit row access
+    static constexpr int BLK_STRIDE = N * PITCH + (N == 32 ? 16 : 8);
+    static constexpr int WARP_WORDS = WB * BLK_STRIDE;
+};
+
+template <int LOG2>
+__global__ void __launch_bounds__(BIG_NT) big_inv_kernel(uint8_t *__restrict__ dst, ptrdiff_t sd, const uint8_t *__restrict__ pred, ptrdiff_t sp,
+                                                         ptrdiff_t fs_dst, ptrdiff_t fs_pred, const int16_t *__restrict__ coeffs, BlockGrid g)
+{
+    using G = BigGeom<LOG2>;
+    constexpr int N = G::N, HW = G::HW;
+    __shared__ __align__(16) uint32_t tmp_all[BIG_NT / 32][G::WARP_WORDS];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    uint32_t *tmp = tmp_all[warp];
+    const int b = lane / HW, uw = lane % HW;
+    const long long gb = ((long long)blockIdx.x * (BIG_NT / 32) + warp) * G::WB + b;
+    const bool valid = gb < g.n;
+
+    if (valid) {  // stage 1: this lane owns columns 2*uw and 2*uw+1 of block b
+        const uint32_t *cw = reinterpret_cast<const uint32_t *>(coeffs + gb * (N * N)) + uw;
+        uint32_t W[N];
+#pragma unroll
+        for (int v = 0; v < N; ++v) W[v] = __ldg(cw + v * HW);
+        uint32_t p[HW];
+        int o0[N], o1[N];
+        static_for<0, HW>([&](auto kk) {
+            constexpr int k = HV_V(kk);
+            p[k] = lolo(W[pair_row(N, k, 0)], W[pair_row(N, k, 1)]);
+        });
+        InvBfly<N>::run(p, o0, 64);
+        static_for<0, HW>([&](auto kk) {
+            constexpr int k = HV_V(kk);
+            p[k] = hihi(W[pair_row(N, k, 0)], W[pair_row(N, k, 1)]);
+        });
+        InvBfly<N>::run(p, o1, 64);
+#pragma unroll
+        for (int r = 0; r < N; ++r) tmp[b * G::BLK_STRIDE + r * G::PITCH + uw] = pack_sat_s16(o0[r] >> 7, o1[r] >> 7);
+    }
+    __syncwarp();
+    if (valid) {  // stage 2: this lane owns rows uw and uw + N/2 of block b
+        int x, y, f;
+        g.locate(gb, LOG2, x, y, f);
+#pragma unroll 1
+        for (int h = 0; h < 2; ++h) {
+            const int r = uw + h * HW;
+            uint32_t Bw[HW];
+            const uint4 *row = reinterpret_cast<const uint4 *>(tmp + b * G::BLK_STRIDE + r * G::PITCH);
+#pragma unroll
+            for (int k = 0; k < HW / 4; ++k) {
+                const uint4 v = row[k];
+                Bw[4 * k] = v.x, Bw[4 * k + 1] = v.y, Bw[4 * k + 2] = v.z, Bw[4 * k + 3] = v.w;
+            }
+            uint32_t p[HW];
+            static_for<0, HW>([&](auto kk) {
+                constexpr int k = HV_V(kk), r0 = pair_row(N, k, 0), r1 = pair_row(N, k, 1);
+                p[k] = (r0 & 1) ? hihi(Bw[r0 / 2], Bw[r1 / 2]) : lolo(Bw[r0 / 2], Bw[r1 / 2]);
+            });
+            int o[N];
+            InvBfly<N>::run(p, o, 2048);
+            uint32_t pw[N / 4], ow[N / 4];
+            load_words<N / 4>(pred + f * fs_pred + (ptrdiff_t)(y + r) * sp + x, pw);
+#pragma unroll
+            for (int k = 0; k < N / 4; ++k) ow[k] = recon_word(pw[k], o + 4 * k);
+            store_words<N / 4>(dst + f * fs_dst + (ptrdiff_t)(y + r) * sd + x, ow);
+        }
+    }
+}
+
+template <int LOG2>
+__global__ void __launch_bounds__(BIG_NT) big_fwd_kernel(int16_t *__restrict__ coeffs, const int16_t *__restrict__ res, ptrdiff_t stride, ptrdiff_t fs,
+                                                         BlockGrid g)
+{
+    using G = BigGeom<LOG2>;
+    constexpr int N = G::N, HW = G::HW, S1 = fwd_shift1(LOG2), S2 = fwd_shift2(LOG2);
+    __shared__ __align__(16) uint32_t tmp_all[BIG_NT / 32][G::WARP_WORDS];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    uint32_t *tmp = tmp_all[warp];
+    const int b = lane / HW, uw = lane % HW;
+    const long long gb = ((long long)blockIdx.x * (BIG_NT / 32) + warp) * G::WB + b;
+    const bool valid = gb < g.n;
+
+    if (valid) {  // stage 1: rows uw and uw + N/2 of block b, along x
+        int x, y, f;
+        g.locate(gb, LOG2, x, y, f);
+#pragma unroll 1
+        for (int h = 0; h < 2; ++h) {
+            const int r = uw + h * HW;
+            uint32_t Xw[HW];
+            load_words<HW>(res + f * fs + (ptrdiff_t)(y + r) * stride + x, Xw);
+            int xv[N], a[N];
+#pragma unroll
+            for (int k = 0; k < HW; ++k) xv[2 * k] = s16lo(Xw[k]), xv[2 * k + 1] = s16hi(Xw[k]);
+            FwdBfly<N>::run(xv, a, 1 << (S1 - 1));
+            uint4 *row = reinterpret_cast<uint4 *>(tmp + b * G::BLK_STRIDE + r * G::PITCH);
+#pragma unroll
+            for (int k = 0; k < HW / 4; ++k)
+                row[k] = make_uint4(lolo((uint32_t)(a[8 * k] >> S1), (uint32_t)(a[8 * k + 1] >> S1)), lolo((uint32_t)(a[8 * k + 2] >> S1), (uint32_t)(a[8 * k + 3] >> S1)),
+                                    lolo((uint32_t)(a[8 * k + 4] >> S1), (uint32_t)(a[8 * k + 5] >> S1)), lolo((uint32_t)(a[8 * k + 6] >> S1), (uint32_t)(a[8 * k + 7] >> S1)));
+        }
+    }
+    __syncwarp();
+    if (valid) {  // stage 2: columns 2*uw and 2*uw+1, along y
+        uint32_t *out = reinterpret_cast<uint32_t *>(coeffs + gb * (N * N)) + uw;
+        int x0[N], c0[N];
+#pragma unroll
+        for (int r = 0; r < N; ++r) x0[r] = s16lo(tmp[b * G::BLK_STRIDE + r * G::PITCH + uw]);
+        FwdBfly<N>::run(x0, c0, 1 << (S2 - 1));
+#pragma unroll
+        for (int r = 0; r < N; ++r) x0[r] = s16hi(tmp[b * G::BLK_STRIDE + r * G::PITCH + uw]);
+        int c1[N];
+        FwdBfly<N>::run(x0, c1, 1 << (S2 - 1));
+#pragma unroll
+        for (int v = 0; v < N; ++v) out[v * HW] = lolo((uint32_t)(c0[v] >> S2), (uint32_t)(c1[v] >> S2));
+    }
+}
+
+}  // namespace hv
+
+// ================================================================================================ C ABI
+using namespace hv;
+
+static int launch_fwd(int16_t *coeffs, const int16_t *res, ptrdiff_t stride, ptrdiff_t fs, int log2, int trType, const BlockGrid &g, void *stream)
+{
+    if (g.n == 0) return 0;
+    if (((uintptr_t)coeffs & 15) != 0) return HEVCASM_ERR_ARGUMENT;
+    const unsigned small_grid = (unsigned)((g.n + SMALL_NT - 1) / SMALL_NT);
+    if (log2 == 2 && trType) return launch(small_fwd_kernel<2, true>, small_grid, SMALL_NT, 0, stream, coeffs, res, stride, fs, g);
+    if (log2 == 2) return launch(small_fwd_kernel<2, false>, small_grid, SMALL_NT, 0, stream, coeffs, res, stride, fs, g);
+    if (log2 == 3) return launch(small_fwd_kernel<3, false>, small_grid, SMALL_NT, 0, stream, coeffs, res, stride, fs, g);
+    if (log2 == 4) return launch(big_fwd_kernel<4>, (unsigned)((g.n + 15) / 16), BIG_NT, 0, stream, coeffs, res, stride, fs, g);
+    return launch(big_fwd_kernel<5>, (unsigned)((g.n + 7) / 8), BIG_NT, 0, stream, coeffs, res, stride, fs, g);
+}
+
+static int launch_inv(uint8_t *dst, ptrdiff_t sd, const uint8_t *pred, ptrdiff_t sp, ptrdiff_t fs_dst, ptrdiff_t fs_pred, const int16_t *coeffs, int log2,
+                      int trType, const BlockGrid &g, void *stream)
+{
+    if (g.n == 0) return 0;
+    if (((uintptr_t)coeffs & 15) != 0) return HEVCASM_ERR_ARGUMENT;
+    const unsigned small_grid = (unsigned)((g.n + SMALL_NT - 1) / SMALL_NT);
+    if (log2 == 2 && trType) return launch(small_inv_kernel<2, true>, small_grid, SMALL_NT, 0, stream, dst, sd, pred, sp, fs_dst, fs_pred, coeffs, g);
+    if (log2 == 2) return launch(small_inv_kernel<2, false>, small_grid, SMALL_NT, 0, stream, dst, sd, pred, sp, fs_dst, fs_pred, coeffs, g);
+    if (log2 == 3) return launch(small_inv_kernel<3, false>, small_grid, SMALL_NT, 0, stream, dst, sd, pred, sp, fs_dst, fs_pred, coeffs, g);
+    if (log2 == 4) return launch(big_inv_kernel<4>, (unsigned)((g.n + 15) / 16), BIG_NT, 0, stream, dst, sd, pred, sp, fs_dst, fs_pred, coeffs, g);
+    return launch(big_inv_kernel<5>, (unsigned)((g.n + 7) / 8), BIG_NT, 0, stream, dst, sd, pred, sp, fs_dst, fs_pred, coeffs, g);
+}
+
+static bool tr_args_ok(int log2, int trType) { return log2 >= 2 && log2 <= 5 && (trType == 0 || (trType == 1 && log2 == 2)); }
+
+extern "C" int hevcasm_transform_batch(int16_t *coeffs, const int16_t *residual, ptrdiff_t stride, int log2size, int trType, const int16_t *blk_xy, int n,
+                                       void *stream)
+{
+    if (!tr_args_ok(log2size, trType) || n < 0 || (n > 0 && !blk_xy)) return HEVCASM_ERR_ARGUMENT;
+    BlockGrid g{blk_xy, 0, 0, n};
+    return launch_fwd(coeffs, residual, stride, 0, log2size, trType, g, stream);
+}
+
+extern "C" int hevcasm_transform_frames(int16_t *coeffs, const int16_t *residual, ptrdiff_t stride, int width, int height, int log2size, int trType,
+                                        int n_frames, ptrdiff_t fs, void *stream)
+{
+    if (!tr_args_ok(log2size, trType) || n_frames < 0 || width < 0 || height < 0) return HEVCASM_ERR_ARGUMENT;
+    BlockGrid g{nullptr, width >> log2size, height >> log2size, 0};
+    g.n = (long long)g.nbx * g.nby * n_frames;
+    return launch_fwd(coeffs, residual, stride, fs, log2size, trType, g, stream);
+}
+
+extern "C" int hevcasm_inverse_transform_add_batch(uint8_t *dst, ptrdiff_t sd, const uint8_t *pred, ptrdiff_t sp, const int16_t *coeffs, int log2size,
+                                                   int trType, const int16_t *blk_xy, int n, void *stream)
+{
+    if (!tr_args_ok(log2size, trType) || n < 0 || (n > 0 && !blk_xy)) return HEVCASM_ERR_ARGUMENT;
+    BlockGrid g{blk_xy, 0, 0, n};
+    return launch_inv(dst, sd, pred, sp, 0, 0, coeffs, log2size, trType, g, stream);
+}
+
+extern "C" int hevcasm_inverse_transform_add_frames(uint8_t *dst, ptrdiff_t sd, const uint8_t *pred, ptrdiff_t sp, const int16_t *coeffs, int width,
+                                                    int height, int log2size, int trType, int n_frames, ptrdiff_t fs_dst, ptrdiff_t fs_pred, void *stream)
+{
+    if (!tr_args_ok(log2size, trType) || n_frames < 0 || width < 0 || height < 0) return HEVCASM_ERR_ARGUMENT;
+    BlockGrid g{nullptr, width >> log2size, height >> log2size, 0};
+    g.n = (long long)g.nbx * g.nby * n_frames;
+    return launch_inv(dst, sd, pred, sp, fs_dst, fs_pred, coeffs, log2size, trType, g, stream);
+}

@@ -1,0 +1,166 @@
+// hevcasm_b200 - exact integer HEVC transform building blocks (device side).
+//
+// Reference semantics (kupix/hevcasm residual_decode.c): forward stages :592-852 (transpose((T*row + 2^(s-1)) >> s),
+// truncating int16 store), inverse stages :69-347 (transposing, clip to int16), matrices :623-629 / :662-672 /
+// :719-735 / :795-826 and the 4x4 DST expressions :69-88, :592-611.
+//
+// A 1-D stage is an exact integer matrix product followed by one rounding shift, and no partial sum can leave 32
+// bits (|sum| <= 32*90*32768 < 2^31), so any association order gives identical bits.  That freedom is used here:
+//   * inverse (inputs are int16): even/odd partial butterflies evaluated with IDP.2A (two 16-bit x 8-bit MACs per
+//     instruction; every HEVC coefficient fits s8); operands are int16 pairs arranged in "butterfly order";
+//   * forward N <= 8 and the DST: plain matrix form with IDP.2A straight on the int16 pairs as they sit in memory;
+//   * forward N >= 16: even/odd partial butterflies in 32-bit IMAD (the first-level sums need 17+ bits).
+// All coefficients are compile-time constants generated from the first column of the 32-point matrix.
+#pragma once
+
+#include "common.cuh"
+
+namespace hv {
+namespace tr {
+
+// first column of the 32-point HEVC matrix: 64*sqrt(2)*cos(m*pi/64) in HEVC's integer approximation
+__host__ __device__ constexpr int col32(int m)
+{
+    constexpr int c[33] = {64, 90, 90, 90, 89, 88, 87, 85, 83, 82, 80, 78, 75, 73, 70, 67, 64, 61, 57, 54, 50, 46, 43, 38, 36, 31, 25, 22, 18, 13, 9, 4, 0};
+    return c[m];
+}
+
+// T_N[k][x] by cosine symmetry
+__host__ __device__ constexpr int dct(int N, int k, int x)
+{
+    int m = (k * (32 / N) * (2 * x + 1)) % 128;
+    if (m > 64) m = 128 - m;
+    return m > 32 ? -col32(64 - m) : col32(m);
+}
+
+// forward 4x4 DST-VII matrix M[k][x]
+__host__ __device__ constexpr int dst4(int k, int x)
+{
+    constexpr int m[4][4] = {{29, 55, 74, 84}, {74, 74, 0, -74}, {84, -29, -74, 55}, {55, -84, 74, -29}};
+    return m[k][x];
+}
+
+// two s8 coefficients in the low half of an IDP.2A "b" operand
+__host__ __device__ constexpr int cpair(int a, int b) { return (a & 0xff) | ((b & 0xff) << 8); }
+
+#define HV_V(ic) (decltype(ic)::value)
+
+template <int I>
+struct IC {
+    static constexpr int value = I;
+};
+
+// compile-time counted loop: f(IC<I>{}) for I in [B, E)
+template <int B, int E, class F>
+__device__ __forceinline__ void static_for(F &&f)
+{
+    if constexpr (B < E) {
+        f(IC<B>{});
+        static_for<B + 1, E>(f);
+    }
+}
+
+// ---- butterfly pair order for the inverse -----------------------------------------------------------
+// Pair i (0 <= i < N/2) of an N-point inverse holds input rows (row0, row1):
+//   the N/4 pairs of odd rows (1,3) (5,7) ..., then recursively the pairs of the N/2-point transform of the even rows.
+__host__ __device__ constexpr int pair_row(int N, int i, int which)
+{
+    int stride = 1;
+    while (N > 2) {
+        if (i < N / 4) return stride * (4 * i + 1 + 2 * which);
+        i -= N / 4;
+        N /= 2;
+        stride *= 2;
+    }
+    return which ? stride : 0;
+}
+
+// out[k] = round + sum_v T_N[v][k] * in[v], k < N, with `p` = the int16 input pairs in butterfly order.
+template <int N>
+struct InvBfly {
+    __device__ static __forceinline__ void run(const uint32_t *p, int *out, int round)
+    {
+        int E[N / 2];
+        InvBfly<N / 2>::run(p + N / 4, E, round);
+        static_for<0, N / 2>([&](auto k) {
+            int o = 0;
+            static_for<0, N / 4>([&](auto j) {
+                constexpr int c = cpair(dct(N, 4 * HV_V(j) + 1, HV_V(k)), dct(N, 4 * HV_V(j) + 3, HV_V(k)));
+                o = dp2a_lo(p[HV_V(j)], c, o);
+            });
+            out[HV_V(k)] = E[HV_V(k)] + o;
+            out[N - 1 - HV_V(k)] = E[HV_V(k)] - o;
+        });
+    }
+};
+template <>
+struct InvBfly<2> {
+    __device__ static __forceinline__ void run(const uint32_t *p, int *out, int round)
+    {
+        out[0] = dp2a_lo(p[0], cpair(64, 64), round);
+        out[1] = dp2a_lo(p[0], cpair(64, -64), round);
+    }
+};
+
+// inverse 4-point DST: out[x] = round + sum_k M[k][x] * in[k]; p = natural pairs (in0,in1), (in2,in3)
+__device__ __forceinline__ void inv_dst4(const uint32_t *p, int *out, int round)
+{
+    static_for<0, 4>([&](auto x) {
+        constexpr int c0 = cpair(dst4(0, HV_V(x)), dst4(1, HV_V(x))), c1 = cpair(dst4(2, HV_V(x)), dst4(3, HV_V(x)));
+        out[HV_V(x)] = dp2a_lo(p[1], c1, dp2a_lo(p[0], c0, round));
+    });
+}
+
+// ---- forward, matrix form on natural int16 pairs (w[j] = (x[2j], x[2j+1])) ---------------------------
+template <int N, bool DST>
+__device__ __forceinline__ void fwd_matrix(const uint32_t *w, int *out, int round)
+{
+    static_for<0, N>([&](auto u) {
+        int a = round;
+        static_for<0, N / 2>([&](auto j) {
+            constexpr int c = DST ? cpair(dst4(HV_V(u), 2 * HV_V(j)), dst4(HV_V(u), 2 * HV_V(j) + 1))
+                                  : cpair(dct(N, HV_V(u), 2 * HV_V(j)), dct(N, HV_V(u), 2 * HV_V(j) + 1));
+            a = dp2a_lo(w[HV_V(j)], c, a);
+        });
+        out[HV_V(u)] = a;
+    });
+}
+
+// ---- forward, even/odd partial butterfly in 32-bit (any int inputs) -----------------------------------
+// out[u] = round + sum_x T_N[u][x] * x[x]; OUT_STRIDE spreads the outputs of the recursive even part.
+template <int N, int OUT_STRIDE = 1>
+struct FwdBfly {
+    __device__ static __forceinline__ void run(const int *x, int *out, int round)
+    {
+        int E[N / 2], O[N / 2];
+        static_for<0, N / 2>([&](auto k) {
+            E[HV_V(k)] = x[HV_V(k)] + x[N - 1 - HV_V(k)];
+            O[HV_V(k)] = x[HV_V(k)] - x[N - 1 - HV_V(k)];
+        });
+        FwdBfly<N / 2, OUT_STRIDE * 2>::run(E, out, round);
+        static_for<0, N / 2>([&](auto w) {
+            int a = round;
+            static_for<0, N / 2>([&](auto k) { a += dct(N, 2 * HV_V(w) + 1, HV_V(k)) * O[HV_V(k)]; });
+            out[(2 * HV_V(w) + 1) * OUT_STRIDE] = a;
+        });
+    }
+};
+template <int OUT_STRIDE>
+struct FwdBfly<2, OUT_STRIDE> {
+    __device__ static __forceinline__ void run(const int *x, int *out, int round)
+    {
+        out[0] = 64 * (x[0] + x[1]) + round;
+        out[OUT_STRIDE] = 64 * (x[0] - x[1]) + round;
+    }
+};
+
+__host__ __device__ constexpr int fwd_shift1(int log2) { return log2 - 1; }   // 1, 2, 3, 4   (residual_decode.c:855-892)
+__host__ __device__ constexpr int fwd_shift2(int log2) { return log2 + 6; }   // 8, 9, 10, 11
+
+__device__ __forceinline__ int s16lo(uint32_t w) { return (int)(short)(w & 0xffffu); }
+__device__ __forceinline__ int s16hi(uint32_t w) { return (int)w >> 16; }
+__device__ __forceinline__ uint32_t lolo(uint32_t a, uint32_t b) { return __byte_perm(a, b, 0x5410); }  // (a.lo, b.lo)
+__device__ __forceinline__ uint32_t hihi(uint32_t a, uint32_t b) { return __byte_perm(a, b, 0x7632); }  // (a.hi, b.hi)
+
+}  // namespace tr
+}  // namespace hv

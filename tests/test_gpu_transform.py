@@ -1,0 +1,111 @@
+"""GPU parity: forward transforms and inverse transform + add (4x4 DST/DCT .. 32x32) vs the CPU oracle, bit-exact."""
+import numpy as np
+import pytest
+
+from hevcasm_b200 import lib, synth
+from oracle.binding import ptr
+from gpu_util import to_dev, dev_full, dptr, to_host
+from test_oracle_vs_reference import TR
+
+pytestmark = pytest.mark.gpu
+
+
+def _res_planes(seed, nf, width, height, lo, hi, pad=4):
+    pitch = synth.pitch_for(width, pad, 64)
+    rows = height + 2 * pad
+    buf = synth.random_int16(seed, nf * rows * pitch, lo, hi).reshape(nf, rows, pitch)
+    return synth.Planes(buf, width, height, pad)
+
+
+@pytest.mark.parametrize("trType,log2", TR)
+@pytest.mark.parametrize("rng", [(-256, 255), (-32768, 32767)])
+def test_forward_frames(oracle, trType, log2, rng):
+    width, height, nf, n = 200, 104, 3, 1 << log2
+    res = _res_planes(60 + log2, nf, width, height, *rng)
+    nb = (width // n) * (height // n)
+    want = np.zeros(nf * nb * n * n, np.int16)
+    oracle.drv("transform_frames", ptr(want), ptr(res.buf, res.origin), res.pitch, width, height, log2, trType, nf, res.frame_stride, threads=8)
+    dres = to_dev(res.buf)
+    got = dev_full(want.shape, np.int16, 0x5a5a)
+    lib.call("transform_frames", dptr(got), dptr(dres, res.origin), res.pitch, width, height, log2, trType, nf, res.frame_stride)
+    assert np.array_equal(to_host(got), want)
+
+
+@pytest.mark.parametrize("trType,log2", TR)
+def test_forward_list_unaligned(oracle, trType, log2):
+    width, height, n = 160, 96, 1 << log2
+    res = _res_planes(70 + log2, 1, width, height, -256, 255, pad=8)
+    xy = synth.grid_xy(width - 5, height - 3, n, n)[::2].copy()
+    xy += np.array([5, 3], np.int16)       # odd x: rows are only 2-byte aligned
+    want = np.zeros(len(xy) * n * n, np.int16)
+    oracle.drv("transform_batch", ptr(want), ptr(res.buf, res.origin), res.pitch, log2, trType, ptr(xy), len(xy), threads=4)
+    dres, dxy = to_dev(res.buf), to_dev(xy)
+    got = dev_full(want.shape, np.int16, 0x5a5a)
+    lib.call("transform_batch", dptr(got), dptr(dres, res.origin), res.pitch, log2, trType, dptr(dxy), len(xy))
+    assert np.array_equal(to_host(got), want)
+
+
+def _coeff_sets(seed, n_coef, n):
+    full = synth.random_int16(seed, n_coef)                      # full-range, reference residual_decode.c:574
+    small = synth.random_int16(seed + 1, n_coef, -600, 600)
+    sparse = np.zeros(n_coef, np.int16)
+    sparse[::n * n] = synth.random_int16(seed + 2, len(sparse[::n * n]), -4000, 4000)   # DC only
+    sparse[1::n * n] = 321
+    extreme = np.where(synth.random_bytes(seed + 3, n_coef) & 1, 32767, -32768).astype(np.int16)
+    return {"full": full, "small": small, "sparse": sparse, "extreme": extreme}
+
+
+@pytest.mark.parametrize("trType,log2", TR)
+def test_inverse_frames(oracle, trType, log2):
+    width, height, nf, n = 200, 104, 2, 1 << log2
+    pred = synth.random_planes(80 + log2, nf, width, height, 8)
+    nb = (width // n) * (height // n)
+    for name, co in _coeff_sets(81 + log2, nf * nb * n * n, n).items():
+        want = synth.random_planes(82, nf, width, height, 8)
+        got = to_dev(want.buf)
+        oracle.drv("inverse_transform_add_frames", ptr(want.buf, want.origin), want.pitch, ptr(pred.buf, pred.origin), pred.pitch, ptr(co), width,
+                   height, log2, trType, nf, want.frame_stride, pred.frame_stride, threads=8)
+        dp, dc = to_dev(pred.buf), to_dev(co)
+        lib.call("inverse_transform_add_frames", dptr(got, want.origin), want.pitch, dptr(dp, pred.origin), pred.pitch, dptr(dc), width, height,
+                 log2, trType, nf, want.frame_stride, pred.frame_stride)
+        assert np.array_equal(to_host(got), want.buf), name
+
+
+@pytest.mark.parametrize("trType,log2", TR)
+def test_inverse_list_unaligned(oracle, trType, log2):
+    width, height, n = 160, 96, 1 << log2
+    pred = synth.random_planes(90 + log2, 1, width, height, 8)
+    xy = synth.grid_xy(width - 3, height - 1, n, n)[::2].copy()
+    xy += np.array([3, 1], np.int16)
+    co = synth.random_int16(91 + log2, len(xy) * n * n, -3000, 3000)
+    want = synth.random_planes(92, 1, width, height, 8)
+    got = to_dev(want.buf)
+    oracle.drv("inverse_transform_add_batch", ptr(want.buf, want.origin), want.pitch, ptr(pred.buf, pred.origin), pred.pitch, ptr(co), log2, trType,
+               ptr(xy), len(xy), threads=4)
+    dp, dc, dxy = to_dev(pred.buf), to_dev(co), to_dev(xy)
+    lib.call("inverse_transform_add_batch", dptr(got, want.origin), want.pitch, dptr(dp, pred.origin), pred.pitch, dptr(dc), log2, trType, dptr(dxy),
+             len(xy))
+    assert np.array_equal(to_host(got), want.buf)
+
+
+@pytest.mark.parametrize("log2", [2, 3, 4, 5])
+def test_roundtrip_property(log2):
+    """size-independent property at 1080p: forward DCT then inverse on a zero predictor reproduces the (clipped)
+    residual to within the transform's rounding (|error| <= 2), and an all-zero residual gives all-zero coefficients."""
+    width, height, n = 1920, 1080, 1 << log2
+    bw, bh = width // n * n, height // n * n
+    res = synth.residual_planes(100 + log2, 1, width, height)
+    dres = to_dev(res.buf)
+    nb = (width // n) * (height // n)
+    co = dev_full((nb * n * n,), np.int16, 0)
+    lib.call("transform_frames", dptr(co), dptr(dres, res.origin), res.pitch, width, height, log2, 0, 1, res.frame_stride)
+    pitch = synth.pitch_for(width, 0)
+    pred = dev_full((1, height, pitch), np.uint8, 128)
+    out = dev_full((1, height, pitch), np.uint8, 0)
+    lib.call("inverse_transform_add_frames", dptr(out), pitch, dptr(pred), pitch, dptr(co), width, height, log2, 0, 1, height * pitch, height * pitch)
+    rec = to_host(out)[0, :bh, :bw].astype(np.int32) - 128
+    src = np.clip(res.interior(0)[:bh, :bw].astype(np.int32), -128, 127)
+    assert np.max(np.abs(rec - src)) <= 2
+    zero = dev_full(res.buf.shape, np.int16, 0)
+    lib.call("transform_frames", dptr(co), dptr(zero, res.origin), res.pitch, width, height, log2, 0, 1, res.frame_stride)
+    assert not to_host(co).any()

@@ -8,8 +8,8 @@
 #include <algorithm>
 #include <cuda_runtime.h>
 
-enum Op { VABSDIFF4, IDP4A, IDP2A, IMAD, SHF, PRMT, IADD3, LOP3, MIX_SAD_SHF, MIX_DP4_DP2, N_OPS };
-static const char *kNames[N_OPS] = {"vabsdiff4_acc", "idp4a", "idp2a", "imad", "shf", "prmt", "iadd3", "lop3", "mix_8sad_1shf", "mix_dp4a_dp2a"};
+enum Op { VABSDIFF4, IDP4A, IDP2A, IMAD, SHF, PRMT, IADD3, LOP3, MIX_SAD_SHF, MIX_DP4_DP2, MIX_SAD_IMAD, MIX_SAD_PRMT, MIX_IDP_IMAD, MIX_IDP_SHF, MIX_IDP_PRMT, MIX_IMAD_SHF, MIX_IDP_SAD, N_OPS };
+static const char *kNames[N_OPS] = {"vabsdiff4_acc", "idp4a", "idp2a", "imad", "shf", "prmt", "iadd3", "lop3", "mix_8sad_1shf", "mix_dp4a_dp2a", "mix_sad_imad", "mix_sad_prmt", "mix_idp_imad", "mix_idp_shf", "mix_idp_prmt", "mix_imad_shf", "mix_idp_sad"};
 
 template <int OP>
 __device__ __forceinline__ uint32_t step(uint32_t acc, uint32_t a, uint32_t b)
@@ -21,7 +21,7 @@ __device__ __forceinline__ uint32_t step(uint32_t acc, uint32_t a, uint32_t b)
     else if (OP == IMAD) asm volatile("mad.lo.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(acc));
     else if (OP == SHF) asm volatile("shf.r.clamp.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(acc), "r"(a), "r"(b));
     else if (OP == PRMT) asm volatile("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(acc), "r"(a), "r"(b));
-    else if (OP == IADD3) asm volatile("add.u32 %0, %1, %2;" : "=r"(d) : "r"(acc), "r"(a));
+    else if (OP == IADD3) asm volatile("add.u32 %0, %1, %2;" : "=r"(d) : "r"(acc), "r"(b + threadIdx.x * (acc & 1)));
     else asm volatile("lop3.b32 %0, %1, %2, %3, 0x96;" : "=r"(d) : "r"(acc), "r"(a), "r"(b));
     return d;
 }
@@ -45,6 +45,20 @@ __global__ void __launch_bounds__(1024, 1) peak_kernel(uint32_t *out, long long 
                     if (i == 7) a = step<SHF>(a, b, 8);
                 } else if (OP == MIX_DP4_DP2) {
                     acc[i] = (i & 1) ? step<IDP4A>(acc[i], a, b) : step<IDP2A>(acc[i], a, b);
+                } else if (OP == MIX_SAD_IMAD) {
+                    acc[i] = (i & 1) ? step<VABSDIFF4>(acc[i], a, b) : step<IMAD>(acc[i], a, b);
+                } else if (OP == MIX_SAD_PRMT) {
+                    acc[i] = (i & 1) ? step<VABSDIFF4>(acc[i], a, b) : step<PRMT>(acc[i], a, b);
+                } else if (OP == MIX_IDP_IMAD) {
+                    acc[i] = (i & 1) ? step<IDP4A>(acc[i], a, b) : step<IMAD>(acc[i], a, b);
+                } else if (OP == MIX_IDP_SHF) {
+                    acc[i] = (i & 1) ? step<IDP4A>(acc[i], a, b) : step<SHF>(acc[i], a, b);
+                } else if (OP == MIX_IDP_PRMT) {
+                    acc[i] = (i & 1) ? step<IDP4A>(acc[i], a, b) : step<PRMT>(acc[i], a, b);
+                } else if (OP == MIX_IMAD_SHF) {
+                    acc[i] = (i & 1) ? step<IMAD>(acc[i], a, b) : step<SHF>(acc[i], a, b);
+                } else if (OP == MIX_IDP_SAD) {
+                    acc[i] = (i & 1) ? step<IDP4A>(acc[i], a, b) : step<VABSDIFF4>(acc[i], a, b);
                 } else {
                     acc[i] = step<OP>(acc[i], a, b);
                 }
@@ -104,6 +118,13 @@ int main()
     run<LOP3>(sms, out, cyc, &r[LOP3], &ms[LOP3]);
     run<MIX_SAD_SHF>(sms, out, cyc, &r[MIX_SAD_SHF], &ms[MIX_SAD_SHF]);
     run<MIX_DP4_DP2>(sms, out, cyc, &r[MIX_DP4_DP2], &ms[MIX_DP4_DP2]);
+    run<MIX_SAD_IMAD>(sms, out, cyc, &r[MIX_SAD_IMAD], &ms[MIX_SAD_IMAD]);
+    run<MIX_SAD_PRMT>(sms, out, cyc, &r[MIX_SAD_PRMT], &ms[MIX_SAD_PRMT]);
+    run<MIX_IDP_IMAD>(sms, out, cyc, &r[MIX_IDP_IMAD], &ms[MIX_IDP_IMAD]);
+    run<MIX_IDP_SHF>(sms, out, cyc, &r[MIX_IDP_SHF], &ms[MIX_IDP_SHF]);
+    run<MIX_IDP_PRMT>(sms, out, cyc, &r[MIX_IDP_PRMT], &ms[MIX_IDP_PRMT]);
+    run<MIX_IMAD_SHF>(sms, out, cyc, &r[MIX_IMAD_SHF], &ms[MIX_IMAD_SHF]);
+    run<MIX_IDP_SAD>(sms, out, cyc, &r[MIX_IDP_SAD], &ms[MIX_IDP_SAD]);
     printf("{\"gpu\": \"%s\", \"sms\": %d, \"clock_khz_max\": %d, \"thread_ops_per_clk_per_sm\": {", prop.name, sms, prop.clockRate);
     for (int i = 0; i < N_OPS; ++i) printf("%s\"%s\": %.2f", i ? ", " : "", kNames[i], r[i]);
     printf("}, \"effective_ghz\": {");
