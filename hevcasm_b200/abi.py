@@ -39,6 +39,13 @@ GPU_ONLY_ABI = {
     "residual_pipeline_frames": [P, PD, P, P, P, PD, P, PD, I, I, I, I, I, I, I, I, I, I, PD, PD, PD],
 }
 
+# host-memory forms: hevcasm_<name>(hevcasm_cuda_context *ctx, ...host pointers...) - no stream argument
+HOST_ABI = {
+    "sad_sweep_pyramid_frames_host": [P, P, PD, P, PD, I, I, I, I, I, I, PD, PD, P, P, P, P],
+    "pred_uni_frames_host": [P, P, PD, P, PD, I, I, I, I, I, I, I, PD, PD],
+    "residual_pipeline_frames_host": [P, P, PD, P, P, P, PD, P, PD, I, I, I, I, I, I, I, I, I, I, PD, PD, PD],
+}
+
 
 def HEVCASM_RECT(w, h):
     """reference hevcasm.h:156"""

@@ -1,0 +1,230 @@
+// hevcasm_b200 - host-memory forms of the batched entry points (hevcasm_batch.h, "host-memory forms").
+//
+// A hevcasm_cuda_context owns three streams (copy-in, compute, copy-out), an event pool and one device arena.  A *_host
+// call cuts the batch into chunks of whole frames, and runs them through a ring of arena slots as a three-stage
+// pipeline: chunk f+1 travels host->device while chunk f is computed and the results of chunk f-1 travel device->host.
+// The data path is the same kernels the device-pointer entry points launch - there is no CPU arithmetic here.
+//
+// Host buffers should be page-locked (hevcasm_cuda_host_alloc) for the copies to overlap; pageable memory works but
+// serialises.
+#include "common.cuh"
+
+#include <algorithm>
+#include <new>
+#include <vector>
+
+struct hevcasm_cuda_context {
+    int device = 0;
+    cudaStream_t s_in = nullptr, s_run = nullptr, s_out = nullptr;
+    uint8_t *arena = nullptr;
+    size_t arena_bytes = 0;
+    std::vector<cudaEvent_t> events;
+    size_t next_event = 0;
+
+    cudaEvent_t event()
+    {
+        if (next_event == events.size()) {
+            cudaEvent_t e;
+            if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+            events.push_back(e);
+        }
+        return events[next_event++];
+    }
+};
+
+namespace {
+
+constexpr size_t kAlign = 256;
+inline size_t round_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+// carves 256-byte aligned pieces out of one arena slot
+struct Carver {
+    uint8_t *base;
+    size_t used = 0;
+    template <class T>
+    T *take(size_t bytes)
+    {
+        T *p = reinterpret_cast<T *>(base + used);
+        used += round_up(bytes, kAlign);
+        return p;
+    }
+};
+
+// a padded plane batch on the device: `frames` planes of (height + 2*pad) rows x pitch bytes, elem bytes per sample
+struct DevPlanes {
+    size_t pitch_elems, rows, frame_elems, elem;
+    int pad;
+    size_t bytes(int frames) const { return (size_t)frames * frame_elems * elem; }
+    size_t origin() const { return (size_t)pad * pitch_elems + pad; }  // element offset of sample (0,0)
+};
+
+DevPlanes plan_planes(int width, int height, int pad, size_t elem)
+{
+    DevPlanes d;
+    d.elem = elem, d.pad = pad;
+    d.pitch_elems = round_up(((size_t)width + 2 * pad) * elem, kAlign) / elem;
+    d.rows = (size_t)height + 2 * pad;
+    d.frame_elems = d.pitch_elems * d.rows;
+    return d;
+}
+
+// host (sample (0,0) of frame f0 at h, row stride hs, frame stride hfs; all in elements) -> device planes, `frames` frames
+int copy_in(const DevPlanes &d, void *dev, const void *h, ptrdiff_t hs, ptrdiff_t hfs, int width, int frames, cudaStream_t s)
+{
+    for (int f = 0; f < frames; ++f) {
+        const uint8_t *src = (const uint8_t *)h + ((ptrdiff_t)f * hfs - (ptrdiff_t)d.pad * hs - d.pad) * (ptrdiff_t)d.elem;
+        uint8_t *dst = (uint8_t *)dev + (size_t)f * d.frame_elems * d.elem;
+        HV_CUDA(cudaMemcpy2DAsync(dst, d.pitch_elems * d.elem, src, (size_t)hs * d.elem, ((size_t)width + 2 * d.pad) * d.elem, d.rows,
+                                  cudaMemcpyHostToDevice, s));
+    }
+    return 0;
+}
+
+// device planes -> host, interior (width x height) only
+int copy_out(const DevPlanes &d, const void *dev, void *h, ptrdiff_t hs, ptrdiff_t hfs, int width, int height, int frames, cudaStream_t s)
+{
+    for (int f = 0; f < frames; ++f) {
+        uint8_t *dst = (uint8_t *)h + (ptrdiff_t)f * hfs * (ptrdiff_t)d.elem;
+        const uint8_t *src = (const uint8_t *)dev + ((size_t)f * d.frame_elems + d.origin()) * d.elem;
+        HV_CUDA(cudaMemcpy2DAsync(dst, (size_t)hs * d.elem, src, d.pitch_elems * d.elem, (size_t)width * d.elem, height, cudaMemcpyDeviceToHost, s));
+    }
+    return 0;
+}
+
+// Three-stage ring pipeline over chunks of frames.  `slot_bytes(frames)` sizes one slot; stage callbacks enqueue on the
+// stream they are given.
+template <class In, class Run, class Out>
+int run_pipeline(hevcasm_cuda_context *ctx, int n_frames, size_t bytes_per_frame, In in, Run run, Out out)
+{
+    if (n_frames == 0) return 0;
+    HV_CUDA(cudaSetDevice(ctx->device));
+    const size_t per_frame = round_up(bytes_per_frame, kAlign) + 16 * kAlign;  // slack for per-piece alignment
+    if (per_frame > ctx->arena_bytes) return HEVCASM_ERR_ARGUMENT;               // arena cannot hold even one frame
+    // chunk = whole frames; aim for >= 3 slots so the three stages overlap, and chunks of >= ~32 MB so launches stay large
+    int max_frames_in_arena = (int)std::min<size_t>(ctx->arena_bytes / per_frame, (size_t)n_frames);
+    int chunk = std::max(1, std::min(max_frames_in_arena / 3, std::max(1, (int)((size_t)(32u << 20) / per_frame))));
+    if (max_frames_in_arena < 3) chunk = 1;
+    const int n_slots = std::max(1, std::min(max_frames_in_arena / chunk, 4));
+    const int n_chunks = (n_frames + chunk - 1) / chunk;
+    const size_t slot_bytes = (size_t)chunk * per_frame;
+    ctx->next_event = 0;
+    std::vector<cudaEvent_t> done_out(n_chunks, nullptr);
+    for (int c = 0; c < n_chunks; ++c) {
+        const int f0 = c * chunk, nf = std::min(chunk, n_frames - f0);
+        uint8_t *slot = ctx->arena + (size_t)(c % n_slots) * slot_bytes;
+        if (c >= n_slots) HV_CUDA(cudaStreamWaitEvent(ctx->s_in, done_out[c - n_slots], 0));  // slot is free again
+        int e = in(slot, f0, nf, ctx->s_in);
+        if (e) return e;
+        cudaEvent_t ev_in = ctx->event(), ev_run = ctx->event(), ev_out = ctx->event();
+        if (!ev_in || !ev_run || !ev_out) return (int)cudaErrorMemoryAllocation;
+        HV_CUDA(cudaEventRecord(ev_in, ctx->s_in));
+        HV_CUDA(cudaStreamWaitEvent(ctx->s_run, ev_in, 0));
+        e = run(slot, f0, nf, ctx->s_run);
+        if (e) return e;
+        HV_CUDA(cudaEventRecord(ev_run, ctx->s_run));
+        HV_CUDA(cudaStreamWaitEvent(ctx->s_out, ev_run, 0));
+        e = out(slot, f0, nf, ctx->s_out);
+        if (e) return e;
+        HV_CUDA(cudaEventRecord(ev_out, ctx->s_out));
+        done_out[c] = ev_out;
+    }
+    HV_CUDA(cudaStreamSynchronize(ctx->s_out));
+    HV_CUDA(cudaStreamSynchronize(ctx->s_run));
+    HV_CUDA(cudaStreamSynchronize(ctx->s_in));
+    return 0;
+}
+
+}  // namespace
+
+extern "C" hevcasm_cuda_context *hevcasm_cuda_context_create(int device, size_t arena_bytes)
+{
+    if (cudaSetDevice(device) != cudaSuccess) return nullptr;
+    hevcasm_cuda_context *ctx = new (std::nothrow) hevcasm_cuda_context;
+    if (!ctx) return nullptr;
+    ctx->device = device;
+    bool ok = cudaStreamCreateWithFlags(&ctx->s_in, cudaStreamNonBlocking) == cudaSuccess &&
+              cudaStreamCreateWithFlags(&ctx->s_run, cudaStreamNonBlocking) == cudaSuccess &&
+              cudaStreamCreateWithFlags(&ctx->s_out, cudaStreamNonBlocking) == cudaSuccess;
+    if (ok && arena_bytes) ok = cudaMalloc((void **)&ctx->arena, arena_bytes) == cudaSuccess;
+    if (!ok) {
+        hevcasm_cuda_context_destroy(ctx);
+        return nullptr;
+    }
+    ctx->arena_bytes = arena_bytes;
+    return ctx;
+}
+
+extern "C" void hevcasm_cuda_context_destroy(hevcasm_cuda_context *ctx)
+{
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    for (cudaEvent_t e : ctx->events) cudaEventDestroy(e);
+    if (ctx->arena) cudaFree(ctx->arena);
+    if (ctx->s_in) cudaStreamDestroy(ctx->s_in);
+    if (ctx->s_run) cudaStreamDestroy(ctx->s_run);
+    if (ctx->s_out) cudaStreamDestroy(ctx->s_out);
+    delete ctx;
+}
+
+extern "C" void *hevcasm_cuda_context_stream(hevcasm_cuda_context *ctx) { return ctx ? (void *)ctx->s_run : nullptr; }
+
+extern "C" void *hevcasm_cuda_host_alloc(size_t bytes)
+{
+    void *p = nullptr;
+    return cudaHostAlloc(&p, bytes, cudaHostAllocDefault) == cudaSuccess ? p : nullptr;
+}
+
+extern "C" void hevcasm_cuda_host_free(void *p)
+{
+    if (p) cudaFreeHost(p);
+}
+
+// ------------------------------------------------------------------------------------------------ SAD pyramid
+
+extern "C" int hevcasm_sad_sweep_pyramid_frames_host(hevcasm_cuda_context *ctx, const uint8_t *src, ptrdiff_t ss, const uint8_t *ref, ptrdiff_t sr,
+                                                     int width, int height, int pad, int dx0, int dy0, int n_frames, ptrdiff_t fs_src,
+                                                     ptrdiff_t fs_ref, int32_t *sad8, int32_t *sad16, int32_t *sad32, int32_t *sad64)
+{
+    if (!ctx || width < 8 || height < 8 || n_frames < 0 || pad < 0) return HEVCASM_ERR_ARGUMENT;
+    // the window [dx0, dx0+8) x [dy0, dy0+8) must lie inside the padding that travels with the frames
+    if (dx0 < -pad || dy0 < -pad || dx0 + 7 > pad || dy0 + 7 > pad) return HEVCASM_ERR_ARGUMENT;
+    const DevPlanes d = plan_planes(width, height, pad, 1);
+    int32_t *host_out[4] = {sad8, sad16, sad32, sad64};
+    size_t out_elems[4];  // per frame
+    for (int l = 0; l < 4; ++l) out_elems[l] = host_out[l] ? (size_t)(width >> (3 + l)) * (height >> (3 + l)) * 64 : 0;
+    size_t per_frame = 2 * (d.frame_elems + kAlign);
+    for (int l = 0; l < 4; ++l) per_frame += out_elems[l] * 4 + kAlign;
+
+    struct Slot {
+        uint8_t *src, *ref;
+        int32_t *out[4];
+    };
+    auto carve = [&](uint8_t *slot, int nf) {
+        Carver c{slot};
+        Slot s;
+        s.src = c.take<uint8_t>(d.bytes(nf));
+        s.ref = c.take<uint8_t>(d.bytes(nf));
+        for (int l = 0; l < 4; ++l) s.out[l] = out_elems[l] ? c.take<int32_t>(out_elems[l] * 4 * nf) : nullptr;
+        return s;
+    };
+    // chunk size is fixed by run_pipeline; slots are carved for `chunk` frames, so carve with the chunk's own nf each time
+    return run_pipeline(
+        ctx, n_frames, per_frame,
+        [&](uint8_t *slot, int f0, int nf, cudaStream_t s) {
+            const Slot k = carve(slot, nf);
+            int e = copy_in(d, k.src, src + (ptrdiff_t)f0 * fs_src, ss, fs_src, width, nf, s);
+            return e ? e : copy_in(d, k.ref, ref + (ptrdiff_t)f0 * fs_ref, sr, fs_ref, width, nf, s);
+        },
+        [&](uint8_t *slot, int, int nf, cudaStream_t s) {
+            const Slot k = carve(slot, nf);
+            return hevcasm_sad_sweep_pyramid_frames(k.src + d.origin(), d.pitch_elems, k.ref + d.origin(), d.pitch_elems, width, height, dx0, dy0, nf,
+                                                    d.frame_elems, d.frame_elems, k.out[0], k.out[1], k.out[2], k.out[3], s);
+        },
+        [&](uint8_t *slot, int f0, int nf, cudaStream_t s) {
+            const Slot k = carve(slot, nf);
+            for (int l = 0; l < 4; ++l)
+                if (host_out[l] && out_elems[l])
+                    HV_CUDA(cudaMemcpyAsync(host_out[l] + (size_t)f0 * out_elems[l], k.out[l], out_elems[l] * 4 * nf, cudaMemcpyDeviceToHost, s));
+            return 0;
+        });
+}

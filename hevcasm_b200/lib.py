@@ -3,7 +3,7 @@ missing or does not export the whole ABI this raises - nothing in this package c
 import ctypes as C
 import os
 
-from .abi import BATCH_ABI, GPU_ONLY_ABI, P
+from .abi import BATCH_ABI, GPU_ONLY_ABI, HOST_ABI, P
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libhevcasm_b200.so")
@@ -29,6 +29,20 @@ def load():
             fn = getattr(lib, "hevcasm_" + name)  # AttributeError if the symbol is missing: fail loudly
             fn.argtypes = list(args) + [P]        # + void *stream
             fn.restype = C.c_int
+    for name, args in HOST_ABI.items():
+        fn = getattr(lib, "hevcasm_" + name)
+        fn.argtypes = list(args)
+        fn.restype = C.c_int
+    lib.hevcasm_cuda_context_create.argtypes = [C.c_int, C.c_size_t]
+    lib.hevcasm_cuda_context_create.restype = P
+    lib.hevcasm_cuda_context_destroy.argtypes = [P]
+    lib.hevcasm_cuda_context_destroy.restype = None
+    lib.hevcasm_cuda_context_stream.argtypes = [P]
+    lib.hevcasm_cuda_context_stream.restype = P
+    lib.hevcasm_cuda_host_alloc.argtypes = [C.c_size_t]
+    lib.hevcasm_cuda_host_alloc.restype = P
+    lib.hevcasm_cuda_host_free.argtypes = [P]
+    lib.hevcasm_cuda_host_free.restype = None
     lib.hevcasm_cuda_error_string.argtypes = [C.c_int]
     lib.hevcasm_cuda_error_string.restype = C.c_char_p
     lib.hevcasm_cuda_launch_count.argtypes = []
@@ -48,6 +62,58 @@ def call(name, *args, stream=None):
     """Enqueue hevcasm_<name>(*args, stream); raises HevcasmError on a non-zero return."""
     fn = getattr(load(), "hevcasm_" + name)
     check(fn(*args, stream))
+
+
+def call_host(name, ctx, *args):
+    """hevcasm_<name>(ctx, *args) for the host-memory forms (synchronous); raises HevcasmError on a non-zero return."""
+    fn = getattr(load(), "hevcasm_" + name)
+    check(fn(ctx, *args))
+
+
+class Context:
+    """hevcasm_cuda_context: streams + device arena for the *_host entry points."""
+
+    def __init__(self, device=0, arena_bytes=1 << 30):
+        self.handle = load().hevcasm_cuda_context_create(device, arena_bytes)
+        if not self.handle:
+            raise HevcasmError(f"hevcasm_cuda_context_create(device={device}, arena_bytes={arena_bytes}) failed")
+
+    def close(self):
+        if self.handle:
+            load().hevcasm_cuda_context_destroy(self.handle)
+            self.handle = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+
+def pinned_array(shape, dtype):
+    """numpy array over page-locked host memory from hevcasm_cuda_host_alloc (kept alive by the array's base)."""
+    import numpy as np
+    n = int(np.prod(shape)) * np.dtype(dtype).itemsize
+    p = load().hevcasm_cuda_host_alloc(max(n, 1))
+    if not p:
+        raise HevcasmError(f"hevcasm_cuda_host_alloc({n}) failed")
+    buf = (C.c_uint8 * max(n, 1)).from_address(p)
+
+    class _Owner:
+        def __init__(self, ptr, keep):
+            self.ptr, self.keep = ptr, keep
+
+        def __del__(self):
+            try:
+                load().hevcasm_cuda_host_free(self.ptr)
+            except Exception:
+                pass
+    arr = np.frombuffer(buf, dtype=np.uint8, count=n).view(dtype).reshape(shape)
+    _PINNED[arr.ctypes.data] = _Owner(p, buf)
+    return arr
+
+
+_PINNED = {}
 
 
 def launch_count():

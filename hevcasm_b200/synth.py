@@ -18,13 +18,29 @@ def splitmix64(seed, n):
         return z ^ (z >> np.uint64(31))
 
 
+def aligned_empty(shape, dtype, align=256):
+    """C-contiguous array whose data pointer is `align`-byte aligned (a codec's frame store is; the reference's SIMD
+    SAD needs 32-byte aligned source rows, reference vp9_sad4d_intrin_avx2.c:34)."""
+    dtype = np.dtype(dtype)
+    n = int(np.prod(shape)) * dtype.itemsize
+    raw = np.empty(n + align, np.uint8)
+    off = (-raw.ctypes.data) % align
+    return raw[off:off + n].view(dtype).reshape(shape)
+
+
+def aligned_copy(a, align=256):
+    out = aligned_empty(a.shape, a.dtype, align)
+    out[...] = a
+    return out
+
+
 def random_bytes(seed, n):
-    return splitmix64(seed, (n + 7) // 8).view(np.uint8)[:n].copy()
+    return aligned_copy(splitmix64(seed, (n + 7) // 8).view(np.uint8)[:n])
 
 
 def random_int16(seed, n, lo=-32768, hi=32767):
     r = splitmix64(seed, (n + 3) // 4).view(np.uint16)[:n].astype(np.int64)
-    return (lo + r % (hi - lo + 1)).astype(np.int16)
+    return aligned_copy((lo + r % (hi - lo + 1)).astype(np.int16))
 
 
 def pitch_for(width, pad, align=256):
@@ -69,7 +85,7 @@ def smooth_planes(seed, n_frames, width, height, pad=80, shift=(0, 0), noise=3):
     rows = height + 2 * pad
     y = np.arange(rows, dtype=np.int64)[:, None] + shift[1]
     x = np.arange(pitch, dtype=np.int64)[None, :] + shift[0]
-    out = np.empty((n_frames, rows, pitch), dtype=np.uint8)
+    out = aligned_empty((n_frames, rows, pitch), np.uint8)
     for f in range(n_frames):
         base = 128 + ((x * 3 + y * 5 + f * 7) % 97) - 48 + (((x >> 4) ^ (y >> 4)) & 1) * 24 + ((x * y) >> 9) % 31
         nz = random_bytes(seed + 1000003 * f, rows * pitch).reshape(rows, pitch).astype(np.int64) % (2 * noise + 1) - noise
@@ -82,7 +98,7 @@ def residual_planes(seed, n_frames, width, height, pad=0):
     pitch = pitch_for(width, pad, align=128)
     rows = height + 2 * pad
     r = splitmix64(seed, (n_frames * rows * pitch + 3) // 4).view(np.uint16)[:n_frames * rows * pitch]
-    return Planes(((r & 0x1FF).astype(np.int16) - 0x100).reshape(n_frames, rows, pitch), width, height, pad)
+    return Planes(aligned_copy(((r & 0x1FF).astype(np.int16) - 0x100).reshape(n_frames, rows, pitch)), width, height, pad)
 
 
 def grid_xy(width, height, w, h):

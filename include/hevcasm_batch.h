@@ -152,6 +152,9 @@ typedef struct hevcasm_cuda_context hevcasm_cuda_context;
 hevcasm_cuda_context HEVCASM_API *hevcasm_cuda_context_create(int device, size_t arena_bytes);
 void HEVCASM_API hevcasm_cuda_context_destroy(hevcasm_cuda_context *ctx);
 void HEVCASM_API *hevcasm_cuda_context_stream(hevcasm_cuda_context *ctx);
+/* page-locked host memory, so that the copies of the *_host forms overlap with compute */
+void HEVCASM_API *hevcasm_cuda_host_alloc(size_t bytes);
+void HEVCASM_API hevcasm_cuda_host_free(void *p);
 
 /* plane-level host forms: each frame is a tightly described plane {pointer to sample (0,0), stride}; `pad` = the number
  * of valid samples around the width x height area that must travel with it (>= candidate range / filter reach). */
