@@ -104,17 +104,11 @@ __device__ __forceinline__ uint32_t recon_word(uint32_t pw, const int *r)
 
 constexpr int SMALL_NT = 128;
 
+// forward transform of the block at src (row stride `stride`), result in coefficient memory order: Yw[v][u/2] = (Y[v][u], Y[v][u+1])
 template <int LOG2, bool DST>
-__global__ void __launch_bounds__(SMALL_NT) small_fwd_kernel(int16_t *__restrict__ coeffs, const int16_t *__restrict__ res, ptrdiff_t stride,
-                                                             ptrdiff_t fs, BlockGrid g)
+__device__ __forceinline__ void small_fwd_core(const int16_t *src, ptrdiff_t stride, uint32_t (&Yw)[1 << LOG2][(1 << LOG2) / 2])
 {
     constexpr int N = 1 << LOG2, HW = N / 2, S1 = fwd_shift1(LOG2), S2 = fwd_shift2(LOG2);
-    const long long i = (long long)blockIdx.x * SMALL_NT + threadIdx.x;
-    if (i >= g.n) return;
-    int x, y, f;
-    g.locate(i, LOG2, x, y, f);
-    const int16_t *src = res + f * fs + (ptrdiff_t)y * stride + x;
-
     uint32_t X[N][HW];
 #pragma unroll
     for (int r = 0; r < N; ++r) load_words<HW>(src + (ptrdiff_t)r * stride, X[r]);
@@ -130,7 +124,6 @@ __global__ void __launch_bounds__(SMALL_NT) small_fwd_kernel(int16_t *__restrict
         for (int u = 0; u < N; ++u) Aw[u][r / 2] = lolo((uint32_t)(a0[u] >> S1), (uint32_t)(a1[u] >> S1));  // truncating, residual_decode.c:674-682
     }
     // stage 2 (along y): Y[v][u], emitted as horizontal pairs (Y[v][u], Y[v][u+1]) = the memory order of coeffs[v*N+u]
-    uint32_t Yw[N][HW];
 #pragma unroll
     for (int u = 0; u < N; u += 2) {
         int b0[N], b1[N];
@@ -139,26 +132,29 @@ __global__ void __launch_bounds__(SMALL_NT) small_fwd_kernel(int16_t *__restrict
 #pragma unroll
         for (int v = 0; v < N; ++v) Yw[v][u / 2] = lolo((uint32_t)(b0[v] >> S2), (uint32_t)(b1[v] >> S2));
     }
-    int16_t *out = coeffs + i * (N * N);
-#pragma unroll
-    for (int v = 0; v < N; ++v) store_words<HW>(out + v * N, Yw[v]);
 }
 
 template <int LOG2, bool DST>
-__global__ void __launch_bounds__(SMALL_NT) small_inv_kernel(uint8_t *__restrict__ dst, ptrdiff_t sd, const uint8_t *__restrict__ pred, ptrdiff_t sp,
-                                                             ptrdiff_t fs_dst, ptrdiff_t fs_pred, const int16_t *__restrict__ coeffs, BlockGrid g)
+__global__ void __launch_bounds__(SMALL_NT) small_fwd_kernel(int16_t *__restrict__ coeffs, const int16_t *__restrict__ res, ptrdiff_t stride,
+                                                             ptrdiff_t fs, BlockGrid g)
 {
     constexpr int N = 1 << LOG2, HW = N / 2;
     const long long i = (long long)blockIdx.x * SMALL_NT + threadIdx.x;
     if (i >= g.n) return;
     int x, y, f;
     g.locate(i, LOG2, x, y, f);
-
-    uint32_t Cw[N][HW];
-    const int16_t *c = coeffs + i * (N * N);
+    uint32_t Yw[N][HW];
+    small_fwd_core<LOG2, DST>(res + f * fs + (ptrdiff_t)y * stride + x, stride, Yw);
+    int16_t *out = coeffs + i * (N * N);
 #pragma unroll
-    for (int v = 0; v < N; ++v) load_words<HW>(c + v * N, Cw[v]);
+    for (int v = 0; v < N; ++v) store_words<HW>(out + v * N, Yw[v]);
+}
 
+// dst = clip8(pred + inverse transform of Cw); Cw in coefficient memory order
+template <int LOG2, bool DST>
+__device__ __forceinline__ void small_inv_core(const uint32_t (&Cw)[1 << LOG2][(1 << LOG2) / 2], uint8_t *dp, ptrdiff_t sd, const uint8_t *pp, ptrdiff_t sp)
+{
+    constexpr int N = 1 << LOG2, HW = N / 2;
     // stage 1 (along v, shift 7, clip16): B[u][y]
     int B[N][N];
 #pragma unroll
@@ -178,8 +174,6 @@ __global__ void __launch_bounds__(SMALL_NT) small_inv_kernel(uint8_t *__restrict
         }
     }
     // stage 2 (along u, shift 12) + add to the predictor
-    const uint8_t *pp = pred + f * fs_pred + (ptrdiff_t)y * sp + x;
-    uint8_t *dp = dst + f * fs_dst + (ptrdiff_t)y * sd + x;
 #pragma unroll
     for (int r = 0; r < N; ++r) {
         uint32_t p[HW];
@@ -198,6 +192,22 @@ __global__ void __launch_bounds__(SMALL_NT) small_inv_kernel(uint8_t *__restrict
     }
 }
 
+template <int LOG2, bool DST>
+__global__ void __launch_bounds__(SMALL_NT) small_inv_kernel(uint8_t *__restrict__ dst, ptrdiff_t sd, const uint8_t *__restrict__ pred, ptrdiff_t sp,
+                                                             ptrdiff_t fs_dst, ptrdiff_t fs_pred, const int16_t *__restrict__ coeffs, BlockGrid g)
+{
+    constexpr int N = 1 << LOG2, HW = N / 2;
+    const long long i = (long long)blockIdx.x * SMALL_NT + threadIdx.x;
+    if (i >= g.n) return;
+    int x, y, f;
+    g.locate(i, LOG2, x, y, f);
+    uint32_t Cw[N][HW];
+    const int16_t *c = coeffs + i * (N * N);
+#pragma unroll
+    for (int v = 0; v < N; ++v) load_words<HW>(c + v * N, Cw[v]);
+    small_inv_core<LOG2, DST>(Cw, dst + f * fs_dst + (ptrdiff_t)y * sd + x, sd, pred + f * fs_pred + (ptrdiff_t)y * sp + x, sp);
+}
+
 // ================================================================================================ 16x16 / 32x32
 
 constexpr int BIG_NT = 128;
@@ -210,24 +220,15 @@ struct BigGeom {
     static constexpr int WARP_WORDS = WB * BLK_STRIDE;
 };
 
+// Inverse of one block by the HW lanes that own it.  W[v] = (C[v][2uw], C[v][2uw+1]) - this lane's two coefficient columns.
+// Must be called by all 32 lanes of the warp (it contains a __syncwarp); lanes with !valid only take part in the barrier.
 template <int LOG2>
-__global__ void __launch_bounds__(BIG_NT) big_inv_kernel(uint8_t *__restrict__ dst, ptrdiff_t sd, const uint8_t *__restrict__ pred, ptrdiff_t sp,
-                                                         ptrdiff_t fs_dst, ptrdiff_t fs_pred, const int16_t *__restrict__ coeffs, BlockGrid g)
+__device__ __forceinline__ void big_inv_core(uint32_t *tmp, int b, int uw, bool valid, const uint32_t (&W)[1 << LOG2], uint8_t *dp, ptrdiff_t sd,
+                                             const uint8_t *pp, ptrdiff_t sp)
 {
     using G = BigGeom<LOG2>;
     constexpr int N = G::N, HW = G::HW;
-    __shared__ __align__(16) uint32_t tmp_all[BIG_NT / 32][G::WARP_WORDS];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    uint32_t *tmp = tmp_all[warp];
-    const int b = lane / HW, uw = lane % HW;
-    const long long gb = ((long long)blockIdx.x * (BIG_NT / 32) + warp) * G::WB + b;
-    const bool valid = gb < g.n;
-
-    if (valid) {  // stage 1: this lane owns columns 2*uw and 2*uw+1 of block b
-        const uint32_t *cw = reinterpret_cast<const uint32_t *>(coeffs + gb * (N * N)) + uw;
-        uint32_t W[N];
-#pragma unroll
-        for (int v = 0; v < N; ++v) W[v] = __ldg(cw + v * HW);
+    if (valid) {  // stage 1: columns 2*uw and 2*uw+1
         uint32_t p[HW];
         int o0[N], o1[N];
         static_for<0, HW>([&](auto kk) {
@@ -245,8 +246,6 @@ __global__ void __launch_bounds__(BIG_NT) big_inv_kernel(uint8_t *__restrict__ d
     }
     __syncwarp();
     if (valid) {  // stage 2: this lane owns rows uw and uw + N/2 of block b
-        int x, y, f;
-        g.locate(gb, LOG2, x, y, f);
 #pragma unroll 1
         for (int h = 0; h < 2; ++h) {
             const int r = uw + h * HW;
@@ -265,35 +264,48 @@ __global__ void __launch_bounds__(BIG_NT) big_inv_kernel(uint8_t *__restrict__ d
             int o[N];
             InvBfly<N>::run(p, o, 2048);
             uint32_t pw[N / 4], ow[N / 4];
-            load_words<N / 4>(pred + f * fs_pred + (ptrdiff_t)(y + r) * sp + x, pw);
+            load_words<N / 4>(pp + (ptrdiff_t)r * sp, pw);
 #pragma unroll
             for (int k = 0; k < N / 4; ++k) ow[k] = recon_word(pw[k], o + 4 * k);
-            store_words<N / 4>(dst + f * fs_dst + (ptrdiff_t)(y + r) * sd + x, ow);
+            store_words<N / 4>(dp + (ptrdiff_t)r * sd, ow);
         }
     }
 }
 
 template <int LOG2>
-__global__ void __launch_bounds__(BIG_NT) big_fwd_kernel(int16_t *__restrict__ coeffs, const int16_t *__restrict__ res, ptrdiff_t stride, ptrdiff_t fs,
-                                                         BlockGrid g)
+__global__ void __launch_bounds__(BIG_NT) big_inv_kernel(uint8_t *__restrict__ dst, ptrdiff_t sd, const uint8_t *__restrict__ pred, ptrdiff_t sp,
+                                                         ptrdiff_t fs_dst, ptrdiff_t fs_pred, const int16_t *__restrict__ coeffs, BlockGrid g)
 {
     using G = BigGeom<LOG2>;
-    constexpr int N = G::N, HW = G::HW, S1 = fwd_shift1(LOG2), S2 = fwd_shift2(LOG2);
+    constexpr int N = G::N, HW = G::HW;
     __shared__ __align__(16) uint32_t tmp_all[BIG_NT / 32][G::WARP_WORDS];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    uint32_t *tmp = tmp_all[warp];
     const int b = lane / HW, uw = lane % HW;
     const long long gb = ((long long)blockIdx.x * (BIG_NT / 32) + warp) * G::WB + b;
     const bool valid = gb < g.n;
-
-    if (valid) {  // stage 1: rows uw and uw + N/2 of block b, along x
-        int x, y, f;
+    uint32_t W[N];
+    int x = 0, y = 0, f = 0;
+    if (valid) {
+        const uint32_t *cw = reinterpret_cast<const uint32_t *>(coeffs + gb * (N * N)) + uw;
+#pragma unroll
+        for (int v = 0; v < N; ++v) W[v] = __ldg(cw + v * HW);
         g.locate(gb, LOG2, x, y, f);
+    }
+    big_inv_core<LOG2>(tmp_all[warp], b, uw, valid, W, dst + f * fs_dst + (ptrdiff_t)y * sd + x, sd, pred + f * fs_pred + (ptrdiff_t)y * sp + x, sp);
+}
+
+// Forward transform of one block by the HW lanes that own it; on return W[v] = (Y[v][2uw], Y[v][2uw+1]).
+template <int LOG2>
+__device__ __forceinline__ void big_fwd_core(uint32_t *tmp, int b, int uw, bool valid, const int16_t *src, ptrdiff_t stride, uint32_t (&W)[1 << LOG2])
+{
+    using G = BigGeom<LOG2>;
+    constexpr int N = G::N, HW = G::HW, S1 = fwd_shift1(LOG2), S2 = fwd_shift2(LOG2);
+    if (valid) {  // stage 1: rows uw and uw + N/2 of block b, along x
 #pragma unroll 1
         for (int h = 0; h < 2; ++h) {
             const int r = uw + h * HW;
             uint32_t Xw[HW];
-            load_words<HW>(res + f * fs + (ptrdiff_t)(y + r) * stride + x, Xw);
+            load_words<HW>(src + (ptrdiff_t)r * stride, Xw);
             int xv[N], a[N];
 #pragma unroll
             for (int k = 0; k < HW; ++k) xv[2 * k] = s16lo(Xw[k]), xv[2 * k + 1] = s16hi(Xw[k]);
@@ -307,7 +319,6 @@ __global__ void __launch_bounds__(BIG_NT) big_fwd_kernel(int16_t *__restrict__ c
     }
     __syncwarp();
     if (valid) {  // stage 2: columns 2*uw and 2*uw+1, along y
-        uint32_t *out = reinterpret_cast<uint32_t *>(coeffs + gb * (N * N)) + uw;
         int x0[N], c0[N];
 #pragma unroll
         for (int r = 0; r < N; ++r) x0[r] = s16lo(tmp[b * G::BLK_STRIDE + r * G::PITCH + uw]);
@@ -317,8 +328,119 @@ __global__ void __launch_bounds__(BIG_NT) big_fwd_kernel(int16_t *__restrict__ c
         int c1[N];
         FwdBfly<N>::run(x0, c1, 1 << (S2 - 1));
 #pragma unroll
-        for (int v = 0; v < N; ++v) out[v * HW] = lolo((uint32_t)(c0[v] >> S2), (uint32_t)(c1[v] >> S2));
+        for (int v = 0; v < N; ++v) W[v] = lolo((uint32_t)(c0[v] >> S2), (uint32_t)(c1[v] >> S2));
     }
+    __syncwarp();  // tmp may be reused by the caller
+}
+
+template <int LOG2>
+__global__ void __launch_bounds__(BIG_NT) big_fwd_kernel(int16_t *__restrict__ coeffs, const int16_t *__restrict__ res, ptrdiff_t stride, ptrdiff_t fs,
+                                                         BlockGrid g)
+{
+    using G = BigGeom<LOG2>;
+    constexpr int N = G::N, HW = G::HW;
+    __shared__ __align__(16) uint32_t tmp_all[BIG_NT / 32][G::WARP_WORDS];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int b = lane / HW, uw = lane % HW;
+    const long long gb = ((long long)blockIdx.x * (BIG_NT / 32) + warp) * G::WB + b;
+    const bool valid = gb < g.n;
+    int x = 0, y = 0, f = 0;
+    if (valid) g.locate(gb, LOG2, x, y, f);
+    uint32_t W[N];
+    big_fwd_core<LOG2>(tmp_all[warp], b, uw, valid, res + f * fs + (ptrdiff_t)y * stride + x, stride, W);
+    if (valid) {
+        uint32_t *out = reinterpret_cast<uint32_t *>(coeffs + gb * (N * N)) + uw;
+#pragma unroll
+        for (int v = 0; v < N; ++v) out[v * HW] = W[v];
+    }
+}
+
+// ================================================================================================ fused residual pipeline
+//
+// forward transform -> quantize (levels + cbf written) -> inverse quantize -> inverse transform -> add to predictor, per block,
+// without the coefficients ever leaving the chip.  Element semantics: the composition of the reference's hevcasm_transform,
+// hevcasm_quantize (quantize.c:160-186), hevcasm_quantize_inverse (quantize.c:53-62) and hevcasm_inverse_transform_add.
+
+struct QuantParams {
+    int q_scale, q_shift, q_off /* offset << (shift-16) */, iq_scale, iq_shift;
+};
+
+// quantise then dequantise one word (two coefficients); the level word goes to `lv`, the OR of the levels into cbf
+__device__ __forceinline__ uint32_t quant_dequant_word(uint32_t w, const QuantParams &q, uint32_t &lv, int &cbf)
+{
+    const int x0 = s16lo(w), x1 = s16hi(w);
+    int l0 = (abs(x0) * q.q_scale + q.q_off) >> q.q_shift, l1 = (abs(x1) * q.q_scale + q.q_off) >> q.q_shift;
+    l0 = x0 < 0 ? -l0 : l0, l1 = x1 < 0 ? -l1 : l1;
+    lv = pack_sat_s16(l0, l1);
+    const int c0 = s16lo(lv), c1 = s16hi(lv);
+    cbf |= c0 | c1;
+    const int add = 1 << (q.iq_shift - 1);
+    return pack_sat_s16((c0 * q.iq_scale + add) >> q.iq_shift, (c1 * q.iq_scale + add) >> q.iq_shift);
+}
+
+struct PipelineParams {
+    uint8_t *rec;
+    const uint8_t *pred;
+    const int16_t *res;
+    int16_t *levels;
+    int32_t *cbf;
+    ptrdiff_t s_rec, s_pred, s_res, fs_rec, fs_pred, fs_res;
+    QuantParams q;
+};
+
+template <int LOG2, bool DST>
+__global__ void __launch_bounds__(SMALL_NT) small_pipeline_kernel(PipelineParams p, BlockGrid g)
+{
+    constexpr int N = 1 << LOG2, HW = N / 2;
+    const long long i = (long long)blockIdx.x * SMALL_NT + threadIdx.x;
+    if (i >= g.n) return;
+    int x, y, f;
+    g.locate(i, LOG2, x, y, f);
+    uint32_t Yw[N][HW];
+    small_fwd_core<LOG2, DST>(p.res + f * p.fs_res + (ptrdiff_t)y * p.s_res + x, p.s_res, Yw);
+    int cbf = 0;
+    int16_t *lv = p.levels + i * (N * N);
+#pragma unroll
+    for (int v = 0; v < N; ++v) {
+        uint32_t L[HW];
+#pragma unroll
+        for (int k = 0; k < HW; ++k) Yw[v][k] = quant_dequant_word(Yw[v][k], p.q, L[k], cbf);
+        store_words<HW>(lv + v * N, L);
+    }
+    if (p.cbf) p.cbf[i] = cbf;
+    small_inv_core<LOG2, DST>(Yw, p.rec + f * p.fs_rec + (ptrdiff_t)y * p.s_rec + x, p.s_rec, p.pred + f * p.fs_pred + (ptrdiff_t)y * p.s_pred + x, p.s_pred);
+}
+
+template <int LOG2>
+__global__ void __launch_bounds__(BIG_NT) big_pipeline_kernel(PipelineParams p, BlockGrid g)
+{
+    using G = BigGeom<LOG2>;
+    constexpr int N = G::N, HW = G::HW;
+    __shared__ __align__(16) uint32_t tmp_all[BIG_NT / 32][G::WARP_WORDS];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int b = lane / HW, uw = lane % HW;
+    const long long gb = ((long long)blockIdx.x * (BIG_NT / 32) + warp) * G::WB + b;
+    const bool valid = gb < g.n;
+    int x = 0, y = 0, f = 0;
+    if (valid) g.locate(gb, LOG2, x, y, f);
+    uint32_t W[N];
+    big_fwd_core<LOG2>(tmp_all[warp], b, uw, valid, p.res + f * p.fs_res + (ptrdiff_t)y * p.s_res + x, p.s_res, W);
+    int cbf = 0;
+    if (valid) {
+        uint32_t *lv = reinterpret_cast<uint32_t *>(p.levels + gb * (N * N)) + uw;
+#pragma unroll
+        for (int v = 0; v < N; ++v) {
+            uint32_t L;
+            W[v] = quant_dequant_word(W[v], p.q, L, cbf);
+            lv[v * HW] = L;
+        }
+    }
+    // OR across the HW lanes that share the block (HW = 8 or 16: groups are aligned, xor stays inside the group)
+#pragma unroll
+    for (int o = 1; o < HW; o <<= 1) cbf |= __shfl_xor_sync(0xffffffffu, cbf, o);
+    if (valid && uw == 0 && p.cbf) p.cbf[gb] = cbf;
+    big_inv_core<LOG2>(tmp_all[warp], b, uw, valid, W, p.rec + f * p.fs_rec + (ptrdiff_t)y * p.s_rec + x, p.s_rec,
+                       p.pred + f * p.fs_pred + (ptrdiff_t)y * p.s_pred + x, p.s_pred);
 }
 
 }  // namespace hv
@@ -385,4 +507,28 @@ extern "C" int hevcasm_inverse_transform_add_frames(uint8_t *dst, ptrdiff_t sd, 
     BlockGrid g{nullptr, width >> log2size, height >> log2size, 0};
     g.n = (long long)g.nbx * g.nby * n_frames;
     return launch_inv(dst, sd, pred, sp, fs_dst, fs_pred, coeffs, log2size, trType, g, stream);
+}
+
+extern "C" int hevcasm_residual_pipeline_frames(uint8_t *rec, ptrdiff_t s_rec, int16_t *levels, int32_t *cbf, const int16_t *residual, ptrdiff_t s_res,
+                                                const uint8_t *pred, ptrdiff_t s_pred, int width, int height, int log2size, int trType, int q_scale,
+                                                int q_shift, int q_offset, int iq_scale, int iq_shift, int n_frames, ptrdiff_t fs_rec, ptrdiff_t fs_res,
+                                                ptrdiff_t fs_pred, void *stream)
+{
+    // quantiser domain of the reference: quantize.c:162-168 asserts; inverse shift must leave a rounding bit
+    if (!tr_args_ok(log2size, trType) || n_frames < 0 || width < 0 || height < 0 || q_shift < 16 || q_shift > 27 || q_scale < 0 || q_scale >= 0x8000 ||
+        q_offset < 0 || q_offset >= 0x8000 || iq_shift < 1 || iq_shift > 30 || ((uintptr_t)levels & 15))
+        return HEVCASM_ERR_ARGUMENT;
+    BlockGrid g{nullptr, width >> log2size, height >> log2size, 0};
+    g.n = (long long)g.nbx * g.nby * n_frames;
+    if (g.n == 0) return 0;
+    PipelineParams p;
+    p.rec = rec, p.pred = pred, p.res = residual, p.levels = levels, p.cbf = cbf;
+    p.s_rec = s_rec, p.s_pred = s_pred, p.s_res = s_res, p.fs_rec = fs_rec, p.fs_pred = fs_pred, p.fs_res = fs_res;
+    p.q = QuantParams{q_scale, q_shift, q_offset << (q_shift - 16), iq_scale, iq_shift};
+    const unsigned small_grid = (unsigned)((g.n + SMALL_NT - 1) / SMALL_NT);
+    if (log2size == 2 && trType) return launch(small_pipeline_kernel<2, true>, small_grid, SMALL_NT, 0, stream, p, g);
+    if (log2size == 2) return launch(small_pipeline_kernel<2, false>, small_grid, SMALL_NT, 0, stream, p, g);
+    if (log2size == 3) return launch(small_pipeline_kernel<3, false>, small_grid, SMALL_NT, 0, stream, p, g);
+    if (log2size == 4) return launch(big_pipeline_kernel<4>, (unsigned)((g.n + 15) / 16), BIG_NT, 0, stream, p, g);
+    return launch(big_pipeline_kernel<5>, (unsigned)((g.n + 7) / 8), BIG_NT, 0, stream, p, g);
 }
