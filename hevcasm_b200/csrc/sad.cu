@@ -15,6 +15,10 @@
 //   * SSD: |a-b| per byte (VABSDIFF4) then IDP.4A.U8.U8 of the difference with itself, 4x4 partials composed in
 //     shared memory.
 #include "common.cuh"
+#include "tma.cuh"
+
+#include <cstdlib>
+#include <cstring>
 
 namespace hv {
 
@@ -49,6 +53,28 @@ struct SadCell {
         }
     }
 
+    // one window row r (0 .. CH+6) given the KW+2 words that start at the cell's x: feeds every candidate the row belongs to
+    __device__ __forceinline__ void consume_row(int r, const uint32_t (&W)[KW + 2])
+    {
+        uint32_t S[4][KW + 1];
+#pragma unroll
+        for (int j = 0; j <= KW; ++j) {
+            S[0][j] = W[j];
+            S[1][j] = shr_bytes(W[j], W[j + 1], 1);
+            S[2][j] = shr_bytes(W[j], W[j + 1], 2);
+            S[3][j] = shr_bytes(W[j], W[j + 1], 3);
+        }
+#pragma unroll
+        for (int dy = 0; dy < 8; ++dy) {
+            const int sr = r - dy;
+            if (sr < 0 || sr >= CH) continue;
+#pragma unroll
+            for (int dx = 0; dx < 8; ++dx)
+#pragma unroll
+                for (int k = 0; k < KW; ++k) acc[dy][dx] = sad4(src[sr][k], S[dx & 3][(dx >> 2) + k], acc[dy][dx]);
+        }
+    }
+
     // win -> the staged window word holding candidate (dx index 0, dy index 0) of this cell, i.e. window row 0 at the
     // cell's x.  Consumes CH+7 window rows of CW+8 bytes.
     __device__ __forceinline__ void run(const uint32_t *win, int pitch_words)
@@ -64,23 +90,31 @@ struct SadCell {
 #pragma unroll
                 for (int j = 0; j < KW + 2; ++j) W[j] = win[r * pitch_words + j];
             }
-            uint32_t S[4][KW + 1];
+            consume_row(r, W);
+        }
+    }
+
+    // The same for a window whose rows sit in shared memory with the byte alignment they have in global memory (TMA boxes
+    // start on 16-byte boundaries): win8 -> the 8-byte aligned word pair that contains the cell's first window byte;
+    // WO1 = 1 if that byte lies in the odd word of the pair, bs = its byte offset inside the word (0 when BS is false).
+    template <int WO1, bool BS>
+    __device__ __forceinline__ void run_aligned(const uint32_t *win8, int pitch_words, int bs)
+    {
+        static_assert(KW == 2, "8-wide cells only");
 #pragma unroll
-            for (int j = 0; j <= KW; ++j) {
-                S[0][j] = W[j];
-                S[1][j] = shr_bytes(W[j], W[j + 1], 1);
-                S[2][j] = shr_bytes(W[j], W[j + 1], 2);
-                S[3][j] = shr_bytes(W[j], W[j + 1], 3);
+        for (int r = 0; r < CH + 7; ++r) {
+            uint32_t L[6];
+            const uint2 a = *reinterpret_cast<const uint2 *>(win8 + r * pitch_words);
+            const uint2 b = *reinterpret_cast<const uint2 *>(win8 + r * pitch_words + 2);
+            L[0] = a.x, L[1] = a.y, L[2] = b.x, L[3] = b.y, L[4] = 0, L[5] = 0;
+            if (WO1 || BS) {
+                const uint2 c = *reinterpret_cast<const uint2 *>(win8 + r * pitch_words + 4);
+                L[4] = c.x, L[5] = c.y;
             }
+            uint32_t W[4];
 #pragma unroll
-            for (int dy = 0; dy < 8; ++dy) {
-                const int sr = r - dy;
-                if (sr < 0 || sr >= CH) continue;
-#pragma unroll
-                for (int dx = 0; dx < 8; ++dx)
-#pragma unroll
-                    for (int k = 0; k < KW; ++k) acc[dy][dx] = sad4(src[sr][k], S[dx & 3][(dx >> 2) + k], acc[dy][dx]);
-            }
+            for (int j = 0; j < 4; ++j) W[j] = BS ? __funnelshift_r(L[WO1 + j], L[WO1 + j + 1], 8 * bs) : L[WO1 + j];
+            consume_row(r, W);
         }
     }
 };
@@ -118,6 +152,7 @@ struct PyramidParams {
     const uint8_t *src, *ref;
     ptrdiff_t ss, sr, fs_src, fs_ref;
     int width, height, dx0, dy0;
+    int tile_x_base;  // first tile column this launch covers (the generic kernel finishes what the fast one leaves)
     int32_t *out[4];  // 8, 16, 32, 64
 };
 
@@ -134,7 +169,7 @@ __global__ void __launch_bounds__(pyr::NT) sad_sweep_pyramid_kernel(PyramidParam
     const int tid = threadIdx.x;
     const int f = blockIdx.z;
     const int npx8 = p.width >> 3, npy8 = p.height >> 3;
-    const int cx0 = blockIdx.x * CX, cy0 = blockIdx.y * CY;  // first cell of the tile
+    const int cx0 = (blockIdx.x + p.tile_x_base) * CX, cy0 = blockIdx.y * CY;  // first cell of the tile
     const int vcx = min(CX, npx8 - cx0), vcy = min(CY, npy8 - cy0);
     const int x0 = cx0 * 8, y0 = cy0 * 8;
 
@@ -198,6 +233,226 @@ __global__ void __launch_bounds__(pyr::NT) sad_sweep_pyramid_kernel(PyramidParam
             const int q00 = ((2 * py) * (CX / 4) + 2 * px) * 16 + g;
             const int4 v = add4(add4(l32[q00], l32[q00 + 16]), add4(l32[q00 + (CX / 4) * 16], l32[q00 + (CX / 4) * 16 + 16]));
             if (px0 + px < npx && py0 + py < npy) o[((size_t)(py0 + py) * npx + (px0 + px)) * 16 + g] = v;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ pyramid sweep, fast path
+//
+// Same tile, same arithmetic, but every loop has a compile-time trip count and compile-time divisors: the generic kernel
+// above spends two thirds of its issue slots on staging index arithmetic (a division by a run-time row length per word)
+// and on bounds logic in the copy-out loops (profiles/r01_sad_pyramid_v1.md).  Preconditions, checked by the host:
+// tiles are full in x (the right-hand strip of a frame whose width is not a multiple of 128 goes to the generic kernel),
+// source rows are 16-byte aligned and window rows 4-byte aligned.  Tiles may be partial in y: row indices are clamped
+// for the loads (never reading below the last needed row) and the stores are masked.
+template <int LEVEL_MASK>
+__global__ void __launch_bounds__(pyr::NT) sad_pyramid_fast_kernel(PyramidParams p)
+{
+    using namespace pyr;
+    extern __shared__ __align__(16) uint8_t smem[];
+    uint32_t *win = reinterpret_cast<uint32_t *>(smem);
+    uint32_t *srct = win + WIN_PITCH * WIN_ROWS;
+    int4 *cb = reinterpret_cast<int4 *>(smem);
+    int4 *l16 = reinterpret_cast<int4 *>(smem + (CB_BYTES > STAGE_BYTES ? CB_BYTES : STAGE_BYTES));
+    int4 *l32 = l16 + L16_BYTES / 16;
+
+    const int tid = threadIdx.x, f = blockIdx.z;
+    const int npx8 = p.width >> 3, npy8 = p.height >> 3;
+    const int cx0 = blockIdx.x * CX, cy0 = blockIdx.y * CY;
+    const int vcy = min(CY, npy8 - cy0);
+    const int x0 = cx0 * 8, y0 = cy0 * 8;
+
+    // ---- stage: source tile with 128-bit loads, window with 32-bit loads (its origin is only 4-byte aligned)
+    {
+        const uint8_t *src = p.src + f * p.fs_src + (ptrdiff_t)y0 * p.ss + x0;
+        const int last = vcy * 8 - 1;
+        int4 v[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int idx = tid + k * NT, row = idx >> 3, ch = idx & 7;
+            v[k] = ldg_stream(reinterpret_cast<const int4 *>(src + (ptrdiff_t)min(row, last) * p.ss) + ch);
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int idx = tid + k * NT, row = idx >> 3, ch = idx & 7;
+            *reinterpret_cast<int4 *>(srct + row * SRC_PITCH + ch * 4) = v[k];
+        }
+        const uint8_t *ref = p.ref + f * p.fs_ref + (ptrdiff_t)(y0 + p.dy0) * p.sr + (x0 + p.dx0);
+        constexpr int WW = TW / 4 + 2, TOTAL = WW * WIN_ROWS, ITERS = (TOTAL + NT - 1) / NT;  // 34 words x 71 rows
+        const int lastw = vcy * 8 + 6;
+        uint32_t w[ITERS];
+#pragma unroll
+        for (int k = 0; k < ITERS; ++k) {
+            const int idx = min(tid + k * NT, TOTAL - 1), row = idx / WW, col = idx - row * WW;
+            w[k] = __ldg(reinterpret_cast<const uint32_t *>(ref + (ptrdiff_t)min(row, lastw) * p.sr) + col);
+        }
+#pragma unroll
+        for (int k = 0; k < ITERS; ++k) {
+            const int idx = tid + k * NT, row = idx / WW, col = idx - row * WW;
+            if (idx < TOTAL) win[row * WIN_PITCH + col] = w[k];
+        }
+    }
+    __syncthreads();
+
+    const int cx = tid % CX, cy = tid / CX;
+    SadCell<8, 8> cell;
+    cell.clear();
+    cell.load_src(srct + cy * 8 * SRC_PITCH + cx * 2, SRC_PITCH);
+    cell.run(win + cy * 8 * WIN_PITCH + cx * 2, WIN_PITCH);
+    __syncthreads();  // staging area is dead from here on; cb aliases it
+    store_cell(cb, tid, cell);
+    __syncthreads();
+
+    // ---- copy-out.  i = tid + 128 k : int4 slot g = tid & 15 of cell / PU (tid >> 4) + 8 k
+    const int g = tid & 15, hi = tid >> 4;  // hi = 0..7
+    if (LEVEL_MASK & 1) {
+        // cell c = hi + 8k -> ccx = hi + 8 (k & 1), ccy = k >> 1
+        int4 *o = reinterpret_cast<int4 *>(p.out[0]) + ((size_t)f * npy8 + cy0) * npx8 * 16 + (size_t)(cx0 + hi) * 16 + g;
+        const int s0 = g ^ hi, s1 = g ^ (hi + 8);
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+            const int ccy = k >> 1, c = hi + 8 * k;
+            const int4 v = cb[c * 16 + ((k & 1) ? s1 : s0)];
+            if (ccy < vcy) o[(size_t)ccy * npx8 * 16 + (k & 1) * 128] = v;
+        }
+    }
+    // level 1 (16x16): PU = hi + 8k -> px = hi, py = k;  cells (2py, 2px), (2py, 2px+1), (2py+1, 2px), (2py+1, 2px+1)
+    {
+        const int npx = p.width >> 4, npy = p.height >> 4, py0 = cy0 >> 1;
+        int4 *o = (LEVEL_MASK & 2) ? reinterpret_cast<int4 *>(p.out[1]) + ((size_t)f * npy + py0) * npx * 16 + (size_t)((cx0 >> 1) + hi) * 16 + g : nullptr;
+        const int sa = g ^ (2 * hi), sb = g ^ (2 * hi + 1);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int c00 = (2 * k) * CX + 2 * hi;
+            const int4 v = add4(add4(cb[c00 * 16 + sa], cb[(c00 + 1) * 16 + sb]), add4(cb[(c00 + CX) * 16 + sa], cb[(c00 + CX + 1) * 16 + sb]));
+            l16[tid + k * NT] = v;
+            if ((LEVEL_MASK & 2) && py0 + k < npy && 2 * k < vcy) o[(size_t)k * npx * 16] = v;
+        }
+    }
+    __syncthreads();
+    // level 2 (32x32): PU = hi (0..7) -> px = hi & 3, py = hi >> 2
+    {
+        const int npx = p.width >> 5, npy = p.height >> 5, px = hi & 3, py = hi >> 2;
+        const int q00 = ((2 * py) * (CX / 2) + 2 * px) * 16 + g;
+        const int4 v = add4(add4(l16[q00], l16[q00 + 16]), add4(l16[q00 + (CX / 2) * 16], l16[q00 + (CX / 2) * 16 + 16]));
+        l32[tid] = v;
+        if ((LEVEL_MASK & 4) && (cy0 >> 2) + py < npy && (cx0 >> 2) + px < npx)
+            reinterpret_cast<int4 *>(p.out[2])[(((size_t)f * npy + (cy0 >> 2) + py) * npx + (cx0 >> 2) + px) * 16 + g] = v;
+    }
+    if (LEVEL_MASK & 8) {
+        __syncthreads();
+        // level 3 (64x64): PU = hi (0..1), first 32 threads
+        if (tid < 32) {
+            const int npx = p.width >> 6, npy = p.height >> 6, px = hi;
+            const int q00 = (2 * px) * 16 + g;
+            const int4 v = add4(add4(l32[q00], l32[q00 + 16]), add4(l32[q00 + (CX / 4) * 16], l32[q00 + (CX / 4) * 16 + 16]));
+            if ((cy0 >> 3) < npy && (cx0 >> 3) + px < npx) reinterpret_cast<int4 *>(p.out[3])[(((size_t)f * npy + (cy0 >> 3)) * npx + (cx0 >> 3) + px) * 16 + g] = v;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ pyramid sweep, TMA staged
+//
+// The preferred path.  One elected thread asks the TMA unit for the two boxes of the tile - the 128 x 64 source tile and
+// the 144 x 71 search window, whose origin (x0 + dx0, y0 + dy0) may have any byte alignment - and every thread then waits
+// on the transaction barrier.  No thread computes a load address, nothing is clamped at frame edges (the hardware
+// zero-fills what lies outside the declared extent; those cells are never stored), and the copy-out is the unrolled one
+// of the fast kernel.  What remains per 8x8 cell is 1024 VABSDIFF4 + 135 funnel shifts + 30 64-bit shared loads + ~50
+// instructions of copy-out / composition.
+struct PyramidTmaParams {
+    CUtensorMap tm_src, tm_ref;
+    int width, height;
+    int win_shift;  // byte offset (0..15) of the window origin inside its 16-byte aligned box
+    int32_t *out[4];
+};
+
+// TMA boxes must start on a 16-byte boundary in global memory (anything else faults - measured with tools/tma_probe.cu), so
+// the window box starts at the 16-byte boundary below the window origin and is 16 bytes wider; the cell indexes it with the
+// residual byte offset (run_aligned).
+namespace pyr {
+constexpr int TMA_WIN_BYTES = TW + 32, TMA_WIN_PITCH = TMA_WIN_BYTES / 4, TMA_WIN_ROWS = TH + 7;  // 160 x 71
+constexpr int TMA_SRC_OFF = (TMA_WIN_BYTES * TMA_WIN_ROWS + 127) / 128 * 128;
+constexpr uint32_t TMA_TX_BYTES = TMA_WIN_BYTES * TMA_WIN_ROWS + TW * TH;
+static_assert(TMA_SRC_OFF + TW * TH <= CB_BYTES, "TMA staging must fit under the copy-out buffer");
+}  // namespace pyr
+
+template <int LEVEL_MASK, int WO1, bool BS>
+__global__ void __launch_bounds__(pyr::NT, 5) sad_pyramid_tma_kernel(const __grid_constant__ PyramidTmaParams p)
+{
+    using namespace pyr;
+    extern __shared__ __align__(128) uint8_t smem[];
+    uint32_t *win = reinterpret_cast<uint32_t *>(smem);                 // 71 rows x 160 bytes
+    uint32_t *srct = reinterpret_cast<uint32_t *>(smem + TMA_SRC_OFF);  // 64 rows x 128 bytes, 128-byte aligned
+    int4 *cb = reinterpret_cast<int4 *>(smem);
+    int4 *l16 = reinterpret_cast<int4 *>(smem + CB_BYTES);
+    int4 *l32 = l16 + L16_BYTES / 16;
+    uint64_t *bar = reinterpret_cast<uint64_t *>(smem + SMEM_BYTES);  // behind everything else; never aliased
+
+    const int tid = threadIdx.x, f = blockIdx.z;
+    const int npx8 = p.width >> 3, npy8 = p.height >> 3;
+    const int cx0 = blockIdx.x * CX, cy0 = blockIdx.y * CY;
+    const int vcx = min(CX, npx8 - cx0), vcy = min(CY, npy8 - cy0);
+    const int x0 = cx0 * 8, y0 = cy0 * 8;
+
+    if (tid == 0) tma::mbar_init(bar, 1);
+    __syncthreads();
+    if (tid == 0) {
+        tma::mbar_expect_tx(bar, TMA_TX_BYTES);  // the two boxes, zero-filled parts included
+        tma::load_box_3d(win, &p.tm_ref, x0, y0, f, bar);
+        tma::load_box_3d(srct, &p.tm_src, x0, y0, f, bar);
+    }
+    tma::mbar_wait(bar, 0);
+
+    const int cx = tid % CX, cy = tid / CX;
+    SadCell<8, 8> cell;
+    cell.clear();
+    cell.load_src(srct + cy * 8 * SRC_PITCH + cx * 2, SRC_PITCH);
+    cell.template run_aligned<WO1, BS>(win + cy * 8 * TMA_WIN_PITCH + cx * 2 + ((p.win_shift >> 3) << 1), TMA_WIN_PITCH, p.win_shift & 3);
+    __syncthreads();  // staging area is dead from here on; cb aliases it
+    store_cell(cb, tid, cell);
+    __syncthreads();
+
+    const int g = tid & 15, hi = tid >> 4;
+    if (LEVEL_MASK & 1) {
+        int4 *o = reinterpret_cast<int4 *>(p.out[0]) + ((size_t)f * npy8 + cy0) * npx8 * 16 + (size_t)(cx0 + hi) * 16 + g;
+        const int s0 = g ^ hi, s1 = g ^ (hi + 8);
+        const bool ok0 = hi < vcx, ok1 = hi + 8 < vcx;
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+            const int ccy = k >> 1, c = hi + 8 * k;
+            const int4 v = cb[c * 16 + ((k & 1) ? s1 : s0)];
+            if (ccy < vcy && ((k & 1) ? ok1 : ok0)) o[(size_t)ccy * npx8 * 16 + (k & 1) * 128] = v;
+        }
+    }
+    {
+        const int npx = p.width >> 4, npy = p.height >> 4, py0 = cy0 >> 1;
+        int4 *o = (LEVEL_MASK & 2) ? reinterpret_cast<int4 *>(p.out[1]) + ((size_t)f * npy + py0) * npx * 16 + (size_t)((cx0 >> 1) + hi) * 16 + g : nullptr;
+        const int sa = g ^ (2 * hi), sb = g ^ (2 * hi + 1);
+        const bool okx = (cx0 >> 1) + hi < npx;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int c00 = (2 * k) * CX + 2 * hi;
+            const int4 v = add4(add4(cb[c00 * 16 + sa], cb[(c00 + 1) * 16 + sb]), add4(cb[(c00 + CX) * 16 + sa], cb[(c00 + CX + 1) * 16 + sb]));
+            l16[tid + k * NT] = v;
+            if ((LEVEL_MASK & 2) && okx && py0 + k < npy) o[(size_t)k * npx * 16] = v;
+        }
+    }
+    __syncthreads();
+    {
+        const int npx = p.width >> 5, npy = p.height >> 5, px = hi & 3, py = hi >> 2;
+        const int q00 = ((2 * py) * (CX / 2) + 2 * px) * 16 + g;
+        const int4 v = add4(add4(l16[q00], l16[q00 + 16]), add4(l16[q00 + (CX / 2) * 16], l16[q00 + (CX / 2) * 16 + 16]));
+        l32[tid] = v;
+        if ((LEVEL_MASK & 4) && (cy0 >> 2) + py < npy && (cx0 >> 2) + px < npx)
+            reinterpret_cast<int4 *>(p.out[2])[(((size_t)f * npy + (cy0 >> 2) + py) * npx + (cx0 >> 2) + px) * 16 + g] = v;
+    }
+    if (LEVEL_MASK & 8) {
+        __syncthreads();
+        if (tid < 32) {
+            const int npx = p.width >> 6, npy = p.height >> 6, px = hi;
+            const int q00 = (2 * px) * 16 + g;
+            const int4 v = add4(add4(l32[q00], l32[q00 + 16]), add4(l32[q00 + (CX / 4) * 16], l32[q00 + (CX / 4) * 16 + 16]));
+            if ((cy0 >> 3) < npy && (cx0 >> 3) + px < npx) reinterpret_cast<int4 *>(p.out[3])[(((size_t)f * npy + (cy0 >> 3)) * npx + (cx0 >> 3) + px) * 16 + g] = v;
         }
     }
 }
@@ -497,12 +752,60 @@ extern "C" int hevcasm_sad_sweep_pyramid_frames(const uint8_t *src, ptrdiff_t ss
     if (n_frames == 0) return 0;
     PyramidParams p;
     p.src = src, p.ref = ref, p.ss = ss, p.sr = sr, p.fs_src = fs_src, p.fs_ref = fs_ref;
-    p.width = width, p.height = height, p.dx0 = dx0, p.dy0 = dy0;
+    p.width = width, p.height = height, p.dx0 = dx0, p.dy0 = dy0, p.tile_x_base = 0;
     p.out[0] = sad8, p.out[1] = sad16, p.out[2] = sad32, p.out[3] = sad64;
     const int npx8 = width >> 3, npy8 = height >> 3;
-    const dim3 grid((npx8 + pyr::CX - 1) / pyr::CX, (npy8 + pyr::CY - 1) / pyr::CY, n_frames);
-    HV_CUDA((cudaError_t)set_max_smem(sad_sweep_pyramid_kernel, pyr::SMEM_BYTES));
-    HV_LAUNCH(sad_sweep_pyramid_kernel, grid, pyr::NT, pyr::SMEM_BYTES, stream, p);
+    const int tiles_x = (npx8 + pyr::CX - 1) / pyr::CX, tiles_y = (npy8 + pyr::CY - 1) / pyr::CY;
+    int full_x = 0;
+    // path selection: TMA staged (any byte alignment, needs 16-byte strides) > LDG fast (4-byte aligned window) > generic.
+    // HEVCASM_SAD_PATH=tma|fast|generic pins one for A/B profiling.
+    const char *pin = getenv("HEVCASM_SAD_PATH");
+    const bool all_levels = sad8 && sad16 && sad32 && sad64;
+    const bool want_tma = !pin || !strcmp(pin, "tma"), want_fast = !pin || !strcmp(pin, "fast");
+    if (want_tma && all_levels && ((uintptr_t)src & 15) == 0 && tma::describable(ss, fs_src, n_frames) && tma::describable(sr, fs_ref, n_frames)) {
+        PyramidTmaParams t;
+        t.width = width, t.height = height;
+        for (int l = 0; l < 4; ++l) t.out[l] = p.out[l];
+        // source: bytes [0, npx8*8) x [0, npy8*8);  window: origin (dx0, dy0), 7 more bytes / rows than the source extent
+        int xs_src = 0;
+        int e = tma::describe_u8(&t.tm_src, src, ss, fs_src, (long long)npx8 * 8, (long long)npy8 * 8, n_frames, pyr::TW, pyr::TH, &xs_src);
+        if (!e)
+            e = tma::describe_u8(&t.tm_ref, ref + (ptrdiff_t)dy0 * sr + dx0, sr, fs_ref, (long long)npx8 * 8 + 7, (long long)npy8 * 8 + 7, n_frames,
+                                 pyr::TMA_WIN_BYTES, pyr::TMA_WIN_ROWS, &t.win_shift);
+        if (!e) {
+            const dim3 grid(tiles_x, tiles_y, n_frames);
+            const size_t smem_bytes = pyr::SMEM_BYTES + 16;
+            const int wo1 = (t.win_shift >> 2) & 1, bs = t.win_shift & 3;
+#define HV_TMA(WO1_, BS_)                                                 \
+    do {                                                                  \
+        auto kern = sad_pyramid_tma_kernel<15, WO1_, BS_>;                \
+        HV_CUDA((cudaError_t)set_max_smem(kern, smem_bytes));             \
+        HV_LAUNCH(kern, grid, pyr::NT, smem_bytes, stream, t);            \
+    } while (0)
+            if (wo1 && bs) HV_TMA(1, true);
+            else if (wo1) HV_TMA(1, false);
+            else if (bs) HV_TMA(0, true);
+            else HV_TMA(0, false);
+#undef HV_TMA
+            return 0;
+        }
+    }
+    // fast path: all four outputs wanted, 16-byte aligned source rows, 4-byte aligned window rows
+    const bool fast = want_fast && all_levels && (((uintptr_t)src | (uintptr_t)ss | (uintptr_t)fs_src) & 15) == 0 &&
+                      ((((uintptr_t)ref + (uintptr_t)(ptrdiff_t)dx0) | (uintptr_t)sr | (uintptr_t)fs_ref) & 3) == 0;
+    if (fast) {
+        full_x = npx8 / pyr::CX;
+        if (full_x > 0) {
+            auto kern = sad_pyramid_fast_kernel<15>;
+            HV_CUDA((cudaError_t)set_max_smem(kern, pyr::SMEM_BYTES));
+            HV_LAUNCH(kern, dim3(full_x, tiles_y, n_frames), pyr::NT, pyr::SMEM_BYTES, stream, p);
+        }
+    }
+    if (full_x < tiles_x) {
+        p.tile_x_base = full_x;
+        HV_CUDA((cudaError_t)set_max_smem(sad_sweep_pyramid_kernel, pyr::SMEM_BYTES));
+        HV_LAUNCH(sad_sweep_pyramid_kernel, dim3(tiles_x - full_x, tiles_y, n_frames), pyr::NT, pyr::SMEM_BYTES, stream, p);
+    }
     return 0;
 }
 

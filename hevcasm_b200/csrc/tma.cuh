@@ -1,0 +1,100 @@
+// hevcasm_b200 - TMA (cp.async.bulk.tensor) staging of byte-plane tiles: host-side descriptor, device-side issue + wait.
+//
+// A frame batch is described to the TMA unit as a 3-D uint8 tensor (x, y, frame).  Tile coordinates are ELEMENT
+// granular, so a search window or a filter footprint that starts at any byte offset lands in shared memory as a dense
+// box with no per-thread address arithmetic at all, and everything outside the declared extent is zero-filled by the
+// hardware instead of being read - that replaces both the alignment handling and the edge clamping of a load loop.
+#pragma once
+
+#include <cuda.h>  // CUtensorMap and enums only; the encoder is fetched from the driver at run time (no -lcuda)
+
+#include "common.cuh"
+
+namespace hv {
+namespace tma {
+
+// ---- host ------------------------------------------------------------------------------------------------------
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *, const cuuint32_t *,
+                                  const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+inline EncodeTiledFn encoder()
+{
+    static EncodeTiledFn fn = [] {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) p = nullptr;
+        return (EncodeTiledFn)p;
+    }();
+    return fn;
+}
+
+// can a plane batch with these byte strides be described at all?  (row / frame strides must be multiples of 16 bytes)
+inline bool describable(ptrdiff_t row_stride, ptrdiff_t frame_stride, int n_frames)
+{
+    return encoder() && row_stride > 0 && (row_stride & 15) == 0 && (n_frames <= 1 || (frame_stride > 0 && (frame_stride & 15) == 0));
+}
+
+// Describes the bytes [first, first + extent_x) x extent_y rows x n_frames, where `first` may have any alignment: the
+// tensor starts at the enclosing 16-byte boundary and *x_shift receives the offset to add to every x coordinate.
+// box = {box_x bytes (multiple of 16, <= 256), box_y rows (<= 256), 1 frame}.
+inline int describe_u8(CUtensorMap *map, const uint8_t *first, ptrdiff_t row_stride, ptrdiff_t frame_stride, long long extent_x, long long extent_y,
+                       int n_frames, int box_x, int box_y, int *x_shift)
+{
+    const uintptr_t a = (uintptr_t)first;
+    const int shift = (int)(a & 15);
+    *x_shift = shift;
+    if (n_frames <= 1) frame_stride = row_stride * (ptrdiff_t)extent_y;  // unused, but must be a legal stride
+    cuuint64_t dim[3] = {(cuuint64_t)(extent_x + shift), (cuuint64_t)extent_y, (cuuint64_t)(n_frames < 1 ? 1 : n_frames)};
+    if (dim[0] > (cuuint64_t)row_stride) dim[0] = (cuuint64_t)row_stride;  // never describe more than one row's worth per row
+    cuuint64_t stride[2] = {(cuuint64_t)row_stride, (cuuint64_t)frame_stride};
+    cuuint32_t box[3] = {(cuuint32_t)box_x, (cuuint32_t)box_y, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    const CUresult r = encoder()(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, (void *)(a - shift), dim, stride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                 CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? 0 : (int)cudaErrorInvalidValue;
+}
+
+// ---- device ----------------------------------------------------------------------------------------------------
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, int count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+// Waits for the phase with the given parity.  A descriptor / coordinate error would leave the barrier incomplete for ever;
+// rather than hang the GPU the wait gives up after ~1 s worth of polls and traps, which surfaces as a launch failure.
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+{
+    const uint32_t addr = smem_u32(bar);
+#pragma unroll 1
+    for (int spin = 0; spin < (1 << 22); ++spin) {
+        uint32_t done;
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(addr), "r"(parity)
+            : "memory");
+        if (done) return;
+    }
+    __trap();
+}
+// one box of a 3-D tensor -> shared memory (dense rows of box_x bytes); completion is signalled on `bar`
+__device__ __forceinline__ void load_box_3d(void *smem_dst, const CUtensorMap *map, int x, int y, int z, uint64_t *bar)
+{
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(smem_u32(smem_dst)),
+                 "l"(map), "r"(x), "r"(y), "r"(z), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void prefetch_descriptor(const CUtensorMap *map) { asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory"); }
+
+}  // namespace tma
+}  // namespace hv
