@@ -365,9 +365,9 @@ def run_gpu(args):
                "steps": e2e_steps, "api": "hevcasm_sad_sweep_pyramid_frames_host", "matches_device_path": same}
 
     if rank == 0:
-        roof = {"bound": "hbm", "kernel": "sad_sweep_pyramid_kernel", "achieved": per_gpu * SAD_BYTES_PER_SAMPLE, "peak": hbm_peak, "unit": "GB/s",
-                "frac": per_gpu * SAD_BYTES_PER_SAMPLE / hbm_peak, "traffic": None, "peak_source": peak_src,
-                "algorithmic_bytes_per_sample": SAD_BYTES_PER_SAMPLE,
+        roof = {"bound": "hbm", "kernel": "sad_pyramid_tma_kernel (hevcasm_sad_sweep_pyramid_frames)", "achieved": per_gpu * SAD_BYTES_PER_SAMPLE, "peak": hbm_peak, "unit": "GB/s",
+                "frac": per_gpu * SAD_BYTES_PER_SAMPLE / hbm_peak, "traffic": 55.63e6 * NF, "traffic_source": "ncu dram__bytes_read+write per launch / 8 frames, profiles/r01_sad_pyramid.md", "peak_source": peak_src,
+                "algorithmic_bytes_per_sample": SAD_BYTES_PER_SAMPLE, "algorithmic_bytes_per_launch": SAD_BYTES_PER_SAMPLE * NF * W4K * H4K,
                 "int_pipe": {"absdiff_per_sample": 64, "achieved_T_absdiff_s": per_gpu * 64 / 1e3, "peak_T_absdiff_s": 73.5,
                              "frac": per_gpu * 64 / 1e3 / 73.5, "peak_source": "profiles/r01_pipe_peak.json (64 VABSDIFF4/clk/SM)"}}
         line = {"metric": METRIC, "value": value, "unit": "Gsamples/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
