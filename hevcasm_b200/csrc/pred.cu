@@ -20,6 +20,8 @@
 // 1 B in + 1 B out per sample (2 + 1 for bi).
 #include "common.cuh"
 
+#include <cstdlib>
+
 namespace hv {
 namespace ip {
 
@@ -327,6 +329,205 @@ __global__ void __launch_bounds__(NT) pred_kernel(PredParams p)
     }
 }
 
+// ------------------------------------------------------------------------------------------------ plane form, fast path
+//
+// Whole planes with 16-byte aligned reference rows (the normal frame store).  Same arithmetic building blocks; what
+// changes is everything around them: the tile and its halo are staged with clamped 128-bit loads (no per-word address
+// arithmetic, no run-time divisions), every loop has a compile-time trip count (edge tiles compute the full tile and
+// mask the stores), and stores are 64-bit when the destination rows are 8-byte aligned.
+//   tile = 128 x 32 outputs, 128 threads.  Staged row: 16-byte chunks from 16 bytes left of the tile when a horizontal
+//   pass needs the left halo (block column 0 at byte XPAD = 16), from the tile's own column 0 otherwise.
+template <int TAPS, int MODE, bool BI>
+struct FastGeom {
+    static constexpr int TW = 128, TH = 32, R = 8;
+    static constexpr bool NEED_H = BI || (MODE & 1), NEED_V = BI || (MODE & 2);
+    static constexpr int LEFT = TAPS / 2 - 1, RIGHT = TAPS / 2;
+    static constexpr int XPAD = NEED_H ? 16 : 0;
+    static constexpr int CHUNKS = NEED_H ? 10 : 8;                 // 16-byte chunks per staged row
+    static constexpr int SPW = CHUNKS * 4;                         // staged pitch in words
+    static constexpr int SROWS = TH + (NEED_V ? TAPS - 1 : 0);
+    static constexpr int TOP = NEED_V ? LEFT : 0;
+    static constexpr int MP = (TW + 16) / 2;                       // intermediate pitch in words (TW + 8 int16, + slack)
+    static constexpr int SRC_WORDS = SPW * SROWS, MID_WORDS = (NEED_H && NEED_V) ? MP * TH : 0;
+    static constexpr int SMEM_BYTES = (SRC_WORDS + MID_WORDS) * 4;
+    static constexpr int Q0 = NEED_H ? 3 : 0;                      // first staged quad the vertical pass visits (x = -4 or 0)
+    static constexpr int NQ = NEED_H ? (TW + 8) / 4 : TW / 4;      // quads per row group
+};
+
+template <class G>
+__device__ __forceinline__ void stage_fast(uint32_t *src_s, const uint8_t *tile /* ref at the tile's (0,0) */, ptrdiff_t sr, int w, int h, int tid)
+{
+    const uint8_t *base = tile - (ptrdiff_t)G::TOP * sr - G::XPAD;
+    const int last_row = h + (G::NEED_V ? G::LEFT + G::RIGHT : 0) - 1;                       // last row anything reads
+    const int last_ch = (G::XPAD + w + (G::NEED_H ? G::RIGHT : 0) - 1) >> 4;                  // last chunk anything reads
+    constexpr int TOTAL = G::CHUNKS * G::SROWS, ITERS = (TOTAL + NT - 1) / NT;
+    int4 v[ITERS];
+#pragma unroll
+    for (int k = 0; k < ITERS; ++k) {
+        const int idx = min(tid + k * NT, TOTAL - 1), row = idx / G::CHUNKS, ch = idx - row * G::CHUNKS;
+        v[k] = __ldg(reinterpret_cast<const int4 *>(base + (ptrdiff_t)min(row, last_row) * sr) + min(ch, last_ch));
+    }
+#pragma unroll
+    for (int k = 0; k < ITERS; ++k) {
+        const int idx = tid + k * NT;
+        if (idx < TOTAL) reinterpret_cast<int4 *>(src_s)[idx] = v[k];   // rows are CHUNKS int4 long: the staged tile is dense
+    }
+}
+
+template <bool DST8>
+__device__ __forceinline__ void put8(uint8_t *p, uint32_t lo, uint32_t hi, int nvalid)
+{
+    if (DST8) {
+        if (nvalid >= 8) *reinterpret_cast<uint2 *>(p) = make_uint2(lo, hi);
+        else if (nvalid > 0) store8(p, lo, hi, nvalid);
+    } else if (nvalid > 0) {
+        store8(p, lo, hi, nvalid);
+    }
+}
+
+// vertical pass of the whole staged tile into `mid` (exact int16 sums), fast-path geometry
+template <int TAPS, class G>
+__device__ __forceinline__ void vertical_to_mid_fast(uint32_t *mid, const uint32_t *src_s, const Coefs<TAPS> &cy, int tid)
+{
+    constexpr int ITEMS = G::NQ * (G::TH / G::R), ITERS = (ITEMS + NT - 1) / NT;
+#pragma unroll 1
+    for (int k = 0; k < ITERS; ++k) {
+        const int id = tid + k * NT;
+        if (id >= ITEMS) break;
+        const int q = id % G::NQ, rg = id / G::NQ;
+        int v[G::R][4];
+        vpass_bytes<TAPS, G::R>(src_s + rg * G::R * G::SPW + G::Q0 + q, G::SPW, cy.p4, v);
+#pragma unroll
+        for (int r = 0; r < G::R; ++r)
+            *reinterpret_cast<uint2 *>(mid + (rg * G::R + r) * G::MP + 2 * q) = make_uint2(pack16(v[r][0], v[r][1]), pack16(v[r][2], v[r][3]));
+    }
+}
+
+template <int TAPS, int MODE, bool BI, bool DST8>
+__global__ void __launch_bounds__(NT) pred_plane_fast_kernel(PredParams p)
+{
+    using G = FastGeom<TAPS, MODE, BI>;
+    extern __shared__ __align__(16) uint32_t smem[];
+    uint32_t *src_s = smem, *mid = smem + G::SRC_WORDS;
+    const int tid = threadIdx.x;
+    const int x0 = blockIdx.x * G::TW, y0 = blockIdx.y * G::TH, f = blockIdx.z;
+    const int w = min(G::TW, p.width - x0), h = min(G::TH, p.height - y0);
+    uint8_t *dst = p.dst + f * p.fs_dst + (ptrdiff_t)y0 * p.sd + x0;
+    const ptrdiff_t ro = f * p.fs_ref + (ptrdiff_t)y0 * p.sr + x0;
+    constexpr int NJ = G::TW / 8, HITEMS = NJ * G::TH / NT;  // 8-wide output groups per row; groups per thread
+
+    if (!BI && MODE == COPY) {
+        // 2 x (LDG.128 -> two 64-bit stores) per thread, straight through registers
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+            const int idx = tid + k * NT, row = idx >> 3, ch = idx & 7;
+            if (row < h && ch * 16 < w) {
+                const int4 v = __ldg(reinterpret_cast<const int4 *>(p.ref0 + ro + (ptrdiff_t)row * p.sr) + ch);  // may read up to 15 bytes right of w (aligned chunk)
+                uint8_t *d = dst + (ptrdiff_t)row * p.sd + ch * 16;
+                put8<DST8>(d, (uint32_t)v.x, (uint32_t)v.y, w - ch * 16);
+                put8<DST8>(d + 8, (uint32_t)v.z, (uint32_t)v.w, w - ch * 16 - 8);
+            }
+        }
+        return;
+    }
+
+    if (!BI) {
+        stage_fast<G>(src_s, p.ref0 + ro, p.sr, w, h, tid);
+        __syncthreads();
+        if (MODE == H_ONLY) {
+            Coefs<TAPS> cx;
+            cx.load(p.xf0);
+#pragma unroll
+            for (int k = 0; k < HITEMS; ++k) {
+                const int id = tid + k * NT, jj = id % NJ, y = id / NJ;
+                int o[8];
+                hpass_bytes<TAPS>(src_s + y * G::SPW + 3 + 2 * jj, cx.p4, 32, o);
+                if (y < h)
+                    put8<DST8>(dst + (ptrdiff_t)y * p.sd + 8 * jj, pack_sat_u8(o[0] >> 6, o[1] >> 6, o[2] >> 6, o[3] >> 6),
+                               pack_sat_u8(o[4] >> 6, o[5] >> 6, o[6] >> 6, o[7] >> 6), w - 8 * jj);
+            }
+        } else if (MODE == V_ONLY) {
+            Coefs<TAPS> cy;
+            cy.load(p.yf0);
+            const int q = tid % G::NQ, rg = tid / G::NQ;  // exactly one item per thread
+            int v[G::R][4];
+            vpass_bytes<TAPS, G::R>(src_s + rg * G::R * G::SPW + q, G::SPW, cy.p4, v);
+#pragma unroll
+            for (int r = 0; r < G::R; ++r) {
+                const int y = rg * G::R + r;
+                if (y < h && 4 * q < w)
+                    store4(dst + (ptrdiff_t)y * p.sd + 4 * q, pack_sat_u8((v[r][0] + 32) >> 6, (v[r][1] + 32) >> 6, (v[r][2] + 32) >> 6, (v[r][3] + 32) >> 6),
+                           w - 4 * q);
+            }
+        } else {
+            Coefs<TAPS> cx, cy;
+            cx.load(p.xf0);
+            cy.load(p.yf0);
+            vertical_to_mid_fast<TAPS, G>(mid, src_s, cy, tid);
+            __syncthreads();
+#pragma unroll
+            for (int k = 0; k < HITEMS; ++k) {
+                const int id = tid + k * NT, jj = id % NJ, y = id / NJ;
+                int o[8];
+                hpass_mid<TAPS>(mid + y * G::MP + 4 * jj, cx.p2, 2048, o);
+                if (y < h)
+                    put8<DST8>(dst + (ptrdiff_t)y * p.sd + 8 * jj, pack_sat_u8(o[0] >> 12, o[1] >> 12, o[2] >> 12, o[3] >> 12),
+                               pack_sat_u8(o[4] >> 12, o[5] >> 12, o[6] >> 12, o[7] >> 12), w - 8 * jj);
+            }
+        }
+    } else {
+        uint32_t va[HITEMS][4];
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            Coefs<TAPS> cx, cy;
+            cx.load(r ? p.xf1 : p.xf0);
+            cy.load(r ? p.yf1 : p.yf0);
+            if (r) __syncthreads();
+            stage_fast<G>(src_s, (r ? p.ref1 : p.ref0) + ro, p.sr, w, h, tid);
+            __syncthreads();
+            vertical_to_mid_fast<TAPS, G>(mid, src_s, cy, tid);
+            __syncthreads();
+#pragma unroll
+            for (int k = 0; k < HITEMS; ++k) {
+                const int id = tid + k * NT, jj = id % NJ, y = id / NJ;
+                int o[8];
+                hpass_mid<TAPS>(mid + y * G::MP + 4 * jj, cx.p2, 0, o);
+                if (r == 0) {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) va[k][i] = pack16(o[2 * i] >> 6, o[2 * i + 1] >> 6);
+                } else {
+                    int s[8];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        s[2 * i] = ((int)(short)(va[k][i] & 0xffff) + (int)(short)(o[2 * i] >> 6) + 64) >> 7;
+                        s[2 * i + 1] = (((int)va[k][i] >> 16) + (int)(short)(o[2 * i + 1] >> 6) + 64) >> 7;
+                    }
+                    if (y < h) put8<DST8>(dst + (ptrdiff_t)y * p.sd + 8 * jj, pack_sat_u8(s[0], s[1], s[2], s[3]), pack_sat_u8(s[4], s[5], s[6], s[7]), w - 8 * jj);
+                }
+            }
+        }
+    }
+}
+
+template <int TAPS, int MODE, bool BI>
+int launch_plane_fast(const PredParams &p, dim3 grid, bool dst8, void *stream)
+{
+    using G = FastGeom<TAPS, MODE, BI>;
+    return dst8 ? launch(pred_plane_fast_kernel<TAPS, MODE, BI, true>, grid, dim3(NT), (size_t)G::SMEM_BYTES, stream, p)
+                : launch(pred_plane_fast_kernel<TAPS, MODE, BI, false>, grid, dim3(NT), (size_t)G::SMEM_BYTES, stream, p);
+}
+
+template <int TAPS>
+int launch_uni_planes_fast(const PredParams &p, dim3 grid, int mode, bool dst8, void *stream)
+{
+    switch (mode) {
+        case COPY: return launch_plane_fast<TAPS, COPY, false>(p, grid, dst8, stream);
+        case H_ONLY: return launch_plane_fast<TAPS, H_ONLY, false>(p, grid, dst8, stream);
+        case V_ONLY: return launch_plane_fast<TAPS, V_ONLY, false>(p, grid, dst8, stream);
+        default: return launch_plane_fast<TAPS, HV, false>(p, grid, dst8, stream);
+    }
+}
+
 template <int TAPS, int TW, int TH, bool BI, int FIXED_MODE>
 int launch_pred(const PredParams &p, dim3 grid, void *stream)
 {
@@ -361,6 +562,22 @@ using namespace hv::ip;
 
 static bool frac_ok(int taps, int f) { return f >= 0 && f < (taps == 8 ? 4 : 8); }
 
+// the fast plane kernels issue aligned 128-bit loads on the reference rows (and may therefore touch up to 16 bytes left and
+// 15 bytes right of the reference's own footprint - hevcasm_batch.h documents the padding this needs)
+static bool planes_fast_ok(const uint8_t *ref0, const uint8_t *ref1, ptrdiff_t sr, ptrdiff_t fs_ref, int n_frames)
+{
+    if (getenv("HEVCASM_PRED_GENERIC")) return false;
+    uintptr_t m = (uintptr_t)ref0 | (uintptr_t)sr | (ref1 ? (uintptr_t)ref1 : 0);
+    if (n_frames > 1) m |= (uintptr_t)fs_ref;
+    return (m & 15) == 0;
+}
+static bool aligned8(const uint8_t *dst, ptrdiff_t sd, ptrdiff_t fs_dst, int n_frames)
+{
+    uintptr_t m = (uintptr_t)dst | (uintptr_t)sd;
+    if (n_frames > 1) m |= (uintptr_t)fs_dst;
+    return (m & 7) == 0;
+}
+
 extern "C" int hevcasm_pred_uni_frames(uint8_t *dst, ptrdiff_t sd, const uint8_t *ref, ptrdiff_t sr, int width, int height, int taps, int xFrac, int yFrac,
                                        int n_frames, ptrdiff_t fs_dst, ptrdiff_t fs_ref, void *stream)
 {
@@ -371,6 +588,10 @@ extern "C" int hevcasm_pred_uni_frames(uint8_t *dst, ptrdiff_t sd, const uint8_t
     p.xf0 = xFrac, p.yf0 = yFrac;
     const dim3 grid((width + PTW - 1) / PTW, (height + PTH - 1) / PTH, n_frames);
     const int mode = (xFrac ? 1 : 0) | (yFrac ? 2 : 0);
+    if (planes_fast_ok(ref, nullptr, sr, fs_ref, n_frames)) {
+        const bool dst8 = aligned8(dst, sd, fs_dst, n_frames);
+        return taps == 8 ? launch_uni_planes_fast<8>(p, grid, mode, dst8, stream) : launch_uni_planes_fast<4>(p, grid, mode, dst8, stream);
+    }
     return taps == 8 ? launch_uni_planes<8>(p, grid, mode, stream) : launch_uni_planes<4>(p, grid, mode, stream);
 }
 
@@ -385,6 +606,10 @@ extern "C" int hevcasm_pred_bi_frames(uint8_t *dst, ptrdiff_t sd, const uint8_t 
     p.dst = dst, p.ref0 = ref0, p.ref1 = ref1, p.sd = sd, p.sr = sr, p.fs_dst = fs_dst, p.fs_ref = fs_ref, p.width = width, p.height = height;
     p.xf0 = xFrac0, p.yf0 = yFrac0, p.xf1 = xFrac1, p.yf1 = yFrac1;
     const dim3 grid((width + PTW - 1) / PTW, (height + PTH - 1) / PTH, n_frames);
+    if (planes_fast_ok(ref0, ref1, sr, fs_ref, n_frames)) {
+        const bool dst8 = aligned8(dst, sd, fs_dst, n_frames);
+        return taps == 8 ? launch_plane_fast<8, HV, true>(p, grid, dst8, stream) : launch_plane_fast<4, HV, true>(p, grid, dst8, stream);
+    }
     return taps == 8 ? launch_pred<8, PTW, PTH, true, RUNTIME>(p, grid, stream) : launch_pred<4, PTW, PTH, true, RUNTIME>(p, grid, stream);
 }
 

@@ -40,6 +40,14 @@ def test_uni_planes_all_fractions(oracle, taps, shape):
 
 
 @pytest.mark.parametrize("taps", [8, 4])
+def test_generic_plane_kernels_all_fractions(oracle, taps, monkeypatch):
+    """the alignment-agnostic plane kernels (taken when reference rows are not 16-byte aligned), forced on aligned planes"""
+    monkeypatch.setenv("HEVCASM_PRED_GENERIC", "1")
+    test_uni_planes_all_fractions(oracle, taps, (200, 136))
+    test_bi_planes(oracle, taps)
+
+
+@pytest.mark.parametrize("taps", [8, 4])
 def test_uni_planes_unaligned_pointers(oracle, taps):
     """destination and reference origins at odd byte offsets, odd pitch"""
     width, height, nf = 77, 45, 1
