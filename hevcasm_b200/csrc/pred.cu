@@ -85,8 +85,8 @@ __device__ __forceinline__ void vpass_bytes(const uint32_t *s, int pitch_words, 
 
 // ---- horizontal pass on the int16 intermediate: 8 adjacent outputs -----------------------------------------
 // m -> 16 intermediates (8 words, 16-byte aligned) starting 4 columns left of the first output
-template <int TAPS>
-__device__ __forceinline__ void hpass_mid(const uint32_t *m, const int (&cx2)[TAPS / 2], int round, int (&out)[8])
+template <int TAPS, int NC>
+__device__ __forceinline__ void hpass_mid(const uint32_t *m, const int (&cx2)[NC], int round, int (&out)[8])
 {
     uint32_t M[8];
     const uint4 a = *reinterpret_cast<const uint4 *>(m), b = *reinterpret_cast<const uint4 *>(m + 4);
@@ -332,14 +332,85 @@ __global__ void __launch_bounds__(NT) pred_kernel(PredParams p)
 // ------------------------------------------------------------------------------------------------ plane form, fast path
 //
 // Whole planes with 16-byte aligned reference rows (the normal frame store).  Same arithmetic building blocks; what
-// changes is everything around them: the tile and its halo are staged with clamped 128-bit loads (no per-word address
-// arithmetic, no run-time divisions), every loop has a compile-time trip count (edge tiles compute the full tile and
-// mask the stores), and stores are 64-bit when the destination rows are 8-byte aligned.
-//   tile = 128 x 32 outputs, 128 threads.  Staged row: 16-byte chunks from 16 bytes left of the tile when a horizontal
-//   pass needs the left halo (block column 0 at byte XPAD = 16), from the tile's own column 0 otherwise.
+// changes is everything around them (profiles/r01_pred.md: the first version spent 40 % of its issue slots outside the
+// filters): the packed coefficients come from the host in the kernel parameters; the tile and its halo are staged with
+// clamped 128-bit loads, three rows per warp instruction, pointers advanced incrementally; every loop has a compile-time
+// trip count (edge tiles compute the full tile and mask the stores); stores are 64-bit when the destination rows are
+// 8-byte aligned; and the tile is 128 x 64 so that the vertical pass (34 column quads x 8 row groups) fills its warps.
+//   Staged row: 16-byte chunks from 16 bytes left of the tile when a horizontal pass needs the left halo (block column 0
+//   at byte XPAD = 16), from the tile's own column 0 otherwise.
+// Coefficients packed on the host the way the dot-product instructions consume them.  Besides the natural packings the
+// fast path uses ROTATED ones: instead of re-aligning the data to the taps (a PRMT / funnel shift per operand) the taps
+// are slid along aligned data words, padded with zeros - one more IDP for a misaligned output, no realignment at all.
+struct PackedCoefs {
+    int x4[2];      // horizontal taps, 4 per word, for dp4a on byte windows (H-only positions)
+    int x2e[4];     // horizontal taps as pairs (c0,c1) (c2,c3) ..           : outputs whose first tap sits on an even intermediate
+    int x2o[5];     // the same slid by one: (0,c0) (c1,c2) (c3,c4) (c5,c6) (c7,0) : outputs whose first tap sits on an odd one
+    int y4s[4][3];  // vertical taps slid by s = 0..3 rows over row groups of four: byte j of word g holds tap 4g + j - s (or 0)
+};
+// vertical pass on bytes with rotated taps: 4 columns x 8 rows.  Rows are gathered once per aligned group of four
+// (32 PRMT per item instead of 76); output row r = 4 k0 + s takes groups k0, k0+1 (and k0+2 when s != 0).
+// s -> staged word of the 4 columns at the first needed row; 4*NG rows are read (the last ones may only meet zero taps).
+template <int TAPS>
+__device__ __forceinline__ void vpass_rot(const uint32_t *s, int pitch_words, const int (&y4s)[4][3], int (&out)[8][4])
+{
+    constexpr int NG = TAPS == 8 ? 4 : 3;  // row groups: rows 0..15 (8-tap) or 0..11 (4-tap)
+    uint32_t T[NG][4];
+#pragma unroll
+    for (int k = 0; k < NG; ++k) {
+        const uint32_t r0 = s[(4 * k) * pitch_words], r1 = s[(4 * k + 1) * pitch_words], r2 = s[(4 * k + 2) * pitch_words], r3 = s[(4 * k + 3) * pitch_words];
+        const uint32_t a01 = __byte_perm(r0, r1, 0x5140), a23 = __byte_perm(r0, r1, 0x7362);
+        const uint32_t b01 = __byte_perm(r2, r3, 0x5140), b23 = __byte_perm(r2, r3, 0x7362);
+        T[k][0] = __byte_perm(a01, b01, 0x5410);
+        T[k][1] = __byte_perm(a01, b01, 0x7632);
+        T[k][2] = __byte_perm(a23, b23, 0x5410);
+        T[k][3] = __byte_perm(a23, b23, 0x7632);
+    }
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+        const int k0 = r >> 2, sft = r & 3;
+        constexpr int FULL = TAPS / 4;  // groups an aligned output needs
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            int a = 0;
+#pragma unroll
+            for (int g = 0; g < FULL; ++g) a = dp4a_us(T[k0 + g][c], y4s[sft][g], a);
+            if (sft) a = dp4a_us(T[k0 + FULL][c], y4s[sft][FULL], a);
+            out[r][c] = a;
+        }
+    }
+}
+
+// horizontal pass on the int16 intermediate with rotated taps: 8 adjacent outputs, no realignment of the pairs
+template <int TAPS>
+__device__ __forceinline__ void hpass_rot(const uint32_t *m, const int (&x2e)[4], const int (&x2o)[5], int round, int (&out)[8])
+{
+    uint32_t M[8];
+    const uint4 a = *reinterpret_cast<const uint4 *>(m), b = *reinterpret_cast<const uint4 *>(m + 4);
+    M[0] = a.x, M[1] = a.y, M[2] = a.z, M[3] = a.w, M[4] = b.x, M[5] = b.y, M[6] = b.z, M[7] = b.w;
+    constexpr int OFF = 4 - (TAPS / 2 - 1);  // odd for both tap counts
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        int acc = round;
+        if ((i + OFF) & 1) {  // first tap on an odd intermediate: slide the taps by one
+#pragma unroll
+            for (int g = 0; g <= TAPS / 2; ++g) acc = dp2a_lo(M[((i + OFF - 1) >> 1) + g], x2o[g], acc);
+        } else {
+#pragma unroll
+            for (int g = 0; g < TAPS / 2; ++g) acc = dp2a_lo(M[((i + OFF) >> 1) + g], x2e[g], acc);
+        }
+        out[i] = acc;
+    }
+}
+
+struct FastParams {
+    PredParams p;
+    PackedCoefs c[2];  // per reference
+};
+
 template <int TAPS, int MODE, bool BI>
 struct FastGeom {
-    static constexpr int TW = 128, TH = 32, R = 8;
+    static constexpr int TW = 128, TH = 64, R = 8;
     static constexpr bool NEED_H = BI || (MODE & 1), NEED_V = BI || (MODE & 2);
     static constexpr int LEFT = TAPS / 2 - 1, RIGHT = TAPS / 2;
     static constexpr int XPAD = NEED_H ? 16 : 0;
@@ -348,29 +419,37 @@ struct FastGeom {
     static constexpr int SROWS = TH + (NEED_V ? TAPS - 1 : 0);
     static constexpr int TOP = NEED_V ? LEFT : 0;
     static constexpr int MP = (TW + 16) / 2;                       // intermediate pitch in words (TW + 8 int16, + slack)
-    static constexpr int SRC_WORDS = SPW * SROWS, MID_WORDS = (NEED_H && NEED_V) ? MP * TH : 0;
+    static constexpr int SRC_ROWS_ALLOC = NEED_V ? TH + (TAPS == 8 ? 8 : 4) : TH;   // vpass_rot reads whole groups of 4 rows (the extra ones meet zero taps)
+    static constexpr int SRC_WORDS = SPW * SRC_ROWS_ALLOC, MID_WORDS = (NEED_H && NEED_V) ? MP * TH : 0;
     static constexpr int SMEM_BYTES = (SRC_WORDS + MID_WORDS) * 4;
     static constexpr int Q0 = NEED_H ? 3 : 0;                      // first staged quad the vertical pass visits (x = -4 or 0)
     static constexpr int NQ = NEED_H ? (TW + 8) / 4 : TW / 4;      // quads per row group
+    static constexpr int ROWS_PER_WARP_LOAD = 32 / CHUNKS;         // 3 (10 chunks) or 4 (8 chunks) rows per warp instruction
+    static constexpr int ROWS_PER_STEP = ROWS_PER_WARP_LOAD * (NT / 32);
+    static constexpr int STEPS = (SROWS + ROWS_PER_STEP - 1) / ROWS_PER_STEP;
 };
 
 template <class G>
 __device__ __forceinline__ void stage_fast(uint32_t *src_s, const uint8_t *tile /* ref at the tile's (0,0) */, ptrdiff_t sr, int w, int h, int tid)
 {
-    const uint8_t *base = tile - (ptrdiff_t)G::TOP * sr - G::XPAD;
+    const int lane = tid & 31, warp = tid >> 5;
+    const int rl = lane / G::CHUNKS, ch = lane - rl * G::CHUNKS;   // row within the warp's group, chunk
+    const bool active = rl < G::ROWS_PER_WARP_LOAD;
     const int last_row = h + (G::NEED_V ? G::LEFT + G::RIGHT : 0) - 1;                       // last row anything reads
     const int last_ch = (G::XPAD + w + (G::NEED_H ? G::RIGHT : 0) - 1) >> 4;                  // last chunk anything reads
-    constexpr int TOTAL = G::CHUNKS * G::SROWS, ITERS = (TOTAL + NT - 1) / NT;
-    int4 v[ITERS];
+    const uint8_t *base = tile - (ptrdiff_t)G::TOP * sr - G::XPAD + 16 * min(ch, last_ch);
+    const int row0 = warp * G::ROWS_PER_WARP_LOAD + rl;
+    int4 v[G::STEPS];
 #pragma unroll
-    for (int k = 0; k < ITERS; ++k) {
-        const int idx = min(tid + k * NT, TOTAL - 1), row = idx / G::CHUNKS, ch = idx - row * G::CHUNKS;
-        v[k] = __ldg(reinterpret_cast<const int4 *>(base + (ptrdiff_t)min(row, last_row) * sr) + min(ch, last_ch));
+    for (int k = 0; k < G::STEPS; ++k) {
+        const int row = row0 + k * G::ROWS_PER_STEP;
+        if (active) v[k] = __ldg(reinterpret_cast<const int4 *>(base + (ptrdiff_t)min(row, last_row) * sr));
     }
+    int4 *d = reinterpret_cast<int4 *>(src_s) + row0 * G::CHUNKS + ch;
 #pragma unroll
-    for (int k = 0; k < ITERS; ++k) {
-        const int idx = tid + k * NT;
-        if (idx < TOTAL) reinterpret_cast<int4 *>(src_s)[idx] = v[k];   // rows are CHUNKS int4 long: the staged tile is dense
+    for (int k = 0; k < G::STEPS; ++k) {
+        const int row = row0 + k * G::ROWS_PER_STEP;
+        if (active && row < G::SROWS) d[k * G::ROWS_PER_STEP * G::CHUNKS] = v[k];
     }
 }
 
@@ -386,8 +465,10 @@ __device__ __forceinline__ void put8(uint8_t *p, uint32_t lo, uint32_t hi, int n
 }
 
 // vertical pass of the whole staged tile into `mid` (exact int16 sums), fast-path geometry
+// (natural taps here: in the two-pass positions the FMA pipe (IDP) is the busier one, so the PRMT-heavy gather of
+// vpass_bytes balances the two integer pipes better than vpass_rot - measured 1.36 vs 1.24 Tsamples/s, profiles/r01_pred.md)
 template <int TAPS, class G>
-__device__ __forceinline__ void vertical_to_mid_fast(uint32_t *mid, const uint32_t *src_s, const Coefs<TAPS> &cy, int tid)
+__device__ __forceinline__ void vertical_to_mid_fast(uint32_t *mid, const uint32_t *src_s, const int (&y4s)[4][3], int tid)
 {
     constexpr int ITEMS = G::NQ * (G::TH / G::R), ITERS = (ITEMS + NT - 1) / NT;
 #pragma unroll 1
@@ -396,17 +477,27 @@ __device__ __forceinline__ void vertical_to_mid_fast(uint32_t *mid, const uint32
         if (id >= ITEMS) break;
         const int q = id % G::NQ, rg = id / G::NQ;
         int v[G::R][4];
-        vpass_bytes<TAPS, G::R>(src_s + rg * G::R * G::SPW + G::Q0 + q, G::SPW, cy.p4, v);
+        int cy4[TAPS / 4];
 #pragma unroll
-        for (int r = 0; r < G::R; ++r)
-            *reinterpret_cast<uint2 *>(mid + (rg * G::R + r) * G::MP + 2 * q) = make_uint2(pack16(v[r][0], v[r][1]), pack16(v[r][2], v[r][3]));
+        for (int g = 0; g < TAPS / 4; ++g) cy4[g] = y4s[0][g];
+        vpass_bytes<TAPS, G::R>(src_s + rg * G::R * G::SPW + G::Q0 + q, G::SPW, cy4, v);
+        uint2 *m = reinterpret_cast<uint2 *>(mid + rg * G::R * G::MP + 2 * q);
+#pragma unroll
+        for (int r = 0; r < G::R; ++r) m[r * (G::MP / 2)] = make_uint2(pack16(v[r][0], v[r][1]), pack16(v[r][2], v[r][3]));
     }
 }
 
+template <int TAPS>
+__device__ __forceinline__ void take(int (&d4)[TAPS / 4], const int (&s4)[2])
+{
+#pragma unroll
+    for (int i = 0; i < TAPS / 4; ++i) d4[i] = s4[i];
+}
 template <int TAPS, int MODE, bool BI, bool DST8>
-__global__ void __launch_bounds__(NT) pred_plane_fast_kernel(PredParams p)
+__global__ void __launch_bounds__(NT) pred_plane_fast_kernel(const __grid_constant__ FastParams fp)
 {
     using G = FastGeom<TAPS, MODE, BI>;
+    const PredParams &p = fp.p;
     extern __shared__ __align__(16) uint32_t smem[];
     uint32_t *src_s = smem, *mid = smem + G::SRC_WORDS;
     const int tid = threadIdx.x;
@@ -414,20 +505,30 @@ __global__ void __launch_bounds__(NT) pred_plane_fast_kernel(PredParams p)
     const int w = min(G::TW, p.width - x0), h = min(G::TH, p.height - y0);
     uint8_t *dst = p.dst + f * p.fs_dst + (ptrdiff_t)y0 * p.sd + x0;
     const ptrdiff_t ro = f * p.fs_ref + (ptrdiff_t)y0 * p.sr + x0;
-    constexpr int NJ = G::TW / 8, HITEMS = NJ * G::TH / NT;  // 8-wide output groups per row; groups per thread
+    constexpr int NJ = G::TW / 8, HITEMS = NJ * G::TH / NT;  // 8-wide output groups per row (16); groups per thread (8)
+    // horizontal-pass ownership: group jj = tid % 16 of rows y = tid / 16 + 8 k
+    const int jj = tid % NJ, yb = tid / NJ;
+    uint8_t *drow = dst + (ptrdiff_t)yb * p.sd + 8 * jj;
+    const ptrdiff_t dstep = (ptrdiff_t)(NT / NJ) * p.sd;
+    const int nvalid = w - 8 * jj;
 
     if (!BI && MODE == COPY) {
-        // 2 x (LDG.128 -> two 64-bit stores) per thread, straight through registers
+        // 128-bit loads -> two 64-bit stores, straight through registers: chunk ch = tid % 8 of rows tid / 8 + 16 k
+        const int ch = tid & 7, r0 = tid >> 3;
+        const uint8_t *s = p.ref0 + ro + (ptrdiff_t)r0 * p.sr + ch * 16;
+        uint8_t *d = dst + (ptrdiff_t)r0 * p.sd + ch * 16;
+        const int nv = w - ch * 16;
+        int4 v[4];
 #pragma unroll
-        for (int k = 0; k < 2; ++k) {
-            const int idx = tid + k * NT, row = idx >> 3, ch = idx & 7;
-            if (row < h && ch * 16 < w) {
-                const int4 v = __ldg(reinterpret_cast<const int4 *>(p.ref0 + ro + (ptrdiff_t)row * p.sr) + ch);  // may read up to 15 bytes right of w (aligned chunk)
-                uint8_t *d = dst + (ptrdiff_t)row * p.sd + ch * 16;
-                put8<DST8>(d, (uint32_t)v.x, (uint32_t)v.y, w - ch * 16);
-                put8<DST8>(d + 8, (uint32_t)v.z, (uint32_t)v.w, w - ch * 16 - 8);
+        for (int k = 0; k < 4; ++k)
+            if (r0 + 16 * k < h && nv > 0) v[k] = __ldg(reinterpret_cast<const int4 *>(s + (ptrdiff_t)(16 * k) * p.sr));  // may read <= 15 bytes right of w
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            if (r0 + 16 * k < h && nv > 0) {
+                uint8_t *dk = d + (ptrdiff_t)(16 * k) * p.sd;
+                put8<DST8>(dk, (uint32_t)v[k].x, (uint32_t)v[k].y, nv);
+                put8<DST8>(dk + 8, (uint32_t)v[k].z, (uint32_t)v[k].w, nv - 8);
             }
-        }
         return;
     }
 
@@ -435,63 +536,65 @@ __global__ void __launch_bounds__(NT) pred_plane_fast_kernel(PredParams p)
         stage_fast<G>(src_s, p.ref0 + ro, p.sr, w, h, tid);
         __syncthreads();
         if (MODE == H_ONLY) {
-            Coefs<TAPS> cx;
-            cx.load(p.xf0);
+            int cx4[TAPS / 4];
+            take<TAPS>(cx4, fp.c[0].x4);
+            const uint32_t *s = src_s + yb * G::SPW + 3 + 2 * jj;
 #pragma unroll
             for (int k = 0; k < HITEMS; ++k) {
-                const int id = tid + k * NT, jj = id % NJ, y = id / NJ;
                 int o[8];
-                hpass_bytes<TAPS>(src_s + y * G::SPW + 3 + 2 * jj, cx.p4, 32, o);
-                if (y < h)
-                    put8<DST8>(dst + (ptrdiff_t)y * p.sd + 8 * jj, pack_sat_u8(o[0] >> 6, o[1] >> 6, o[2] >> 6, o[3] >> 6),
-                               pack_sat_u8(o[4] >> 6, o[5] >> 6, o[6] >> 6, o[7] >> 6), w - 8 * jj);
+                hpass_bytes<TAPS>(s + k * (NT / NJ) * G::SPW, cx4, 32, o);
+                if (yb + k * (NT / NJ) < h)
+                    put8<DST8>(drow + k * dstep, pack_sat_u8(o[0] >> 6, o[1] >> 6, o[2] >> 6, o[3] >> 6), pack_sat_u8(o[4] >> 6, o[5] >> 6, o[6] >> 6, o[7] >> 6),
+                               nvalid);
             }
         } else if (MODE == V_ONLY) {
-            Coefs<TAPS> cy;
-            cy.load(p.yf0);
-            const int q = tid % G::NQ, rg = tid / G::NQ;  // exactly one item per thread
-            int v[G::R][4];
-            vpass_bytes<TAPS, G::R>(src_s + rg * G::R * G::SPW + q, G::SPW, cy.p4, v);
+            constexpr int ITERS = G::NQ * (G::TH / G::R) / NT;  // 2
+#pragma unroll 1
+            for (int k = 0; k < ITERS; ++k) {
+                const int id = tid + k * NT, q = id % G::NQ, rg = id / G::NQ;
+                int v[G::R][4];
+                vpass_rot<TAPS>(src_s + rg * G::R * G::SPW + q, G::SPW, fp.c[0].y4s, v);
+                uint8_t *d = dst + (ptrdiff_t)(rg * G::R) * p.sd + 4 * q;
 #pragma unroll
-            for (int r = 0; r < G::R; ++r) {
-                const int y = rg * G::R + r;
-                if (y < h && 4 * q < w)
-                    store4(dst + (ptrdiff_t)y * p.sd + 4 * q, pack_sat_u8((v[r][0] + 32) >> 6, (v[r][1] + 32) >> 6, (v[r][2] + 32) >> 6, (v[r][3] + 32) >> 6),
-                           w - 4 * q);
+                for (int r = 0; r < G::R; ++r)
+                    if (rg * G::R + r < h && 4 * q < w)
+                        store4(d + (ptrdiff_t)r * p.sd, pack_sat_u8((v[r][0] + 32) >> 6, (v[r][1] + 32) >> 6, (v[r][2] + 32) >> 6, (v[r][3] + 32) >> 6), w - 4 * q);
             }
         } else {
-            Coefs<TAPS> cx, cy;
-            cx.load(p.xf0);
-            cy.load(p.yf0);
-            vertical_to_mid_fast<TAPS, G>(mid, src_s, cy, tid);
+            vertical_to_mid_fast<TAPS, G>(mid, src_s, fp.c[0].y4s, tid);
             __syncthreads();
+            const uint32_t *m = mid + yb * G::MP + 4 * jj;
 #pragma unroll
             for (int k = 0; k < HITEMS; ++k) {
-                const int id = tid + k * NT, jj = id % NJ, y = id / NJ;
                 int o[8];
-                hpass_mid<TAPS>(mid + y * G::MP + 4 * jj, cx.p2, 2048, o);
-                if (y < h)
-                    put8<DST8>(dst + (ptrdiff_t)y * p.sd + 8 * jj, pack_sat_u8(o[0] >> 12, o[1] >> 12, o[2] >> 12, o[3] >> 12),
-                               pack_sat_u8(o[4] >> 12, o[5] >> 12, o[6] >> 12, o[7] >> 12), w - 8 * jj);
+#ifdef HV_HROT  // experiment: slid taps in the horizontal pass too (slower: FMA-pipe bound)
+                hpass_rot<TAPS>(m + k * (NT / NJ) * G::MP, fp.c[0].x2e, fp.c[0].x2o, 2048, o);
+#else
+                hpass_mid<TAPS>(m + k * (NT / NJ) * G::MP, fp.c[0].x2e, 2048, o);
+#endif
+                if (yb + k * (NT / NJ) < h)
+                    put8<DST8>(drow + k * dstep, pack_sat_u8(o[0] >> 12, o[1] >> 12, o[2] >> 12, o[3] >> 12),
+                               pack_sat_u8(o[4] >> 12, o[5] >> 12, o[6] >> 12, o[7] >> 12), nvalid);
             }
         }
     } else {
         uint32_t va[HITEMS][4];
 #pragma unroll
         for (int r = 0; r < 2; ++r) {
-            Coefs<TAPS> cx, cy;
-            cx.load(r ? p.xf1 : p.xf0);
-            cy.load(r ? p.yf1 : p.yf0);
             if (r) __syncthreads();
             stage_fast<G>(src_s, (r ? p.ref1 : p.ref0) + ro, p.sr, w, h, tid);
             __syncthreads();
-            vertical_to_mid_fast<TAPS, G>(mid, src_s, cy, tid);
+            vertical_to_mid_fast<TAPS, G>(mid, src_s, fp.c[r].y4s, tid);
             __syncthreads();
+            const uint32_t *m = mid + yb * G::MP + 4 * jj;
 #pragma unroll
             for (int k = 0; k < HITEMS; ++k) {
-                const int id = tid + k * NT, jj = id % NJ, y = id / NJ;
                 int o[8];
-                hpass_mid<TAPS>(mid + y * G::MP + 4 * jj, cx.p2, 0, o);
+#ifdef HV_HROT  // experiment: slid taps in the horizontal pass too (slower: FMA-pipe bound)
+                hpass_rot<TAPS>(m + k * (NT / NJ) * G::MP, fp.c[r].x2e, fp.c[r].x2o, 0, o);
+#else
+                hpass_mid<TAPS>(m + k * (NT / NJ) * G::MP, fp.c[r].x2e, 0, o);
+#endif
                 if (r == 0) {
 #pragma unroll
                     for (int i = 0; i < 4; ++i) va[k][i] = pack16(o[2 * i] >> 6, o[2 * i + 1] >> 6);
@@ -502,7 +605,7 @@ __global__ void __launch_bounds__(NT) pred_plane_fast_kernel(PredParams p)
                         s[2 * i] = ((int)(short)(va[k][i] & 0xffff) + (int)(short)(o[2 * i] >> 6) + 64) >> 7;
                         s[2 * i + 1] = (((int)va[k][i] >> 16) + (int)(short)(o[2 * i + 1] >> 6) + 64) >> 7;
                     }
-                    if (y < h) put8<DST8>(dst + (ptrdiff_t)y * p.sd + 8 * jj, pack_sat_u8(s[0], s[1], s[2], s[3]), pack_sat_u8(s[4], s[5], s[6], s[7]), w - 8 * jj);
+                    if (yb + k * (NT / NJ) < h) put8<DST8>(drow + k * dstep, pack_sat_u8(s[0], s[1], s[2], s[3]), pack_sat_u8(s[4], s[5], s[6], s[7]), nvalid);
                 }
             }
         }
@@ -510,23 +613,31 @@ __global__ void __launch_bounds__(NT) pred_plane_fast_kernel(PredParams p)
 }
 
 template <int TAPS, int MODE, bool BI>
-int launch_plane_fast(const PredParams &p, dim3 grid, bool dst8, void *stream)
+int launch_plane_fast(const FastParams &fp, dim3 grid, bool dst8, void *stream)
 {
     using G = FastGeom<TAPS, MODE, BI>;
-    return dst8 ? launch(pred_plane_fast_kernel<TAPS, MODE, BI, true>, grid, dim3(NT), (size_t)G::SMEM_BYTES, stream, p)
-                : launch(pred_plane_fast_kernel<TAPS, MODE, BI, false>, grid, dim3(NT), (size_t)G::SMEM_BYTES, stream, p);
+    if (dst8) {
+        auto kern = pred_plane_fast_kernel<TAPS, MODE, BI, true>;
+        if (G::SMEM_BYTES > 48 * 1024 && set_max_smem(kern, G::SMEM_BYTES)) return (int)cudaErrorInvalidValue;
+        return launch(kern, grid, dim3(NT), (size_t)G::SMEM_BYTES, stream, fp);
+    }
+    auto kern = pred_plane_fast_kernel<TAPS, MODE, BI, false>;
+    if (G::SMEM_BYTES > 48 * 1024 && set_max_smem(kern, G::SMEM_BYTES)) return (int)cudaErrorInvalidValue;
+    return launch(kern, grid, dim3(NT), (size_t)G::SMEM_BYTES, stream, fp);
 }
 
 template <int TAPS>
-int launch_uni_planes_fast(const PredParams &p, dim3 grid, int mode, bool dst8, void *stream)
+int launch_uni_planes_fast(const FastParams &fp, dim3 grid, int mode, bool dst8, void *stream)
 {
     switch (mode) {
-        case COPY: return launch_plane_fast<TAPS, COPY, false>(p, grid, dst8, stream);
-        case H_ONLY: return launch_plane_fast<TAPS, H_ONLY, false>(p, grid, dst8, stream);
-        case V_ONLY: return launch_plane_fast<TAPS, V_ONLY, false>(p, grid, dst8, stream);
-        default: return launch_plane_fast<TAPS, HV, false>(p, grid, dst8, stream);
+        case COPY: return launch_plane_fast<TAPS, COPY, false>(fp, grid, dst8, stream);
+        case H_ONLY: return launch_plane_fast<TAPS, H_ONLY, false>(fp, grid, dst8, stream);
+        case V_ONLY: return launch_plane_fast<TAPS, V_ONLY, false>(fp, grid, dst8, stream);
+        default: return launch_plane_fast<TAPS, HV, false>(fp, grid, dst8, stream);
     }
 }
+
+constexpr int FTW = 128, FTH = 64;  // fast-path tile
 
 template <int TAPS, int TW, int TH, bool BI, int FIXED_MODE>
 int launch_pred(const PredParams &p, dim3 grid, void *stream)
@@ -562,6 +673,27 @@ using namespace hv::ip;
 
 static bool frac_ok(int taps, int f) { return f >= 0 && f < (taps == 8 ? 4 : 8); }
 
+// H.265 8.5.3.3.3 filters on the host (the device copy is c_luma / c_chroma), packed the way the dot-product instructions take them
+static PackedCoefs pack_coefs(int taps, int xFrac, int yFrac)
+{
+    static const int8_t luma[4][8] = {{0, 0, 0, 64, 0, 0, 0, 0}, {-1, 4, -10, 58, 17, -5, 1, 0}, {-1, 4, -11, 40, 40, -11, 4, -1}, {0, 1, -5, 17, 58, -10, 4, -1}};
+    static const int8_t chroma[8][4] = {{0, 64, 0, 0}, {-2, 58, 10, -2}, {-4, 54, 16, -2}, {-6, 46, 28, -4}, {-4, 36, 36, -4}, {-4, 28, 46, -6}, {-2, 16, 54, -4}, {-2, 10, 58, -2}};
+    int cx[8] = {0}, cy[8] = {0};
+    for (int k = 0; k < taps; ++k) cx[k] = taps == 8 ? luma[xFrac][k] : chroma[xFrac][k], cy[k] = taps == 8 ? luma[yFrac][k] : chroma[yFrac][k];
+    PackedCoefs c{};
+    auto tap = [&](const int *t, int k) { return (k >= 0 && k < taps) ? (t[k] & 0xff) : 0; };
+    for (int g = 0; g < 2; ++g) c.x4[g] = tap(cx, 4 * g) | (tap(cx, 4 * g + 1) << 8) | (tap(cx, 4 * g + 2) << 16) | (tap(cx, 4 * g + 3) << 24);
+    for (int g = 0; g < 4; ++g) c.x2e[g] = tap(cx, 2 * g) | (tap(cx, 2 * g + 1) << 8);
+    for (int g = 0; g < 5; ++g) c.x2o[g] = tap(cx, 2 * g - 1) | (tap(cx, 2 * g) << 8);
+    for (int sft = 0; sft < 4; ++sft)
+        for (int g = 0; g < 3; ++g) {
+            int w = 0;
+            for (int j = 0; j < 4; ++j) w |= tap(cy, 4 * g + j - sft) << (8 * j);
+            c.y4s[sft][g] = w;
+        }
+    return c;
+}
+
 // the fast plane kernels issue aligned 128-bit loads on the reference rows (and may therefore touch up to 16 bytes left and
 // 15 bytes right of the reference's own footprint - hevcasm_batch.h documents the padding this needs)
 static bool planes_fast_ok(const uint8_t *ref0, const uint8_t *ref1, ptrdiff_t sr, ptrdiff_t fs_ref, int n_frames)
@@ -590,7 +722,10 @@ extern "C" int hevcasm_pred_uni_frames(uint8_t *dst, ptrdiff_t sd, const uint8_t
     const int mode = (xFrac ? 1 : 0) | (yFrac ? 2 : 0);
     if (planes_fast_ok(ref, nullptr, sr, fs_ref, n_frames)) {
         const bool dst8 = aligned8(dst, sd, fs_dst, n_frames);
-        return taps == 8 ? launch_uni_planes_fast<8>(p, grid, mode, dst8, stream) : launch_uni_planes_fast<4>(p, grid, mode, dst8, stream);
+        FastParams fp{};
+        fp.p = p, fp.c[0] = pack_coefs(taps, xFrac, yFrac);
+        const dim3 fgrid((width + FTW - 1) / FTW, (height + FTH - 1) / FTH, n_frames);
+        return taps == 8 ? launch_uni_planes_fast<8>(fp, fgrid, mode, dst8, stream) : launch_uni_planes_fast<4>(fp, fgrid, mode, dst8, stream);
     }
     return taps == 8 ? launch_uni_planes<8>(p, grid, mode, stream) : launch_uni_planes<4>(p, grid, mode, stream);
 }
@@ -608,7 +743,10 @@ extern "C" int hevcasm_pred_bi_frames(uint8_t *dst, ptrdiff_t sd, const uint8_t 
     const dim3 grid((width + PTW - 1) / PTW, (height + PTH - 1) / PTH, n_frames);
     if (planes_fast_ok(ref0, ref1, sr, fs_ref, n_frames)) {
         const bool dst8 = aligned8(dst, sd, fs_dst, n_frames);
-        return taps == 8 ? launch_plane_fast<8, HV, true>(p, grid, dst8, stream) : launch_plane_fast<4, HV, true>(p, grid, dst8, stream);
+        FastParams fp{};
+        fp.p = p, fp.c[0] = pack_coefs(taps, xFrac0, yFrac0), fp.c[1] = pack_coefs(taps, xFrac1, yFrac1);
+        const dim3 fgrid((width + FTW - 1) / FTW, (height + FTH - 1) / FTH, n_frames);
+        return taps == 8 ? launch_plane_fast<8, HV, true>(fp, fgrid, dst8, stream) : launch_plane_fast<4, HV, true>(fp, fgrid, dst8, stream);
     }
     return taps == 8 ? launch_pred<8, PTW, PTH, true, RUNTIME>(p, grid, stream) : launch_pred<4, PTW, PTH, true, RUNTIME>(p, grid, stream);
 }

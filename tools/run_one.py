@@ -1,0 +1,47 @@
+"""Runs one entry point a few times on a 16-frame 4K batch (for ncu captures: `ncu ... python tools/run_one.py <name>`)."""
+import ctypes as C, os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from hevcasm_b200 import lib, synth
+
+W, H, NF, PAD = 3840, 2160, 16, 64
+name = sys.argv[1]
+iters = int(sys.argv[2]) if len(sys.argv) > 2 else 3
+pitch = synth.pitch_for(W, PAD); rows = H + 2 * PAD; org = PAD * pitch + PAD; fs = rows * pitch
+g = torch.Generator(device="cuda").manual_seed(7)
+a = torch.randint(0, 256, (NF, rows, pitch), dtype=torch.uint8, device="cuda", generator=g)
+b = torch.randint(0, 256, (NF, rows, pitch), dtype=torch.uint8, device="cuda", generator=g)
+o8 = torch.empty_like(a)
+n = NF * W * H
+rp = synth.pitch_for(W, 0, 128)
+res = torch.randint(-256, 256, (NF, H, rp), dtype=torch.int16, device="cuda", generator=g)
+co = torch.randint(-600, 600, (n,), dtype=torch.int16, device="cuda", generator=g)
+co2 = torch.empty((n,), dtype=torch.int16, device="cuda")
+cbf = torch.empty((n // 16,), dtype=torch.int32, device="cuda")
+def d(t, off=0): return C.c_void_p(t.data_ptr() + off * t.element_size())
+calls = {
+    "pred_hv": lambda: lib.call("pred_uni_frames", d(o8, org), pitch, d(a, org), pitch, W, H, 8, 1, 3, NF, fs, fs),
+    "pred_h": lambda: lib.call("pred_uni_frames", d(o8, org), pitch, d(a, org), pitch, W, H, 8, 1, 0, NF, fs, fs),
+    "pred_v": lambda: lib.call("pred_uni_frames", d(o8, org), pitch, d(a, org), pitch, W, H, 8, 0, 2, NF, fs, fs),
+    "pred_chroma_hv": lambda: lib.call("pred_uni_frames", d(o8, org), pitch, d(a, org), pitch, W, H, 4, 3, 5, NF, fs, fs),
+    "pred_bi": lambda: lib.call("pred_bi_frames", d(o8, org), pitch, d(a, org), d(b, org), pitch, W, H, 8, 1, 2, 3, 1, NF, fs, fs),
+    "fwd8": lambda: lib.call("transform_frames", d(co2), d(res), rp, W, H, 3, 0, NF, H * rp),
+    "fwd4": lambda: lib.call("transform_frames", d(co2), d(res), rp, W, H, 2, 0, NF, H * rp),
+    "fwd16": lambda: lib.call("transform_frames", d(co2), d(res), rp, W, H, 4, 0, NF, H * rp),
+    "fwd32": lambda: lib.call("transform_frames", d(co2), d(res), rp, W, H, 5, 0, NF, H * rp),
+    "inv4": lambda: lib.call("inverse_transform_add_frames", d(o8, org), pitch, d(a, org), pitch, d(co), W, H, 2, 0, NF, fs, fs),
+    "inv8": lambda: lib.call("inverse_transform_add_frames", d(o8, org), pitch, d(a, org), pitch, d(co), W, H, 3, 0, NF, fs, fs),
+    "inv16": lambda: lib.call("inverse_transform_add_frames", d(o8, org), pitch, d(a, org), pitch, d(co), W, H, 4, 0, NF, fs, fs),
+    "inv32": lambda: lib.call("inverse_transform_add_frames", d(o8, org), pitch, d(a, org), pitch, d(co), W, H, 5, 0, NF, fs, fs),
+    "recon8": lambda: lib.call("quantize_reconstruct_frames", d(o8, org), pitch, d(a, org), pitch, d(co), W, H, 3, NF, fs, fs),
+    "pipe8": lambda: lib.call("residual_pipeline_frames", d(o8, org), pitch, d(co2), d(cbf), d(res), rp, d(a, org), pitch, W, H, 3, 0, 26214, 18, 171 << 7, 18432, 6, NF, fs, H * rp, fs),
+}
+for _ in range(iters):
+    calls[name]()
+torch.cuda.synchronize()
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+e0.record()
+for _ in range(iters):
+    calls[name]()
+e1.record(); torch.cuda.synchronize()
+print(name, "ms/launch", e0.elapsed_time(e1) / iters)
