@@ -36,9 +36,27 @@ struct BlockGrid {
 };
 
 // ---- alignment-agnostic row access (NW 32-bit words) ---------------------------------------------------
-template <int NW>
+// PA ("plane aligned", decided on the host): base pointers, row strides and frame strides are multiples of 16 bytes and the
+// block grid is regular, so a row segment of NW words is naturally aligned to its own size - no run-time alignment dispatch.
+template <int NW, bool PA = false>
 __device__ __forceinline__ void load_words(const void *ptr, uint32_t *w)
 {
+    if (PA) {
+        if (NW % 4 == 0) {
+#pragma unroll
+            for (int i = 0; i < NW / 4; ++i) {
+                const uint4 v = __ldg(reinterpret_cast<const uint4 *>(ptr) + i);
+                w[4 * i] = v.x, w[4 * i + 1] = v.y, w[4 * i + 2] = v.z, w[4 * i + 3] = v.w;
+            }
+        } else if (NW == 2) {
+            const uint2 v = __ldg(reinterpret_cast<const uint2 *>(ptr));
+            w[0] = v.x, w[1] = v.y;
+        } else {
+#pragma unroll
+            for (int i = 0; i < NW; ++i) w[i] = __ldg(reinterpret_cast<const uint32_t *>(ptr) + i);
+        }
+        return;
+    }
     const uintptr_t a = (uintptr_t)ptr;
     if (NW % 4 == 0 && (a & 15) == 0) {
 #pragma unroll
@@ -68,9 +86,21 @@ __device__ __forceinline__ void load_words(const void *ptr, uint32_t *w)
     }
 }
 
-template <int NW>
+template <int NW, bool PA = false>
 __device__ __forceinline__ void store_words(void *ptr, const uint32_t *w)
 {
+    if (PA) {
+        if (NW % 4 == 0) {
+#pragma unroll
+            for (int i = 0; i < NW / 4; ++i) reinterpret_cast<uint4 *>(ptr)[i] = make_uint4(w[4 * i], w[4 * i + 1], w[4 * i + 2], w[4 * i + 3]);
+        } else if (NW == 2) {
+            *reinterpret_cast<uint2 *>(ptr) = make_uint2(w[0], w[1]);
+        } else {
+#pragma unroll
+            for (int i = 0; i < NW; ++i) reinterpret_cast<uint32_t *>(ptr)[i] = w[i];
+        }
+        return;
+    }
     const uintptr_t a = (uintptr_t)ptr;
     if (NW % 4 == 0 && (a & 15) == 0) {
 #pragma unroll
@@ -104,14 +134,75 @@ __device__ __forceinline__ uint32_t recon_word(uint32_t pw, const int *r)
 
 constexpr int SMALL_NT = 128;
 
+// Coefficient arrays are N*N contiguous int16 per block, so a thread-per-block kernel would touch them with 16-byte
+// accesses 32 or 128 bytes apart - half-used sectors on every request (ncu: 1.6x L2 over-fetch for the 8x8 inverse,
+// profiles/r01_transforms.md).  Instead a warp moves the 32 consecutive blocks it owns (1 KB / 4 KB contiguous) with fully
+// coalesced 128-bit accesses and transposes them through a swizzled, conflict-free shared-memory tile private to the warp.
+template <int LOG2>
+struct SmallIo {
+    static constexpr int N = 1 << LOG2, HW = N / 2, CH = N * N * 2 / 16;  // 16-byte chunks per block: 2 (4x4) or 8 (8x8)
+    static constexpr int WARP_CHUNKS = 32 * CH;
+    __device__ static __forceinline__ int pos(int b, int c) { return b * CH + (CH == 8 ? (c ^ (b & 7)) : (c ^ ((b >> 2) & 1))); }
+
+    // global (blocks first .. first+31, clipped to n) -> Cw of this lane's block
+    __device__ static __forceinline__ void load(const int16_t *coeffs, long long first, long long n, int lane, int4 *sm, uint32_t (&Cw)[N][HW])
+    {
+        const int4 *g = reinterpret_cast<const int4 *>(coeffs + first * (N * N));
+        const long long valid_chunks = (n - first < 32 ? n - first : 32) * CH;
+        int4 v[CH];
+#pragma unroll
+        for (int k = 0; k < CH; ++k) {
+            const int j = lane + 32 * k;
+            v[k] = j < valid_chunks ? ldg_stream(g + j) : make_int4(0, 0, 0, 0);
+        }
+#pragma unroll
+        for (int k = 0; k < CH; ++k) {
+            const int j = lane + 32 * k;
+            sm[pos(j / CH, j % CH)] = v[k];
+        }
+        __syncwarp();
+#pragma unroll
+        for (int c = 0; c < CH; ++c) {
+            const int4 t = sm[pos(lane, c)];
+            if (CH == 8) {
+                Cw[c][0] = t.x, Cw[c][1] = t.y, Cw[c][HW - 2] = t.z, Cw[c][HW - 1] = t.w;
+            } else {
+                Cw[2 * c][0] = t.x, Cw[2 * c][1] = t.y, Cw[(2 * c + 1) % N][0] = t.z, Cw[(2 * c + 1) % N][1] = t.w;
+            }
+        }
+        __syncwarp();
+    }
+
+    // Yw of this lane's block -> global
+    __device__ static __forceinline__ void store(int16_t *coeffs, long long first, long long n, int lane, int4 *sm, const uint32_t (&Yw)[N][HW])
+    {
+#pragma unroll
+        for (int c = 0; c < CH; ++c) {
+            int4 t;
+            if (CH == 8) t = make_int4((int)Yw[c][0], (int)Yw[c][1], (int)Yw[c][HW - 2], (int)Yw[c][HW - 1]);
+            else t = make_int4((int)Yw[2 * c][0], (int)Yw[2 * c][1], (int)Yw[(2 * c + 1) % N][0], (int)Yw[(2 * c + 1) % N][1]);
+            sm[pos(lane, c)] = t;
+        }
+        __syncwarp();
+        int4 *g = reinterpret_cast<int4 *>(coeffs + first * (N * N));
+        const long long valid_chunks = (n - first < 32 ? n - first : 32) * CH;
+#pragma unroll
+        for (int k = 0; k < CH; ++k) {
+            const int j = lane + 32 * k;
+            if (j < valid_chunks) stg_stream(g + j, sm[pos(j / CH, j % CH)]);
+        }
+        __syncwarp();
+    }
+};
+
 // forward transform of the block at src (row stride `stride`), result in coefficient memory order: Yw[v][u/2] = (Y[v][u], Y[v][u+1])
-template <int LOG2, bool DST>
+template <int LOG2, bool DST, bool PA>
 __device__ __forceinline__ void small_fwd_core(const int16_t *src, ptrdiff_t stride, uint32_t (&Yw)[1 << LOG2][(1 << LOG2) / 2])
 {
     constexpr int N = 1 << LOG2, HW = N / 2, S1 = fwd_shift1(LOG2), S2 = fwd_shift2(LOG2);
     uint32_t X[N][HW];
 #pragma unroll
-    for (int r = 0; r < N; ++r) load_words<HW>(src + (ptrdiff_t)r * stride, X[r]);
+    for (int r = 0; r < N; ++r) load_words<HW, PA>(src + (ptrdiff_t)r * stride, X[r]);
 
     // stage 1 (along x): A[u][y]; kept as vertical pairs Aw[u][y/2] = (A[u][y], A[u][y+1]), the operand order stage 2 needs
     uint32_t Aw[N][HW];
@@ -134,25 +225,37 @@ __device__ __forceinline__ void small_fwd_core(const int16_t *src, ptrdiff_t str
     }
 }
 
-template <int LOG2, bool DST>
+template <int LOG2, bool DST, bool PA>
 __global__ void __launch_bounds__(SMALL_NT) small_fwd_kernel(int16_t *__restrict__ coeffs, const int16_t *__restrict__ res, ptrdiff_t stride,
                                                              ptrdiff_t fs, BlockGrid g)
 {
+    using Io = SmallIo<LOG2>;
     constexpr int N = 1 << LOG2, HW = N / 2;
-    const long long i = (long long)blockIdx.x * SMALL_NT + threadIdx.x;
-    if (i >= g.n) return;
-    int x, y, f;
-    g.locate(i, LOG2, x, y, f);
+    __shared__ __align__(16) int4 io[SMALL_NT / 32][Io::WARP_CHUNKS];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const long long i = (long long)blockIdx.x * SMALL_NT + threadIdx.x, first = i - lane;
+    if (first >= g.n) return;  // whole warp out of range
     uint32_t Yw[N][HW];
-    small_fwd_core<LOG2, DST>(res + f * fs + (ptrdiff_t)y * stride + x, stride, Yw);
-    int16_t *out = coeffs + i * (N * N);
-#pragma unroll
-    for (int v = 0; v < N; ++v) store_words<HW>(out + v * N, Yw[v]);
+    if (i < g.n) {
+        int x, y, f;
+        g.locate(i, LOG2, x, y, f);
+        small_fwd_core<LOG2, DST, PA>(res + f * fs + (ptrdiff_t)y * stride + x, stride, Yw);
+    }
+    Io::store(coeffs, first, g.n, lane, io[warp], Yw);
 }
 
 // dst = clip8(pred + inverse transform of Cw); Cw in coefficient memory order
-template <int LOG2, bool DST>
-__device__ __forceinline__ void small_inv_core(const uint32_t (&Cw)[1 << LOG2][(1 << LOG2) / 2], uint8_t *dp, ptrdiff_t sd, const uint8_t *pp, ptrdiff_t sp)
+// the predictor block, fetched before the arithmetic starts so that its latency hides behind the transform
+template <int N, bool PA>
+__device__ __forceinline__ void load_pred(const uint8_t *pp, ptrdiff_t sp, uint32_t (&pw)[N][N / 4])
+{
+#pragma unroll
+    for (int r = 0; r < N; ++r) load_words<N / 4, PA>(pp + (ptrdiff_t)r * sp, pw[r]);
+}
+
+template <int LOG2, bool DST, bool PA>
+__device__ __forceinline__ void small_inv_core(const uint32_t (&Cw)[1 << LOG2][(1 << LOG2) / 2], uint8_t *dp, ptrdiff_t sd,
+                                               const uint32_t (&pw)[1 << LOG2][(1 << LOG2) / 4])
 {
     constexpr int N = 1 << LOG2, HW = N / 2;
     // stage 1 (along v, shift 7, clip16): B[u][y]
@@ -184,28 +287,33 @@ __device__ __forceinline__ void small_inv_core(const uint32_t (&Cw)[1 << LOG2][(
         int o[N];
         if (DST) inv_dst4(p, o, 2048);
         else InvBfly<N>::run(p, o, 2048);
-        uint32_t pw[N / 4], ow[N / 4];
-        load_words<N / 4>(pp + (ptrdiff_t)r * sp, pw);
+        uint32_t ow[N / 4];
 #pragma unroll
-        for (int k = 0; k < N / 4; ++k) ow[k] = recon_word(pw[k], o + 4 * k);
-        store_words<N / 4>(dp + (ptrdiff_t)r * sd, ow);
+        for (int k = 0; k < N / 4; ++k) ow[k] = recon_word(pw[r][k], o + 4 * k);
+        store_words<N / 4, PA>(dp + (ptrdiff_t)r * sd, ow);
     }
 }
 
-template <int LOG2, bool DST>
+template <int LOG2, bool DST, bool PA>
 __global__ void __launch_bounds__(SMALL_NT) small_inv_kernel(uint8_t *__restrict__ dst, ptrdiff_t sd, const uint8_t *__restrict__ pred, ptrdiff_t sp,
                                                              ptrdiff_t fs_dst, ptrdiff_t fs_pred, const int16_t *__restrict__ coeffs, BlockGrid g)
 {
+    using Io = SmallIo<LOG2>;
     constexpr int N = 1 << LOG2, HW = N / 2;
-    const long long i = (long long)blockIdx.x * SMALL_NT + threadIdx.x;
-    if (i >= g.n) return;
-    int x, y, f;
-    g.locate(i, LOG2, x, y, f);
+    __shared__ __align__(16) int4 io[SMALL_NT / 32][Io::WARP_CHUNKS];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const long long i = (long long)blockIdx.x * SMALL_NT + threadIdx.x, first = i - lane;
+    if (first >= g.n) return;
+    const bool valid = i < g.n;
+    int x = 0, y = 0, f = 0;
+    uint32_t pw[N][N / 4];
+    if (valid) {
+        g.locate(i, LOG2, x, y, f);
+        load_pred<N, PA>(pred + f * fs_pred + (ptrdiff_t)y * sp + x, sp, pw);
+    }
     uint32_t Cw[N][HW];
-    const int16_t *c = coeffs + i * (N * N);
-#pragma unroll
-    for (int v = 0; v < N; ++v) load_words<HW>(c + v * N, Cw[v]);
-    small_inv_core<LOG2, DST>(Cw, dst + f * fs_dst + (ptrdiff_t)y * sd + x, sd, pred + f * fs_pred + (ptrdiff_t)y * sp + x, sp);
+    Io::load(coeffs, first, g.n, lane, io[warp], Cw);
+    if (valid) small_inv_core<LOG2, DST, PA>(Cw, dst + f * fs_dst + (ptrdiff_t)y * sd + x, sd, pw);
 }
 
 // ================================================================================================ 16x16 / 32x32
@@ -222,7 +330,7 @@ struct BigGeom {
 
 // Inverse of one block by the HW lanes that own it.  W[v] = (C[v][2uw], C[v][2uw+1]) - this lane's two coefficient columns.
 // Must be called by all 32 lanes of the warp (it contains a __syncwarp); lanes with !valid only take part in the barrier.
-template <int LOG2>
+template <int LOG2, bool PA>
 __device__ __forceinline__ void big_inv_core(uint32_t *tmp, int b, int uw, bool valid, const uint32_t (&W)[1 << LOG2], uint8_t *dp, ptrdiff_t sd,
                                              const uint8_t *pp, ptrdiff_t sp)
 {
@@ -264,15 +372,15 @@ __device__ __forceinline__ void big_inv_core(uint32_t *tmp, int b, int uw, bool 
             int o[N];
             InvBfly<N>::run(p, o, 2048);
             uint32_t pw[N / 4], ow[N / 4];
-            load_words<N / 4>(pp + (ptrdiff_t)r * sp, pw);
+            load_words<N / 4, PA>(pp + (ptrdiff_t)r * sp, pw);
 #pragma unroll
             for (int k = 0; k < N / 4; ++k) ow[k] = recon_word(pw[k], o + 4 * k);
-            store_words<N / 4>(dp + (ptrdiff_t)r * sd, ow);
+            store_words<N / 4, PA>(dp + (ptrdiff_t)r * sd, ow);
         }
     }
 }
 
-template <int LOG2>
+template <int LOG2, bool PA>
 __global__ void __launch_bounds__(BIG_NT) big_inv_kernel(uint8_t *__restrict__ dst, ptrdiff_t sd, const uint8_t *__restrict__ pred, ptrdiff_t sp,
                                                          ptrdiff_t fs_dst, ptrdiff_t fs_pred, const int16_t *__restrict__ coeffs, BlockGrid g)
 {
@@ -291,11 +399,11 @@ __global__ void __launch_bounds__(BIG_NT) big_inv_kernel(uint8_t *__restrict__ d
         for (int v = 0; v < N; ++v) W[v] = __ldg(cw + v * HW);
         g.locate(gb, LOG2, x, y, f);
     }
-    big_inv_core<LOG2>(tmp_all[warp], b, uw, valid, W, dst + f * fs_dst + (ptrdiff_t)y * sd + x, sd, pred + f * fs_pred + (ptrdiff_t)y * sp + x, sp);
+    big_inv_core<LOG2, PA>(tmp_all[warp], b, uw, valid, W, dst + f * fs_dst + (ptrdiff_t)y * sd + x, sd, pred + f * fs_pred + (ptrdiff_t)y * sp + x, sp);
 }
 
 // Forward transform of one block by the HW lanes that own it; on return W[v] = (Y[v][2uw], Y[v][2uw+1]).
-template <int LOG2>
+template <int LOG2, bool PA>
 __device__ __forceinline__ void big_fwd_core(uint32_t *tmp, int b, int uw, bool valid, const int16_t *src, ptrdiff_t stride, uint32_t (&W)[1 << LOG2])
 {
     using G = BigGeom<LOG2>;
@@ -305,7 +413,7 @@ __device__ __forceinline__ void big_fwd_core(uint32_t *tmp, int b, int uw, bool 
         for (int h = 0; h < 2; ++h) {
             const int r = uw + h * HW;
             uint32_t Xw[HW];
-            load_words<HW>(src + (ptrdiff_t)r * stride, Xw);
+            load_words<HW, PA>(src + (ptrdiff_t)r * stride, Xw);
             int xv[N], a[N];
 #pragma unroll
             for (int k = 0; k < HW; ++k) xv[2 * k] = s16lo(Xw[k]), xv[2 * k + 1] = s16hi(Xw[k]);
@@ -333,7 +441,7 @@ __device__ __forceinline__ void big_fwd_core(uint32_t *tmp, int b, int uw, bool 
     __syncwarp();  // tmp may be reused by the caller
 }
 
-template <int LOG2>
+template <int LOG2, bool PA>
 __global__ void __launch_bounds__(BIG_NT) big_fwd_kernel(int16_t *__restrict__ coeffs, const int16_t *__restrict__ res, ptrdiff_t stride, ptrdiff_t fs,
                                                          BlockGrid g)
 {
@@ -347,7 +455,7 @@ __global__ void __launch_bounds__(BIG_NT) big_fwd_kernel(int16_t *__restrict__ c
     int x = 0, y = 0, f = 0;
     if (valid) g.locate(gb, LOG2, x, y, f);
     uint32_t W[N];
-    big_fwd_core<LOG2>(tmp_all[warp], b, uw, valid, res + f * fs + (ptrdiff_t)y * stride + x, stride, W);
+    big_fwd_core<LOG2, PA>(tmp_all[warp], b, uw, valid, res + f * fs + (ptrdiff_t)y * stride + x, stride, W);
     if (valid) {
         uint32_t *out = reinterpret_cast<uint32_t *>(coeffs + gb * (N * N)) + uw;
 #pragma unroll
@@ -388,30 +496,34 @@ struct PipelineParams {
     QuantParams q;
 };
 
-template <int LOG2, bool DST>
+template <int LOG2, bool DST, bool PA>
 __global__ void __launch_bounds__(SMALL_NT) small_pipeline_kernel(PipelineParams p, BlockGrid g)
 {
+    using Io = SmallIo<LOG2>;
     constexpr int N = 1 << LOG2, HW = N / 2;
-    const long long i = (long long)blockIdx.x * SMALL_NT + threadIdx.x;
-    if (i >= g.n) return;
-    int x, y, f;
-    g.locate(i, LOG2, x, y, f);
-    uint32_t Yw[N][HW];
-    small_fwd_core<LOG2, DST>(p.res + f * p.fs_res + (ptrdiff_t)y * p.s_res + x, p.s_res, Yw);
+    __shared__ __align__(16) int4 io[SMALL_NT / 32][Io::WARP_CHUNKS];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const long long i = (long long)blockIdx.x * SMALL_NT + threadIdx.x, first = i - lane;
+    if (first >= g.n) return;
+    const bool valid = i < g.n;
+    int x = 0, y = 0, f = 0;
+    uint32_t Yw[N][HW], L[N][HW], pw[N][N / 4];
     int cbf = 0;
-    int16_t *lv = p.levels + i * (N * N);
+    if (valid) {
+        g.locate(i, LOG2, x, y, f);
+        load_pred<N, PA>(p.pred + f * p.fs_pred + (ptrdiff_t)y * p.s_pred + x, p.s_pred, pw);
+        small_fwd_core<LOG2, DST, PA>(p.res + f * p.fs_res + (ptrdiff_t)y * p.s_res + x, p.s_res, Yw);
 #pragma unroll
-    for (int v = 0; v < N; ++v) {
-        uint32_t L[HW];
+        for (int v = 0; v < N; ++v)
 #pragma unroll
-        for (int k = 0; k < HW; ++k) Yw[v][k] = quant_dequant_word(Yw[v][k], p.q, L[k], cbf);
-        store_words<HW>(lv + v * N, L);
+            for (int k = 0; k < HW; ++k) Yw[v][k] = quant_dequant_word(Yw[v][k], p.q, L[v][k], cbf);
+        if (p.cbf) p.cbf[i] = cbf;
     }
-    if (p.cbf) p.cbf[i] = cbf;
-    small_inv_core<LOG2, DST>(Yw, p.rec + f * p.fs_rec + (ptrdiff_t)y * p.s_rec + x, p.s_rec, p.pred + f * p.fs_pred + (ptrdiff_t)y * p.s_pred + x, p.s_pred);
+    Io::store(p.levels, first, g.n, lane, io[warp], L);
+    if (valid) small_inv_core<LOG2, DST, PA>(Yw, p.rec + f * p.fs_rec + (ptrdiff_t)y * p.s_rec + x, p.s_rec, pw);
 }
 
-template <int LOG2>
+template <int LOG2, bool PA>
 __global__ void __launch_bounds__(BIG_NT) big_pipeline_kernel(PipelineParams p, BlockGrid g)
 {
     using G = BigGeom<LOG2>;
@@ -424,7 +536,7 @@ __global__ void __launch_bounds__(BIG_NT) big_pipeline_kernel(PipelineParams p, 
     int x = 0, y = 0, f = 0;
     if (valid) g.locate(gb, LOG2, x, y, f);
     uint32_t W[N];
-    big_fwd_core<LOG2>(tmp_all[warp], b, uw, valid, p.res + f * p.fs_res + (ptrdiff_t)y * p.s_res + x, p.s_res, W);
+    big_fwd_core<LOG2, PA>(tmp_all[warp], b, uw, valid, p.res + f * p.fs_res + (ptrdiff_t)y * p.s_res + x, p.s_res, W);
     int cbf = 0;
     if (valid) {
         uint32_t *lv = reinterpret_cast<uint32_t *>(p.levels + gb * (N * N)) + uw;
@@ -439,7 +551,7 @@ __global__ void __launch_bounds__(BIG_NT) big_pipeline_kernel(PipelineParams p, 
 #pragma unroll
     for (int o = 1; o < HW; o <<= 1) cbf |= __shfl_xor_sync(0xffffffffu, cbf, o);
     if (valid && uw == 0 && p.cbf) p.cbf[gb] = cbf;
-    big_inv_core<LOG2>(tmp_all[warp], b, uw, valid, W, p.rec + f * p.fs_rec + (ptrdiff_t)y * p.s_rec + x, p.s_rec,
+    big_inv_core<LOG2, PA>(tmp_all[warp], b, uw, valid, W, p.rec + f * p.fs_rec + (ptrdiff_t)y * p.s_rec + x, p.s_rec,
                        p.pred + f * p.fs_pred + (ptrdiff_t)y * p.s_pred + x, p.s_pred);
 }
 
@@ -448,16 +560,40 @@ __global__ void __launch_bounds__(BIG_NT) big_pipeline_kernel(PipelineParams p, 
 // ================================================================================================ C ABI
 using namespace hv;
 
+static bool aligned16(const void *a, ptrdiff_t s1_bytes, ptrdiff_t s2_bytes = 0, const void *b = nullptr, ptrdiff_t s3_bytes = 0, ptrdiff_t s4_bytes = 0)
+{
+    return (((uintptr_t)a | (uintptr_t)b | (uintptr_t)s1_bytes | (uintptr_t)s2_bytes | (uintptr_t)s3_bytes | (uintptr_t)s4_bytes) & 15) == 0;
+}
+
+template <bool PA>
+static int launch_fwd_t(int16_t *coeffs, const int16_t *res, ptrdiff_t stride, ptrdiff_t fs, int log2, int trType, const BlockGrid &g, void *stream)
+{
+    const unsigned small_grid = (unsigned)((g.n + SMALL_NT - 1) / SMALL_NT);
+    if (log2 == 2 && trType) return launch(small_fwd_kernel<2, true, PA>, small_grid, SMALL_NT, 0, stream, coeffs, res, stride, fs, g);
+    if (log2 == 2) return launch(small_fwd_kernel<2, false, PA>, small_grid, SMALL_NT, 0, stream, coeffs, res, stride, fs, g);
+    if (log2 == 3) return launch(small_fwd_kernel<3, false, PA>, small_grid, SMALL_NT, 0, stream, coeffs, res, stride, fs, g);
+    if (log2 == 4) return launch(big_fwd_kernel<4, PA>, (unsigned)((g.n + 15) / 16), BIG_NT, 0, stream, coeffs, res, stride, fs, g);
+    return launch(big_fwd_kernel<5, PA>, (unsigned)((g.n + 7) / 8), BIG_NT, 0, stream, coeffs, res, stride, fs, g);
+}
+
 static int launch_fwd(int16_t *coeffs, const int16_t *res, ptrdiff_t stride, ptrdiff_t fs, int log2, int trType, const BlockGrid &g, void *stream)
 {
     if (g.n == 0) return 0;
     if (((uintptr_t)coeffs & 15) != 0) return HEVCASM_ERR_ARGUMENT;
+    const bool pa = !g.blk_xy && aligned16(res, stride * 2, fs * 2);
+    return pa ? launch_fwd_t<true>(coeffs, res, stride, fs, log2, trType, g, stream) : launch_fwd_t<false>(coeffs, res, stride, fs, log2, trType, g, stream);
+}
+
+template <bool PA>
+static int launch_inv_t(uint8_t *dst, ptrdiff_t sd, const uint8_t *pred, ptrdiff_t sp, ptrdiff_t fs_dst, ptrdiff_t fs_pred, const int16_t *coeffs, int log2,
+                        int trType, const BlockGrid &g, void *stream)
+{
     const unsigned small_grid = (unsigned)((g.n + SMALL_NT - 1) / SMALL_NT);
-    if (log2 == 2 && trType) return launch(small_fwd_kernel<2, true>, small_grid, SMALL_NT, 0, stream, coeffs, res, stride, fs, g);
-    if (log2 == 2) return launch(small_fwd_kernel<2, false>, small_grid, SMALL_NT, 0, stream, coeffs, res, stride, fs, g);
-    if (log2 == 3) return launch(small_fwd_kernel<3, false>, small_grid, SMALL_NT, 0, stream, coeffs, res, stride, fs, g);
-    if (log2 == 4) return launch(big_fwd_kernel<4>, (unsigned)((g.n + 15) / 16), BIG_NT, 0, stream, coeffs, res, stride, fs, g);
-    return launch(big_fwd_kernel<5>, (unsigned)((g.n + 7) / 8), BIG_NT, 0, stream, coeffs, res, stride, fs, g);
+    if (log2 == 2 && trType) return launch(small_inv_kernel<2, true, PA>, small_grid, SMALL_NT, 0, stream, dst, sd, pred, sp, fs_dst, fs_pred, coeffs, g);
+    if (log2 == 2) return launch(small_inv_kernel<2, false, PA>, small_grid, SMALL_NT, 0, stream, dst, sd, pred, sp, fs_dst, fs_pred, coeffs, g);
+    if (log2 == 3) return launch(small_inv_kernel<3, false, PA>, small_grid, SMALL_NT, 0, stream, dst, sd, pred, sp, fs_dst, fs_pred, coeffs, g);
+    if (log2 == 4) return launch(big_inv_kernel<4, PA>, (unsigned)((g.n + 15) / 16), BIG_NT, 0, stream, dst, sd, pred, sp, fs_dst, fs_pred, coeffs, g);
+    return launch(big_inv_kernel<5, PA>, (unsigned)((g.n + 7) / 8), BIG_NT, 0, stream, dst, sd, pred, sp, fs_dst, fs_pred, coeffs, g);
 }
 
 static int launch_inv(uint8_t *dst, ptrdiff_t sd, const uint8_t *pred, ptrdiff_t sp, ptrdiff_t fs_dst, ptrdiff_t fs_pred, const int16_t *coeffs, int log2,
@@ -465,12 +601,9 @@ static int launch_inv(uint8_t *dst, ptrdiff_t sd, const uint8_t *pred, ptrdiff_t
 {
     if (g.n == 0) return 0;
     if (((uintptr_t)coeffs & 15) != 0) return HEVCASM_ERR_ARGUMENT;
-    const unsigned small_grid = (unsigned)((g.n + SMALL_NT - 1) / SMALL_NT);
-    if (log2 == 2 && trType) return launch(small_inv_kernel<2, true>, small_grid, SMALL_NT, 0, stream, dst, sd, pred, sp, fs_dst, fs_pred, coeffs, g);
-    if (log2 == 2) return launch(small_inv_kernel<2, false>, small_grid, SMALL_NT, 0, stream, dst, sd, pred, sp, fs_dst, fs_pred, coeffs, g);
-    if (log2 == 3) return launch(small_inv_kernel<3, false>, small_grid, SMALL_NT, 0, stream, dst, sd, pred, sp, fs_dst, fs_pred, coeffs, g);
-    if (log2 == 4) return launch(big_inv_kernel<4>, (unsigned)((g.n + 15) / 16), BIG_NT, 0, stream, dst, sd, pred, sp, fs_dst, fs_pred, coeffs, g);
-    return launch(big_inv_kernel<5>, (unsigned)((g.n + 7) / 8), BIG_NT, 0, stream, dst, sd, pred, sp, fs_dst, fs_pred, coeffs, g);
+    const bool pa = !g.blk_xy && aligned16(dst, sd, fs_dst, pred, sp, fs_pred);
+    return pa ? launch_inv_t<true>(dst, sd, pred, sp, fs_dst, fs_pred, coeffs, log2, trType, g, stream)
+              : launch_inv_t<false>(dst, sd, pred, sp, fs_dst, fs_pred, coeffs, log2, trType, g, stream);
 }
 
 static bool tr_args_ok(int log2, int trType) { return log2 >= 2 && log2 <= 5 && (trType == 0 || (trType == 1 && log2 == 2)); }
@@ -509,6 +642,17 @@ extern "C" int hevcasm_inverse_transform_add_frames(uint8_t *dst, ptrdiff_t sd, 
     return launch_inv(dst, sd, pred, sp, fs_dst, fs_pred, coeffs, log2size, trType, g, stream);
 }
 
+template <bool PA>
+static int launch_pipeline_t(const PipelineParams &p, const BlockGrid &g, int log2size, int trType, void *stream)
+{
+    const unsigned small_grid = (unsigned)((g.n + SMALL_NT - 1) / SMALL_NT);
+    if (log2size == 2 && trType) return launch(small_pipeline_kernel<2, true, PA>, small_grid, SMALL_NT, 0, stream, p, g);
+    if (log2size == 2) return launch(small_pipeline_kernel<2, false, PA>, small_grid, SMALL_NT, 0, stream, p, g);
+    if (log2size == 3) return launch(small_pipeline_kernel<3, false, PA>, small_grid, SMALL_NT, 0, stream, p, g);
+    if (log2size == 4) return launch(big_pipeline_kernel<4, PA>, (unsigned)((g.n + 15) / 16), BIG_NT, 0, stream, p, g);
+    return launch(big_pipeline_kernel<5, PA>, (unsigned)((g.n + 7) / 8), BIG_NT, 0, stream, p, g);
+}
+
 extern "C" int hevcasm_residual_pipeline_frames(uint8_t *rec, ptrdiff_t s_rec, int16_t *levels, int32_t *cbf, const int16_t *residual, ptrdiff_t s_res,
                                                 const uint8_t *pred, ptrdiff_t s_pred, int width, int height, int log2size, int trType, int q_scale,
                                                 int q_shift, int q_offset, int iq_scale, int iq_shift, int n_frames, ptrdiff_t fs_rec, ptrdiff_t fs_res,
@@ -525,10 +669,6 @@ extern "C" int hevcasm_residual_pipeline_frames(uint8_t *rec, ptrdiff_t s_rec, i
     p.rec = rec, p.pred = pred, p.res = residual, p.levels = levels, p.cbf = cbf;
     p.s_rec = s_rec, p.s_pred = s_pred, p.s_res = s_res, p.fs_rec = fs_rec, p.fs_pred = fs_pred, p.fs_res = fs_res;
     p.q = QuantParams{q_scale, q_shift, q_offset << (q_shift - 16), iq_scale, iq_shift};
-    const unsigned small_grid = (unsigned)((g.n + SMALL_NT - 1) / SMALL_NT);
-    if (log2size == 2 && trType) return launch(small_pipeline_kernel<2, true>, small_grid, SMALL_NT, 0, stream, p, g);
-    if (log2size == 2) return launch(small_pipeline_kernel<2, false>, small_grid, SMALL_NT, 0, stream, p, g);
-    if (log2size == 3) return launch(small_pipeline_kernel<3, false>, small_grid, SMALL_NT, 0, stream, p, g);
-    if (log2size == 4) return launch(big_pipeline_kernel<4>, (unsigned)((g.n + 15) / 16), BIG_NT, 0, stream, p, g);
-    return launch(big_pipeline_kernel<5>, (unsigned)((g.n + 7) / 8), BIG_NT, 0, stream, p, g);
+    const bool pa = aligned16(rec, s_rec, fs_rec, pred, s_pred, fs_pred) && aligned16(residual, s_res * 2, fs_res * 2);
+    return pa ? launch_pipeline_t<true>(p, g, log2size, trType, stream) : launch_pipeline_t<false>(p, g, log2size, trType, stream);
 }
