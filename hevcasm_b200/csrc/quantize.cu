@@ -162,47 +162,58 @@ struct ReconParams {
     const uint8_t *pred;
     const int16_t *res;
     ptrdiff_t sr, sp, fs_rec, fs_pred;
-    int log2, nbx, nby;          // frames form: block grid per frame
-    const int16_t *blk_xy;       // list form (nbx = number of blocks, nby = 1)
+    int nbx, nby;                // frames form: block grid per frame (blockIdx.y = block row, blockIdx.z = frame)
+    const int16_t *blk_xy;       // list form: nbx = number of blocks, nby = 1
 };
 
-// One thread per 8-sample unit of a block (a row segment for n >= 8, two rows for n == 4).  Units are numbered
-// x-fastest across the blocks of a block row so that pred / rec accesses of a warp are contiguous.
+// The residual of a block row is one flat run of int16 (blocks are N*N contiguous), so the kernel streams it: unit u is
+// the u-th group of 8 residuals of the block row (for 4x4: 8 residuals = two block rows of 4), decoded with compile-time
+// divisors into (block, row, 8-sample segment).  A warp's residual loads are 512 contiguous bytes, its predictor /
+// reconstruction accesses whole 32-byte sectors; every thread keeps UNR independent units in flight.
+// PA: plane pointers and strides are 16-byte multiples (regular grid only) -> natural-width vector accesses, no checks.
+template <int LOG2, bool PA>
 __global__ void __launch_bounds__(256) reconstruct_kernel(ReconParams p)
 {
-    const int n = 1 << p.log2;
-    const int f = blockIdx.z;
-    const int upr = n >= 8 ? n / 8 : 1;           // units per block row-of-samples
-    const int rows = n >= 8 ? n : 2;              // unit rows per block
-    const long long units_x = (long long)p.nbx * upr;
-    const long long u = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (u >= units_x * rows) return;
-    const int r = (int)(u / units_x);
-    const long long ux = u - (long long)r * units_x;
-    const int bx = (int)(ux / upr), seg = (int)(ux - (long long)bx * upr);
-    const int by = blockIdx.y;
-    int x, y;
-    size_t blk;
-    if (p.blk_xy) {
-        x = p.blk_xy[2 * bx], y = p.blk_xy[2 * bx + 1], blk = (size_t)bx;
-    } else {
-        x = bx * n, y = by * n, blk = ((size_t)f * p.nby + by) * p.nbx + bx;
+    constexpr int N = 1 << LOG2, UNR = 4;
+    constexpr int UPB = N * N / 8;  // units per block
+    const int f = blockIdx.z, by = blockIdx.y;
+    const int units = p.nbx * UPB;
+    const int u0 = blockIdx.x * (256 * UNR) + threadIdx.x;
+    int4 rv[UNR];
+    uint2 pv[UNR];
+    const uint8_t *pp[UNR];
+    ptrdiff_t ro[UNR];
+#pragma unroll
+    for (int k = 0; k < UNR; ++k) {
+        const int u = u0 + k * 256;
+        if (u >= units) continue;
+        const int bx = u / UPB, w = u % UPB;  // block, unit within the block
+        int x, y, r, xs;
+        size_t blk;
+        if (N == 4) r = 2 * w, xs = 0;
+        else r = w / (N / 8), xs = (w % (N / 8)) * 8;
+        if (p.blk_xy) x = p.blk_xy[2 * bx], y = p.blk_xy[2 * bx + 1], blk = (size_t)bx;
+        else x = bx * N, y = by * N, blk = ((size_t)f * p.nby + by) * p.nbx + bx;
+        rv[k] = ldg_stream(reinterpret_cast<const int4 *>(p.res + blk * (N * N)) + w);
+        pp[k] = p.pred + f * p.fs_pred + (ptrdiff_t)(y + r) * p.sp + x + xs;
+        ro[k] = f * p.fs_rec + (ptrdiff_t)(y + r) * p.sr + x + xs;
+        if (N == 4) pv[k] = make_uint2(PA ? __ldg(reinterpret_cast<const uint32_t *>(pp[k])) : ld4(pp[k]),
+                                       PA ? __ldg(reinterpret_cast<const uint32_t *>(pp[k] + p.sp)) : ld4(pp[k] + p.sp));
+        else pv[k] = PA ? __ldg(reinterpret_cast<const uint2 *>(pp[k])) : make_uint2(ld4(pp[k]), ld4(pp[k] + 4));
     }
-    const int16_t *res = p.res + blk * n * n;
-    const uint8_t *pred = p.pred + f * p.fs_pred + (ptrdiff_t)y * p.sp + x;
-    uint8_t *rec = p.rec + f * p.fs_rec + (ptrdiff_t)y * p.sr + x;
-    if (n >= 8) {
-        const int4 rv = *reinterpret_cast<const int4 *>(res + r * n + seg * 8);
-        const uint8_t *pp = pred + (ptrdiff_t)r * p.sp + seg * 8;
-        uint8_t *rp = rec + (ptrdiff_t)r * p.sr + seg * 8;
-        const uint2 o = recon8(make_uint2(ld4(pp), ld4(pp + 4)), rv);
-        st4(rp, o.x), st4(rp + 4, o.y);
-    } else {
-        const int4 rv = *reinterpret_cast<const int4 *>(res + r * 8);
-        const uint8_t *pp = pred + (ptrdiff_t)(2 * r) * p.sp;
-        uint8_t *rp = rec + (ptrdiff_t)(2 * r) * p.sr;
-        const uint2 o = recon8(make_uint2(ld4(pp), ld4(pp + p.sp)), rv);
-        st4(rp, o.x), st4(rp + p.sr, o.y);
+#pragma unroll
+    for (int k = 0; k < UNR; ++k) {
+        const int u = u0 + k * 256;
+        if (u >= units) continue;
+        const uint2 o = recon8(pv[k], rv[k]);
+        uint8_t *rp = p.rec + ro[k];
+        if (N == 4) {
+            if (PA) *reinterpret_cast<uint32_t *>(rp) = o.x, *reinterpret_cast<uint32_t *>(rp + p.sr) = o.y;
+            else st4(rp, o.x), st4(rp + p.sr, o.y);
+        } else {
+            if (PA) *reinterpret_cast<uint2 *>(rp) = o;
+            else st4(rp, o.x), st4(rp + 4, o.y);
+        }
     }
 }
 
@@ -252,13 +263,26 @@ extern "C" int hevcasm_quantize_inverse_batch(int16_t *dst, const int16_t *src, 
     return 0;
 }
 
-static int launch_reconstruct(ReconParams &p, int n_frames, void *stream)
+template <int LOG2>
+static int launch_reconstruct_t(const ReconParams &p, int n_frames, bool pa, void *stream)
 {
-    const int n = 1 << p.log2;
-    const long long units = (long long)p.nbx * (n >= 8 ? n / 8 : 1) * (n >= 8 ? n : 2);
-    const dim3 grid((unsigned)((units + 255) / 256), p.nby, n_frames);
-    HV_LAUNCH(reconstruct_kernel, grid, 256, 0, stream, p);
+    constexpr int N = 1 << LOG2, UPB = N * N / 8;
+    const long long units = (long long)p.nbx * UPB;
+    const dim3 grid((unsigned)((units + 1023) / 1024), p.nby, n_frames);
+    if (pa) HV_LAUNCH((reconstruct_kernel<LOG2, true>), grid, 256, 0, stream, p);
+    else HV_LAUNCH((reconstruct_kernel<LOG2, false>), grid, 256, 0, stream, p);
     return 0;
+}
+
+static int launch_reconstruct(const ReconParams &p, int log2, int n_frames, void *stream)
+{
+    const bool pa = !p.blk_xy && ((((uintptr_t)p.rec | (uintptr_t)p.pred | (uintptr_t)p.sr | (uintptr_t)p.sp | (uintptr_t)p.fs_rec | (uintptr_t)p.fs_pred) & 15) == 0);
+    switch (log2) {
+        case 2: return launch_reconstruct_t<2>(p, n_frames, pa, stream);
+        case 3: return launch_reconstruct_t<3>(p, n_frames, pa, stream);
+        case 4: return launch_reconstruct_t<4>(p, n_frames, pa, stream);
+        default: return launch_reconstruct_t<5>(p, n_frames, pa, stream);
+    }
 }
 
 extern "C" int hevcasm_quantize_reconstruct_batch(uint8_t *rec, ptrdiff_t sr, const uint8_t *pred, ptrdiff_t sp, const int16_t *res,
@@ -268,8 +292,8 @@ extern "C" int hevcasm_quantize_reconstruct_batch(uint8_t *rec, ptrdiff_t sr, co
     if (n == 0) return 0;
     ReconParams p;
     p.rec = rec, p.pred = pred, p.res = res, p.sr = sr, p.sp = sp, p.fs_rec = 0, p.fs_pred = 0;
-    p.log2 = log2size, p.nbx = n, p.nby = 1, p.blk_xy = blk_xy;
-    return launch_reconstruct(p, 1, stream);
+    p.nbx = n, p.nby = 1, p.blk_xy = blk_xy;
+    return launch_reconstruct(p, log2size, 1, stream);
 }
 
 extern "C" int hevcasm_quantize_reconstruct_frames(uint8_t *rec, ptrdiff_t sr, const uint8_t *pred, ptrdiff_t sp, const int16_t *res, int width,
@@ -278,7 +302,7 @@ extern "C" int hevcasm_quantize_reconstruct_frames(uint8_t *rec, ptrdiff_t sr, c
     if (log2size < 2 || log2size > 5 || n_frames < 0 || width < 0 || height < 0 || ((uintptr_t)res & 15)) return HEVCASM_ERR_ARGUMENT;
     ReconParams p;
     p.rec = rec, p.pred = pred, p.res = res, p.sr = sr, p.sp = sp, p.fs_rec = fs_rec, p.fs_pred = fs_pred;
-    p.log2 = log2size, p.nbx = width >> log2size, p.nby = height >> log2size, p.blk_xy = nullptr;
+    p.nbx = width >> log2size, p.nby = height >> log2size, p.blk_xy = nullptr;
     if (p.nbx == 0 || p.nby == 0 || n_frames == 0) return 0;
-    return launch_reconstruct(p, n_frames, stream);
+    return launch_reconstruct(p, log2size, n_frames, stream);
 }

@@ -43,6 +43,45 @@ __host__ __device__ constexpr int dst4(int k, int x)
 // two s8 coefficients in the low half of an IDP.2A "b" operand
 __host__ __device__ constexpr int cpair(int a, int b) { return (a & 0xff) | ((b & 0xff) << 8); }
 
+// ---- coefficient pairs in constant memory ------------------------------------------------------------------
+// IDP takes its coefficient operand from a (uniform) register, never as an immediate: with the pairs written as
+// compile-time immediates ptxas materialises every one with its own UMOV - 20 % of all issued instructions in the 32x32
+// inverse (profiles/r01_transforms.md).  Stored in constant memory IN THE ORDER THE BUTTERFLIES CONSUME THEM they arrive
+// four at a time (LDCU.128).
+struct InvTab {
+    // inverse partial butterflies: for N = 32, 16, 8, 4 the odd-part pairs [k][j] = (T_N[4j+1][k], T_N[4j+3][k]), k < N/2, j < N/4
+    int v[16 * 8 + 8 * 4 + 4 * 2 + 2 * 1];
+    int two[2];     // (64, 64), (64, -64)
+    int dst[4][2];  // inverse 4x4 DST: [x][h] = (M[2h][x], M[2h+1][x])
+};
+__host__ __device__ constexpr int inv_tab_offset(int N) { return N == 32 ? 0 : N == 16 ? 128 : N == 8 ? 160 : 168; }
+constexpr InvTab make_inv_tab()
+{
+    InvTab t{};
+    for (int N = 32; N >= 4; N /= 2)
+        for (int k = 0; k < N / 2; ++k)
+            for (int j = 0; j < N / 4; ++j) t.v[inv_tab_offset(N) + k * (N / 4) + j] = cpair(dct(N, 4 * j + 1, k), dct(N, 4 * j + 3, k));
+    t.two[0] = cpair(64, 64), t.two[1] = cpair(64, -64);
+    for (int x = 0; x < 4; ++x) t.dst[x][0] = cpair(dst4(0, x), dst4(1, x)), t.dst[x][1] = cpair(dst4(2, x), dst4(3, x));
+    return t;
+}
+__constant__ InvTab c_inv = make_inv_tab();
+
+// forward matrix form (4x4 DCT, 4x4 DST, 8x8 DCT): [u][j] = (T[u][2j], T[u][2j+1])
+struct FwdTab {
+    int dct4[4][2], dst4[4][2], dct8[8][4];
+};
+constexpr FwdTab make_fwd_tab()
+{
+    FwdTab t{};
+    for (int u = 0; u < 4; ++u)
+        for (int j = 0; j < 2; ++j) t.dct4[u][j] = cpair(dct(4, u, 2 * j), dct(4, u, 2 * j + 1)), t.dst4[u][j] = cpair(dst4(u, 2 * j), dst4(u, 2 * j + 1));
+    for (int u = 0; u < 8; ++u)
+        for (int j = 0; j < 4; ++j) t.dct8[u][j] = cpair(dct(8, u, 2 * j), dct(8, u, 2 * j + 1));
+    return t;
+}
+__constant__ FwdTab c_fwd = make_fwd_tab();
+
 #define HV_V(ic) (decltype(ic)::value)
 
 template <int I>
@@ -84,10 +123,7 @@ struct InvBfly {
         InvBfly<N / 2>::run(p + N / 4, E, round);
         static_for<0, N / 2>([&](auto k) {
             int o = 0;
-            static_for<0, N / 4>([&](auto j) {
-                constexpr int c = cpair(dct(N, 4 * HV_V(j) + 1, HV_V(k)), dct(N, 4 * HV_V(j) + 3, HV_V(k)));
-                o = dp2a_lo(p[HV_V(j)], c, o);
-            });
+            static_for<0, N / 4>([&](auto j) { o = dp2a_lo(p[HV_V(j)], c_inv.v[inv_tab_offset(N) + HV_V(k) * (N / 4) + HV_V(j)], o); });
             out[HV_V(k)] = E[HV_V(k)] + o;
             out[N - 1 - HV_V(k)] = E[HV_V(k)] - o;
         });
@@ -97,18 +133,15 @@ template <>
 struct InvBfly<2> {
     __device__ static __forceinline__ void run(const uint32_t *p, int *out, int round)
     {
-        out[0] = dp2a_lo(p[0], cpair(64, 64), round);
-        out[1] = dp2a_lo(p[0], cpair(64, -64), round);
+        out[0] = dp2a_lo(p[0], c_inv.two[0], round);
+        out[1] = dp2a_lo(p[0], c_inv.two[1], round);
     }
 };
 
 // inverse 4-point DST: out[x] = round + sum_k M[k][x] * in[k]; p = natural pairs (in0,in1), (in2,in3)
 __device__ __forceinline__ void inv_dst4(const uint32_t *p, int *out, int round)
 {
-    static_for<0, 4>([&](auto x) {
-        constexpr int c0 = cpair(dst4(0, HV_V(x)), dst4(1, HV_V(x))), c1 = cpair(dst4(2, HV_V(x)), dst4(3, HV_V(x)));
-        out[HV_V(x)] = dp2a_lo(p[1], c1, dp2a_lo(p[0], c0, round));
-    });
+    static_for<0, 4>([&](auto x) { out[HV_V(x)] = dp2a_lo(p[1], c_inv.dst[HV_V(x)][1], dp2a_lo(p[0], c_inv.dst[HV_V(x)][0], round)); });
 }
 
 // ---- forward, matrix form on natural int16 pairs (w[j] = (x[2j], x[2j+1])) ---------------------------
@@ -118,8 +151,7 @@ __device__ __forceinline__ void fwd_matrix(const uint32_t *w, int *out, int roun
     static_for<0, N>([&](auto u) {
         int a = round;
         static_for<0, N / 2>([&](auto j) {
-            constexpr int c = DST ? cpair(dst4(HV_V(u), 2 * HV_V(j)), dst4(HV_V(u), 2 * HV_V(j) + 1))
-                                  : cpair(dct(N, HV_V(u), 2 * HV_V(j)), dct(N, HV_V(u), 2 * HV_V(j) + 1));
+            const int c = DST ? c_fwd.dst4[HV_V(u) & 3][HV_V(j) & 1] : (N == 4 ? c_fwd.dct4[HV_V(u) & 3][HV_V(j) & 1] : c_fwd.dct8[HV_V(u) & 7][HV_V(j) & 3]);
             a = dp2a_lo(w[HV_V(j)], c, a);
         });
         out[HV_V(u)] = a;
