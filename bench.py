@@ -361,7 +361,7 @@ def run_gpu(args):
             dt = float(t.item())
         # cheap integrity check: the host results must equal the device-resident results of the same inputs
         same = all(bool(np.array_equal(o_p[:4096], o_d[:4096].cpu().numpy())) for o_p, o_d in zip(outs_p, outs_d))
-        e2e = {"value": samples_per_step * e2e_steps / dt / 1e9, "unit": "Gsamples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+        e2e = {"value": samples_per_step * e2e_steps / dt / 1e9, "unit": "Gsamples/s", "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": d2h * world,
                "steps": e2e_steps, "api": "hevcasm_sad_sweep_pyramid_frames_host", "matches_device_path": same}
 
     if rank == 0:

@@ -228,3 +228,86 @@ extern "C" int hevcasm_sad_sweep_pyramid_frames_host(hevcasm_cuda_context *ctx, 
             return 0;
         });
 }
+
+// ------------------------------------------------------------------------------------------------ inter prediction planes
+
+extern "C" int hevcasm_pred_uni_frames_host(hevcasm_cuda_context *ctx, uint8_t *dst, ptrdiff_t sd, const uint8_t *ref, ptrdiff_t sr, int width, int height,
+                                            int pad, int taps, int xFrac, int yFrac, int n_frames, ptrdiff_t fs_dst, ptrdiff_t fs_ref)
+{
+    if (!ctx || width <= 0 || height <= 0 || n_frames < 0 || (taps != 8 && taps != 4)) return HEVCASM_ERR_ARGUMENT;
+    // the filter reads taps/2-1 samples before and taps/2 after the plane; the aligned kernels touch whole 16-byte chunks
+    if (pad < 16) return HEVCASM_ERR_ARGUMENT;
+    const DevPlanes din = plan_planes(width, height, pad, 1), dout = plan_planes(width, height, 0, 1);
+    const size_t per_frame = din.frame_elems + dout.frame_elems + 2 * kAlign;
+    struct Slot {
+        uint8_t *ref, *dst;
+    };
+    auto carve = [&](uint8_t *slot, int nf) {
+        Carver c{slot};
+        Slot s;
+        s.ref = c.take<uint8_t>(din.bytes(nf));
+        s.dst = c.take<uint8_t>(dout.bytes(nf));
+        return s;
+    };
+    return run_pipeline(
+        ctx, n_frames, per_frame,
+        [&](uint8_t *slot, int f0, int nf, cudaStream_t s) { return copy_in(din, carve(slot, nf).ref, ref + (ptrdiff_t)f0 * fs_ref, sr, fs_ref, width, nf, s); },
+        [&](uint8_t *slot, int, int nf, cudaStream_t s) {
+            const Slot k = carve(slot, nf);
+            return hevcasm_pred_uni_frames(k.dst, dout.pitch_elems, k.ref + din.origin(), din.pitch_elems, width, height, taps, xFrac, yFrac, nf, dout.frame_elems,
+                                           din.frame_elems, s);
+        },
+        [&](uint8_t *slot, int f0, int nf, cudaStream_t s) {
+            return copy_out(dout, carve(slot, nf).dst, dst + (ptrdiff_t)f0 * fs_dst, sd, fs_dst, width, height, nf, s);
+        });
+}
+
+// ------------------------------------------------------------------------------------------------ fused residual pipeline
+
+extern "C" int hevcasm_residual_pipeline_frames_host(hevcasm_cuda_context *ctx, uint8_t *rec, ptrdiff_t s_rec, int16_t *levels, int32_t *cbf,
+                                                     const int16_t *residual, ptrdiff_t s_res, const uint8_t *pred, ptrdiff_t s_pred, int width, int height,
+                                                     int log2size, int trType, int q_scale, int q_shift, int q_offset, int iq_scale, int iq_shift,
+                                                     int n_frames, ptrdiff_t fs_rec, ptrdiff_t fs_res, ptrdiff_t fs_pred)
+{
+    if (!ctx || width <= 0 || height <= 0 || n_frames < 0 || log2size < 2 || log2size > 5 || !levels) return HEVCASM_ERR_ARGUMENT;
+    const int n = 1 << log2size;
+    const size_t nb = (size_t)(width >> log2size) * (height >> log2size);  // blocks per frame
+    const DevPlanes d8 = plan_planes(width, height, 0, 1), d16 = plan_planes(width, height, 0, 2);
+    const size_t per_frame = 2 * d8.frame_elems + d16.frame_elems * 2 + nb * n * n * 2 + nb * 4 + 5 * kAlign;
+    struct Slot {
+        uint8_t *pred, *rec;
+        int16_t *res, *levels;
+        int32_t *cbf;
+    };
+    auto carve = [&](uint8_t *slot, int nf) {
+        Carver c{slot};
+        Slot s;
+        s.pred = c.take<uint8_t>(d8.bytes(nf));
+        s.rec = c.take<uint8_t>(d8.bytes(nf));
+        s.res = c.take<int16_t>(d16.bytes(nf));
+        s.levels = c.take<int16_t>(nb * n * n * 2 * nf);
+        s.cbf = c.take<int32_t>(nb * 4 * nf);
+        return s;
+    };
+    return run_pipeline(
+        ctx, n_frames, per_frame,
+        [&](uint8_t *slot, int f0, int nf, cudaStream_t s) {
+            const Slot k = carve(slot, nf);
+            int e = copy_in(d8, k.pred, pred + (ptrdiff_t)f0 * fs_pred, s_pred, fs_pred, width, nf, s);
+            return e ? e : copy_in(d16, k.res, residual + (ptrdiff_t)f0 * fs_res, s_res, fs_res, width, nf, s);
+        },
+        [&](uint8_t *slot, int, int nf, cudaStream_t s) {
+            const Slot k = carve(slot, nf);
+            return hevcasm_residual_pipeline_frames(k.rec, d8.pitch_elems, k.levels, k.cbf, k.res, d16.pitch_elems, k.pred, d8.pitch_elems, width, height, log2size,
+                                                    trType, q_scale, q_shift, q_offset, iq_scale, iq_shift, nf, d8.frame_elems, d16.frame_elems, d8.frame_elems, s);
+        },
+        [&](uint8_t *slot, int f0, int nf, cudaStream_t s) {
+            const Slot k = carve(slot, nf);
+            // only the area the block grid covers is defined (and may be written)
+            int e = copy_out(d8, k.rec, rec + (ptrdiff_t)f0 * fs_rec, s_rec, fs_rec, (width >> log2size) << log2size, (height >> log2size) << log2size, nf, s);
+            if (e) return e;
+            HV_CUDA(cudaMemcpyAsync(levels + (size_t)f0 * nb * n * n, k.levels, nb * n * n * 2 * nf, cudaMemcpyDeviceToHost, s));
+            if (cbf) HV_CUDA(cudaMemcpyAsync(cbf + (size_t)f0 * nb, k.cbf, nb * 4 * nf, cudaMemcpyDeviceToHost, s));
+            return 0;
+        });
+}
