@@ -13,6 +13,11 @@
 // The second inverse stage skips the reference's clip to int16: |value| <= 23040 there, so the clip can never bind,
 // and for the same reason the int16 truncation inside hevcasm_clip (:350-356) is the identity.
 #include "transform.cuh"
+#include "transform_imma.cuh"
+
+#include <algorithm>
+#include <cstdlib>
+#include <cstring>
 
 namespace hv {
 using namespace tr;
@@ -463,6 +468,141 @@ __global__ void __launch_bounds__(BIG_NT) big_fwd_kernel(int16_t *__restrict__ c
     }
 }
 
+// ================================================================================================ 16x16 / 32x32 inverse on IMMA
+
+constexpr int IMMA_NT = 128;
+
+template <int LOG2, bool PA>
+__global__ void __launch_bounds__(IMMA_NT) imma_inv_kernel(uint8_t *__restrict__ dst, ptrdiff_t sd, const uint8_t *__restrict__ pred, ptrdiff_t sp,
+                                                           ptrdiff_t fs_dst, ptrdiff_t fs_pred, const int16_t *__restrict__ coeffs, BlockGrid grid)
+{
+    constexpr int N = 1 << LOG2, MT = N / 16, NTL = N / 8;  // m-tiles, n-tiles
+    constexpr int PITCH = 2 * N + 16;                       // bytes per tile row: N int16 + 16 bytes of padding (conflict-free ldmatrix / row access)
+    using MM = Imma<N>;
+    __shared__ __align__(16) uint8_t tiles[IMMA_NT / 32][N * PITCH];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
+    uint8_t *tile = tiles[warp];
+
+    // constant fragments with the slot permutation baked in
+    uint32_t A1[MT][MM::AR];   // stage 1: A[m = y][slot] = T[kperm(slot)][y]
+    uint32_t B2[NTL][MM::BR];  // stage 2: B[slot][n = x] = T[kperm(slot)][x]
+#pragma unroll
+    for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+        for (int r = 0; r < MM::AR; ++r) {
+            const int y = 16 * mt + g + 8 * (r & 1), s0 = 16 * (r >> 1) + 4 * t;
+            A1[mt][r] = pack4(tcoef<N>(kperm(s0), y), tcoef<N>(kperm(s0 + 1), y), tcoef<N>(kperm(s0 + 2), y), tcoef<N>(kperm(s0 + 3), y));
+        }
+#pragma unroll
+    for (int nt = 0; nt < NTL; ++nt)
+#pragma unroll
+        for (int r = 0; r < MM::BR; ++r) {
+            const int x = 8 * nt + g, s0 = 16 * r + 4 * t;
+            B2[nt][r] = pack4(tcoef<N>(kperm(s0), x), tcoef<N>(kperm(s0 + 1), x), tcoef<N>(kperm(s0 + 2), x), tcoef<N>(kperm(s0 + 3), x));
+        }
+
+    const long long n_warps = (long long)gridDim.x * (IMMA_NT / 32);
+    for (long long blk = (long long)blockIdx.x * (IMMA_NT / 32) + warp; blk < grid.n; blk += n_warps) {
+        // ---- block -> padded shared tile (coalesced 128-bit loads)
+        {
+            const int4 *src = reinterpret_cast<const int4 *>(coeffs + blk * (N * N));
+            constexpr int CPR = N / 8, TOTAL = N * CPR;  // 16-byte chunks per row / per block
+#pragma unroll
+            for (int k = 0; k < TOTAL / 32; ++k) {
+                const int i = lane + 32 * k;
+                *reinterpret_cast<int4 *>(tile + (i / CPR) * PITCH + (i % CPR) * 16) = ldg_stream(src + i);
+            }
+        }
+        int x0, y0, f;
+        grid.locate(blk, LOG2, x0, y0, f);
+        // predictor segment of this lane for the epilogue: 16 samples of row (lane*16) / N ...
+        constexpr int SEGW = N == 32 ? 16 : 8, SEGS = N / SEGW;  // samples per epilogue unit, units per row
+        constexpr int EITER = N * SEGS / 32;                     // epilogue iterations per lane (2 for 32x32, 1 for 16x16)
+        uint32_t pw[EITER][SEGW / 4];
+#pragma unroll
+        for (int e = 0; e < EITER; ++e) {
+            const int u = lane + 32 * e, row = u / SEGS, seg = u % SEGS;
+            load_words<SEGW / 4, PA>(pred + f * fs_pred + (ptrdiff_t)(y0 + row) * sp + x0 + SEGW * seg, pw[e]);
+        }
+        __syncwarp();
+
+        // ---- stage 1: Bt[y][u], kept as packed int16 pairs w[mt][nt][h] = (Bt[y][8nt+2t], Bt[y][8nt+2t+1]), y = 16mt + g + 8h
+        uint32_t w[MT][NTL][2];
+#pragma unroll
+        for (int nt = 0; nt < NTL; nt += (N == 32 ? 1 : 2)) {
+            uint32_t r[4];
+            uint32_t bh[2][MM::BR], bl[2][MM::BR];
+            if (N == 32) {  // four 8x8 matrices down the 32 rows of one 8-column slab
+                ldmatrix_x4_trans(r, tile + (8 * (lane >> 3) + (lane & 7)) * PITCH + nt * 16);
+                bh[0][0] = __byte_perm(r[0], r[1], 0x7531), bl[0][0] = __byte_perm(r[0], r[1], 0x6420);
+                bh[0][MM::BR - 1] = __byte_perm(r[2], r[3], 0x7531), bl[0][MM::BR - 1] = __byte_perm(r[2], r[3], 0x6420);
+            } else {        // 16 rows: matrices (v 0-7, 8-15) x (slab nt, slab nt+1)
+                ldmatrix_x4_trans(r, tile + (8 * ((lane >> 3) & 1) + (lane & 7)) * PITCH + (nt + (lane >> 4)) * 16);
+                bh[0][0] = __byte_perm(r[0], r[1], 0x7531), bl[0][0] = __byte_perm(r[0], r[1], 0x6420);
+                bh[1][0] = __byte_perm(r[2], r[3], 0x7531), bl[1][0] = __byte_perm(r[2], r[3], 0x6420);
+            }
+#pragma unroll
+            for (int q = 0; q < (N == 32 ? 1 : 2); ++q)
+#pragma unroll
+                for (int mt = 0; mt < MT; ++mt) {
+                    int dh[4], d[4];
+                    const int zero[4] = {0, 0, 0, 0};
+                    MM::s8s8(dh, A1[mt], bh[q], zero);
+                    const int c[4] = {dh[0] * 256 + 64, dh[1] * 256 + 64, dh[2] * 256 + 64, dh[3] * 256 + 64};
+                    MM::s8u8(d, A1[mt], bl[q], c);
+                    w[mt][nt + q][0] = pack_sat_s16(d[0] >> 7, d[1] >> 7);
+                    w[mt][nt + q][1] = pack_sat_s16(d[2] >> 7, d[3] >> 7);
+                }
+        }
+        __syncwarp();  // every lane is done reading the coefficient tile: it now receives the residual
+
+        // ---- stage 2: R[y][x] = sum_u Bt[y][u] T[u][x]; A fragments straight from the stage-1 registers
+#pragma unroll
+        for (int mt = 0; mt < MT; ++mt) {
+            uint32_t ah[MM::AR], al[MM::AR];
+#pragma unroll
+            for (int r = 0; r < MM::AR; ++r) {
+                const int h = r & 1, n0 = 2 * (r >> 1);  // row g + 8h; slots 16*(r>>1) + 4t.. <- n-tiles n0, n0+1
+                ah[r] = __byte_perm(w[mt][n0][h], w[mt][n0 + 1][h], 0x7531);
+                al[r] = __byte_perm(w[mt][n0][h], w[mt][n0 + 1][h], 0x6420);
+            }
+#pragma unroll
+            for (int nt = 0; nt < NTL; ++nt) {
+                int eh[4], e[4];
+                const int zero[4] = {0, 0, 0, 0};
+                MM::s8s8(eh, ah, B2[nt], zero);
+                const int c[4] = {eh[0] * 256 + 2048, eh[1] * 256 + 2048, eh[2] * 256 + 2048, eh[3] * 256 + 2048};
+                MM::u8s8(e, al, B2[nt], c);
+                // |R| <= 23040: the reference's clip to int16 can never bind here
+                *reinterpret_cast<uint32_t *>(tile + (16 * mt + g) * PITCH + (8 * nt + 2 * t) * 2) = pack16(e[0] >> 12, e[1] >> 12);
+                *reinterpret_cast<uint32_t *>(tile + (16 * mt + g + 8) * PITCH + (8 * nt + 2 * t) * 2) = pack16(e[2] >> 12, e[3] >> 12);
+            }
+        }
+        __syncwarp();
+
+        // ---- epilogue: 16 residuals + 16 predictor samples -> 16 reconstructed bytes per lane and iteration
+#pragma unroll
+        for (int e = 0; e < EITER; ++e) {
+            const int u = lane + 32 * e, row = u / SEGS, seg = u % SEGS;
+            uint32_t rw[SEGW / 2];
+#pragma unroll
+            for (int k = 0; k < SEGW / 8; ++k) {
+                const uint4 v = *reinterpret_cast<const uint4 *>(tile + row * PITCH + seg * (SEGW * 2) + 16 * k);
+                rw[4 * k] = v.x, rw[4 * k + 1] = v.y, rw[4 * k + 2] = v.z, rw[4 * k + 3] = v.w;
+            }
+            uint32_t ow[SEGW / 4];
+#pragma unroll
+            for (int k = 0; k < SEGW / 4; ++k) {
+                const uint32_t p = pw[e][k];
+                ow[k] = pack_sat_u8((int)(p & 0xff) + s16lo(rw[2 * k]), (int)((p >> 8) & 0xff) + s16hi(rw[2 * k]), (int)((p >> 16) & 0xff) + s16lo(rw[2 * k + 1]),
+                                    (int)(p >> 24) + s16hi(rw[2 * k + 1]));
+            }
+            store_words<SEGW / 4, PA>(dst + f * fs_dst + (ptrdiff_t)(y0 + row) * sd + x0 + SEGW * seg, ow);
+        }
+        __syncwarp();  // the tile is overwritten by the next block
+    }
+}
+
 // ================================================================================================ fused residual pipeline
 //
 // forward transform -> quantize (levels + cbf written) -> inverse quantize -> inverse transform -> add to predictor, per block,
@@ -592,6 +732,15 @@ static int launch_inv_t(uint8_t *dst, ptrdiff_t sd, const uint8_t *pred, ptrdiff
     if (log2 == 2 && trType) return launch(small_inv_kernel<2, true, PA>, small_grid, SMALL_NT, 0, stream, dst, sd, pred, sp, fs_dst, fs_pred, coeffs, g);
     if (log2 == 2) return launch(small_inv_kernel<2, false, PA>, small_grid, SMALL_NT, 0, stream, dst, sd, pred, sp, fs_dst, fs_pred, coeffs, g);
     if (log2 == 3) return launch(small_inv_kernel<3, false, PA>, small_grid, SMALL_NT, 0, stream, dst, sd, pred, sp, fs_dst, fs_pred, coeffs, g);
+    // The tensor-core formulation is exact and tested, but NOT adopted: on B200 legacy mma.sync s8 issues at 512 MAC/clk/SM and
+    // the kernel runs 178 us vs 145 us (32x32) / 200 vs 119 us (16x16) for the butterfly (profiles/r01_transforms.md).
+    // HEVCASM_INV_PATH=imma selects it for A/B profiling.
+    const char *pin = getenv("HEVCASM_INV_PATH");
+    if (pin && !strcmp(pin, "imma") && imma_tables_init() == 0) {
+        const unsigned blocks = (unsigned)std::min<long long>((g.n + IMMA_NT / 32 - 1) / (IMMA_NT / 32), 148 * 8);  // persistent warps, 8 CTAs per SM
+        if (log2 == 4) return launch(imma_inv_kernel<4, PA>, blocks, IMMA_NT, 0, stream, dst, sd, pred, sp, fs_dst, fs_pred, coeffs, g);
+        return launch(imma_inv_kernel<5, PA>, blocks, IMMA_NT, 0, stream, dst, sd, pred, sp, fs_dst, fs_pred, coeffs, g);
+    }
     if (log2 == 4) return launch(big_inv_kernel<4, PA>, (unsigned)((g.n + 15) / 16), BIG_NT, 0, stream, dst, sd, pred, sp, fs_dst, fs_pred, coeffs, g);
     return launch(big_inv_kernel<5, PA>, (unsigned)((g.n + 7) / 8), BIG_NT, 0, stream, dst, sd, pred, sp, fs_dst, fs_pred, coeffs, g);
 }

@@ -71,6 +71,24 @@ def test_inverse_frames(oracle, trType, log2):
         assert np.array_equal(to_host(got), want.buf), name
 
 
+@pytest.mark.parametrize("log2", [4, 5])
+def test_inverse_frames_imma_variant(oracle, log2, monkeypatch):
+    """the exact tensor-core (mma.sync s8/u8 -> s32) formulation of the 16x16 / 32x32 inverse, kept for A/B profiling"""
+    monkeypatch.setenv("HEVCASM_INV_PATH", "imma")
+    test_inverse_frames(oracle, 0, log2)
+    width, height, nf, n = 256, 128, 2, 1 << log2          # 16-byte aligned planes: the plane-aligned instantiation
+    pred = synth.random_planes(85, nf, width, height, 16)
+    co = synth.random_int16(86 + log2, nf * (width // n) * (height // n) * n * n)
+    want = synth.random_planes(87, nf, width, height, 16)
+    got = to_dev(want.buf)
+    oracle.drv("inverse_transform_add_frames", ptr(want.buf, want.origin), want.pitch, ptr(pred.buf, pred.origin), pred.pitch, ptr(co), width, height, log2, 0, nf,
+               want.frame_stride, pred.frame_stride, threads=8)
+    dp, dc = to_dev(pred.buf), to_dev(co)
+    lib.call("inverse_transform_add_frames", dptr(got, want.origin), want.pitch, dptr(dp, pred.origin), pred.pitch, dptr(dc), width, height, log2, 0, nf,
+             want.frame_stride, pred.frame_stride)
+    assert np.array_equal(to_host(got), want.buf)
+
+
 @pytest.mark.parametrize("trType,log2", TR)
 def test_inverse_list_unaligned(oracle, trType, log2):
     width, height, n = 160, 96, 1 << log2
