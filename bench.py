@@ -212,6 +212,11 @@ def kernel_table(torch, lib, synth, stream, hbm_peak):
         out[name] = r
 
     i32 = torch.empty((NF * (W4K // 4) * (H4K // 4),), dtype=torch.int32, device="cuda")
+    best = [torch.empty((NF * (W4K // s) * (H4K // s) * 2,), dtype=torch.int32, device="cuda") for s in (8, 16, 32, 64)]
+    ms = time_on_stream(torch, lambda: lib.call("sad_sweep_pyramid_best_frames", dptr(a, org), pitch, dptr(b, org), pitch, W4K, H4K, -4, -4, NF, fs, fs,
+                                                *[dptr(o) for o in best], stream=stream), 10, 3)
+    rec("sad_pyramid_best (argmin folded in)", ms, n, 2 + 8 * (1 / 64 + 1 / 256 + 1 / 1024 + 1 / 4096), bound="int-pipe (VABSDIFF4)",
+        extra={"absdiff_pipe_frac": round(n / ms / 1e6 * 64 / 1e3 / 73.5, 3)})
     for log2 in (3, 4):
         N = 1 << log2
         ms = time_on_stream(torch, lambda: lib.call("ssd_frames", dptr(a, org), pitch, dptr(b, org), pitch, W4K, H4K, log2, NF, fs, fs, dptr(i32),
@@ -364,6 +369,29 @@ def run_gpu(args):
         e2e = {"value": samples_per_step * e2e_steps / dt / 1e9, "unit": "Gsamples/s", "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": d2h * world,
                "steps": e2e_steps, "api": "hevcasm_sad_sweep_pyramid_frames_host", "matches_device_path": same}
 
+    # ---- the same end to end with the argmin folded in (hevcasm_sad_sweep_pyramid_best_frames_host): 1/32 of the result bytes
+    e2e_best = None
+    if not args.no_e2e:
+        best_p = [lib.pinned_array((NF * (W4K // s) * (H4K // s) * 2,), np.int32) for s in sizes]
+        with lib.Context(local, arena_bytes=1 << 30) as ctx:
+            def best_step():
+                lib.call_host("sad_sweep_pyramid_best_frames_host", ctx.handle, C.c_void_p(src_p.ctypes.data + org), pitch, C.c_void_p(ref_p.ctypes.data + org),
+                              pitch, W4K, H4K, PAD, -4, -4, NF, fs, fs, *[C.c_void_p(o.ctypes.data) for o in best_p])
+            best_step()
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(e2e_steps):
+                best_step()
+            barrier()
+            dtb = time.perf_counter() - t0
+        if dist is not None:
+            t = torch.tensor([dtb], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dtb = float(t.item())
+        e2e_best = {"value": samples_per_step * e2e_steps / dtb / 1e9, "unit": "Gsamples/s", "h2d_bytes_per_step": h2d * world,
+                    "d2h_bytes_per_step": sum(o.nbytes for o in best_p) * world, "api": "hevcasm_sad_sweep_pyramid_best_frames_host",
+                    "note": "min SAD + candidate index per PU instead of all 64 SADs"}
+
     if rank == 0:
         roof = {"bound": "hbm", "kernel": "sad_pyramid_tma_kernel (hevcasm_sad_sweep_pyramid_frames)", "achieved": per_gpu * SAD_BYTES_PER_SAMPLE, "peak": hbm_peak, "unit": "GB/s",
                 "frac": per_gpu * SAD_BYTES_PER_SAMPLE / hbm_peak, "traffic": 55.63e6 * NF, "traffic_source": "ncu dram__bytes_read+write per launch / 8 frames, profiles/r01_sad_pyramid.md", "peak_source": peak_src,
@@ -378,6 +406,8 @@ def run_gpu(args):
                 "roofline": roof, "gpu_launches": int(launches), "clocks": clocks.summary()}
         if e2e:
             line["e2e"] = e2e
+        if e2e_best:
+            line["e2e_best"] = e2e_best
         if world == 1 and not args.no_cpu:
             cpu, kind = cpu_library()
             threads = os.cpu_count() or 1

@@ -181,17 +181,17 @@ extern "C" void hevcasm_cuda_host_free(void *p)
 
 // ------------------------------------------------------------------------------------------------ SAD pyramid
 
-extern "C" int hevcasm_sad_sweep_pyramid_frames_host(hevcasm_cuda_context *ctx, const uint8_t *src, ptrdiff_t ss, const uint8_t *ref, ptrdiff_t sr,
-                                                     int width, int height, int pad, int dx0, int dy0, int n_frames, ptrdiff_t fs_src,
-                                                     ptrdiff_t fs_ref, int32_t *sad8, int32_t *sad16, int32_t *sad32, int32_t *sad64)
+// full = 64 SADs per PU (hevcasm_sad_sweep_pyramid_frames), !full = {min SAD, candidate} per PU (..._best_frames)
+static int sad_pyramid_host(bool full, hevcasm_cuda_context *ctx, const uint8_t *src, ptrdiff_t ss, const uint8_t *ref, ptrdiff_t sr, int width, int height, int pad,
+                            int dx0, int dy0, int n_frames, ptrdiff_t fs_src, ptrdiff_t fs_ref, int32_t *const host_out[4])
 {
     if (!ctx || width < 8 || height < 8 || n_frames < 0 || pad < 0) return HEVCASM_ERR_ARGUMENT;
     // the window [dx0, dx0+8) x [dy0, dy0+8) must lie inside the padding that travels with the frames
     if (dx0 < -pad || dy0 < -pad || dx0 + 7 > pad || dy0 + 7 > pad) return HEVCASM_ERR_ARGUMENT;
     const DevPlanes d = plan_planes(width, height, pad, 1);
-    int32_t *host_out[4] = {sad8, sad16, sad32, sad64};
+    const size_t per_pu = full ? 64 : 2;
     size_t out_elems[4];  // per frame
-    for (int l = 0; l < 4; ++l) out_elems[l] = host_out[l] ? (size_t)(width >> (3 + l)) * (height >> (3 + l)) * 64 : 0;
+    for (int l = 0; l < 4; ++l) out_elems[l] = host_out[l] ? (size_t)(width >> (3 + l)) * (height >> (3 + l)) * per_pu : 0;
     size_t per_frame = 2 * (d.frame_elems + kAlign);
     for (int l = 0; l < 4; ++l) per_frame += out_elems[l] * 4 + kAlign;
 
@@ -207,7 +207,6 @@ extern "C" int hevcasm_sad_sweep_pyramid_frames_host(hevcasm_cuda_context *ctx, 
         for (int l = 0; l < 4; ++l) s.out[l] = out_elems[l] ? c.take<int32_t>(out_elems[l] * 4 * nf) : nullptr;
         return s;
     };
-    // chunk size is fixed by run_pipeline; slots are carved for `chunk` frames, so carve with the chunk's own nf each time
     return run_pipeline(
         ctx, n_frames, per_frame,
         [&](uint8_t *slot, int f0, int nf, cudaStream_t s) {
@@ -217,8 +216,10 @@ extern "C" int hevcasm_sad_sweep_pyramid_frames_host(hevcasm_cuda_context *ctx, 
         },
         [&](uint8_t *slot, int, int nf, cudaStream_t s) {
             const Slot k = carve(slot, nf);
-            return hevcasm_sad_sweep_pyramid_frames(k.src + d.origin(), d.pitch_elems, k.ref + d.origin(), d.pitch_elems, width, height, dx0, dy0, nf,
-                                                    d.frame_elems, d.frame_elems, k.out[0], k.out[1], k.out[2], k.out[3], s);
+            return full ? hevcasm_sad_sweep_pyramid_frames(k.src + d.origin(), d.pitch_elems, k.ref + d.origin(), d.pitch_elems, width, height, dx0, dy0, nf,
+                                                           d.frame_elems, d.frame_elems, k.out[0], k.out[1], k.out[2], k.out[3], s)
+                        : hevcasm_sad_sweep_pyramid_best_frames(k.src + d.origin(), d.pitch_elems, k.ref + d.origin(), d.pitch_elems, width, height, dx0, dy0, nf,
+                                                                d.frame_elems, d.frame_elems, k.out[0], k.out[1], k.out[2], k.out[3], s);
         },
         [&](uint8_t *slot, int f0, int nf, cudaStream_t s) {
             const Slot k = carve(slot, nf);
@@ -227,6 +228,23 @@ extern "C" int hevcasm_sad_sweep_pyramid_frames_host(hevcasm_cuda_context *ctx, 
                     HV_CUDA(cudaMemcpyAsync(host_out[l] + (size_t)f0 * out_elems[l], k.out[l], out_elems[l] * 4 * nf, cudaMemcpyDeviceToHost, s));
             return 0;
         });
+}
+
+extern "C" int hevcasm_sad_sweep_pyramid_frames_host(hevcasm_cuda_context *ctx, const uint8_t *src, ptrdiff_t ss, const uint8_t *ref, ptrdiff_t sr,
+                                                     int width, int height, int pad, int dx0, int dy0, int n_frames, ptrdiff_t fs_src,
+                                                     ptrdiff_t fs_ref, int32_t *sad8, int32_t *sad16, int32_t *sad32, int32_t *sad64)
+{
+    int32_t *const out[4] = {sad8, sad16, sad32, sad64};
+    return sad_pyramid_host(true, ctx, src, ss, ref, sr, width, height, pad, dx0, dy0, n_frames, fs_src, fs_ref, out);
+}
+
+extern "C" int hevcasm_sad_sweep_pyramid_best_frames_host(hevcasm_cuda_context *ctx, const uint8_t *src, ptrdiff_t ss, const uint8_t *ref, ptrdiff_t sr,
+                                                          int width, int height, int pad, int dx0, int dy0, int n_frames, ptrdiff_t fs_src,
+                                                          ptrdiff_t fs_ref, int32_t *best8, int32_t *best16, int32_t *best32, int32_t *best64)
+{
+    if (!best8 || !best16 || !best32 || !best64) return HEVCASM_ERR_ARGUMENT;
+    int32_t *const out[4] = {best8, best16, best32, best64};
+    return sad_pyramid_host(false, ctx, src, ss, ref, sr, width, height, pad, dx0, dy0, n_frames, fs_src, fs_ref, out);
 }
 
 // ------------------------------------------------------------------------------------------------ inter prediction planes

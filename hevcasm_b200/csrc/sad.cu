@@ -159,7 +159,7 @@ struct PyramidParams {
 __global__ void __launch_bounds__(pyr::NT) sad_sweep_pyramid_kernel(PyramidParams p)
 {
     using namespace pyr;
-    extern __shared__ __align__(16) uint8_t smem[];
+    extern __shared__ __align__(128) uint8_t smem[];
     uint32_t *win = reinterpret_cast<uint32_t *>(smem);
     uint32_t *srct = win + WIN_PITCH * WIN_ROWS;
     int4 *cb = reinterpret_cast<int4 *>(smem);
@@ -249,7 +249,7 @@ template <int LEVEL_MASK>
 __global__ void __launch_bounds__(pyr::NT) sad_pyramid_fast_kernel(PyramidParams p)
 {
     using namespace pyr;
-    extern __shared__ __align__(16) uint8_t smem[];
+    extern __shared__ __align__(128) uint8_t smem[];
     uint32_t *win = reinterpret_cast<uint32_t *>(smem);
     uint32_t *srct = win + WIN_PITCH * WIN_ROWS;
     int4 *cb = reinterpret_cast<int4 *>(smem);
@@ -376,7 +376,24 @@ constexpr uint32_t TMA_TX_BYTES = TMA_WIN_BYTES * TMA_WIN_ROWS + TW * TH;
 static_assert(TMA_SRC_OFF + TW * TH <= CB_BYTES, "TMA staging must fit under the copy-out buffer");
 }  // namespace pyr
 
-template <int LEVEL_MASK, int WO1, bool BS>
+// key of a candidate for the fused argmin: SAD in the high bits, candidate index in the low 6 -> the minimum key is the
+// smallest SAD and, among equals, the first candidate in raster order (64x64: 1044480 * 64 < 2^31)
+__device__ __forceinline__ uint32_t best_key4(int4 v, int g)
+{
+    const uint32_t c = 4 * g;
+    return min(min((uint32_t)v.x * 64 + c, (uint32_t)v.y * 64 + c + 1), min((uint32_t)v.z * 64 + c + 2, (uint32_t)v.w * 64 + c + 3));
+}
+// minimum over the 16 lanes that share a PU (lanes differ in their low 4 bits)
+__device__ __forceinline__ uint32_t best_reduce16(uint32_t k)
+{
+#pragma unroll
+    for (int o = 8; o; o >>= 1) k = min(k, __shfl_xor_sync(0xffffffffu, k, o));
+    return k;
+}
+__device__ __forceinline__ void best_store(int32_t *out, size_t pu, uint32_t key) { reinterpret_cast<int2 *>(out)[pu] = make_int2((int)(key >> 6), (int)(key & 63)); }
+
+// BEST = false: out[l] receive the 64 SADs of every PU.  BEST = true: out[l] receive {min SAD, candidate index} per PU.
+template <int LEVEL_MASK, int WO1, bool BS, bool BEST>
 __global__ void __launch_bounds__(pyr::NT, 5) sad_pyramid_tma_kernel(const __grid_constant__ PyramidTmaParams p)
 {
     using namespace pyr;
@@ -413,6 +430,49 @@ __global__ void __launch_bounds__(pyr::NT, 5) sad_pyramid_tma_kernel(const __gri
     __syncthreads();
 
     const int g = tid & 15, hi = tid >> 4;
+    if (BEST) {
+        // level 0: every thread reduces its own cell straight from the accumulators
+        if ((LEVEL_MASK & 1) && cx < vcx && cy < vcy) {
+            uint32_t k = 0xffffffffu;
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+#pragma unroll
+                for (int i = 0; i < 8; ++i) k = min(k, cell.acc[j][i] * 64 + (uint32_t)(8 * j + i));
+            best_store(p.out[0], ((size_t)f * npy8 + cy0 + cy) * npx8 + cx0 + cx, k);
+        }
+        {
+            const int npx = p.width >> 4, npy = p.height >> 4, py0 = cy0 >> 1;
+            const int sa = g ^ (2 * hi), sb = g ^ (2 * hi + 1);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int c00 = (2 * k) * CX + 2 * hi;
+                const int4 v = add4(add4(cb[c00 * 16 + sa], cb[(c00 + 1) * 16 + sb]), add4(cb[(c00 + CX) * 16 + sa], cb[(c00 + CX + 1) * 16 + sb]));
+                l16[tid + k * NT] = v;
+                const uint32_t key = best_reduce16(best_key4(v, g));
+                if ((LEVEL_MASK & 2) && g == 0 && (cx0 >> 1) + hi < npx && py0 + k < npy) best_store(p.out[1], ((size_t)f * npy + py0 + k) * npx + (cx0 >> 1) + hi, key);
+            }
+        }
+        __syncthreads();
+        {
+            const int npx = p.width >> 5, npy = p.height >> 5, px = hi & 3, py = hi >> 2;
+            const int q00 = ((2 * py) * (CX / 2) + 2 * px) * 16 + g;
+            const int4 v = add4(add4(l16[q00], l16[q00 + 16]), add4(l16[q00 + (CX / 2) * 16], l16[q00 + (CX / 2) * 16 + 16]));
+            l32[tid] = v;
+            const uint32_t key = best_reduce16(best_key4(v, g));
+            if ((LEVEL_MASK & 4) && g == 0 && (cy0 >> 2) + py < npy && (cx0 >> 2) + px < npx) best_store(p.out[2], ((size_t)f * npy + (cy0 >> 2) + py) * npx + (cx0 >> 2) + px, key);
+        }
+        if (LEVEL_MASK & 8) {
+            __syncthreads();
+            if (tid < 32) {
+                const int npx = p.width >> 6, npy = p.height >> 6, px = hi;
+                const int q00 = (2 * px) * 16 + g;
+                const int4 v = add4(add4(l32[q00], l32[q00 + 16]), add4(l32[q00 + (CX / 4) * 16], l32[q00 + (CX / 4) * 16 + 16]));
+                const uint32_t key = best_reduce16(best_key4(v, g));
+                if (g == 0 && (cy0 >> 3) < npy && (cx0 >> 3) + px < npx) best_store(p.out[3], ((size_t)f * npy + (cy0 >> 3)) * npx + (cx0 >> 3) + px, key);
+            }
+        }
+        return;
+    }
     if (LEVEL_MASK & 1) {
         int4 *o = reinterpret_cast<int4 *>(p.out[0]) + ((size_t)f * npy8 + cy0) * npx8 * 16 + (size_t)(cx0 + hi) * 16 + g;
         const int s0 = g ^ hi, s1 = g ^ (hi + 8);
@@ -480,7 +540,7 @@ constexpr int SWEEP_SMEM_BYTES = SWEEP_STAGE_BYTES + SWEEP_CB_BYTES;
 template <int CW, int CH>
 __global__ void __launch_bounds__(SWEEP_NT) sad_sweep_kernel(SweepParams p)
 {
-    extern __shared__ __align__(16) uint8_t smem[];
+    extern __shared__ __align__(128) uint8_t smem[];
     uint32_t *win = reinterpret_cast<uint32_t *>(smem);
     uint32_t *srct = win + SWEEP_WIN_PITCH * SWEEP_WIN_ROWS;
     int4 *cb = reinterpret_cast<int4 *>(smem + SWEEP_STAGE_BYTES);
@@ -778,7 +838,7 @@ extern "C" int hevcasm_sad_sweep_pyramid_frames(const uint8_t *src, ptrdiff_t ss
             const int wo1 = (t.win_shift >> 2) & 1, bs = t.win_shift & 3;
 #define HV_TMA(WO1_, BS_)                                                 \
     do {                                                                  \
-        auto kern = sad_pyramid_tma_kernel<15, WO1_, BS_>;                \
+        auto kern = sad_pyramid_tma_kernel<15, WO1_, BS_, false>;         \
         HV_CUDA((cudaError_t)set_max_smem(kern, smem_bytes));             \
         HV_LAUNCH(kern, grid, pyr::NT, smem_bytes, stream, t);            \
     } while (0)
@@ -806,6 +866,41 @@ extern "C" int hevcasm_sad_sweep_pyramid_frames(const uint8_t *src, ptrdiff_t ss
         HV_CUDA((cudaError_t)set_max_smem(sad_sweep_pyramid_kernel, pyr::SMEM_BYTES));
         HV_LAUNCH(sad_sweep_pyramid_kernel, dim3(tiles_x - full_x, tiles_y, n_frames), pyr::NT, pyr::SMEM_BYTES, stream, p);
     }
+    return 0;
+}
+
+extern "C" int hevcasm_sad_sweep_pyramid_best_frames(const uint8_t *src, ptrdiff_t ss, const uint8_t *ref, ptrdiff_t sr, int width, int height, int dx0, int dy0,
+                                                     int n_frames, ptrdiff_t fs_src, ptrdiff_t fs_ref, int32_t *best8, int32_t *best16, int32_t *best32,
+                                                     int32_t *best64, void *stream)
+{
+    if (width < 8 || height < 8 || n_frames < 0 || !best8 || !best16 || !best32 || !best64) return HEVCASM_ERR_ARGUMENT;
+    if (n_frames == 0) return 0;
+    // TMA staged only: needs a 16-byte aligned source origin and 16-byte multiples for all strides
+    if (((uintptr_t)src & 15) != 0 || !tma::describable(ss, fs_src, n_frames) || !tma::describable(sr, fs_ref, n_frames)) return HEVCASM_ERR_ARGUMENT;
+    const int npx8 = width >> 3, npy8 = height >> 3;
+    PyramidTmaParams t;
+    t.width = width, t.height = height;
+    t.out[0] = best8, t.out[1] = best16, t.out[2] = best32, t.out[3] = best64;
+    int xs_src = 0;
+    int e = tma::describe_u8(&t.tm_src, src, ss, fs_src, (long long)npx8 * 8, (long long)npy8 * 8, n_frames, pyr::TW, pyr::TH, &xs_src);
+    if (!e)
+        e = tma::describe_u8(&t.tm_ref, ref + (ptrdiff_t)dy0 * sr + dx0, sr, fs_ref, (long long)npx8 * 8 + 7, (long long)npy8 * 8 + 7, n_frames, pyr::TMA_WIN_BYTES,
+                             pyr::TMA_WIN_ROWS, &t.win_shift);
+    if (e) return e;
+    const dim3 grid((npx8 + pyr::CX - 1) / pyr::CX, (npy8 + pyr::CY - 1) / pyr::CY, n_frames);
+    const size_t smem_bytes = pyr::SMEM_BYTES + 16;
+    const int wo1 = (t.win_shift >> 2) & 1, bs = t.win_shift & 3;
+#define HV_TMA_BEST(WO1_, BS_)                                            \
+    do {                                                                  \
+        auto kern = sad_pyramid_tma_kernel<15, WO1_, BS_, true>;          \
+        HV_CUDA((cudaError_t)set_max_smem(kern, smem_bytes));             \
+        HV_LAUNCH(kern, grid, pyr::NT, smem_bytes, stream, t);            \
+    } while (0)
+    if (wo1 && bs) HV_TMA_BEST(1, true);
+    else if (wo1) HV_TMA_BEST(1, false);
+    else if (bs) HV_TMA_BEST(0, true);
+    else HV_TMA_BEST(0, false);
+#undef HV_TMA_BEST
     return 0;
 }
 

@@ -67,6 +67,16 @@ int HEVCASM_API hevcasm_sad_sweep_pyramid_frames(const uint8_t *src, ptrdiff_t s
                                                  ptrdiff_t frame_stride_src, ptrdiff_t frame_stride_ref, int32_t *sad8,
                                                  int32_t *sad16, int32_t *sad32, int32_t *sad64, void *stream);
 
+/* The pyramid sweep with the motion-search argmin folded in (the step a caller runs right after the SAD kernel): for every PU
+ * the smallest of its 64 SADs and the index c = (dy-dy0)*8 + (dx-dx0) of the candidate that reaches it - the FIRST such
+ * candidate in raster order on ties, i.e. what a scan `if (sad[c] < best)` over hevcasm_sad_multiref results returns.
+ * bestN[frame][py][px] = {sad, c} as two int32.  All four outputs are required; src must be 16-byte aligned and every stride a
+ * multiple of 16 bytes (HEVCASM_ERR_ARGUMENT otherwise).  Writes 1/32 of the bytes of the full sweep. */
+int HEVCASM_API hevcasm_sad_sweep_pyramid_best_frames(const uint8_t *src, ptrdiff_t stride_src, const uint8_t *ref, ptrdiff_t stride_ref,
+                                                      int width, int height, int dx0, int dy0, int n_frames,
+                                                      ptrdiff_t frame_stride_src, ptrdiff_t frame_stride_ref, int32_t *best8,
+                                                      int32_t *best16, int32_t *best32, int32_t *best64, void *stream);
+
 /* ------------------------------------------------------------------------------------------------ SSD
  * element semantics: reference ssd.h:53 / ssd.c:43-55, square blocks of size 1<<log2size (2..6) */
 int HEVCASM_API hevcasm_ssd_batch(const uint8_t *srcA, ptrdiff_t stride_srcA, const uint8_t *srcB, ptrdiff_t stride_srcB,
@@ -163,6 +173,11 @@ int HEVCASM_API hevcasm_sad_sweep_pyramid_frames_host(hevcasm_cuda_context *ctx,
                                                       int dx0, int dy0, int n_frames, ptrdiff_t frame_stride_src,
                                                       ptrdiff_t frame_stride_ref, int32_t *sad8, int32_t *sad16, int32_t *sad32,
                                                       int32_t *sad64);
+int HEVCASM_API hevcasm_sad_sweep_pyramid_best_frames_host(hevcasm_cuda_context *ctx, const uint8_t *src, ptrdiff_t stride_src,
+                                                           const uint8_t *ref, ptrdiff_t stride_ref, int width, int height, int pad,
+                                                           int dx0, int dy0, int n_frames, ptrdiff_t frame_stride_src,
+                                                           ptrdiff_t frame_stride_ref, int32_t *best8, int32_t *best16, int32_t *best32,
+                                                           int32_t *best64);
 int HEVCASM_API hevcasm_pred_uni_frames_host(hevcasm_cuda_context *ctx, uint8_t *dst, ptrdiff_t stride_dst, const uint8_t *ref,
                                              ptrdiff_t stride_ref, int width, int height, int pad, int taps, int xFrac, int yFrac,
                                              int n_frames, ptrdiff_t frame_stride_dst, ptrdiff_t frame_stride_ref);

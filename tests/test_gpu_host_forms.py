@@ -70,3 +70,19 @@ def test_residual_pipeline_host(oracle, log2):
         lib.call_host("residual_pipeline_frames_host", ctx.handle, hp(rec_g.buf, rec_g.origin), rec_g.pitch, hp(lv_g), hp(cbf_g), hp(res.buf, res.origin), res.pitch,
                       hp(pred.buf, pred.origin), pred.pitch, width, height, log2, 0, *qp, nf, rec_g.frame_stride, res.frame_stride, pred.frame_stride)
     assert np.array_equal(lv_g, lv_w) and np.array_equal(cbf_g, cbf_w) and np.array_equal(rec_g.buf, rec_w.buf)
+
+
+def test_sad_pyramid_best_host(oracle):
+    width, height, nf, pad = 256, 192, 5, 16
+    src = synth.smooth_planes(431, nf, width, height, pad)
+    ref = synth.smooth_planes(431, nf, width, height, pad, shift=(-2, 1), noise=4)
+    outs = [np.full(nf * (width // s) * (height // s) * 2, -1, np.int32) for s in (8, 16, 32, 64)]
+    with lib.Context(0, 2 << 20) as ctx:
+        lib.call_host("sad_sweep_pyramid_best_frames_host", ctx.handle, hp(src.buf, src.origin), src.pitch, hp(ref.buf, ref.origin), ref.pitch, width, height, pad,
+                      -4, -4, nf, src.frame_stride, ref.frame_stride, *[hp(o) for o in outs])
+    for s, o in zip((8, 16, 32, 64), outs):
+        sad = np.zeros((nf * (width // s) * (height // s), 64), np.int32)
+        oracle.drv("sad_sweep_frames", ptr(src.buf, src.origin), src.pitch, ptr(ref.buf, ref.origin), ref.pitch, width, height, HEVCASM_RECT(s, s), -4, -4, 8, 8,
+                   nf, src.frame_stride, ref.frame_stride, ptr(sad), threads=4)
+        got = o.reshape(-1, 2)
+        assert np.array_equal(got[:, 0], sad.min(-1)) and np.array_equal(got[:, 1], sad.argmin(-1)), s

@@ -157,3 +157,43 @@ def test_ssd(oracle, log2, shape):
         dxy = to_dev(xy)
         lib.call("ssd_batch", dptr(da, a.origin), a.pitch, dptr(db, b.origin), b.pitch, log2, dptr(dxy), len(xy), dptr(got2))
         assert np.array_equal(to_host(got2), want2)
+
+
+@pytest.mark.parametrize("width,height,dx0,dy0", [(256, 128, -4, -4), (200, 136, -4, -4), (136, 72, -3, 1), (64, 64, 0, 0)])
+@pytest.mark.parametrize("kind", ["smooth", "flat"])
+def test_pyramid_best(oracle, width, height, dx0, dy0, kind):
+    """fused argmin: {min SAD, first candidate index reaching it} per PU == numpy argmin over the oracle's 64 SADs;
+    "flat" frames make every candidate tie, so the first-in-raster-order rule is exercised"""
+    nf = 2
+    if kind == "smooth":
+        src, ref = _frames(nf, width, height, pad=32)     # 16-byte aligned source origin, as the entry point requires
+    else:
+        src = synth.Planes(synth.aligned_copy(np.full((nf, height + 64, synth.pitch_for(width, 32)), 90, np.uint8)), width, height, 32)
+        ref = synth.Planes(synth.aligned_copy(np.full((nf, height + 64, synth.pitch_for(width, 32)), 93, np.uint8)), width, height, 32)
+        ref.buf[:, 32 + 5:32 + 40, 32 + 7:32 + 90] = 91   # a patch that makes some candidates strictly better for some PUs
+    ds, dr = to_dev(src.buf), to_dev(ref.buf)
+    outs = []
+    for s in (8, 16, 32, 64):
+        npu = (width // s) * (height // s)
+        outs.append(dev_full((nf, max(npu, 1), 2), np.int32, -1))
+    lib.call("sad_sweep_pyramid_best_frames", dptr(ds, src.origin), src.pitch, dptr(dr, ref.origin), ref.pitch, width, height, dx0, dy0, nf,
+             src.frame_stride, ref.frame_stride, *[dptr(o) for o in outs])
+    for s, o in zip((8, 16, 32, 64), outs):
+        npu = (width // s) * (height // s)
+        if not npu:
+            continue
+        sad = np.zeros((nf, npu, 64), np.int32)
+        oracle.drv("sad_sweep_frames", ptr(src.buf, src.origin), src.pitch, ptr(ref.buf, ref.origin), ref.pitch, width, height, HEVCASM_RECT(s, s), dx0, dy0, 8, 8,
+                   nf, src.frame_stride, ref.frame_stride, ptr(sad), threads=8)
+        got = to_host(o)[:, :npu]
+        assert np.array_equal(got[..., 1], sad.argmin(-1)), s
+        assert np.array_equal(got[..., 0], sad.min(-1)), s
+
+
+def test_pyramid_best_rejects_unaligned():
+    src, ref = _frames(1, 64, 64, pad=32)
+    ds, dr = to_dev(src.buf), to_dev(ref.buf)
+    o = dev_full((64,), np.int32, 0)
+    with pytest.raises(lib.HevcasmError):
+        lib.call("sad_sweep_pyramid_best_frames", dptr(ds, src.origin + 1), src.pitch, dptr(dr, ref.origin), ref.pitch, 32, 32, -4, -4, 1, src.frame_stride,
+                 ref.frame_stride, dptr(o), dptr(o), dptr(o), dptr(o))
