@@ -517,6 +517,80 @@ __global__ void __launch_bounds__(pyr::NT, 5) sad_pyramid_tma_kernel(const __gri
     }
 }
 
+// ------------------------------------------------------------------------------------------------ one PU size, TMA staged
+//
+// hevcasm_sad_sweep_frames for PUs whose sides are 8, 16, 32 or 64 (14 of the reference's 23 partitions, sad.c:231-240): the
+// same tile, staging and cell arithmetic as the pyramid kernel; the copy-out composes mx x my cells into the one requested
+// PU size and places the 8 x 8 candidate tile (dx0+wx .., dy0+wy ..) inside the caller's ncx x ncy window.
+struct RectTmaParams {
+    CUtensorMap tm_src, tm_ref;
+    int width, height, win_shift;
+    int lmx, lmy;             // log2 of cells per PU in x / y
+    int npx, npy;             // PU grid per frame
+    int ncx, nc, wx, wy, nvx, nvy;  // window row length, candidates per PU, position and valid size of this 8 x 8 candidate tile
+    int32_t *out;
+};
+
+template <int WO1, bool BS>
+__global__ void __launch_bounds__(pyr::NT, 5) sad_rect_tma_kernel(const __grid_constant__ RectTmaParams p)
+{
+    using namespace pyr;
+    extern __shared__ __align__(128) uint8_t smem[];
+    uint32_t *win = reinterpret_cast<uint32_t *>(smem);
+    uint32_t *srct = reinterpret_cast<uint32_t *>(smem + TMA_SRC_OFF);
+    int4 *cb = reinterpret_cast<int4 *>(smem);
+    uint64_t *bar = reinterpret_cast<uint64_t *>(smem + SMEM_BYTES);
+
+    const int tid = threadIdx.x, f = blockIdx.z;
+    const int cx0 = blockIdx.x * CX, cy0 = blockIdx.y * CY;
+    const int x0 = cx0 * 8, y0 = cy0 * 8;
+
+    if (tid == 0) tma::mbar_init(bar, 1);
+    __syncthreads();
+    if (tid == 0) {
+        tma::mbar_expect_tx(bar, TMA_TX_BYTES);
+        tma::load_box_3d(win, &p.tm_ref, x0, y0, f, bar);
+        tma::load_box_3d(srct, &p.tm_src, x0, y0, f, bar);
+    }
+    tma::mbar_wait(bar, 0);
+
+    const int cx = tid % CX, cy = tid / CX;
+    SadCell<8, 8> cell;
+    cell.clear();
+    cell.load_src(srct + cy * 8 * SRC_PITCH + cx * 2, SRC_PITCH);
+    cell.template run_aligned<WO1, BS>(win + cy * 8 * TMA_WIN_PITCH + cx * 2 + ((p.win_shift >> 3) << 1), TMA_WIN_PITCH, p.win_shift & 3);
+    __syncthreads();
+    store_cell(cb, tid, cell);
+    __syncthreads();
+
+    // PUs of this tile: (CX >> lmx) x (CY >> lmy); item = (PU, slot g of 4 candidates)
+    const int lpx = 4 - p.lmx, npu_tile = (CX >> p.lmx) * (CY >> p.lmy), mx = 1 << p.lmx, my = 1 << p.lmy;
+    const int pu_x0 = cx0 >> p.lmx, pu_y0 = cy0 >> p.lmy;
+    const bool vec = ((p.ncx | p.wx) & 3) == 0 && p.nvx == 8;
+    for (int i = tid; i < npu_tile * 16; i += NT) {
+        const int pu = i >> 4, g = i & 15, ppx = pu & ((1 << lpx) - 1), ppy = pu >> lpx;
+        const int gx = pu_x0 + ppx, gy = pu_y0 + ppy;
+        if (gx >= p.npx || gy >= p.npy) continue;
+        int4 v = make_int4(0, 0, 0, 0);
+        for (int b = 0; b < my; ++b)
+            for (int a = 0; a < mx; ++a) {
+                const int c = ((ppy << p.lmy) + b) * CX + (ppx << p.lmx) + a;
+                v = add4(v, cb[cb_index(c, g)]);
+            }
+        const int dyi = g >> 1, dxi = (g & 1) * 4;
+        if (dyi >= p.nvy) continue;
+        int32_t *o = p.out + (((size_t)f * p.npy + gy) * p.npx + gx) * p.nc + (p.wy + dyi) * p.ncx + p.wx + dxi;
+        if (vec) {
+            *reinterpret_cast<int4 *>(o) = v;
+        } else {
+            if (dxi + 0 < p.nvx) o[0] = v.x;
+            if (dxi + 1 < p.nvx) o[1] = v.y;
+            if (dxi + 2 < p.nvx) o[2] = v.z;
+            if (dxi + 3 < p.nvx) o[3] = v.w;
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------------------ single-size sweep
 //
 // Any PU size w x h (multiples of 4, <= 64), any dense candidate window, processed in tiles of 8 x 8 candidates.
@@ -786,6 +860,44 @@ extern "C" int hevcasm_sad_sweep_frames(const uint8_t *src, ptrdiff_t ss, const 
     p.w = w, p.h = h, p.npx = width / w, p.npy = height / h;
     p.dx0 = dx0, p.dy0 = dy0, p.ncx = ncx, p.ncy = ncy, p.out = sad;
     if (p.npx == 0 || p.npy == 0 || n_frames == 0) return 0;
+    // sides of 8, 16, 32, 64 with TMA-describable planes: the TMA-staged kernel, one launch per 8 x 8 tile of the candidate window
+    {
+        const char *pin = getenv("HEVCASM_SAD_PATH");
+        auto pow2_8_64 = [](int v) { return v == 8 || v == 16 || v == 32 || v == 64; };
+        if ((!pin || !strcmp(pin, "tma")) && pow2_8_64(w) && pow2_8_64(h) && ((uintptr_t)src & 15) == 0 && ((uintptr_t)sad & 15) == 0 &&
+            tma::describable(ss, fs_src, n_frames) && tma::describable(sr, fs_ref, n_frames)) {
+            RectTmaParams t;
+            const int ext_x = p.npx * w, ext_y = p.npy * h;  // area covered by whole PUs
+            t.width = ext_x, t.height = ext_y;
+            t.lmx = w == 8 ? 0 : w == 16 ? 1 : w == 32 ? 2 : 3, t.lmy = h == 8 ? 0 : h == 16 ? 1 : h == 32 ? 2 : 3;
+            t.npx = p.npx, t.npy = p.npy, t.ncx = ncx, t.nc = ncx * ncy, t.out = sad;
+            int xs = 0;
+            int e = tma::describe_u8(&t.tm_src, src, ss, fs_src, ext_x, ext_y, n_frames, pyr::TW, pyr::TH, &xs);
+            const dim3 grid((ext_x / 8 + pyr::CX - 1) / pyr::CX, (ext_y / 8 + pyr::CY - 1) / pyr::CY, n_frames);
+            const size_t smem_bytes = pyr::SMEM_BYTES + 16;
+            for (int wy = 0; wy < ncy && !e; wy += 8)
+                for (int wx = 0; wx < ncx && !e; wx += 8) {
+                    t.wx = wx, t.wy = wy, t.nvx = ncx - wx < 8 ? ncx - wx : 8, t.nvy = ncy - wy < 8 ? ncy - wy : 8;
+                    e = tma::describe_u8(&t.tm_ref, ref + (ptrdiff_t)(dy0 + wy) * sr + (dx0 + wx), sr, fs_ref, (long long)ext_x + 7, (long long)ext_y + 7, n_frames,
+                                         pyr::TMA_WIN_BYTES, pyr::TMA_WIN_ROWS, &t.win_shift);
+                    if (e) break;
+                    const int wo1 = (t.win_shift >> 2) & 1, bs = t.win_shift & 3;
+#define HV_RECT(WO1_, BS_)                                                \
+    do {                                                                  \
+        auto kern = sad_rect_tma_kernel<WO1_, BS_>;                       \
+        HV_CUDA((cudaError_t)set_max_smem(kern, smem_bytes));             \
+        HV_LAUNCH(kern, grid, pyr::NT, smem_bytes, stream, t);            \
+    } while (0)
+                    if (wo1 && bs) HV_RECT(1, true);
+                    else if (wo1) HV_RECT(1, false);
+                    else if (bs) HV_RECT(0, true);
+                    else HV_RECT(0, false);
+#undef HV_RECT
+                }
+            if (!e) return 0;
+            return e;
+        }
+    }
     const int cw = (w & 7) ? 4 : 8, ch = (h & 7) ? 4 : 8;
     p.tpx = (16 * cw) / w > 0 ? (16 * cw) / w : 1;
     p.tpy = (8 * ch) / h > 0 ? (8 * ch) / h : 1;

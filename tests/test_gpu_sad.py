@@ -34,6 +34,22 @@ def test_sweep_all_partitions(oracle, w, h):
     assert np.array_equal(to_host(got), want)
 
 
+@pytest.mark.parametrize("w,h", [p for p in PARTITIONS if p[0] in (8, 16, 32, 64) and p[1] in (8, 16, 32, 64)])
+def test_sweep_tma_partitions(oracle, w, h):
+    """the 14 reference partitions with sides 8/16/32/64 on 16-byte aligned planes: the TMA-staged single-size kernel"""
+    width, height, nf = 328, 200, 2
+    src, ref = _frames(nf, width, height, pad=32)
+    npu = (width // w) * (height // h)
+    want = np.zeros((nf, npu, 64), np.int32)
+    oracle.drv("sad_sweep_frames", ptr(src.buf, src.origin), src.pitch, ptr(ref.buf, ref.origin), ref.pitch, width, height,
+               HEVCASM_RECT(w, h), -4, -4, 8, 8, nf, src.frame_stride, ref.frame_stride, ptr(want), threads=8)
+    ds, dr = to_dev(src.buf), to_dev(ref.buf)
+    got = dev_full((nf, npu, 64), np.int32, -1)
+    lib.call("sad_sweep_frames", dptr(ds, src.origin), src.pitch, dptr(dr, ref.origin), ref.pitch, width, height, HEVCASM_RECT(w, h), -4, -4,
+             8, 8, nf, src.frame_stride, ref.frame_stride, dptr(got))
+    assert np.array_equal(to_host(got), want)
+
+
 @pytest.mark.parametrize("win", [(-3, -2, 5, 3), (-8, -8, 16, 16), (1, 0, 9, 1), (-7, 3, 13, 11)])
 def test_sweep_windows(oracle, win):
     dx0, dy0, ncx, ncy = win

@@ -29,7 +29,7 @@ def time_call(fn, iters=10, warm=3):
 
 
 def main():
-    W, H, NF, PAD = 3840, 2160, 16, 80
+    W, H, NF, PAD = 3840, 2160, 16, 64
     pitch = synth.pitch_for(W, PAD)
     rows = H + 2 * PAD
     g = torch.Generator(device="cuda").manual_seed(1)
