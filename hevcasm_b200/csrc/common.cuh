@@ -48,6 +48,18 @@ inline int set_max_smem(K kernel, size_t bytes)
 // bytes [8*s .. 8*s+32) of the 64-bit value hi:lo  (s in 0..3 => byte-granular realignment of two words)
 __device__ __forceinline__ uint32_t shr_bytes(uint32_t lo, uint32_t hi, int s) { return __funnelshift_r(lo, hi, 8 * s); }
 
+// the same value computed on the FMA pipe: (lo >> 8s) + (hi << (32 - 8s)) = hi32(lo * C) + hi * C with C = 2^(32-8s), two IMADs.
+// The SAD kernels saturate the ALU pipe (VABSDIFF4 + SHF share it) while the FMA pipe idles, so moving the realignment
+// shifts there raises the VABSDIFF4 issue rate (profiles/r01_sad_pyramid.md).  C must reach the kernel as a run-time value
+// (kernel parameter): as a literal ptxas strength-reduces the pair back into a shift + LEA.HI on the ALU pipe.
+__device__ __forceinline__ uint32_t shr_bytes_fma(uint32_t lo, uint32_t hi, uint32_t c)
+{
+    uint32_t t, d;
+    asm("mul.lo.u32 %0, %1, %2;" : "=r"(t) : "r"(hi), "r"(c));
+    asm("mad.hi.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(lo), "r"(c), "r"(t));
+    return d;
+}
+
 // acc + sum of |a.b[i] - b.b[i]| over the four bytes : one VABSDIFF4.U8.ACC
 // (inline PTX on purpose: written as __vsadu4(a,b)+acc the compiler re-associates pairs into 2 x VABSDIFF4 + IADD3)
 __device__ __forceinline__ uint32_t sad4(uint32_t a, uint32_t b, uint32_t acc)

@@ -53,16 +53,24 @@ struct SadCell {
         }
     }
 
-    // one window row r (0 .. CH+6) given the KW+2 words that start at the cell's x: feeds every candidate the row belongs to
-    __device__ __forceinline__ void consume_row(int r, const uint32_t (&W)[KW + 2])
+    // one window row r (0 .. CH+6) given the KW+2 words that start at the cell's x: feeds every candidate the row belongs to.
+    // shc = nullptr: realignment by funnel shift (ALU pipe); else shc[s-1] = 2^(32-8s) and the shifts run on the FMA pipe.
+    template <bool FS = false>
+    __device__ __forceinline__ void consume_row(int r, const uint32_t (&W)[KW + 2], const uint32_t *shc = nullptr)
     {
         uint32_t S[4][KW + 1];
 #pragma unroll
         for (int j = 0; j <= KW; ++j) {
             S[0][j] = W[j];
-            S[1][j] = shr_bytes(W[j], W[j + 1], 1);
-            S[2][j] = shr_bytes(W[j], W[j + 1], 2);
-            S[3][j] = shr_bytes(W[j], W[j + 1], 3);
+            if (FS) {
+                S[1][j] = shr_bytes_fma(W[j], W[j + 1], shc[0]);
+                S[2][j] = shr_bytes_fma(W[j], W[j + 1], shc[1]);
+                S[3][j] = shr_bytes_fma(W[j], W[j + 1], shc[2]);
+            } else {
+                S[1][j] = shr_bytes(W[j], W[j + 1], 1);
+                S[2][j] = shr_bytes(W[j], W[j + 1], 2);
+                S[3][j] = shr_bytes(W[j], W[j + 1], 3);
+            }
         }
 #pragma unroll
         for (int dy = 0; dy < 8; ++dy) {
@@ -97,8 +105,8 @@ struct SadCell {
     // The same for a window whose rows sit in shared memory with the byte alignment they have in global memory (TMA boxes
     // start on 16-byte boundaries): win8 -> the 8-byte aligned word pair that contains the cell's first window byte;
     // WO1 = 1 if that byte lies in the odd word of the pair, bs = its byte offset inside the word (0 when BS is false).
-    template <int WO1, bool BS>
-    __device__ __forceinline__ void run_aligned(const uint32_t *win8, int pitch_words, int bs)
+    template <int WO1, bool BS, bool FS>
+    __device__ __forceinline__ void run_aligned(const uint32_t *win8, int pitch_words, int bs, const uint32_t *shc)
     {
         static_assert(KW == 2, "8-wide cells only");
 #pragma unroll
@@ -114,7 +122,7 @@ struct SadCell {
             uint32_t W[4];
 #pragma unroll
             for (int j = 0; j < 4; ++j) W[j] = BS ? __funnelshift_r(L[WO1 + j], L[WO1 + j + 1], 8 * bs) : L[WO1 + j];
-            consume_row(r, W);
+            consume_row<FS>(r, W, shc);
         }
     }
 };
@@ -363,6 +371,7 @@ struct PyramidTmaParams {
     CUtensorMap tm_src, tm_ref;
     int width, height;
     int win_shift;  // byte offset (0..15) of the window origin inside its 16-byte aligned box
+    uint32_t shc[3];  // 2^24, 2^16, 2^8 as run-time values (see shr_bytes_fma); used by the FS = true instantiations
     int32_t *out[4];
 };
 
@@ -393,7 +402,7 @@ __device__ __forceinline__ uint32_t best_reduce16(uint32_t k)
 __device__ __forceinline__ void best_store(int32_t *out, size_t pu, uint32_t key) { reinterpret_cast<int2 *>(out)[pu] = make_int2((int)(key >> 6), (int)(key & 63)); }
 
 // BEST = false: out[l] receive the 64 SADs of every PU.  BEST = true: out[l] receive {min SAD, candidate index} per PU.
-template <int LEVEL_MASK, int WO1, bool BS, bool BEST>
+template <int LEVEL_MASK, int WO1, bool BS, bool BEST, bool FS>
 __global__ void __launch_bounds__(pyr::NT, 5) sad_pyramid_tma_kernel(const __grid_constant__ PyramidTmaParams p)
 {
     using namespace pyr;
@@ -424,7 +433,7 @@ __global__ void __launch_bounds__(pyr::NT, 5) sad_pyramid_tma_kernel(const __gri
     SadCell<8, 8> cell;
     cell.clear();
     cell.load_src(srct + cy * 8 * SRC_PITCH + cx * 2, SRC_PITCH);
-    cell.template run_aligned<WO1, BS>(win + cy * 8 * TMA_WIN_PITCH + cx * 2 + ((p.win_shift >> 3) << 1), TMA_WIN_PITCH, p.win_shift & 3);
+    cell.template run_aligned<WO1, BS, FS>(win + cy * 8 * TMA_WIN_PITCH + cx * 2 + ((p.win_shift >> 3) << 1), TMA_WIN_PITCH, p.win_shift & 3, p.shc);
     __syncthreads();  // staging area is dead from here on; cb aliases it
     store_cell(cb, tid, cell);
     __syncthreads();
@@ -528,10 +537,11 @@ struct RectTmaParams {
     int lmx, lmy;             // log2 of cells per PU in x / y
     int npx, npy;             // PU grid per frame
     int ncx, nc, wx, wy, nvx, nvy;  // window row length, candidates per PU, position and valid size of this 8 x 8 candidate tile
+    uint32_t shc[3];
     int32_t *out;
 };
 
-template <int WO1, bool BS>
+template <int WO1, bool BS, bool FS>
 __global__ void __launch_bounds__(pyr::NT, 5) sad_rect_tma_kernel(const __grid_constant__ RectTmaParams p)
 {
     using namespace pyr;
@@ -558,7 +568,7 @@ __global__ void __launch_bounds__(pyr::NT, 5) sad_rect_tma_kernel(const __grid_c
     SadCell<8, 8> cell;
     cell.clear();
     cell.load_src(srct + cy * 8 * SRC_PITCH + cx * 2, SRC_PITCH);
-    cell.template run_aligned<WO1, BS>(win + cy * 8 * TMA_WIN_PITCH + cx * 2 + ((p.win_shift >> 3) << 1), TMA_WIN_PITCH, p.win_shift & 3);
+    cell.template run_aligned<WO1, BS, FS>(win + cy * 8 * TMA_WIN_PITCH + cx * 2 + ((p.win_shift >> 3) << 1), TMA_WIN_PITCH, p.win_shift & 3, p.shc);
     __syncthreads();
     store_cell(cb, tid, cell);
     __syncthreads();
@@ -820,6 +830,14 @@ __global__ void __launch_bounds__(ssdk::NT) ssd_frames_kernel(SsdParams p)
 
 using namespace hv;
 
+// realignment shifts on the FMA pipe unless HEVCASM_SAD_SHIFT=alu (A/B switch)
+static void fill_shc(uint32_t (&shc)[3])
+{
+    const char *e = getenv("HEVCASM_SAD_SHIFT");
+    const bool alu = e && !strcmp(e, "alu");
+    shc[0] = alu ? 0u : 1u << 24, shc[1] = 1u << 16, shc[2] = 1u << 8;
+}
+
 static bool rect_ok(uint32_t rect, int &w, int &h)
 {
     w = (int)(rect >> 8), h = (int)(rect & 0xff);
@@ -867,6 +885,7 @@ extern "C" int hevcasm_sad_sweep_frames(const uint8_t *src, ptrdiff_t ss, const 
         if ((!pin || !strcmp(pin, "tma")) && pow2_8_64(w) && pow2_8_64(h) && ((uintptr_t)src & 15) == 0 && ((uintptr_t)sad & 15) == 0 &&
             tma::describable(ss, fs_src, n_frames) && tma::describable(sr, fs_ref, n_frames)) {
             RectTmaParams t;
+            fill_shc(t.shc);
             const int ext_x = p.npx * w, ext_y = p.npy * h;  // area covered by whole PUs
             t.width = ext_x, t.height = ext_y;
             t.lmx = w == 8 ? 0 : w == 16 ? 1 : w == 32 ? 2 : 3, t.lmy = h == 8 ? 0 : h == 16 ? 1 : h == 32 ? 2 : 3;
@@ -884,9 +903,15 @@ extern "C" int hevcasm_sad_sweep_frames(const uint8_t *src, ptrdiff_t ss, const 
                     const int wo1 = (t.win_shift >> 2) & 1, bs = t.win_shift & 3;
 #define HV_RECT(WO1_, BS_)                                                \
     do {                                                                  \
-        auto kern = sad_rect_tma_kernel<WO1_, BS_>;                       \
-        HV_CUDA((cudaError_t)set_max_smem(kern, smem_bytes));             \
-        HV_LAUNCH(kern, grid, pyr::NT, smem_bytes, stream, t);            \
+        if (t.shc[0]) {                                                   \
+            auto kern = sad_rect_tma_kernel<WO1_, BS_, true>;             \
+            HV_CUDA((cudaError_t)set_max_smem(kern, smem_bytes));         \
+            HV_LAUNCH(kern, grid, pyr::NT, smem_bytes, stream, t);        \
+        } else {                                                          \
+            auto kern = sad_rect_tma_kernel<WO1_, BS_, false>;            \
+            HV_CUDA((cudaError_t)set_max_smem(kern, smem_bytes));         \
+            HV_LAUNCH(kern, grid, pyr::NT, smem_bytes, stream, t);        \
+        }                                                                 \
     } while (0)
                     if (wo1 && bs) HV_RECT(1, true);
                     else if (wo1) HV_RECT(1, false);
@@ -937,6 +962,7 @@ extern "C" int hevcasm_sad_sweep_pyramid_frames(const uint8_t *src, ptrdiff_t ss
     if (want_tma && all_levels && ((uintptr_t)src & 15) == 0 && tma::describable(ss, fs_src, n_frames) && tma::describable(sr, fs_ref, n_frames)) {
         PyramidTmaParams t;
         t.width = width, t.height = height;
+        fill_shc(t.shc);
         for (int l = 0; l < 4; ++l) t.out[l] = p.out[l];
         // source: bytes [0, npx8*8) x [0, npy8*8);  window: origin (dx0, dy0), 7 more bytes / rows than the source extent
         int xs_src = 0;
@@ -950,9 +976,15 @@ extern "C" int hevcasm_sad_sweep_pyramid_frames(const uint8_t *src, ptrdiff_t ss
             const int wo1 = (t.win_shift >> 2) & 1, bs = t.win_shift & 3;
 #define HV_TMA(WO1_, BS_)                                                 \
     do {                                                                  \
-        auto kern = sad_pyramid_tma_kernel<15, WO1_, BS_, false>;         \
-        HV_CUDA((cudaError_t)set_max_smem(kern, smem_bytes));             \
-        HV_LAUNCH(kern, grid, pyr::NT, smem_bytes, stream, t);            \
+        if (t.shc[0]) {                                                   \
+            auto kern = sad_pyramid_tma_kernel<15, WO1_, BS_, false, true>;  \
+            HV_CUDA((cudaError_t)set_max_smem(kern, smem_bytes));         \
+            HV_LAUNCH(kern, grid, pyr::NT, smem_bytes, stream, t);        \
+        } else {                                                          \
+            auto kern = sad_pyramid_tma_kernel<15, WO1_, BS_, false, false>; \
+            HV_CUDA((cudaError_t)set_max_smem(kern, smem_bytes));         \
+            HV_LAUNCH(kern, grid, pyr::NT, smem_bytes, stream, t);        \
+        }                                                                 \
     } while (0)
             if (wo1 && bs) HV_TMA(1, true);
             else if (wo1) HV_TMA(1, false);
@@ -992,6 +1024,7 @@ extern "C" int hevcasm_sad_sweep_pyramid_best_frames(const uint8_t *src, ptrdiff
     const int npx8 = width >> 3, npy8 = height >> 3;
     PyramidTmaParams t;
     t.width = width, t.height = height;
+    fill_shc(t.shc);
     t.out[0] = best8, t.out[1] = best16, t.out[2] = best32, t.out[3] = best64;
     int xs_src = 0;
     int e = tma::describe_u8(&t.tm_src, src, ss, fs_src, (long long)npx8 * 8, (long long)npy8 * 8, n_frames, pyr::TW, pyr::TH, &xs_src);
@@ -1004,9 +1037,15 @@ extern "C" int hevcasm_sad_sweep_pyramid_best_frames(const uint8_t *src, ptrdiff
     const int wo1 = (t.win_shift >> 2) & 1, bs = t.win_shift & 3;
 #define HV_TMA_BEST(WO1_, BS_)                                            \
     do {                                                                  \
-        auto kern = sad_pyramid_tma_kernel<15, WO1_, BS_, true>;          \
-        HV_CUDA((cudaError_t)set_max_smem(kern, smem_bytes));             \
-        HV_LAUNCH(kern, grid, pyr::NT, smem_bytes, stream, t);            \
+        if (t.shc[0]) {                                                   \
+            auto kern = sad_pyramid_tma_kernel<15, WO1_, BS_, true, true>;   \
+            HV_CUDA((cudaError_t)set_max_smem(kern, smem_bytes));         \
+            HV_LAUNCH(kern, grid, pyr::NT, smem_bytes, stream, t);        \
+        } else {                                                          \
+            auto kern = sad_pyramid_tma_kernel<15, WO1_, BS_, true, false>;  \
+            HV_CUDA((cudaError_t)set_max_smem(kern, smem_bytes));         \
+            HV_LAUNCH(kern, grid, pyr::NT, smem_bytes, stream, t);        \
+        }                                                                 \
     } while (0)
     if (wo1 && bs) HV_TMA_BEST(1, true);
     else if (wo1) HV_TMA_BEST(1, false);
