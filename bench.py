@@ -223,6 +223,12 @@ def kernel_table(torch, lib, synth, stream, hbm_peak):
                                                     stream=stream), 10, 3)
         rec(f"ssd_{N}x{N}", ms, n, 2 + 4 / (N * N))
 
+    for log2 in (2, 3):
+        N = 1 << log2
+        ms = time_on_stream(torch, lambda: lib.call("hadamard_satd_frames", dptr(a, org), pitch, dptr(b, org), pitch, W4K, H4K, log2, NF, fs, fs, dptr(i32),
+                                                    stream=stream), 10, 3)
+        rec(f"hadamard_satd_{N}x{N}", ms, n, 2 + 4 / (N * N))
+
     # interpolation (whole planes, one fractional position per launch)
     for name, taps, xf, yf in (("pred_uni_luma_copy", 8, 0, 0), ("pred_uni_luma_h", 8, 1, 0), ("pred_uni_luma_v", 8, 0, 2), ("pred_uni_luma_hv", 8, 1, 3),
                                ("pred_uni_chroma_hv", 4, 3, 5)):

@@ -19,6 +19,9 @@ BATCH_ABI = {
     "sad_sweep_frames": [P, PD, P, PD, I, I, U32, I, I, I, I, I, PD, PD, P],
     "ssd_batch": [P, PD, P, PD, I, P, I, P],
     "ssd_frames": [P, PD, P, PD, I, I, I, I, PD, PD, P],
+    "hadamard_satd_batch": [P, PD, P, PD, I, P, I, P],
+    "hadamard_satd_frames": [P, PD, P, PD, I, I, I, I, PD, PD, P],
+    "ssd_linear_batch": [P, PD, P, PD, I, I, P],
     "pred_uni_frames": [P, PD, P, PD, I, I, I, I, I, I, PD, PD],
     "pred_uni_batch": [P, PD, P, PD, I, P, I],
     "pred_bi_frames": [P, PD, P, P, PD, I, I, I, I, I, I, I, I, PD, PD],

@@ -19,6 +19,8 @@
 #include "pred_inter.h"
 #include "residual_decode.h"
 #include "quantize.h"
+#include "hadamard.h"
+#include "diff.h"
 
 #include <cstdlib>
 #include <cstring>
@@ -133,6 +135,41 @@ int ssd_cuda(const uint8_t *a, ptrdiff_t sa, const uint8_t *b, ptrdiff_t sb, int
     Scratch::check_hv(hevcasm_ssd_batch(sc.region(R_A), kPitch, sc.region(R_B), kPitch, log2, (const int16_t *)sc.region(R_ZERO), 1,
                                         (int32_t *)sc.region(R_OUT), sc.s),
                       "hevcasm_ssd_batch");
+    int32_t out = 0;
+    sc.down(&out, sc.region(R_OUT), sizeof out);
+    sc.sync();
+    return out;
+}
+
+template <int LOG2>
+int hadamard_satd_cuda(const uint8_t *a, ptrdiff_t sa, const uint8_t *b, ptrdiff_t sb)
+{
+    constexpr int N = 1 << LOG2;
+    Locked l;
+    Scratch &sc = l.sc;
+    sc.up2d(sc.region(R_A), kPitch, a, (size_t)sa, N, N);
+    sc.up2d(sc.region(R_B), kPitch, b, (size_t)sb, N, N);
+    Scratch::check_hv(hevcasm_hadamard_satd_batch(sc.region(R_A), kPitch, sc.region(R_B), kPitch, LOG2, (const int16_t *)sc.region(R_ZERO), 1,
+                                                  (int32_t *)sc.region(R_OUT), sc.s),
+                      "hevcasm_hadamard_satd_batch");
+    int32_t out = 0;
+    sc.down(&out, sc.region(R_OUT), sizeof out);
+    sc.sync();
+    return out;
+}
+
+int ssd_linear_cuda(const uint8_t *p0, const uint8_t *p1, int size)
+{
+    if (size <= 0) return 0;
+    if ((size_t)size > kRegion) {
+        fprintf(stderr, "hevcasm_b200: ssd_linear slot serves size <= %zu (got %d)\n", kRegion, size);
+        abort();
+    }
+    Locked l;
+    Scratch &sc = l.sc;
+    sc.up(sc.region(R_A), p0, (size_t)size);
+    sc.up(sc.region(R_B), p1, (size_t)size);
+    Scratch::check_hv(hevcasm_ssd_linear_batch(sc.region(R_A), 0, sc.region(R_B), 0, size, 1, (int32_t *)sc.region(R_OUT), sc.s), "hevcasm_ssd_linear_batch");
     int32_t out = 0;
     sc.down(&out, sc.region(R_OUT), sizeof out);
     sc.sync();
@@ -294,6 +331,20 @@ extern "C" void hevcasm_populate_sad_multiref(hevcasm_table_sad_multiref *table,
 extern "C" void hevcasm_populate_ssd(hevcasm_table_ssd *table, hevcasm_instruction_set mask)
 {
     for (int log2 = 2; log2 <= 6; ++log2) *hevcasm_get_ssd(table, log2) = cuda_bit(mask) ? &ssd_cuda : 0;
+}
+
+extern "C" void hevcasm_populate_hadamard_satd(hevcasm_table_hadamard_satd *table, hevcasm_instruction_set mask)
+{
+    const bool on = cuda_bit(mask);  // reference hadamard.c:137-160
+    *hevcasm_get_hadamard_satd(table, 1) = on ? &hadamard_satd_cuda<1> : 0;
+    *hevcasm_get_hadamard_satd(table, 2) = on ? &hadamard_satd_cuda<2> : 0;
+    *hevcasm_get_hadamard_satd(table, 3) = on ? &hadamard_satd_cuda<3> : 0;
+}
+
+extern "C" hevcasm_ssd_linear *hevcasm_get_ssd_linear(int size, hevcasm_instruction_set mask)
+{
+    (void)size;  // reference diff.c:54-63: one implementation for every size
+    return cuda_bit(mask) ? &ssd_linear_cuda : 0;
 }
 
 extern "C" void hevcasm_populate_pred_uni_8to8(hevcasm_table_pred_uni_8to8 *table, hevcasm_instruction_set mask)

@@ -86,6 +86,20 @@ int HEVCASM_API hevcasm_ssd_frames(const uint8_t *srcA, ptrdiff_t stride_srcA, c
                                    int height, int log2size, int n_frames, ptrdiff_t frame_stride_srcA,
                                    ptrdiff_t frame_stride_srcB, int32_t *ssd, void *stream);
 
+/* ------------------------------------------------------------------------------------------------ SATD, linear SSD
+ * element semantics: reference hadamard.h:55 / hadamard.c:75-131 (compute_satd: 2-D Hadamard transform of the difference,
+ * (N/4 + sum of absolute values) / (N/2)), blocks of size 1<<log2size with log2size 1..3; and diff.h:48 / diff.c:45-54
+ * (hevcasm_ssd_linear over a flat run of `size` samples). */
+int HEVCASM_API hevcasm_hadamard_satd_batch(const uint8_t *srcA, ptrdiff_t stride_srcA, const uint8_t *srcB, ptrdiff_t stride_srcB,
+                                            int log2size, const int16_t *blk_xy, int n, int32_t *satd, void *stream);
+/* satd[frame][by][bx] over the regular grid of floor(width/N) x floor(height/N) blocks */
+int HEVCASM_API hevcasm_hadamard_satd_frames(const uint8_t *srcA, ptrdiff_t stride_srcA, const uint8_t *srcB, ptrdiff_t stride_srcB,
+                                             int width, int height, int log2size, int n_frames, ptrdiff_t frame_stride_srcA,
+                                             ptrdiff_t frame_stride_srcB, int32_t *satd, void *stream);
+/* ssd[i] = sum over `size` samples of (src0[i*run_stride0 + k] - src1[i*run_stride1 + k])^2, i < n_runs; size * 255^2 must fit int32 */
+int HEVCASM_API hevcasm_ssd_linear_batch(const uint8_t *src0, ptrdiff_t run_stride0, const uint8_t *src1, ptrdiff_t run_stride1, int size,
+                                         int n_runs, int32_t *ssd, void *stream);
+
 /* ------------------------------------------------------------------------------------------------ inter prediction
  * element semantics: reference pred_inter.h:56 (hevcasm_pred_uni_8to8; C path pred_inter.c:90-228) and
  * pred_inter.h:76 (hevcasm_pred_bi_8to8; pred_inter.c:490-530).  taps = 8 (luma, fractions 0..3) or 4 (chroma, 0..7). */

@@ -27,6 +27,8 @@ _BLOCK_ABI = {  # per-block functions, argument order of hevc_oracle.h
     "quantize": ([P, P, I, I, I, I], I),
     "quantize_inverse": ([P, P, I, I, I], None),
     "pred_coefficient": ([I, I, I], I),
+    "hadamard_satd": ([P, PD, P, PD, I], I),
+    "ssd_linear": ([P, P, I], I),
 }
 
 

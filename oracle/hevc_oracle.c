@@ -44,6 +44,42 @@ int oracle_ssd(const uint8_t *a, ptrdiff_t sa, const uint8_t *b, ptrdiff_t sb, i
     return s;
 }
 
+/* hadamard.c:75-131: D = A - B; T = H D H^T with the +-1 Sylvester matrix H (the order of the outputs is irrelevant to the sum);
+ * result = (N/4 + sum |T|) / (N/2) in integer arithmetic */
+int oracle_hadamard_satd(const uint8_t *a, ptrdiff_t sa, const uint8_t *b, ptrdiff_t sb, int log2)
+{
+    const int n = 1 << log2;
+    int d[8][8], t[8][8];
+    for (int y = 0; y < n; ++y)
+        for (int x = 0; x < n; ++x) d[y][x] = (int)a[y * sa + x] - (int)b[y * sb + x];
+    /* H[k][x] = (-1)^popcount(k & x) */
+    for (int y = 0; y < n; ++y)
+        for (int k = 0; k < n; ++k) {
+            int s = 0;
+            for (int x = 0; x < n; ++x) s += (__builtin_popcount(k & x) & 1) ? -d[y][x] : d[y][x];
+            t[y][k] = s;
+        }
+    int sum = n / 4;
+    for (int k = 0; k < n; ++k)
+        for (int j = 0; j < n; ++j) {
+            int s = 0;
+            for (int y = 0; y < n; ++y) s += (__builtin_popcount(j & y) & 1) ? -t[y][k] : t[y][k];
+            sum += abs(s);
+        }
+    return sum / (n / 2);
+}
+
+/* diff.c:45-54 */
+int oracle_ssd_linear(const uint8_t *p0, const uint8_t *p1, int size)
+{
+    int s = 0;
+    for (int i = 0; i < size; ++i) {
+        const int d = (int)p0[i] - (int)p1[i];
+        s += d * d;
+    }
+    return s;
+}
+
 /* ------------------------------------------------------------------ interpolation */
 
 /* HEVC (H.265 8.5.3.3.3) interpolation filters; equal to pred_inter.c:57-63 and :69-79 */
@@ -222,6 +258,8 @@ void oracle_quantize_reconstruct(uint8_t *rec, ptrdiff_t sr, const uint8_t *pred
 #define BLK_SAD(src, ss, ref, sr, rect) oracle_sad(src, ss, ref, sr, rect)
 #define BLK_SAD4(src, ss, refs, sr, sad, rect) oracle_sad_multiref_4(src, ss, refs, sr, sad, rect)
 #define BLK_SSD(a, sa, b, sb, log2) oracle_ssd(a, sa, b, sb, 1 << (log2), 1 << (log2))
+#define BLK_SATD(a, sa, b, sb, log2) oracle_hadamard_satd(a, sa, b, sb, log2)
+#define BLK_SSD_LINEAR(p0, p1, size) oracle_ssd_linear(p0, p1, size)
 #define BLK_PRED_UNI(dst, sd, ref, sr, taps, w, h, xf, yf) oracle_pred_uni(dst, sd, ref, sr, taps, w, h, xf, yf)
 #define BLK_PRED_BI(dst, sd, r0, r1, sr, taps, w, h, xf0, yf0, xf1, yf1) \
     oracle_pred_bi(dst, sd, r0, r1, sr, taps, w, h, xf0, yf0, xf1, yf1)

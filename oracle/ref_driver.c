@@ -15,6 +15,8 @@
 #include "pred_inter.h"
 #include "residual_decode.h"
 #include "quantize.h"
+#include "hadamard.h"
+#include "diff.h"
 
 static const hevcasm_instruction_set k_mask = (hevcasm_instruction_set)(HEVCASM_C_REF | HEVCASM_C_OPT);
 
@@ -28,6 +30,7 @@ static hevcasm_table_inverse_transform_add t_inv;
 static hevcasm_table_quantize t_q;
 static hevcasm_table_quantize_inverse t_iq;
 static hevcasm_table_quantize_reconstruct t_rec;
+static hevcasm_table_hadamard_satd t_satd;
 static int g_ready = 0;
 static int g_avx2_sad = 0;
 
@@ -48,6 +51,7 @@ static int ref_tables_init(void)
     hevcasm_populate_quantize(&t_q, k_mask);
     hevcasm_populate_quantize_inverse(&t_iq, k_mask);
     hevcasm_populate_quantize_reconstruct(&t_rec, k_mask);
+    hevcasm_populate_hadamard_satd(&t_satd, k_mask);
     g_ready = 1;
     return 0;
 }
@@ -125,6 +129,17 @@ void ref_quantize_reconstruct(uint8_t *rec, ptrdiff_t sr, const uint8_t *pred, p
     (*hevcasm_get_quantize_reconstruct(&t_rec, log2))(rec, sr, pred, sp, res, 1 << log2);
 }
 
+int ref_hadamard_satd(const uint8_t *a, ptrdiff_t sa, const uint8_t *b, ptrdiff_t sb, int log2)
+{
+    ref_tables_init();
+    return (*hevcasm_get_hadamard_satd(&t_satd, log2))(a, sa, b, sb);
+}
+
+int ref_ssd_linear(const uint8_t *p0, const uint8_t *p1, int size)
+{
+    return hevcasm_get_ssd_linear(size, k_mask)(p0, p1, size);
+}
+
 int ref_pred_coefficient(int taps, int frac, int k)
 {
     extern int hevcasm_pred_coefficient(int n, int fractionalPosition, int k);
@@ -136,6 +151,8 @@ int ref_pred_coefficient(int taps, int frac, int k)
 #define BLK_SAD(src, ss, ref, sr, rect) ref_sad(src, ss, ref, sr, rect)
 #define BLK_SAD4(src, ss, refs, sr, sad, rect) ref_sad_multiref_4(src, ss, refs, sr, sad, rect)
 #define BLK_SSD(a, sa, b, sb, log2) ref_ssd(a, sa, b, sb, log2)
+#define BLK_SATD(a, sa, b, sb, log2) ref_hadamard_satd(a, sa, b, sb, log2)
+#define BLK_SSD_LINEAR(p0, p1, size) ref_ssd_linear(p0, p1, size)
 #define BLK_PRED_UNI(dst, sd, ref, sr, taps, w, h, xf, yf) ref_pred_uni(dst, sd, ref, sr, taps, w, h, xf, yf)
 #define BLK_PRED_BI(dst, sd, r0, r1, sr, taps, w, h, xf0, yf0, xf1, yf1) \
     ref_pred_bi(dst, sd, r0, r1, sr, taps, w, h, xf0, yf0, xf1, yf1)

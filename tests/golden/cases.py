@@ -92,6 +92,26 @@ def cases():
             return _sha(b.get(out))
         yield f"ssd_{1 << log2}", ssd
 
+    for log2 in (1, 2, 3):
+        def satd(b, log2=log2):
+            n = NF * (W >> log2) * (H >> log2)
+            out = b.buf(np.zeros(n, np.int32))
+            da, db = b.buf(rnd.buf), b.buf(ref.buf)
+            b.call("hadamard_satd_frames", b.ptr(da, rnd.origin), rnd.pitch, b.ptr(db, ref.origin), ref.pitch, W, H, log2, NF, rnd.frame_stride, ref.frame_stride,
+                   b.ptr(out))
+            return _sha(b.get(out))
+        yield f"hadamard_satd_{1 << log2}", satd
+
+    def ssd_linear(b):
+        digests = []
+        da, db = b.buf(rnd.buf), b.buf(ref.buf)
+        for size, runs in ((16, 40), (333, 25), (512, 30)):
+            out = b.buf(np.zeros(runs, np.int32))
+            b.call("ssd_linear_batch", b.ptr(da, rnd.origin), rnd.pitch, b.ptr(db, ref.origin + 3), ref.pitch, size, runs, b.ptr(out))
+            digests.append(_sha(b.get(out)))
+        return _sha(np.frombuffer("".join(digests).encode(), np.uint8))
+    yield "ssd_linear", ssd_linear
+
     for taps, nfrac in ((8, 4), (4, 8)):
         def uni(b, taps=taps, nfrac=nfrac):
             dr = b.buf(rnd.buf)

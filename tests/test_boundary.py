@@ -17,7 +17,7 @@ ALL_CPU_BITS = (1 << 9) - 1
 
 TABLES = {  # populate function -> number of function-pointer slots in the table struct
     "sad": 12, "sad_multiref": 16 * 16 + 1, "ssd": 5, "pred_uni_8to8": 2 * 9 * 2 * 2, "pred_bi_8to8": 2 * 5 * 2, "transform": 5,
-    "inverse_transform_add": 5, "quantize": 1, "quantize_inverse": 1, "quantize_reconstruct": 4}
+    "inverse_transform_add": 5, "quantize": 1, "quantize_inverse": 1, "quantize_reconstruct": 4, "hadamard_satd": 3}
 
 
 @pytest.fixture(scope="module")
@@ -95,6 +95,8 @@ C_PROBE = r"""
 #include "pred_inter.h"
 #include "residual_decode.h"
 #include "quantize.h"
+#include "hadamard.h"
+#include "diff.h"
 int main(void) {
     hevcasm_table_sad t; hevcasm_table_pred_uni_8to8 u; hevcasm_table_pred_bi_8to8 b; hevcasm_table_sad_multiref m;
     printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\n", sizeof(hevcasm_table_sad), sizeof(hevcasm_table_sad_multiref), sizeof(hevcasm_table_ssd),
@@ -105,6 +107,7 @@ int main(void) {
            (char *)hevcasm_get_sad(&t, 12, 16) - (char *)&t, (char *)hevcasm_get_pred_uni_8to8(&u, 4, 9, 8, 1, 0) - (char *)&u,
            (char *)hevcasm_get_pred_bi_8to8(&b, 8, 33, 8, 0, 0, 0, 2) - (char *)&b);
     printf("%td %d %d\n", (char *)hevcasm_get_sad_multiref(&m, 4, 24, 32) - (char *)&m, (int)HEVCASM_RECT(48, 64), (int)HEVCASM_AVX2);
+    { hevcasm_table_hadamard_satd h; printf("%zu %td\n", sizeof h, (char *)hevcasm_get_hadamard_satd(&h, 3) - (char *)&h); }
     return 0;
 }
 """
@@ -125,6 +128,13 @@ def test_headers_are_c99_and_match_the_reference_layout(tmp_path):
     if os.path.isdir(REF_INC):
         theirs = _compile_and_run(tmp_path, [REF_INC], "ref")
         assert ours == theirs   # same struct sizes, same slot addresses for the same getter arguments, same macros
+
+
+def test_ssd_linear_getter_has_no_cpu_fallback(lib):
+    lib.hevcasm_get_ssd_linear.argtypes = [C.c_int, C.c_int]
+    lib.hevcasm_get_ssd_linear.restype = C.c_void_p
+    assert not lib.hevcasm_get_ssd_linear(64, ALL_CPU_BITS) and not lib.hevcasm_get_ssd_linear(64, 0)
+    assert lib.hevcasm_get_ssd_linear(64, HEVCASM_CUDA)
 
 
 def test_selftest_binary_fails_loudly_without_a_gpu():

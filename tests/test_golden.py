@@ -17,7 +17,7 @@ CASES = dict(cases.cases())
 
 
 def test_golden_file_covers_every_case():
-    assert set(GOLDEN) == set(CASES) and len(GOLDEN) >= 35
+    assert set(GOLDEN) == set(CASES) and len(GOLDEN) >= 39
 
 
 @pytest.mark.parametrize("name", sorted(CASES))

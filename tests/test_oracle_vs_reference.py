@@ -188,3 +188,26 @@ def test_quantize_reconstruct(oracle, reference, log2):
         oracle.blk.quantize_reconstruct(ptr(da), 32, ptr(pred), 32, ptr(res), log2)
         reference.blk.quantize_reconstruct(ptr(db), 32, ptr(pred), 32, ptr(res), log2)
         assert np.array_equal(da, db)
+
+
+@pytest.mark.parametrize("log2", [1, 2, 3])
+def test_hadamard_satd(oracle, reference, log2):
+    # reference hadamard.c:200-230 tests 8x8 arrays of rand() bytes; here: many positions, strides and the extremes
+    a = synth.random_bytes(20, 96 * 64)
+    b = synth.random_bytes(21, 96 * 64)
+    for off in (0, 1, 7 + 64, 33 + 5 * 64, 50 + 80 * 64):
+        for stride in (64, 96):
+            assert oracle.blk.hadamard_satd(ptr(a, off), stride, ptr(b, off + 2), stride, log2) == \
+                reference.blk.hadamard_satd(ptr(a, off), stride, ptr(b, off + 2), stride, log2)
+    z, f = np.zeros(64 * 64, np.uint8), np.full(64 * 64, 255, np.uint8)
+    n = 1 << log2
+    assert oracle.blk.hadamard_satd(ptr(z), 64, ptr(f), 64, log2) == reference.blk.hadamard_satd(ptr(z), 64, ptr(f), 64, log2) == (n // 4 + 255 * n * n) // (n // 2)
+    chk = ((np.arange(64)[:, None] + np.arange(64)[None, :]) & 1).astype(np.uint8).reshape(-1) * 255
+    assert oracle.blk.hadamard_satd(ptr(chk), 64, ptr(z), 64, log2) == reference.blk.hadamard_satd(ptr(chk), 64, ptr(z), 64, log2)
+
+
+def test_ssd_linear(oracle, reference):
+    a = synth.random_bytes(22, 4096)
+    b = synth.random_bytes(23, 4096)
+    for size in (0, 1, 15, 16, 64, 333, 512, 4000):
+        assert oracle.blk.ssd_linear(ptr(a, 3), ptr(b, 5), size) == reference.blk.ssd_linear(ptr(a, 3), ptr(b, 5), size)
