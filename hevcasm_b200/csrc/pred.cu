@@ -21,6 +21,7 @@
 #include "common.cuh"
 
 #include <cstdlib>
+#include <cstring>
 
 namespace hv {
 namespace ip {
@@ -347,6 +348,7 @@ struct PackedCoefs {
     int x2e[4];     // horizontal taps as pairs (c0,c1) (c2,c3) ..           : outputs whose first tap sits on an even intermediate
     int x2o[5];     // the same slid by one: (0,c0) (c1,c2) (c3,c4) (c5,c6) (c7,0) : outputs whose first tap sits on an odd one
     int y4s[4][3];  // vertical taps slid by s = 0..3 rows over row groups of four: byte j of word g holds tap 4g + j - s (or 0)
+    int y2[4];      // vertical taps as pairs (c0,c1) (c2,c3) .. for dp2a on vertically packed int16 pairs (streaming kernel)
 };
 // vertical pass on bytes with rotated taps: 4 columns x 8 rows.  Rows are gathered once per aligned group of four
 // (32 PRMT per item instead of 76); output row r = 4 k0 + s takes groups k0, k0+1 (and k0+2 when s != 0).
@@ -612,6 +614,177 @@ __global__ void __launch_bounds__(NT) pred_plane_fast_kernel(const __grid_consta
     }
 }
 
+// ------------------------------------------------------------------------------------------------ plane form, streaming path
+//
+// The tile kernels above pay ~18 issue slots per two-pass sample, a third of them for moving the intermediate through shared
+// memory and re-pairing it (profiles/r01_pred.md).  This kernel has no shared memory and no barrier at all: a thread owns
+// FOUR ADJACENT OUTPUT COLUMNS and walks down a strip of rows.  Per source row it loads the 16 bytes around its columns
+// (three aligned words, neighbours overlap in L1), runs the HORIZONTAL filter on bytes (IDP.4A on funnel-shifted windows -
+// here the reference's own order, horizontal first, is the cheap one), packs the exact int16 result with the previous
+// row's into a vertical pair (one PRMT per column) and keeps the last eight pairs in a register ring; every pair feeds the
+// four output rows whose tap pairs it completes (IDP.2A), so the VERTICAL filter never re-reads or re-aligns anything.
+//   per two-pass sample: 2.2 IDP.4A + 1.7 SHF (H) + 1 PRMT (pair) + 4 IDP.2A (V) + 1 SHF + 0.5 I2IP + 1 LDG + 0.25 STG = ~12
+// Needs 4-byte aligned reference rows and destination rows; anything else goes to the tile kernels.
+constexpr int STRIP = 64;  // output rows per thread
+
+template <int TAPS>
+__device__ __forceinline__ void hrow4(const uint32_t (&W)[3], const int (&cx4)[TAPS / 4], int (&t)[4])
+{
+    constexpr int LEFT = TAPS / 2 - 1;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        int acc = 0;
+#pragma unroll
+        for (int g = 0; g < TAPS / 4; ++g) {
+            const int o = i - LEFT + 4 * g + 4;  // byte offset of the window inside W (W[0] starts 4 bytes left of column 0)
+            const uint32_t win = (o & 3) ? shr_bytes(W[o >> 2], W[((o >> 2) + 1) % 3], o & 3) : W[o >> 2];
+            acc = dp4a_us(win, cx4[g], acc);
+        }
+        t[i] = acc;
+    }
+}
+
+// one reference of the streaming filter: ring of vertical pairs + the running previous row
+template <int TAPS>
+struct StreamRef {
+    static constexpr int RING = TAPS;          // pairs ending at the last TAPS rows
+    uint32_t ring[RING][4];
+    int prev[4];
+};
+
+// One trip of TAPS input rows: all loads first, then the arithmetic row by row.  CHECK = false: every row exists and every
+// output row of the trip is inside the strip (the common case: whole strips, all trips but the first and the tail), so
+// nothing is clamped or tested; FIRST = the trip that only primes the ring (its single output comes from its last row).
+// Measured alternatives that lost (profiles/r01_pred.md): a register double buffer for the next trip's loads (121-192
+// registers, half the occupancy) and L1 prefetches of the next trip.
+template <int TAPS, int MODE, bool BI, bool FIRST, bool CHECK>
+__device__ __forceinline__ void stream_trip(const FastParams &fp, StreamRef<TAPS> (&st)[BI ? 2 : 1], const uint8_t *(&src)[BI ? 2 : 1], uint8_t *&d, int r0,
+                                            int rows_in, int h, int nvalid)
+{
+    constexpr bool NEED_H = BI || (MODE & 1), NEED_V = BI || (MODE & 2);
+    constexpr int NREF = BI ? 2 : 1;
+    const PredParams &p = fp.p;
+    uint32_t W[NREF][TAPS][3];
+#pragma unroll
+    for (int k = 0; k < TAPS; ++k)
+#pragma unroll
+        for (int rf = 0; rf < NREF; ++rf) {
+            const ptrdiff_t off = CHECK ? (ptrdiff_t)(min(r0 + k, rows_in - 1) - r0) * p.sr : (ptrdiff_t)k * p.sr;
+            const uint32_t *row = reinterpret_cast<const uint32_t *>(src[rf] + off);
+            if (NEED_H) {
+#pragma unroll
+                for (int j = 0; j < 3; ++j) W[rf][k][j] = __ldg(row + j);   // bytes x-4 .. x+7 cover every tap of the four columns
+            } else {
+                W[rf][k][0] = __ldg(row);
+            }
+        }
+#pragma unroll
+    for (int rf = 0; rf < NREF; ++rf) src[rf] += (ptrdiff_t)TAPS * p.sr;
+#pragma unroll
+    for (int k = 0; k < TAPS; ++k) {
+        int vout[NREF][4];
+#pragma unroll
+        for (int rf = 0; rf < NREF; ++rf) {
+            int t[4];
+            if (NEED_H) {
+                int cx4[TAPS / 4];
+                take<TAPS>(cx4, fp.c[rf].x4);
+                hrow4<TAPS>(W[rf][k], cx4, t);
+            } else {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) t[i] = (int)((W[rf][k][0] >> (8 * i)) & 0xff);
+            }
+            if (NEED_V) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    st[rf].ring[k][i] = pack16(st[rf].prev[i], t[i]);   // pair (rr-1, rr); slot k = rr mod TAPS
+                    st[rf].prev[i] = t[i];
+                }
+                if (FIRST && k != TAPS - 1) continue;                   // priming rows: no output yet
+                // output row y = rr - (TAPS-1) uses the pairs ending at rows y+1, y+3, .. = slots (k + 2 + 2g) mod TAPS
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    int acc = BI ? 0 : (NEED_H ? 2048 : 32);
+#pragma unroll
+                    for (int g = 0; g < TAPS / 2; ++g) acc = dp2a_lo(st[rf].ring[(k + 2 + 2 * g) % TAPS][i], fp.c[rf].y2[g], acc);
+                    vout[rf][i] = acc;
+                }
+            } else {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) vout[rf][i] = t[i] + 32;
+            }
+        }
+        if (NEED_V && FIRST && k != TAPS - 1) continue;
+        if (CHECK) {
+            const int y = NEED_V ? r0 + k - (TAPS - 1) : r0 + k;
+            if (y < 0 || y >= h) continue;
+        }
+        uint32_t o;
+        if (BI) {
+            int s4[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) s4[i] = ((int)(short)(vout[0][i] >> 6) + (int)(short)(vout[1][i] >> 6) + 64) >> 7;   // int16 wrap as in the reference's C
+            o = pack_sat_u8(s4[0], s4[1], s4[2], s4[3]);
+        } else {
+            constexpr int SH = (NEED_H && NEED_V) ? 12 : 6;
+            o = pack_sat_u8(vout[0][0] >> SH, vout[0][1] >> SH, vout[0][2] >> SH, vout[0][3] >> SH);
+        }
+        if (nvalid >= 4) *reinterpret_cast<uint32_t *>(d) = o;
+        else store4(d, o, nvalid);
+        d += p.sd;   // the destination pointer follows the output rows
+    }
+}
+
+template <int TAPS, int MODE, bool BI>
+__global__ void __launch_bounds__(NT) pred_stream_kernel(const __grid_constant__ FastParams fp)
+{
+    constexpr bool NEED_H = BI || (MODE & 1), NEED_V = BI || (MODE & 2);
+    constexpr int LEFT = TAPS / 2 - 1, NREF = BI ? 2 : 1;
+    const PredParams &p = fp.p;
+    const int q = blockIdx.x * NT + threadIdx.x, x = 4 * q, f = blockIdx.z;
+    if (x >= p.width) return;
+    const int y0 = blockIdx.y * STRIP, h = min(STRIP, p.height - y0), nvalid = p.width - x;
+    uint8_t *d = p.dst + f * p.fs_dst + (ptrdiff_t)y0 * p.sd + x;
+    const uint8_t *src[NREF];
+    src[0] = p.ref0 + f * p.fs_ref + (ptrdiff_t)(y0 - (NEED_V ? LEFT : 0)) * p.sr + x - (NEED_H ? 4 : 0);
+    if (BI) src[1] = p.ref1 + f * p.fs_ref + (ptrdiff_t)(y0 - LEFT) * p.sr + x - 4;
+    const int rows_in = h + (NEED_V ? TAPS - 1 : 0);
+    StreamRef<TAPS> st[NREF];
+
+    if (h == STRIP) {
+        // whole strip: unchecked trips (+ the priming trip and a checked tail when a vertical pass runs)
+        if (NEED_V) {
+            stream_trip<TAPS, MODE, BI, true, false>(fp, st, src, d, 0, rows_in, h, nvalid);
+#pragma unroll 1
+            for (int r0 = TAPS; r0 + TAPS <= STRIP; r0 += TAPS) stream_trip<TAPS, MODE, BI, false, false>(fp, st, src, d, r0, rows_in, h, nvalid);
+            stream_trip<TAPS, MODE, BI, false, true>(fp, st, src, d, STRIP, rows_in, h, nvalid);   // rows STRIP .. STRIP+TAPS-2
+        } else {
+#pragma unroll 1
+            for (int r0 = 0; r0 < STRIP; r0 += TAPS) stream_trip<TAPS, MODE, BI, false, false>(fp, st, src, d, r0, rows_in, h, nvalid);
+        }
+    } else {
+#pragma unroll 1
+        for (int r0 = 0; r0 < rows_in; r0 += TAPS) stream_trip<TAPS, MODE, BI, false, true>(fp, st, src, d, r0, rows_in, h, nvalid);
+    }
+}
+
+template <int TAPS, int MODE, bool BI>
+int launch_stream(const FastParams &fp, int n_frames, void *stream)
+{
+    const dim3 grid(((fp.p.width + 3) / 4 + NT - 1) / NT, (fp.p.height + STRIP - 1) / STRIP, n_frames);
+    return launch(pred_stream_kernel<TAPS, MODE, BI>, grid, dim3(NT), 0, stream, fp);
+}
+
+template <int TAPS>
+int launch_uni_stream(const FastParams &fp, int mode, int n_frames, void *stream)
+{
+    switch (mode) {
+        case H_ONLY: return launch_stream<TAPS, H_ONLY, false>(fp, n_frames, stream);
+        case V_ONLY: return launch_stream<TAPS, V_ONLY, false>(fp, n_frames, stream);
+        default: return launch_stream<TAPS, HV, false>(fp, n_frames, stream);
+    }
+}
+
 template <int TAPS, int MODE, bool BI>
 int launch_plane_fast(const FastParams &fp, dim3 grid, bool dst8, void *stream)
 {
@@ -685,6 +858,7 @@ static PackedCoefs pack_coefs(int taps, int xFrac, int yFrac)
     for (int g = 0; g < 2; ++g) c.x4[g] = tap(cx, 4 * g) | (tap(cx, 4 * g + 1) << 8) | (tap(cx, 4 * g + 2) << 16) | (tap(cx, 4 * g + 3) << 24);
     for (int g = 0; g < 4; ++g) c.x2e[g] = tap(cx, 2 * g) | (tap(cx, 2 * g + 1) << 8);
     for (int g = 0; g < 5; ++g) c.x2o[g] = tap(cx, 2 * g - 1) | (tap(cx, 2 * g) << 8);
+    for (int g = 0; g < 4; ++g) c.y2[g] = tap(cy, 2 * g) | (tap(cy, 2 * g + 1) << 8);
     for (int sft = 0; sft < 4; ++sft)
         for (int g = 0; g < 3; ++g) {
             int w = 0;
@@ -703,6 +877,15 @@ static bool planes_fast_ok(const uint8_t *ref0, const uint8_t *ref1, ptrdiff_t s
     if (n_frames > 1) m |= (uintptr_t)fs_ref;
     return (m & 15) == 0;
 }
+// the streaming kernels issue aligned 32-bit loads / stores: everything 4-byte aligned (HEVCASM_PRED_PATH=tile pins the tile kernels)
+static bool stream_ok(const uint8_t *dst, ptrdiff_t sd, ptrdiff_t fs_dst, const uint8_t *ref0, const uint8_t *ref1, ptrdiff_t sr, ptrdiff_t fs_ref, int n_frames)
+{
+    const char *pin = getenv("HEVCASM_PRED_PATH");
+    if (getenv("HEVCASM_PRED_GENERIC") || (pin && strcmp(pin, "stream"))) return false;
+    uintptr_t m = (uintptr_t)dst | (uintptr_t)sd | (uintptr_t)ref0 | (uintptr_t)sr | (ref1 ? (uintptr_t)ref1 : 0);
+    if (n_frames > 1) m |= (uintptr_t)fs_dst | (uintptr_t)fs_ref;
+    return (m & 3) == 0;
+}
 static bool aligned8(const uint8_t *dst, ptrdiff_t sd, ptrdiff_t fs_dst, int n_frames)
 {
     uintptr_t m = (uintptr_t)dst | (uintptr_t)sd;
@@ -720,6 +903,14 @@ extern "C" int hevcasm_pred_uni_frames(uint8_t *dst, ptrdiff_t sd, const uint8_t
     p.xf0 = xFrac, p.yf0 = yFrac;
     const dim3 grid((width + PTW - 1) / PTW, (height + PTH - 1) / PTH, n_frames);
     const int mode = (xFrac ? 1 : 0) | (yFrac ? 2 : 0);
+    // two-pass positions: the streaming kernel (1.65 vs 1.36 Tsamples/s); one-pass positions and copies: the tile kernels when the
+    // planes are 16-byte aligned (2.2-2.4 vs 2.0), the streaming kernel when they are only 4-byte aligned
+    const bool tile_ok = planes_fast_ok(ref, nullptr, sr, fs_ref, n_frames);
+    if (mode != COPY && (mode == HV || !tile_ok) && stream_ok(dst, sd, fs_dst, ref, nullptr, sr, fs_ref, n_frames)) {
+        FastParams fp{};
+        fp.p = p, fp.c[0] = pack_coefs(taps, xFrac, yFrac);
+        return taps == 8 ? launch_uni_stream<8>(fp, mode, n_frames, stream) : launch_uni_stream<4>(fp, mode, n_frames, stream);
+    }
     if (planes_fast_ok(ref, nullptr, sr, fs_ref, n_frames)) {
         const bool dst8 = aligned8(dst, sd, fs_dst, n_frames);
         FastParams fp{};
@@ -741,6 +932,11 @@ extern "C" int hevcasm_pred_bi_frames(uint8_t *dst, ptrdiff_t sd, const uint8_t 
     p.dst = dst, p.ref0 = ref0, p.ref1 = ref1, p.sd = sd, p.sr = sr, p.fs_dst = fs_dst, p.fs_ref = fs_ref, p.width = width, p.height = height;
     p.xf0 = xFrac0, p.yf0 = yFrac0, p.xf1 = xFrac1, p.yf1 = yFrac1;
     const dim3 grid((width + PTW - 1) / PTW, (height + PTH - 1) / PTH, n_frames);
+    if (stream_ok(dst, sd, fs_dst, ref0, ref1, sr, fs_ref, n_frames)) {
+        FastParams fp{};
+        fp.p = p, fp.c[0] = pack_coefs(taps, xFrac0, yFrac0), fp.c[1] = pack_coefs(taps, xFrac1, yFrac1);
+        return taps == 8 ? launch_stream<8, HV, true>(fp, n_frames, stream) : launch_stream<4, HV, true>(fp, n_frames, stream);
+    }
     if (planes_fast_ok(ref0, ref1, sr, fs_ref, n_frames)) {
         const bool dst8 = aligned8(dst, sd, fs_dst, n_frames);
         FastParams fp{};
