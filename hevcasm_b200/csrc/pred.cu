@@ -625,7 +625,7 @@ __global__ void __launch_bounds__(NT) pred_plane_fast_kernel(const __grid_consta
 // four output rows whose tap pairs it completes (IDP.2A), so the VERTICAL filter never re-reads or re-aligns anything.
 //   per two-pass sample: 2.2 IDP.4A + 1.7 SHF (H) + 1 PRMT (pair) + 4 IDP.2A (V) + 1 SHF + 0.5 I2IP + 1 LDG + 0.25 STG = ~12
 // Needs 4-byte aligned reference rows and destination rows; anything else goes to the tile kernels.
-constexpr int STRIP = 64;  // output rows per thread
+constexpr int STRIP = 64;  // output rows per thread (32 and 128 measured: no better)
 
 template <int TAPS>
 __device__ __forceinline__ void hrow4(const uint32_t (&W)[3], const int (&cx4)[TAPS / 4], int (&t)[4])
