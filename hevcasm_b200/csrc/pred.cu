@@ -785,6 +785,122 @@ int launch_uni_stream(const FastParams &fp, int mode, int n_frames, void *stream
     }
 }
 
+// ------------------------------------------------------------------------------------------------ PU lists, streaming
+//
+// Prediction-unit lists (per-PU size and quarter / eighth-sample motion vector) with the streaming formulation: a CTA takes
+// 32 descriptors, a warp scan turns their widths into a prefix of 4-column work items, and every thread picks items off that
+// list - so 8x8 PUs fill the CTA as well as 64x64 ones do (the tile kernel spent a 128-thread CTA per PU: 58 Gsamples/s on
+// 8x8 PUs).  Every PU runs the two-pass arithmetic; a zero fraction is the {64} filter, for which the two-pass rounding
+// (sum + 2048) >> 12 reduces exactly to the one-pass (sum + 32) >> 6 and to a copy, so one code path serves all positions
+// without divergence.  Reference rows may have any alignment (a funnel shift per loaded word re-aligns them).
+template <int TAPS, bool BI>
+__global__ void __launch_bounds__(NT) pred_list_stream_kernel(PredParams p)
+{
+    constexpr int G = 32, NREF = BI ? 2 : 1, DW = BI ? 8 : 6, LEFT = TAPS / 2 - 1, FB = TAPS == 8 ? 2 : 3, FM = (1 << FB) - 1;
+    __shared__ int s_prefix[G + 1];
+    __shared__ short s_desc[G][8];
+    const int tid = threadIdx.x, lane = tid & 31, first = blockIdx.x * G;
+    if (tid < 32) {
+        int nq = 0;
+        if (first + lane < p.n_pu) {
+            const int16_t *dsc = p.pus + (size_t)(first + lane) * DW;
+#pragma unroll
+            for (int j = 0; j < DW; ++j) s_desc[lane][j] = dsc[j];
+            const int w = dsc[2], h = dsc[3];
+            if (w > 0 && h > 0 && w <= 64 && h <= 64) nq = (w + 3) >> 2;
+        }
+        int incl = nq;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int v = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += v;
+        }
+        s_prefix[lane + 1] = incl;
+        if (lane == 0) s_prefix[0] = 0;
+    }
+    __syncthreads();
+    const int total = s_prefix[G];
+    // blockIdx.y slices the item list, so that 32 large PUs (512 items) spread over four CTAs; for small PUs the extra CTAs find
+    // nothing beyond `total` and leave
+    for (int item = tid + NT * blockIdx.y; item < total; item += NT * gridDim.y) {
+        int pu = 0;
+#pragma unroll
+        for (int step = G / 2; step; step >>= 1)
+            if (s_prefix[pu + step] <= item) pu += step;
+        const int q = item - s_prefix[pu];
+        const int x = s_desc[pu][0], y = s_desc[pu][1], w = s_desc[pu][2], h = s_desc[pu][3];
+        const int nvalid = w - 4 * q, rows_in = h + TAPS - 1;
+        uint8_t *d = p.dst + (ptrdiff_t)y * p.sd + x + 4 * q;
+        const uint8_t *src[NREF];
+        int cx4[NREF][TAPS / 4], cy2[NREF][TAPS / 2];
+#pragma unroll
+        for (int rf = 0; rf < NREF; ++rf) {
+            const int mvx = s_desc[pu][4 + 2 * rf], mvy = s_desc[pu][5 + 2 * rf];
+            src[rf] = (rf ? p.ref1 : p.ref0) + (ptrdiff_t)(y + (mvy >> FB) - LEFT) * p.sr + x + (mvx >> FB) + 4 * q - 4;
+            Coefs<TAPS> c;
+            c.load(mvx & FM);
+#pragma unroll
+            for (int g = 0; g < TAPS / 4; ++g) cx4[rf][g] = c.p4[g];
+            c.load(mvy & FM);
+#pragma unroll
+            for (int g = 0; g < TAPS / 2; ++g) cy2[rf][g] = c.p2[g];
+        }
+        StreamRef<TAPS> st[NREF];
+#pragma unroll 1
+        for (int r0 = 0; r0 < rows_in; r0 += TAPS) {
+            uint32_t W[NREF][TAPS][3];
+#pragma unroll
+            for (int k = 0; k < TAPS; ++k)
+#pragma unroll
+                for (int rf = 0; rf < NREF; ++rf) {
+                    const uint8_t *row = src[rf] + (ptrdiff_t)min(r0 + k, rows_in - 1) * p.sr;
+                    const int a = (int)((uintptr_t)row & 3);
+                    const uint32_t *ra = reinterpret_cast<const uint32_t *>(row - a);
+                    const uint32_t l0 = __ldg(ra), l1 = __ldg(ra + 1), l2 = __ldg(ra + 2);
+                    if (a) {
+                        const uint32_t l3 = __ldg(ra + 3);
+                        W[rf][k][0] = __funnelshift_r(l0, l1, 8 * a), W[rf][k][1] = __funnelshift_r(l1, l2, 8 * a), W[rf][k][2] = __funnelshift_r(l2, l3, 8 * a);
+                    } else {
+                        W[rf][k][0] = l0, W[rf][k][1] = l1, W[rf][k][2] = l2;
+                    }
+                }
+#pragma unroll
+            for (int k = 0; k < TAPS; ++k) {
+                int vout[NREF][4];
+#pragma unroll
+                for (int rf = 0; rf < NREF; ++rf) {
+                    int t[4];
+                    hrow4<TAPS>(W[rf][k], cx4[rf], t);
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        st[rf].ring[k][i] = pack16(st[rf].prev[i], t[i]);
+                        st[rf].prev[i] = t[i];
+                    }
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        int acc = BI ? 0 : 2048;
+#pragma unroll
+                        for (int g = 0; g < TAPS / 2; ++g) acc = dp2a_lo(st[rf].ring[(k + 2 + 2 * g) % TAPS][i], cy2[rf][g], acc);
+                        vout[rf][i] = acc;
+                    }
+                }
+                const int yo = r0 + k - (TAPS - 1);
+                if (yo < 0 || yo >= h) continue;
+                uint32_t o;
+                if (BI) {
+                    int s4[4];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) s4[i] = ((int)(short)(vout[0][i] >> 6) + (int)(short)(vout[1][i] >> 6) + 64) >> 7;
+                    o = pack_sat_u8(s4[0], s4[1], s4[2], s4[3]);
+                } else {
+                    o = pack_sat_u8(vout[0][0] >> 12, vout[0][1] >> 12, vout[0][2] >> 12, vout[0][3] >> 12);
+                }
+                store4(d + (ptrdiff_t)yo * p.sd, o, nvalid);
+            }
+        }
+    }
+}
+
 template <int TAPS, int MODE, bool BI>
 int launch_plane_fast(const FastParams &fp, dim3 grid, bool dst8, void *stream)
 {
@@ -886,6 +1002,13 @@ static bool stream_ok(const uint8_t *dst, ptrdiff_t sd, ptrdiff_t fs_dst, const 
     if (n_frames > 1) m |= (uintptr_t)fs_dst | (uintptr_t)fs_ref;
     return (m & 3) == 0;
 }
+// PU lists: streaming kernel unless HEVCASM_PRED_PATH=tile / HEVCASM_PRED_GENERIC pins the tile kernel (A/B, and the tile
+// kernel reads exactly the reference's footprint per position while the streaming one always reads the two-pass footprint)
+static bool list_stream_ok()
+{
+    const char *pin = getenv("HEVCASM_PRED_PATH");
+    return !getenv("HEVCASM_PRED_GENERIC") && !(pin && strcmp(pin, "stream"));
+}
 static bool aligned8(const uint8_t *dst, ptrdiff_t sd, ptrdiff_t fs_dst, int n_frames)
 {
     uintptr_t m = (uintptr_t)dst | (uintptr_t)sd;
@@ -953,6 +1076,10 @@ extern "C" int hevcasm_pred_uni_batch(uint8_t *dst, ptrdiff_t sd, const uint8_t 
     if (n_pu == 0) return 0;
     PredParams p{};
     p.dst = dst, p.ref0 = ref, p.sd = sd, p.sr = sr, p.pus = pus, p.n_pu = n_pu;
+    if (list_stream_ok()) {
+        const dim3 grid((n_pu + 31) / 32, 4);
+        return taps == 8 ? launch(pred_list_stream_kernel<8, false>, grid, dim3(NT), 0, stream, p) : launch(pred_list_stream_kernel<4, false>, grid, dim3(NT), 0, stream, p);
+    }
     return taps == 8 ? launch_pred<8, LTW, LTH, false, RUNTIME>(p, dim3(n_pu), stream) : launch_pred<4, LTW, LTH, false, RUNTIME>(p, dim3(n_pu), stream);
 }
 
@@ -963,5 +1090,9 @@ extern "C" int hevcasm_pred_bi_batch(uint8_t *dst, ptrdiff_t sd, const uint8_t *
     if (n_pu == 0) return 0;
     PredParams p{};
     p.dst = dst, p.ref0 = ref0, p.ref1 = ref1, p.sd = sd, p.sr = sr, p.pus = pus, p.n_pu = n_pu;
+    if (list_stream_ok()) {
+        const dim3 grid((n_pu + 31) / 32, 4);
+        return taps == 8 ? launch(pred_list_stream_kernel<8, true>, grid, dim3(NT), 0, stream, p) : launch(pred_list_stream_kernel<4, true>, grid, dim3(NT), 0, stream, p);
+    }
     return taps == 8 ? launch_pred<8, LTW, LTH, true, RUNTIME>(p, dim3(n_pu), stream) : launch_pred<4, LTW, LTH, true, RUNTIME>(p, dim3(n_pu), stream);
 }

@@ -36,6 +36,18 @@ calls = {
     "recon8": lambda: lib.call("quantize_reconstruct_frames", d(o8, org), pitch, d(a, org), pitch, d(co), W, H, 3, NF, fs, fs),
     "pipe8": lambda: lib.call("residual_pipeline_frames", d(o8, org), pitch, d(co2), d(cbf), d(res), rp, d(a, org), pitch, W, H, 3, 0, 26214, 18, 171 << 7, 18432, 6, NF, fs, H * rp, fs),
 }
+import numpy as np
+def pu_list(sz, bi=False, seed=5):
+    xs, ys = np.meshgrid(np.arange(W // sz) * sz, np.arange(H // sz) * sz)
+    n = xs.size
+    r = synth.splitmix64(seed, 4 * n).astype(np.int64)
+    cols = [xs.reshape(-1), ys.reshape(-1), np.full(n, sz), np.full(n, sz), r[:n] % 129 - 64, r[n:2 * n] % 129 - 64]
+    if bi:
+        cols += [r[2 * n:3 * n] % 129 - 64, r[3 * n:] % 129 - 64]
+    return torch.from_numpy(np.stack(cols, -1).astype(np.int16)).cuda()
+for sz in (8, 16, 32, 64):
+    calls[f"pred_list{sz}"] = (lambda pl: (lambda: lib.call("pred_uni_batch", d(o8, org), pitch, d(a, org), pitch, 8, d(pl), pl.shape[0])))(pu_list(sz))
+    calls[f"pred_bilist{sz}"] = (lambda pl: (lambda: lib.call("pred_bi_batch", d(o8, org), pitch, d(a, org), d(b, org), pitch, 8, d(pl), pl.shape[0])))(pu_list(sz, True))
 for _ in range(iters):
     calls[name]()
 torch.cuda.synchronize()
