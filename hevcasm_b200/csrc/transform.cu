@@ -357,9 +357,19 @@ __device__ __forceinline__ void big_inv_core(uint32_t *tmp, int b, int uw, bool 
 #pragma unroll
         for (int r = 0; r < N; ++r) tmp[b * G::BLK_STRIDE + r * G::PITCH + uw] = pack_sat_s16(o0[r] >> 7, o1[r] >> 7);
     }
+    // the two predictor rows of stage 2 are requested here, between the stages: the coefficient words are dead by now, and
+    // the transpose + the first row's butterfly hide the latency (ncu: 24 % of all stall samples sat on the first use of a
+    // predictor word loaded right before it, profiles/r01_transforms.md)
+    // (16x16 only: at 32x32 the 16 extra live registers and the unrolled second stage cost more occupancy than the latency they hide)
+    constexpr bool EARLY = N == 16;
+    uint32_t pw2[2][N / 4];
+    if (EARLY && valid) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) load_words<N / 4, PA>(pp + (ptrdiff_t)(uw + h * HW) * sp, pw2[h]);
+    }
     __syncwarp();
     if (valid) {  // stage 2: this lane owns rows uw and uw + N/2 of block b
-#pragma unroll 1
+#pragma unroll(EARLY ? 2 : 1)
         for (int h = 0; h < 2; ++h) {
             const int r = uw + h * HW;
             uint32_t Bw[HW];
@@ -376,10 +386,10 @@ __device__ __forceinline__ void big_inv_core(uint32_t *tmp, int b, int uw, bool 
             });
             int o[N];
             InvBfly<N>::run(p, o, 2048);
-            uint32_t pw[N / 4], ow[N / 4];
-            load_words<N / 4, PA>(pp + (ptrdiff_t)r * sp, pw);
+            uint32_t ow[N / 4];
+            if (!EARLY) load_words<N / 4, PA>(pp + (ptrdiff_t)r * sp, pw2[0]);
 #pragma unroll
-            for (int k = 0; k < N / 4; ++k) ow[k] = recon_word(pw[k], o + 4 * k);
+            for (int k = 0; k < N / 4; ++k) ow[k] = recon_word(pw2[EARLY ? h : 0][k], o + 4 * k);
             store_words<N / 4, PA>(dp + (ptrdiff_t)r * sd, ow);
         }
     }
