@@ -341,6 +341,10 @@ __device__ __forceinline__ void big_inv_core(uint32_t *tmp, int b, int uw, bool 
 {
     using G = BigGeom<LOG2>;
     constexpr int N = G::N, HW = G::HW;
+    if (N == 32 && valid) {  // 32x32: the stage-2 predictor rows are pulled into L1 now (no registers held across stage 1)
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(pp + (ptrdiff_t)uw * sp));
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(pp + (ptrdiff_t)(uw + HW) * sp));
+    }
     if (valid) {  // stage 1: columns 2*uw and 2*uw+1
         uint32_t p[HW];
         int o0[N], o1[N];
