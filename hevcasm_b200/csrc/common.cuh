@@ -43,6 +43,14 @@ inline int set_max_smem(K kernel, size_t bytes)
     return (int)cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
 }
 
+// SMs of the current device (148 on a B200); grids are sized against it
+inline int sm_count()
+{
+    int dev = 0, n = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n < 1) n = 148;
+    return n;
+}
+
 // ---- small device primitives --------------------------------------------------------------------
 
 // bytes [8*s .. 8*s+32) of the 64-bit value hi:lo  (s in 0..3 => byte-granular realignment of two words)

@@ -19,6 +19,7 @@
 // Everything is staged once per CTA tile (source tile + filter halo) in shared memory; HBM traffic is the algorithmic
 // 1 B in + 1 B out per sample (2 + 1 for bi).
 #include "common.cuh"
+#include "tma.cuh"
 
 #include <cstdlib>
 #include <cstring>
@@ -657,7 +658,12 @@ struct StreamRef {
 // nothing is clamped or tested; FIRST = the trip that only primes the ring (its single output comes from its last row).
 // Measured alternatives that lost (profiles/r01_pred.md): a register double buffer for the next trip's loads (121-192
 // registers, half the occupancy) and L1 prefetches of the next trip.
-template <int TAPS, int MODE, bool BI, bool FIRST, bool CHECK>
+//   SM = true: the rows come from a TMA-staged box in shared memory (pred_stream_tma_kernel): src[] then points at the
+// thread's first word of the trip's first row inside the box, rows are SM_PITCH bytes apart, nothing needs clamping
+// (rows outside the tensor arrive zero-filled and only feed output rows that are skipped) and src[] is not advanced.
+constexpr int SM_PITCH = 544;  // bytes per staged row: 16-byte aligned start + up to 12 bytes of shift + 4 + 512 + 8, rounded to 16
+//   NR < TAPS: the unchecked tail of a strip (its last TAPS-1 input rows).
+template <int TAPS, int MODE, bool BI, bool FIRST, bool CHECK, bool SM = false, int NR = TAPS>
 __device__ __forceinline__ void stream_trip(const FastParams &fp, StreamRef<TAPS> (&st)[BI ? 2 : 1], const uint8_t *(&src)[BI ? 2 : 1], uint8_t *&d, int r0,
                                             int rows_in, int h, int nvalid)
 {
@@ -666,9 +672,19 @@ __device__ __forceinline__ void stream_trip(const FastParams &fp, StreamRef<TAPS
     const PredParams &p = fp.p;
     uint32_t W[NREF][TAPS][3];
 #pragma unroll
-    for (int k = 0; k < TAPS; ++k)
+    for (int k = 0; k < NR; ++k)
 #pragma unroll
         for (int rf = 0; rf < NREF; ++rf) {
+            if (SM) {
+                const uint32_t *row = reinterpret_cast<const uint32_t *>(src[rf] + k * SM_PITCH);
+                if (NEED_H) {
+#pragma unroll
+                    for (int j = 0; j < 3; ++j) W[rf][k][j] = row[j];
+                } else {
+                    W[rf][k][0] = row[0];
+                }
+                continue;
+            }
             const ptrdiff_t off = CHECK ? (ptrdiff_t)(min(r0 + k, rows_in - 1) - r0) * p.sr : (ptrdiff_t)k * p.sr;
             const uint32_t *row = reinterpret_cast<const uint32_t *>(src[rf] + off);
             if (NEED_H) {
@@ -678,10 +694,12 @@ __device__ __forceinline__ void stream_trip(const FastParams &fp, StreamRef<TAPS
                 W[rf][k][0] = __ldg(row);
             }
         }
+    if (!SM) {
 #pragma unroll
-    for (int rf = 0; rf < NREF; ++rf) src[rf] += (ptrdiff_t)TAPS * p.sr;
+        for (int rf = 0; rf < NREF; ++rf) src[rf] += (ptrdiff_t)TAPS * p.sr;
+    }
 #pragma unroll
-    for (int k = 0; k < TAPS; ++k) {
+    for (int k = 0; k < NR; ++k) {
         int vout[NREF][4];
 #pragma unroll
         for (int rf = 0; rf < NREF; ++rf) {
@@ -690,11 +708,22 @@ __device__ __forceinline__ void stream_trip(const FastParams &fp, StreamRef<TAPS
                 int cx4[TAPS / 4];
                 take<TAPS>(cx4, fp.c[rf].x4);
                 hrow4<TAPS>(W[rf][k], cx4, t);
-            } else {
-#pragma unroll
-                for (int i = 0; i < 4; ++i) t[i] = (int)((W[rf][k][0] >> (8 * i)) & 0xff);
             }
-            if (NEED_V) {
+            if (NEED_V && !NEED_H) {
+                // vertical pass alone: stay on bytes.  Per column a sliding QUAD of the last four rows (one PRMT shifts the new
+                // row's byte in); slot k holds the quad ending at row rr, and an output row takes the quads ending at its 4th
+                // (and 8th) tap row: one PRMT + TAPS/4 IDP.4A per sample instead of unpack + pair + TAPS/2 IDP.2A.
+#pragma unroll
+                for (int i = 0; i < 4; ++i) st[rf].ring[k][i] = __byte_perm(st[rf].ring[(k + TAPS - 1) % TAPS][i], W[rf][k][0], 0x4321 + (i << 12));
+                if (FIRST && k != TAPS - 1) continue;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    int acc = 32;
+#pragma unroll
+                    for (int g = 0; g < TAPS / 4; ++g) acc = dp4a_us(st[rf].ring[(k + 4 + 4 * g) % TAPS][i], fp.c[rf].y4s[0][g], acc);
+                    vout[rf][i] = acc;
+                }
+            } else if (NEED_V) {
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
                     st[rf].ring[k][i] = pack16(st[rf].prev[i], t[i]);   // pair (rr-1, rr); slot k = rr mod TAPS
@@ -709,7 +738,7 @@ __device__ __forceinline__ void stream_trip(const FastParams &fp, StreamRef<TAPS
                     for (int g = 0; g < TAPS / 2; ++g) acc = dp2a_lo(st[rf].ring[(k + 2 + 2 * g) % TAPS][i], fp.c[rf].y2[g], acc);
                     vout[rf][i] = acc;
                 }
-            } else {
+            } else if (NEED_H) {
 #pragma unroll
                 for (int i = 0; i < 4; ++i) vout[rf][i] = t[i] + 32;
             }
@@ -720,7 +749,9 @@ __device__ __forceinline__ void stream_trip(const FastParams &fp, StreamRef<TAPS
             if (y < 0 || y >= h) continue;
         }
         uint32_t o;
-        if (BI) {
+        if (!NEED_H && !NEED_V) {
+            o = W[0][k][0];   // full-sample position: the row passes through (TMA-fed kernel only)
+        } else if (BI) {
             int s4[4];
 #pragma unroll
             for (int i = 0; i < 4; ++i) s4[i] = ((int)(short)(vout[0][i] >> 6) + (int)(short)(vout[1][i] >> 6) + 64) >> 7;   // int16 wrap as in the reference's C
@@ -729,7 +760,9 @@ __device__ __forceinline__ void stream_trip(const FastParams &fp, StreamRef<TAPS
             constexpr int SH = (NEED_H && NEED_V) ? 12 : 6;
             o = pack_sat_u8(vout[0][0] >> SH, vout[0][1] >> SH, vout[0][2] >> SH, vout[0][3] >> SH);
         }
-        if (nvalid >= 4) *reinterpret_cast<uint32_t *>(d) = o;
+        // (the TMA-fed kernel runs unchecked trips only in warps without a right-edge lane: no branch per row there.  The LDG
+        // kernel keeps the test: without it ptxas schedules its loads across rows and spills at 64 registers)
+        if ((SM && !CHECK) || nvalid >= 4) *reinterpret_cast<uint32_t *>(d) = o;
         else store4(d, o, nvalid);
         d += p.sd;   // the destination pointer follows the output rows
     }
@@ -782,6 +815,156 @@ int launch_uni_stream(const FastParams &fp, int mode, int n_frames, void *stream
         case H_ONLY: return launch_stream<TAPS, H_ONLY, false>(fp, n_frames, stream);
         case V_ONLY: return launch_stream<TAPS, V_ONLY, false>(fp, n_frames, stream);
         default: return launch_stream<TAPS, HV, false>(fp, n_frames, stream);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ plane form, streaming path fed by TMA
+//
+// pred_stream_kernel issues its loads and then waits for them: ncu shows 49 % of its stall samples on the long scoreboard
+// and every attempt to prefetch in registers cost more occupancy than it hid (profiles/r01_pred.md).  Here the same
+// arithmetic (stream_trip<.., SM = true>) reads its rows from shared memory, and the rows get there by TMA.  A CTA owns
+// 512 columns x one strip; the reference is described as a tensor of 32-bit words so that one box can be a whole
+// 544-byte row segment (the 512 columns + the filter halo, starting on a 16-byte boundary as the TMA unit requires) x 16
+// (or 8) rows.  3 (or 4) such boxes form a ring with a `full` mbarrier (armed with the byte count, completed by the TMA unit)
+// and an `empty` mbarrier (one arrival per warp) each; thread 0 re-arms the box the CTA consumed one iteration earlier,
+// so all boxes but one are in flight per CTA and no thread waits on DRAM with an instruction slot to fill.  There
+// is no CTA-wide barrier in the loop.  Rows outside the declared tensor are zero-filled by the hardware, so strips at the
+// bottom edge need no clamping.  (First version: a private ring of 160-byte boxes per warp - the TMA unit then delivers
+// only ~2.4 TB/s, 80 us for ANY filter position; wide boxes fix that.)
+constexpr int TS_COLS = 4 * NT;                                         // 512 output columns per CTA
+
+struct alignas(64) StreamMaps {
+    CUtensorMap tm[2];   // per reference: 32-bit words from (x = -4 or 0, y = -(TAPS/2-1) or 0) of the plane, 16-byte aligned start
+    int shift[2];        // bytes between that aligned start and the first byte the kernel wants (0, 4, 8 or 12)
+};
+
+// ring geometry: 3 boxes of 16 rows (one reference) or 4 x 2 boxes of 8 rows (two references) - 26 / 35 KB per CTA
+template <bool BI>
+struct TsRing {
+    static constexpr int ROWS = BI ? 8 : 16, STAGES = BI ? 4 : 3, BOX = SM_PITCH * ROWS;   // BOX is a multiple of 128 bytes
+};
+template <int TAPS, int MODE, bool BI>
+struct TsGeom {
+    static constexpr int NREF = BI ? 2 : 1;
+    static constexpr int RING_BYTES = TsRing<BI>::STAGES * NREF * TsRing<BI>::BOX;
+    static constexpr int SMEM_BYTES = RING_BYTES + 2 * TsRing<BI>::STAGES * 8;
+};
+
+template <int TAPS, int MODE, bool BI>
+__global__ void __launch_bounds__(NT, BI ? (TAPS == 8 ? 4 : 6) : 8)
+    pred_stream_tma_kernel(const __grid_constant__ FastParams fp, const __grid_constant__ StreamMaps sm, int strip /* output rows per CTA, a multiple of 8 */)
+{
+    using G = TsGeom<TAPS, MODE, BI>;
+    constexpr bool NEED_V = BI || (MODE & 2);
+    constexpr int NREF = G::NREF, TS_ROWS = TsRing<BI>::ROWS, TS_STAGES = TsRing<BI>::STAGES, TS_BOX = TsRing<BI>::BOX;
+    constexpr int TRIPS = TS_ROWS / TAPS;   // trips of TAPS rows per staged box
+    extern __shared__ __align__(128) uint8_t ts_smem[];
+    uint8_t *const box = ts_smem;
+    uint64_t *const full = reinterpret_cast<uint64_t *>(ts_smem + G::RING_BYTES), *const empty = full + TS_STAGES;
+    const PredParams &p = fp.p;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int x0 = blockIdx.x * TS_COLS, x = x0 + 4 * tid, f = blockIdx.z;
+    const int y0 = blockIdx.y * strip, h = min(strip, p.height - y0), nvalid = p.width - x;
+    const int rows_in = h + (NEED_V ? TAPS - 1 : 0), nbox = (rows_in + TS_ROWS - 1) / TS_ROWS;
+    const bool active = x0 + 128 * (tid >> 5) < p.width;          // warp-uniform: the warp owns at least one column
+    const bool inner = x0 + 128 * (tid >> 5) + 128 <= p.width;    // warp-uniform: no lane at the right edge
+    uint8_t *d = p.dst + f * p.fs_dst + (ptrdiff_t)y0 * p.sd + x;
+
+    auto arm = [&](int b) {   // thread 0: request box b of the strip into its ring slot
+        const int s = b % TS_STAGES;
+        tma::mbar_expect_tx(full + s, NREF * TS_BOX);
+#pragma unroll
+        for (int rf = 0; rf < NREF; ++rf) tma::load_box_3d(box + (s * NREF + rf) * TS_BOX, &sm.tm[rf], x0 / 4, y0 + b * TS_ROWS, f, full + s);
+    };
+    if (tid == 0) {
+#pragma unroll
+        for (int s = 0; s < TS_STAGES; ++s) tma::mbar_init(full + s, 1), tma::mbar_init(empty + s, NT / 32);
+    }
+    __syncthreads();
+    if (tid == 0) {
+#pragma unroll
+        for (int b = 0; b < TS_STAGES; ++b)
+            if (b < nbox) arm(b);
+    }
+
+    StreamRef<TAPS> st[NREF];
+#pragma unroll 1
+    for (int b = 0; b < nbox; ++b) {
+        const int s = b % TS_STAGES;
+        if (tid == 0 && b >= 1 && b - 1 + TS_STAGES < nbox) {   // the box consumed one iteration ago: every warp has (nearly always) let go of it
+            tma::mbar_wait(empty + (b - 1) % TS_STAGES, ((b - 1) / TS_STAGES) & 1);
+            arm(b - 1 + TS_STAGES);
+        }
+        tma::mbar_wait(full + s, (b / TS_STAGES) & 1);
+        if (active) {
+            const uint8_t *src[NREF];
+#pragma unroll
+            for (int u = 0; u < TRIPS; ++u) {
+                const int r0 = b * TS_ROWS + u * TAPS;
+                if (r0 >= rows_in) break;
+#pragma unroll
+                for (int rf = 0; rf < NREF; ++rf) src[rf] = box + (s * NREF + rf) * TS_BOX + u * TAPS * SM_PITCH + sm.shift[rf] + 4 * tid;
+                // trips whose output rows all exist run unchecked: the priming trip (one output row), the trips inside the strip,
+                // and - when the strip height is a multiple of TAPS - the tail of TAPS-1 rows
+                if (inner && NEED_V && r0 == 0) stream_trip<TAPS, MODE, BI, true, false, true>(fp, st, src, d, r0, rows_in, h, nvalid);
+                else if (inner && (!NEED_V || r0 > 0) && r0 + TAPS <= h) stream_trip<TAPS, MODE, BI, false, false, true>(fp, st, src, d, r0, rows_in, h, nvalid);
+                else if (inner && NEED_V && r0 == h) stream_trip<TAPS, MODE, BI, false, false, true, TAPS - 1>(fp, st, src, d, r0, rows_in, h, nvalid);
+                else stream_trip<TAPS, MODE, BI, false, true, true>(fp, st, src, d, r0, rows_in, h, nvalid);
+            }
+        }
+        __syncwarp();   // every lane of the warp has read the box
+        if (lane == 0) tma::mbar_arrive(empty + s);
+    }
+}
+
+// strip height: about 128 rows (the priming and tail trips of a strip cost ~1.5 trips of overhead), nudged so that the grid
+// fills whole waves of resident CTAs - at 4K x 16 frames 120 rows give 1.95 waves where 128 would give 1.84
+static int pick_strip(int height, int ctas_per_strip_row, int slots)
+{
+    int best = 64;
+    double best_score = -1;
+    for (int strip = 64; strip <= 160; strip += 8) {
+        const long long ctas = (long long)ctas_per_strip_row * ((height + strip - 1) / strip);
+        const long long waves = (ctas + slots - 1) / slots;
+        const double fill = (double)ctas / (double)(waves * slots);
+        const double score = fill * (1.0 - 12.0 / (strip + 12.0));   // wave fill x share of rows that are not priming / tail overhead
+        if (score > best_score) best_score = score, best = strip;
+    }
+    return best;
+}
+
+template <int TAPS, int MODE, bool BI>
+int launch_stream_tma(const FastParams &fp, const StreamMaps &sm, int n_frames, void *stream)
+{
+    using G = TsGeom<TAPS, MODE, BI>;
+    auto kern = pred_stream_tma_kernel<TAPS, MODE, BI>;
+    if (G::SMEM_BYTES > 48 * 1024 && set_max_smem(kern, G::SMEM_BYTES)) return (int)cudaErrorInvalidValue;
+    static int per_sm = 0;   // resident CTAs per SM of this instantiation (a property of the binary: benign race)
+    if (!per_sm) {
+        int n = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kern, NT, (size_t)G::SMEM_BYTES) != cudaSuccess || n < 1) n = 1;
+        per_sm = n;
+    }
+    const int cols = (fp.p.width + TS_COLS - 1) / TS_COLS;
+    // one-pass positions and copies are bound by memory: short strips, whose two or three boxes are all requested at once,
+    // measured best (32 rows: 45-46 us per 16 4K planes; 64: 47-48; 120: 50-53).  Two-pass positions: see pick_strip.
+    int strip = (BI || MODE == HV) ? pick_strip(fp.p.height, cols * n_frames, per_sm * sm_count()) : 32;
+    if (const char *e = getenv("HEVCASM_PRED_STRIP")) {   // tuning knob: rows per CTA (rounded to a multiple of 8)
+        const int v = atoi(e) & ~7;
+        if (v >= 8 && v <= 1024) strip = v;
+    }
+    const dim3 grid(cols, (fp.p.height + strip - 1) / strip, n_frames);
+    return launch(kern, grid, dim3(NT), (size_t)G::SMEM_BYTES, stream, fp, sm, strip);
+}
+
+template <int TAPS>
+int launch_uni_stream_tma(const FastParams &fp, const StreamMaps &sm, int mode, int n_frames, void *stream)
+{
+    switch (mode) {
+        case COPY: return launch_stream_tma<TAPS, COPY, false>(fp, sm, n_frames, stream);
+        case H_ONLY: return launch_stream_tma<TAPS, H_ONLY, false>(fp, sm, n_frames, stream);
+        case V_ONLY: return launch_stream_tma<TAPS, V_ONLY, false>(fp, sm, n_frames, stream);
+        default: return launch_stream_tma<TAPS, HV, false>(fp, sm, n_frames, stream);
     }
 }
 
@@ -1009,6 +1192,26 @@ static bool list_stream_ok()
     const char *pin = getenv("HEVCASM_PRED_PATH");
     return !getenv("HEVCASM_PRED_GENERIC") && !(pin && strcmp(pin, "stream"));
 }
+// TMA-fed streaming kernel: describes each reference as a (x, y, frame) byte tensor starting at the first byte the filter
+// footprint touches (x = -4 with a horizontal pass, y = -(taps/2-1) with a vertical one).  Not possible (-> LDG streaming kernel)
+// when the strides are not multiples of 16, or when a row's footprint does not fit its stride (the right halo would then
+// lie in the next row, outside the declared row).  HEVCASM_PRED_STREAM=ldg / =tma pin one kernel (A/B runs).
+static bool stream_maps(StreamMaps *sm, const PredParams &p, int taps, int mode, bool bi, int n_frames)
+{
+    const char *pin = getenv("HEVCASM_PRED_STREAM");
+    if (pin && !strcmp(pin, "ldg")) return false;
+    if (!tma::describable(p.sr, p.fs_ref, n_frames)) return false;
+    const bool need_h = bi || (mode & 1), need_v = bi || (mode & 2);
+    const int left = need_h ? 4 : 0, top = need_v ? taps / 2 - 1 : 0;
+    const long long ext_x = (long long)left + p.width + (need_h ? 8 : 0), ext_y = (long long)p.height + (need_v ? taps - 1 : 0);
+    const uint8_t *refs[2] = {p.ref0, p.ref1};
+    for (int rf = 0; rf < (bi ? 2 : 1); ++rf) {
+        const uint8_t *first = refs[rf] - (ptrdiff_t)top * p.sr - left;
+        if ((long long)((uintptr_t)first & 15) + ext_x > (long long)p.sr) return false;
+        if (tma::describe_u32(&sm->tm[rf], first, p.sr, p.fs_ref, ext_x, ext_y, n_frames, SM_PITCH, bi ? TsRing<true>::ROWS : TsRing<false>::ROWS, &sm->shift[rf])) return false;
+    }
+    return true;
+}
 static bool aligned8(const uint8_t *dst, ptrdiff_t sd, ptrdiff_t fs_dst, int n_frames)
 {
     uintptr_t m = (uintptr_t)dst | (uintptr_t)sd;
@@ -1026,13 +1229,18 @@ extern "C" int hevcasm_pred_uni_frames(uint8_t *dst, ptrdiff_t sd, const uint8_t
     p.xf0 = xFrac, p.yf0 = yFrac;
     const dim3 grid((width + PTW - 1) / PTW, (height + PTH - 1) / PTH, n_frames);
     const int mode = (xFrac ? 1 : 0) | (yFrac ? 2 : 0);
-    // two-pass positions: the streaming kernel (1.65 vs 1.36 Tsamples/s); one-pass positions and copies: the tile kernels when the
-    // planes are 16-byte aligned (2.2-2.4 vs 2.0), the streaming kernel when they are only 4-byte aligned
-    const bool tile_ok = planes_fast_ok(ref, nullptr, sr, fs_ref, n_frames);
-    if (mode != COPY && (mode == HV || !tile_ok) && stream_ok(dst, sd, fs_dst, ref, nullptr, sr, fs_ref, n_frames)) {
+    // every position: the TMA-fed streaming kernel when the planes can be described to the TMA unit (strides multiples
+    // of 16, 4-byte aligned rows).  Otherwise: two-pass positions -> LDG streaming kernel; one-pass positions -> tile kernels on
+    // 16-byte aligned planes (2.2-2.4 vs 2.0 Tsamples/s), LDG streaming kernel on 4-byte aligned ones; copies -> tile kernels.
+    const char *pin = getenv("HEVCASM_PRED_PATH");
+    const bool tile_ok = planes_fast_ok(ref, nullptr, sr, fs_ref, n_frames) && !(pin && !strcmp(pin, "stream"));
+    if (stream_ok(dst, sd, fs_dst, ref, nullptr, sr, fs_ref, n_frames)) {
         FastParams fp{};
         fp.p = p, fp.c[0] = pack_coefs(taps, xFrac, yFrac);
-        return taps == 8 ? launch_uni_stream<8>(fp, mode, n_frames, stream) : launch_uni_stream<4>(fp, mode, n_frames, stream);
+        StreamMaps sm;
+        if (stream_maps(&sm, p, taps, mode, false, n_frames))
+            return taps == 8 ? launch_uni_stream_tma<8>(fp, sm, mode, n_frames, stream) : launch_uni_stream_tma<4>(fp, sm, mode, n_frames, stream);
+        if (mode != COPY && (mode == HV || !tile_ok)) return taps == 8 ? launch_uni_stream<8>(fp, mode, n_frames, stream) : launch_uni_stream<4>(fp, mode, n_frames, stream);
     }
     if (planes_fast_ok(ref, nullptr, sr, fs_ref, n_frames)) {
         const bool dst8 = aligned8(dst, sd, fs_dst, n_frames);
@@ -1058,6 +1266,9 @@ extern "C" int hevcasm_pred_bi_frames(uint8_t *dst, ptrdiff_t sd, const uint8_t 
     if (stream_ok(dst, sd, fs_dst, ref0, ref1, sr, fs_ref, n_frames)) {
         FastParams fp{};
         fp.p = p, fp.c[0] = pack_coefs(taps, xFrac0, yFrac0), fp.c[1] = pack_coefs(taps, xFrac1, yFrac1);
+        StreamMaps sm;
+        if (stream_maps(&sm, p, taps, HV, true, n_frames))
+            return taps == 8 ? launch_stream_tma<8, HV, true>(fp, sm, n_frames, stream) : launch_stream_tma<4, HV, true>(fp, sm, n_frames, stream);
         return taps == 8 ? launch_stream<8, HV, true>(fp, n_frames, stream) : launch_stream<4, HV, true>(fp, n_frames, stream);
     }
     if (planes_fast_ok(ref0, ref1, sr, fs_ref, n_frames)) {

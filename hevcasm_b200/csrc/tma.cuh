@@ -38,21 +38,34 @@ inline bool describable(ptrdiff_t row_stride, ptrdiff_t frame_stride, int n_fram
 // Describes the bytes [first, first + extent_x) x extent_y rows x n_frames, where `first` may have any alignment: the
 // tensor starts at the enclosing 16-byte boundary and *x_shift receives the offset to add to every x coordinate.
 // box = {box_x bytes (multiple of 16, <= 256), box_y rows (<= 256), 1 frame}.
-inline int describe_u8(CUtensorMap *map, const uint8_t *first, ptrdiff_t row_stride, ptrdiff_t frame_stride, long long extent_x, long long extent_y,
-                       int n_frames, int box_x, int box_y, int *x_shift)
+inline int describe_bytes(CUtensorMap *map, const uint8_t *first, ptrdiff_t row_stride, ptrdiff_t frame_stride, long long extent_x, long long extent_y,
+                          int n_frames, int box_x, int box_y, int *x_shift, int elem /* 1: uint8 elements, 4: 32-bit words */)
 {
     const uintptr_t a = (uintptr_t)first;
     const int shift = (int)(a & 15);
     *x_shift = shift;
     if (n_frames <= 1) frame_stride = row_stride * (ptrdiff_t)extent_y;  // unused, but must be a legal stride
-    cuuint64_t dim[3] = {(cuuint64_t)(extent_x + shift), (cuuint64_t)extent_y, (cuuint64_t)(n_frames < 1 ? 1 : n_frames)};
-    if (dim[0] > (cuuint64_t)row_stride) dim[0] = (cuuint64_t)row_stride;  // never describe more than one row's worth per row
+    long long row_bytes = extent_x + shift;
+    if (row_bytes > (long long)row_stride) row_bytes = (long long)row_stride;  // never describe more than one row's worth per row
+    cuuint64_t dim[3] = {(cuuint64_t)((row_bytes + elem - 1) / elem), (cuuint64_t)extent_y, (cuuint64_t)(n_frames < 1 ? 1 : n_frames)};
     cuuint64_t stride[2] = {(cuuint64_t)row_stride, (cuuint64_t)frame_stride};
-    cuuint32_t box[3] = {(cuuint32_t)box_x, (cuuint32_t)box_y, 1};
+    cuuint32_t box[3] = {(cuuint32_t)(box_x / elem), (cuuint32_t)box_y, 1};
     cuuint32_t estr[3] = {1, 1, 1};
-    const CUresult r = encoder()(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, (void *)(a - shift), dim, stride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                                 CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    const CUresult r = encoder()(map, elem == 4 ? CU_TENSOR_MAP_DATA_TYPE_UINT32 : CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, (void *)(a - shift), dim, stride, box, estr,
+                                 CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     return r == CUDA_SUCCESS ? 0 : (int)cudaErrorInvalidValue;
+}
+inline int describe_u8(CUtensorMap *map, const uint8_t *first, ptrdiff_t row_stride, ptrdiff_t frame_stride, long long extent_x, long long extent_y,
+                       int n_frames, int box_x, int box_y, int *x_shift)
+{
+    return describe_bytes(map, first, row_stride, frame_stride, extent_x, extent_y, n_frames, box_x, box_y, x_shift, 1);
+}
+// the same bytes described as 32-bit words: boxes may then be up to 1024 bytes wide (box_x still in BYTES, a multiple of 16);
+// the x coordinate of a load is in words, and the zero-fill edge is rounded up to a word
+inline int describe_u32(CUtensorMap *map, const uint8_t *first, ptrdiff_t row_stride, ptrdiff_t frame_stride, long long extent_x, long long extent_y,
+                        int n_frames, int box_x, int box_y, int *x_shift)
+{
+    return describe_bytes(map, first, row_stride, frame_stride, extent_x, extent_y, n_frames, box_x, box_y, x_shift, 4);
 }
 
 // ---- device ----------------------------------------------------------------------------------------------------
@@ -68,6 +81,7 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
 {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory"); }
 // Waits for the phase with the given parity.  A descriptor / coordinate error would leave the barrier incomplete for ever;
 // rather than hang the GPU the wait gives up after ~1 s worth of polls and traps, which surfaces as a launch failure.
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)

@@ -21,6 +21,7 @@ cbf = torch.empty((n // 16,), dtype=torch.int32, device="cuda")
 def d(t, off=0): return C.c_void_p(t.data_ptr() + off * t.element_size())
 calls = {
     "pred_hv": lambda: lib.call("pred_uni_frames", d(o8, org), pitch, d(a, org), pitch, W, H, 8, 1, 3, NF, fs, fs),
+    "pred_copy": lambda: lib.call("pred_uni_frames", d(o8, org), pitch, d(a, org), pitch, W, H, 8, 0, 0, NF, fs, fs),
     "pred_h": lambda: lib.call("pred_uni_frames", d(o8, org), pitch, d(a, org), pitch, W, H, 8, 1, 0, NF, fs, fs),
     "pred_v": lambda: lib.call("pred_uni_frames", d(o8, org), pitch, d(a, org), pitch, W, H, 8, 0, 2, NF, fs, fs),
     "pred_chroma_hv": lambda: lib.call("pred_uni_frames", d(o8, org), pitch, d(a, org), pitch, W, H, 4, 3, 5, NF, fs, fs),
