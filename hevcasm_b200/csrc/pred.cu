@@ -667,7 +667,7 @@ template <int TAPS, int MODE, bool BI, bool FIRST, bool CHECK, bool SM = false, 
 __device__ __forceinline__ void stream_trip(const FastParams &fp, StreamRef<TAPS> (&st)[BI ? 2 : 1], const uint8_t *(&src)[BI ? 2 : 1], uint8_t *&d, int r0,
                                             int rows_in, int h, int nvalid)
 {
-    constexpr bool NEED_H = BI || (MODE & 1), NEED_V = BI || (MODE & 2);
+    constexpr bool NEED_H = (BI && MODE != COPY) || (MODE & 1), NEED_V = (BI && MODE != COPY) || (MODE & 2);   // bi: both passes, except the full-sample average (MODE = COPY)
     constexpr int NREF = BI ? 2 : 1;
     const PredParams &p = fp.p;
     uint32_t W[NREF][TAPS][3];
@@ -750,7 +750,7 @@ __device__ __forceinline__ void stream_trip(const FastParams &fp, StreamRef<TAPS
         }
         uint32_t o;
         if (!NEED_H && !NEED_V) {
-            o = W[0][k][0];   // full-sample position: the row passes through (TMA-fed kernel only)
+            o = BI ? __vavgu4(W[0][k][0], W[NREF - 1][k][0]) : W[0][k][0];   // full-sample position(s): the row passes through / (a + b + 1) >> 1 (TMA-fed kernel only)
         } else if (BI) {
             int s4[4];
 #pragma unroll
@@ -851,11 +851,11 @@ struct TsGeom {
 };
 
 template <int TAPS, int MODE, bool BI>
-__global__ void __launch_bounds__(NT, BI ? (TAPS == 8 ? 4 : 6) : 8)
+__global__ void __launch_bounds__(NT, (BI && MODE != COPY) ? (TAPS == 8 ? 4 : 6) : 8)
     pred_stream_tma_kernel(const __grid_constant__ FastParams fp, const __grid_constant__ StreamMaps sm, int strip /* output rows per CTA, a multiple of 8 */)
 {
     using G = TsGeom<TAPS, MODE, BI>;
-    constexpr bool NEED_V = BI || (MODE & 2);
+    constexpr bool NEED_V = (BI && MODE != COPY) || (MODE & 2);
     constexpr int NREF = G::NREF, TS_ROWS = TsRing<BI>::ROWS, TS_STAGES = TsRing<BI>::STAGES, TS_BOX = TsRing<BI>::BOX;
     constexpr int TRIPS = TS_ROWS / TAPS;   // trips of TAPS rows per staged box
     extern __shared__ __align__(128) uint8_t ts_smem[];
@@ -948,7 +948,7 @@ int launch_stream_tma(const FastParams &fp, const StreamMaps &sm, int n_frames, 
     const int cols = (fp.p.width + TS_COLS - 1) / TS_COLS;
     // one-pass positions and copies are bound by memory: short strips, whose two or three boxes are all requested at once,
     // measured best (32 rows: 45-46 us per 16 4K planes; 64: 47-48; 120: 50-53).  Two-pass positions: see pick_strip.
-    int strip = (BI || MODE == HV) ? pick_strip(fp.p.height, cols * n_frames, per_sm * sm_count()) : 32;
+    int strip = (MODE == HV) ? pick_strip(fp.p.height, cols * n_frames, per_sm * sm_count()) : 32;
     if (const char *e = getenv("HEVCASM_PRED_STRIP")) {   // tuning knob: rows per CTA (rounded to a multiple of 8)
         const int v = atoi(e) & ~7;
         if (v >= 8 && v <= 1024) strip = v;
@@ -1201,7 +1201,7 @@ static bool stream_maps(StreamMaps *sm, const PredParams &p, int taps, int mode,
     const char *pin = getenv("HEVCASM_PRED_STREAM");
     if (pin && !strcmp(pin, "ldg")) return false;
     if (!tma::describable(p.sr, p.fs_ref, n_frames)) return false;
-    const bool need_h = bi || (mode & 1), need_v = bi || (mode & 2);
+    const bool need_h = (bi && mode != COPY) || (mode & 1), need_v = (bi && mode != COPY) || (mode & 2);
     const int left = need_h ? 4 : 0, top = need_v ? taps / 2 - 1 : 0;
     const long long ext_x = (long long)left + p.width + (need_h ? 8 : 0), ext_y = (long long)p.height + (need_v ? taps - 1 : 0);
     const uint8_t *refs[2] = {p.ref0, p.ref1};
@@ -1267,8 +1267,13 @@ extern "C" int hevcasm_pred_bi_frames(uint8_t *dst, ptrdiff_t sd, const uint8_t 
         FastParams fp{};
         fp.p = p, fp.c[0] = pack_coefs(taps, xFrac0, yFrac0), fp.c[1] = pack_coefs(taps, xFrac1, yFrac1);
         StreamMaps sm;
-        if (stream_maps(&sm, p, taps, HV, true, n_frames))
+        // both references at a full-sample position: (64a + 64b + 64) >> 7 = (a + b + 1) >> 1, a byte average (the reference's own
+        // assembly has the same shortcut, pred_inter_a.asm:580-608); anything else runs both passes on both references as the C does
+        const bool avg = !xFrac0 && !yFrac0 && !xFrac1 && !yFrac1;
+        if (stream_maps(&sm, p, taps, avg ? COPY : HV, true, n_frames)) {
+            if (avg) return taps == 8 ? launch_stream_tma<8, COPY, true>(fp, sm, n_frames, stream) : launch_stream_tma<4, COPY, true>(fp, sm, n_frames, stream);
             return taps == 8 ? launch_stream_tma<8, HV, true>(fp, sm, n_frames, stream) : launch_stream_tma<4, HV, true>(fp, sm, n_frames, stream);
+        }
         return taps == 8 ? launch_stream<8, HV, true>(fp, n_frames, stream) : launch_stream<4, HV, true>(fp, n_frames, stream);
     }
     if (planes_fast_ok(ref0, ref1, sr, fs_ref, n_frames)) {

@@ -25,6 +25,7 @@ calls = {
     "pred_h": lambda: lib.call("pred_uni_frames", d(o8, org), pitch, d(a, org), pitch, W, H, 8, 1, 0, NF, fs, fs),
     "pred_v": lambda: lib.call("pred_uni_frames", d(o8, org), pitch, d(a, org), pitch, W, H, 8, 0, 2, NF, fs, fs),
     "pred_chroma_hv": lambda: lib.call("pred_uni_frames", d(o8, org), pitch, d(a, org), pitch, W, H, 4, 3, 5, NF, fs, fs),
+    "pred_bi_avg": lambda: lib.call("pred_bi_frames", d(o8, org), pitch, d(a, org), d(b, org), pitch, W, H, 8, 0, 0, 0, 0, NF, fs, fs),
     "pred_bi": lambda: lib.call("pred_bi_frames", d(o8, org), pitch, d(a, org), d(b, org), pitch, W, H, 8, 1, 2, 3, 1, NF, fs, fs),
     "fwd8": lambda: lib.call("transform_frames", d(co2), d(res), rp, W, H, 3, 0, NF, H * rp),
     "fwd4": lambda: lib.call("transform_frames", d(co2), d(res), rp, W, H, 2, 0, NF, H * rp),
