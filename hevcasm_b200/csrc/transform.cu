@@ -13,6 +13,7 @@
 // The second inverse stage skips the reference's clip to int16: |value| <= 23040 there, so the clip can never bind,
 // and for the same reason the int16 truncation inside hevcasm_clip (:350-356) is the identity.
 #include "transform.cuh"
+#include "tma.cuh"
 #include "transform_imma.cuh"
 
 #include <algorithm>
@@ -23,14 +24,43 @@ namespace hv {
 using namespace tr;
 
 // where block i of a batch lives: explicit list, or raster order over a regular grid of n_frames planes
+// unsigned 32-bit division by a run-time constant as multiply-high + shifts (Granlund-Montgomery, round-up variant:
+// exact for every 32-bit numerator): 4 integer instructions instead of the ~20 (32-bit) / ~100 (64-bit) of a division
+struct FastDiv {
+    uint32_t d, m, s;   // divisor, magic multiplier, shift;  s == 0 <=> d == 1
+    __host__ static FastDiv make(uint32_t d)
+    {
+        FastDiv f{d ? d : 1u, 0, 0};
+        while ((1ull << f.s) < f.d) ++f.s;   // ceil(log2 d)
+        f.m = (uint32_t)((((1ull << f.s) - f.d) << 32) / f.d + 1);
+        return f;
+    }
+    __device__ __forceinline__ uint32_t div(uint32_t n) const
+    {
+        if (s == 0) return n;
+        const uint32_t t = __umulhi(n, m);
+        return (((n - t) >> 1) + t) >> (s - 1);
+    }
+};
+
 struct BlockGrid {
     const int16_t *blk_xy;
     int nbx, nby;
     long long n;
+    FastDiv per_frame, per_row;   // blocks per frame / per block row (regular grids with n < 2^32; finish() fills them)
+    bool fast;
+    void finish()
+    {
+        fast = !blk_xy && n > 0 && n < (1ll << 32) && nbx > 0 && nby > 0;
+        if (fast) per_frame = FastDiv::make((uint32_t)(nbx * nby)), per_row = FastDiv::make((uint32_t)nbx);
+    }
     __device__ __forceinline__ void locate(long long i, int log2, int &x, int &y, int &f) const
     {
         if (blk_xy) {
             x = blk_xy[2 * i], y = blk_xy[2 * i + 1], f = 0;
+        } else if (fast) {
+            const uint32_t u = (uint32_t)i, fr = per_frame.div(u), r = u - fr * per_frame.d, row = per_row.div(r);
+            f = (int)fr, y = (int)(row << log2), x = (int)((r - row * per_row.d) << log2);
         } else {
             const long long per = (long long)nbx * nby;
             f = (int)(i / per);
@@ -482,6 +512,8 @@ __global__ void __launch_bounds__(BIG_NT) big_fwd_kernel(int16_t *__restrict__ c
     }
 }
 
+#include "transform_umma.cuh"  // 16x16 / 32x32 inverse on tcgen05 (needs BlockGrid, load_words, store_words)
+
 // ================================================================================================ 16x16 / 32x32 inverse on IMMA
 
 constexpr int IMMA_NT = 128;
@@ -755,6 +787,13 @@ static int launch_inv_t(uint8_t *dst, ptrdiff_t sd, const uint8_t *pred, ptrdiff
         if (log2 == 4) return launch(imma_inv_kernel<4, PA>, blocks, IMMA_NT, 0, stream, dst, sd, pred, sp, fs_dst, fs_pred, coeffs, g);
         return launch(imma_inv_kernel<5, PA>, blocks, IMMA_NT, 0, stream, dst, sd, pred, sp, fs_dst, fs_pred, coeffs, g);
     }
+    // tcgen05 (kind::i8, TMEM accumulators) formulation: HEVCASM_INV_PATH=umma (transform_umma.cuh)
+    if (pin && !strcmp(pin, "umma")) {
+        const long long groups = log2 == 4 ? (g.n + 7) / 8 : (g.n + 3) / 4;
+        const unsigned blocks = (unsigned)std::min<long long>(groups, (long long)sm_count() * 6);   // persistent CTAs, 6 per SM
+        if (log2 == 4) return launch(umma_inv_kernel<4, PA>, blocks, UMMA_NT, 0, stream, dst, sd, pred, sp, fs_dst, fs_pred, coeffs, g);
+        return launch(umma_inv_kernel<5, PA>, blocks, UMMA_NT, 0, stream, dst, sd, pred, sp, fs_dst, fs_pred, coeffs, g);
+    }
     if (log2 == 4) return launch(big_inv_kernel<4, PA>, (unsigned)((g.n + 15) / 16), BIG_NT, 0, stream, dst, sd, pred, sp, fs_dst, fs_pred, coeffs, g);
     return launch(big_inv_kernel<5, PA>, (unsigned)((g.n + 7) / 8), BIG_NT, 0, stream, dst, sd, pred, sp, fs_dst, fs_pred, coeffs, g);
 }
@@ -776,6 +815,7 @@ extern "C" int hevcasm_transform_batch(int16_t *coeffs, const int16_t *residual,
 {
     if (!tr_args_ok(log2size, trType) || n < 0 || (n > 0 && !blk_xy)) return HEVCASM_ERR_ARGUMENT;
     BlockGrid g{blk_xy, 0, 0, n};
+    g.finish();
     return launch_fwd(coeffs, residual, stride, 0, log2size, trType, g, stream);
 }
 
@@ -785,6 +825,7 @@ extern "C" int hevcasm_transform_frames(int16_t *coeffs, const int16_t *residual
     if (!tr_args_ok(log2size, trType) || n_frames < 0 || width < 0 || height < 0) return HEVCASM_ERR_ARGUMENT;
     BlockGrid g{nullptr, width >> log2size, height >> log2size, 0};
     g.n = (long long)g.nbx * g.nby * n_frames;
+    g.finish();
     return launch_fwd(coeffs, residual, stride, fs, log2size, trType, g, stream);
 }
 
@@ -793,6 +834,7 @@ extern "C" int hevcasm_inverse_transform_add_batch(uint8_t *dst, ptrdiff_t sd, c
 {
     if (!tr_args_ok(log2size, trType) || n < 0 || (n > 0 && !blk_xy)) return HEVCASM_ERR_ARGUMENT;
     BlockGrid g{blk_xy, 0, 0, n};
+    g.finish();
     return launch_inv(dst, sd, pred, sp, 0, 0, coeffs, log2size, trType, g, stream);
 }
 
@@ -802,6 +844,7 @@ extern "C" int hevcasm_inverse_transform_add_frames(uint8_t *dst, ptrdiff_t sd, 
     if (!tr_args_ok(log2size, trType) || n_frames < 0 || width < 0 || height < 0) return HEVCASM_ERR_ARGUMENT;
     BlockGrid g{nullptr, width >> log2size, height >> log2size, 0};
     g.n = (long long)g.nbx * g.nby * n_frames;
+    g.finish();
     return launch_inv(dst, sd, pred, sp, fs_dst, fs_pred, coeffs, log2size, trType, g, stream);
 }
 
@@ -827,6 +870,7 @@ extern "C" int hevcasm_residual_pipeline_frames(uint8_t *rec, ptrdiff_t s_rec, i
         return HEVCASM_ERR_ARGUMENT;
     BlockGrid g{nullptr, width >> log2size, height >> log2size, 0};
     g.n = (long long)g.nbx * g.nby * n_frames;
+    g.finish();
     if (g.n == 0) return 0;
     PipelineParams p;
     p.rec = rec, p.pred = pred, p.res = residual, p.levels = levels, p.cbf = cbf;

@@ -71,10 +71,12 @@ def test_inverse_frames(oracle, trType, log2):
         assert np.array_equal(to_host(got), want.buf), name
 
 
+@pytest.mark.parametrize("path", ["imma", "umma"])
 @pytest.mark.parametrize("log2", [4, 5])
-def test_inverse_frames_imma_variant(oracle, log2, monkeypatch):
-    """the exact tensor-core (mma.sync s8/u8 -> s32) formulation of the 16x16 / 32x32 inverse, kept for A/B profiling"""
-    monkeypatch.setenv("HEVCASM_INV_PATH", "imma")
+def test_inverse_frames_imma_variant(oracle, log2, path, monkeypatch):
+    """the exact tensor-core formulations of the 16x16 / 32x32 inverse: legacy mma.sync s8/u8 -> s32 ("imma", kept for A/B
+    profiling) and tcgen05 kind::i8 with TMEM accumulators ("umma")"""
+    monkeypatch.setenv("HEVCASM_INV_PATH", path)
     test_inverse_frames(oracle, 0, log2)
     width, height, nf, n = 256, 128, 2, 1 << log2          # 16-byte aligned planes: the plane-aligned instantiation
     pred = synth.random_planes(85, nf, width, height, 16)
