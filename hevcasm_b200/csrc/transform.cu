@@ -464,9 +464,11 @@ __device__ __forceinline__ void big_fwd_core(uint32_t *tmp, int b, int uw, bool 
             uint32_t Xw[HW];
             load_words<HW, PA>(src + (ptrdiff_t)r * stride, Xw);
             int xv[N], a[N];
+            uint32_t range = 0;
 #pragma unroll
-            for (int k = 0; k < HW; ++k) xv[2 * k] = s16lo(Xw[k]), xv[2 * k + 1] = s16hi(Xw[k]);
-            FwdBfly<N>::run(xv, a, 1 << (S1 - 1));
+            for (int k = 0; k < HW; ++k) xv[2 * k] = s16lo(Xw[k]), xv[2 * k + 1] = s16hi(Xw[k]), range = fits15_acc(range, Xw[k]);
+            if (N == 32 && fits15(range)) FwdBflyPacked<N>::run(xv, a, 1 << (S1 - 1));   // top-level odd part on IDP.2A (transform.cuh); 16x16: measured slower (141 vs 130 us)
+            else FwdBfly<N>::run(xv, a, 1 << (S1 - 1));
             uint4 *row = reinterpret_cast<uint4 *>(tmp + b * G::BLK_STRIDE + r * G::PITCH);
 #pragma unroll
             for (int k = 0; k < HW / 4; ++k)
@@ -477,13 +479,20 @@ __device__ __forceinline__ void big_fwd_core(uint32_t *tmp, int b, int uw, bool 
     __syncwarp();
     if (valid) {  // stage 2: columns 2*uw and 2*uw+1, along y
         int x0[N], c0[N];
+        uint32_t range = 0;
 #pragma unroll
-        for (int r = 0; r < N; ++r) x0[r] = s16lo(tmp[b * G::BLK_STRIDE + r * G::PITCH + uw]);
-        FwdBfly<N>::run(x0, c0, 1 << (S2 - 1));
+        for (int r = 0; r < N; ++r) {
+            const uint32_t w = tmp[b * G::BLK_STRIDE + r * G::PITCH + uw];
+            x0[r] = s16lo(w), range = fits15_acc(range, w);
+        }
+        const bool packed = N == 32 && fits15(range);   // both columns of this lane
+        if (packed) FwdBflyPacked<N>::run(x0, c0, 1 << (S2 - 1));
+        else FwdBfly<N>::run(x0, c0, 1 << (S2 - 1));
 #pragma unroll
         for (int r = 0; r < N; ++r) x0[r] = s16hi(tmp[b * G::BLK_STRIDE + r * G::PITCH + uw]);
         int c1[N];
-        FwdBfly<N>::run(x0, c1, 1 << (S2 - 1));
+        if (packed) FwdBflyPacked<N>::run(x0, c1, 1 << (S2 - 1));
+        else FwdBfly<N>::run(x0, c1, 1 << (S2 - 1));
 #pragma unroll
         for (int v = 0; v < N; ++v) W[v] = lolo((uint32_t)(c0[v] >> S2), (uint32_t)(c1[v] >> S2));
     }
