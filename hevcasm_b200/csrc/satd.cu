@@ -10,12 +10,54 @@
 // summed with IDP.4A.
 #include "common.cuh"
 
+#include <cstdlib>
+
 namespace hv {
+
+// unsigned 32-bit division by a run-time constant as multiply-high + shifts (exact for every 32-bit numerator)
+struct SatdDiv {
+    uint32_t d, m, s;
+    static SatdDiv make(uint32_t d)
+    {
+        SatdDiv f{d ? d : 1u, 0, 0};
+        while ((1ull << f.s) < f.d) ++f.s;
+        f.m = (uint32_t)((((1ull << f.s) - f.d) << 32) / f.d + 1);
+        return f;
+    }
+    __device__ __forceinline__ uint32_t div(uint32_t n) const
+    {
+        if (s == 0) return n;
+        const uint32_t t = __umulhi(n, m);
+        return (((n - t) >> 1) + t) >> (s - 1);
+    }
+};
 
 struct SatdGrid {
     const int16_t *blk_xy;
     int nbx, nby;
     long long n;
+    SatdDiv per_frame, per_row;
+    bool fast;   // regular grid, n < 2^32: locate by multiply-high
+    void finish()
+    {
+        fast = !blk_xy && n > 0 && n < (1ll << 32) && nbx > 0 && nby > 0;
+        if (fast) per_frame = SatdDiv::make((uint32_t)(nbx * nby)), per_row = SatdDiv::make((uint32_t)nbx);
+    }
+    __device__ __forceinline__ void locate(long long i, int log2, int &x, int &y, int &f) const
+    {
+        f = 0;
+        if (blk_xy) {
+            x = blk_xy[2 * i], y = blk_xy[2 * i + 1];
+        } else if (fast) {
+            const uint32_t u = (uint32_t)i, fr = per_frame.div(u), r = u - fr * per_frame.d, row = per_row.div(r);
+            f = (int)fr, y = (int)(row << log2), x = (int)((r - row * per_row.d) << log2);
+        } else {
+            const long long per = (long long)nbx * nby;
+            f = (int)(i / per);
+            const int r = (int)(i - f * per);
+            y = (r / nbx) << log2, x = (r % nbx) << log2;
+        }
+    }
 };
 
 template <int N>
@@ -49,22 +91,71 @@ __device__ __forceinline__ void hadamard(int (&v)[N])
             }
 }
 
+// 4-point Hadamard rows as IDP.4A byte patterns (+1 = 0x01, -1 = 0xff), and their negatives for the subtrahend
+__device__ __forceinline__ int had4_row(uint32_t a, uint32_t b, int u)
+{
+    constexpr uint32_t P[4] = {0x01010101u, 0xff01ff01u, 0xffff0101u, 0x01ffff01u}, M[4] = {0xffffffffu, 0x01ff01ffu, 0x0101ffffu, 0xff0101ffu};
+    return dp4a_us(b, (int)M[u], dp4a_us(a, (int)P[u], 0));
+}
+
+// One thread per block.  The horizontal pass never unpacks a byte: output u of a 4-sample group is IDP.4A(a, H_u) +
+// IDP.4A(b, -H_u), on the FMA pipe; for 8x8 the two groups of a row are chained with equal / opposite signs, so the whole
+// horizontal pass is 32 IDP.4A per row and the ALU pipe is left to the vertical butterflies (192 add/sub) and the
+// |.| accumulation (one VABSDIFF each): 256 instructions per pipe per block, 8 per sample, where the byte-unpacking
+// version needed ~17 on the ALU pipe alone (1.15 -> see profiles/r01_satd.md).  Needs 4-byte aligned rows; others take
+// satd_generic_kernel.
 template <int LOG2>
 __global__ void __launch_bounds__(128) satd_kernel(const uint8_t *__restrict__ a, ptrdiff_t sa, const uint8_t *__restrict__ b, ptrdiff_t sb, ptrdiff_t fs_a,
                                                    ptrdiff_t fs_b, SatdGrid g, int32_t *__restrict__ out)
 {
     constexpr int N = 1 << LOG2;
+    static_assert(N == 4 || N == 8, "byte-wise horizontal pass: 4x4 and 8x8");
     const long long i = (long long)blockIdx.x * 128 + threadIdx.x;
     if (i >= g.n) return;
-    int x, y, f = 0;
-    if (g.blk_xy) {
-        x = g.blk_xy[2 * i], y = g.blk_xy[2 * i + 1];
-    } else {
-        const long long per = (long long)g.nbx * g.nby;
-        f = (int)(i / per);
-        const int r = (int)(i - f * per);
-        y = (r / g.nbx) << LOG2, x = (r % g.nbx) << LOG2;
+    int x, y, f;
+    g.locate(i, LOG2, x, y, f);
+    const uint8_t *pa = a + f * fs_a + (ptrdiff_t)y * sa + x, *pb = b + f * fs_b + (ptrdiff_t)y * sb + x;
+    int d[N][N];
+#pragma unroll
+    for (int r = 0; r < N; ++r) {
+        const uint32_t *ra = reinterpret_cast<const uint32_t *>(pa + (ptrdiff_t)r * sa), *rb = reinterpret_cast<const uint32_t *>(pb + (ptrdiff_t)r * sb);
+        if (N == 4) {
+            const uint32_t wa = __ldg(ra), wb = __ldg(rb);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) d[r][u] = had4_row(wa, wb, u);
+        } else {
+            const uint32_t a0 = __ldg(ra), a1 = __ldg(ra + 1), b0 = __ldg(rb), b1 = __ldg(rb + 1);
+            constexpr uint32_t P[4] = {0x01010101u, 0xff01ff01u, 0xffff0101u, 0x01ffff01u}, M[4] = {0xffffffffu, 0x01ff01ffu, 0x0101ffffu, 0xff0101ffu};
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int lo = dp4a_us(b0, (int)M[u], dp4a_us(a0, (int)P[u], 0));
+                d[r][u] = dp4a_us(b1, (int)M[u], dp4a_us(a1, (int)P[u], lo));       // group 0 + group 1
+                d[r][u + 4] = dp4a_us(b1, (int)P[u], dp4a_us(a1, (int)M[u], lo));   // group 0 - group 1
+            }
+        }
     }
+    int sum = N / 4;
+#pragma unroll
+    for (int c = 0; c < N; ++c) {
+        int col[N];
+#pragma unroll
+        for (int r = 0; r < N; ++r) col[r] = d[r][c];
+        hadamard<N>(col);   // along y
+#pragma unroll
+        for (int r = 0; r < N; ++r) sum = (int)__sad(col[r], 0, (unsigned)sum);
+    }
+    out[i] = sum / (N / 2);
+}
+
+template <int LOG2>
+__global__ void __launch_bounds__(128) satd_generic_kernel(const uint8_t *__restrict__ a, ptrdiff_t sa, const uint8_t *__restrict__ b, ptrdiff_t sb,
+                                                           ptrdiff_t fs_a, ptrdiff_t fs_b, SatdGrid g, int32_t *__restrict__ out)
+{
+    constexpr int N = 1 << LOG2;
+    const long long i = (long long)blockIdx.x * 128 + threadIdx.x;
+    if (i >= g.n) return;
+    int x, y, f;
+    g.locate(i, LOG2, x, y, f);
     const uint8_t *pa = a + f * fs_a + (ptrdiff_t)y * sa + x, *pb = b + f * fs_b + (ptrdiff_t)y * sb + x;
     const bool al = ((((uintptr_t)pa | (uintptr_t)pb | (uintptr_t)sa | (uintptr_t)sb) & 3) == 0);
     int d[N][N];
@@ -129,9 +220,16 @@ static int launch_satd(const uint8_t *a, ptrdiff_t sa, const uint8_t *b, ptrdiff
 {
     if (g.n == 0) return 0;
     const unsigned grid = (unsigned)((g.n + 127) / 128);
-    if (log2size == 1) return launch(satd_kernel<1>, grid, 128, 0, stream, a, sa, b, sb, fs_a, fs_b, g, out);
-    if (log2size == 2) return launch(satd_kernel<2>, grid, 128, 0, stream, a, sa, b, sb, fs_a, fs_b, g, out);
-    return launch(satd_kernel<3>, grid, 128, 0, stream, a, sa, b, sb, fs_a, fs_b, g, out);
+    // byte-wise kernels: every row of every block starts on a 4-byte boundary (regular grids of 4x4 / 8x8 blocks on 4-byte aligned planes)
+    uintptr_t m = (uintptr_t)a | (uintptr_t)b | (uintptr_t)sa | (uintptr_t)sb;
+    if (g.n > g.nbx * (long long)g.nby) m |= (uintptr_t)fs_a | (uintptr_t)fs_b;
+    const bool bytewise = !g.blk_xy && (m & 3) == 0 && !getenv("HEVCASM_SATD_GENERIC");
+    if (log2size == 1) return launch(satd_generic_kernel<1>, grid, 128, 0, stream, a, sa, b, sb, fs_a, fs_b, g, out);
+    if (log2size == 2)
+        return bytewise ? launch(satd_kernel<2>, grid, 128, 0, stream, a, sa, b, sb, fs_a, fs_b, g, out)
+                        : launch(satd_generic_kernel<2>, grid, 128, 0, stream, a, sa, b, sb, fs_a, fs_b, g, out);
+    return bytewise ? launch(satd_kernel<3>, grid, 128, 0, stream, a, sa, b, sb, fs_a, fs_b, g, out)
+                    : launch(satd_generic_kernel<3>, grid, 128, 0, stream, a, sa, b, sb, fs_a, fs_b, g, out);
 }
 
 extern "C" int hevcasm_hadamard_satd_batch(const uint8_t *a, ptrdiff_t sa, const uint8_t *b, ptrdiff_t sb, int log2size, const int16_t *blk_xy, int n,
@@ -139,6 +237,7 @@ extern "C" int hevcasm_hadamard_satd_batch(const uint8_t *a, ptrdiff_t sa, const
 {
     if (log2size < 1 || log2size > 3 || n < 0 || (n > 0 && !blk_xy)) return HEVCASM_ERR_ARGUMENT;
     SatdGrid g{blk_xy, 0, 0, n};
+    g.finish();
     return launch_satd(a, sa, b, sb, 0, 0, log2size, g, satd, stream);
 }
 
@@ -148,6 +247,7 @@ extern "C" int hevcasm_hadamard_satd_frames(const uint8_t *a, ptrdiff_t sa, cons
     if (log2size < 1 || log2size > 3 || n_frames < 0 || width < 0 || height < 0) return HEVCASM_ERR_ARGUMENT;
     SatdGrid g{nullptr, width >> log2size, height >> log2size, 0};
     g.n = (long long)g.nbx * g.nby * n_frames;
+    g.finish();
     return launch_satd(a, sa, b, sb, fs_a, fs_b, log2size, g, satd, stream);
 }
 

@@ -21,6 +21,8 @@ cbf = torch.empty((n // 16,), dtype=torch.int32, device="cuda")
 def d(t, off=0): return C.c_void_p(t.data_ptr() + off * t.element_size())
 calls = {
     "pred_hv": lambda: lib.call("pred_uni_frames", d(o8, org), pitch, d(a, org), pitch, W, H, 8, 1, 3, NF, fs, fs),
+    "satd4": lambda: lib.call("hadamard_satd_frames", d(a, org), pitch, d(b, org), pitch, W, H, 2, NF, fs, fs, d(cbf)),
+    "satd8": lambda: lib.call("hadamard_satd_frames", d(a, org), pitch, d(b, org), pitch, W, H, 3, NF, fs, fs, d(cbf)),
     "pred_copy": lambda: lib.call("pred_uni_frames", d(o8, org), pitch, d(a, org), pitch, W, H, 8, 0, 0, NF, fs, fs),
     "pred_h": lambda: lib.call("pred_uni_frames", d(o8, org), pitch, d(a, org), pitch, W, H, 8, 1, 0, NF, fs, fs),
     "pred_v": lambda: lib.call("pred_uni_frames", d(o8, org), pitch, d(a, org), pitch, W, H, 8, 0, 2, NF, fs, fs),
