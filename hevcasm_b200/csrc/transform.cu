@@ -161,8 +161,9 @@ __device__ __forceinline__ void store_words(void *ptr, const uint32_t *w)
 // four reconstructed samples: clip8(pred byte + (r >> 12)), packed
 __device__ __forceinline__ uint32_t recon_word(uint32_t pw, const int *r)
 {
-    return pack_sat_u8((int)(pw & 0xff) + (r[0] >> 12), (int)((pw >> 8) & 0xff) + (r[1] >> 12), (int)((pw >> 16) & 0xff) + (r[2] >> 12),
-                       (int)(pw >> 24) + (r[3] >> 12));
+    // the predictor byte is picked out of its word and added by one IDP.4A (pattern 1 in byte j) on the FMA pipe
+    return pack_sat_u8((int)dp4a_uu(pw, 0x00000001u, (uint32_t)(r[0] >> 12)), (int)dp4a_uu(pw, 0x00000100u, (uint32_t)(r[1] >> 12)),
+                       (int)dp4a_uu(pw, 0x00010000u, (uint32_t)(r[2] >> 12)), (int)dp4a_uu(pw, 0x01000000u, (uint32_t)(r[3] >> 12)));
 }
 
 // ================================================================================================ 4x4 / 8x8
