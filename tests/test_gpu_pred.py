@@ -47,6 +47,18 @@ def test_generic_plane_kernels_all_fractions(oracle, taps, monkeypatch):
     test_bi_planes(oracle, taps)
 
 
+@pytest.mark.parametrize("env", [{"HEVCASM_PRED_STREAM": "ldg"}, {"HEVCASM_PRED_STREAM": "ldg", "HEVCASM_PRED_PATH": "stream"}, {"HEVCASM_PRED_PATH": "tile"}])
+@pytest.mark.parametrize("taps", [8, 4])
+def test_fallback_plane_kernels_all_fractions(oracle, taps, env, monkeypatch):
+    """the kernels behind the TMA-fed one: LDG-fed streaming kernel (planes the TMA unit cannot describe) and the shared-memory
+    tile kernels, each forced on planes the default dispatch would hand to the TMA kernel"""
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    test_uni_planes_all_fractions(oracle, taps, (200, 136))
+    test_uni_planes_all_fractions(oracle, taps, (131, 37))
+    test_bi_planes(oracle, taps)
+
+
 @pytest.mark.parametrize("taps", [8, 4])
 def test_uni_planes_unaligned_pointers(oracle, taps):
     """destination and reference origins at odd byte offsets, odd pitch"""
