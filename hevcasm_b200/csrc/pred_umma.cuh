@@ -1,0 +1,217 @@
+// hevcasm_b200 - two-pass interpolation positions with the HORIZONTAL pass on the 5th-generation tensor cores.
+// (included by pred.cu inside namespace hv::ip, after PredParams / PackedCoefs / pack16 / dp2a_lo)
+//
+// The streaming kernels spend 6.1 IDP + 8 other instructions per two-pass sample and are bound by the FMA pipe and by
+// issue slots (profiles/r01_pred.md).  The horizontal pass is a banded matrix product, and int8 x int8 -> int32 is exactly
+// what tcgen05.mma kind::i8 computes:
+//     D[m][n] = sum_k A[m][k] * B[k][n],   m = output column of the tile (128), n = row of the tile (80), k = input column (160)
+//     A[m][k] = tap[k - m - (16 - LEFT)]   (a Toeplitz band, s8, built once per CTA in shared memory, K-major)
+//     B[k][n] = ref[y0 - TOP + n][x0 - 16 + k]   (u8: the image rows themselves, K-major as they lie in memory)
+// The image operand arrives by two TMA boxes per tile - {128 bytes x 80 rows} with the 128-byte swizzle (K-steps 0..3) and
+// {32 bytes x 80 rows} with the 32-byte swizzle (K-step 4) - which land as the tensor cores' swizzled K-major operand
+// form, so no thread ever touches an input byte.  (A single 4-D box (16 bytes, rows, 16-byte chunks) gives the no-swizzle
+// form and is just as exact, but its 800 16-byte pieces per tile throttle the TMA unit: 166 us per 16 4K planes.)  Five
+// K-steps of 32 accumulate the 160 input columns.  The exact horizontal sums come back from TMEM with thread = output
+// column, 16 rows per tcgen05.ld - precisely the "thread walks down its column" form the vertical pass wants: pairs of
+// consecutive rows in a register ring, IDP.2A with the vertical taps, rounding shift, clip.  What remains on the CUDA
+// cores per sample is 4 IDP.2A + 1 PRMT + ~4.  tools/umma_fir_probe.cu pinned the TMA stride order and the descriptors.
+#pragma once
+
+namespace um {
+
+constexpr int TCOLS = 128;                 // output columns per tile = MMA M = TMEM lanes = threads
+constexpr int TROWS = 72;                  // output rows per tile
+constexpr int NROWS = 80;                  // MMA N: staged rows (TROWS + TAPS - 1 <= 80, a multiple of 16)
+constexpr int KBYTES = 160, KCH = KBYTES / 16;   // staged bytes per row: 16 left of the tile + 128 + 16
+constexpr int A_BYTES = TCOLS * KBYTES;    // 20480: Toeplitz operand, [chunk][m][16]
+constexpr int B1_BYTES = NROWS * 128, B2_BYTES = NROWS * 32;   // image operand: 128-byte-swizzled part (k < 128), 32-byte-swizzled part (k >= 128)
+constexpr int B_BYTES = 13 * 1024;         // one staged operand (12800 bytes), padded so that every one starts on a 1024-byte boundary
+constexpr int STAGES = 2;
+
+struct alignas(64) Params {
+    CUtensorMap tm128[2], tm32[2];   // per reference: bytes from x = -16, rows from -(TAPS/2-1), frames; boxes of 128 / 32 bytes x NROWS rows
+    uint8_t *dst;
+    ptrdiff_t sd, fs_dst;
+    int width, height;
+    int dst16;                // destination rows are 16-byte aligned (pointer and strides): 128-bit stores
+    int tiles_x, tiles_y, n_tiles;
+    int8_t xtap[2][8];        // horizontal taps per reference
+    int y2[2][4];             // vertical tap pairs per reference (PackedCoefs::y2)
+};
+
+// One CTA per SM holds NWG independent WARPGROUPS of 128 threads (6, or 3 for bi-prediction).  Each warpgroup walks over its own
+// tiles with its own image stages, barriers and accumulator columns, so the tensor-core latency of one overlaps the
+// vertical passes of the others; they share the Toeplitz operand and one 512-column TMEM allocation.
+template <int TAPS, bool BI>
+struct Geom {
+    static constexpr int NREF = BI ? 2 : 1, NWG = BI ? 3 : 6;
+    static constexpr int WG_BYTES = STAGES * NREF * B_BYTES;       // image stages of one warpgroup
+    static constexpr int BAR_OFF = NREF * A_BYTES + NWG * WG_BYTES;
+    static constexpr int SMEM_BYTES = 1024 + BAR_OFF + NWG * 32 + 16;   // alignment slack + operands + per-warpgroup barriers + the TMEM slot
+    static constexpr int ACC_COLS = BI ? 160 : 80;                 // accumulator columns per warpgroup (reference r at + 80 r)
+    static constexpr int THREADS = NWG * TCOLS;
+};
+
+// The vertical pass of one tile for one thread (= one output column).  Everything about the row index is compile-time (the
+// 80 staged rows are fully unrolled), the output byte goes to shared memory at an immediate offset.
+template <int TAPS, bool BI>
+__device__ __forceinline__ void vertical_pass(const Params &P, uint32_t tlane, uint8_t *ocol /* obuf + column */)
+{
+    constexpr int NREF = BI ? 2 : 1;
+    uint32_t ring[NREF][TAPS];
+    int prev[NREF];
+#pragma unroll
+    for (int rf = 0; rf < NREF; ++rf) {
+        prev[rf] = 0;
+#pragma unroll
+        for (int k = 0; k < TAPS; ++k) ring[rf][k] = 0;
+    }
+    int y2[NREF][TAPS / 2];
+#pragma unroll
+    for (int rf = 0; rf < NREF; ++rf)
+#pragma unroll
+        for (int g = 0; g < TAPS / 2; ++g) y2[rf][g] = P.y2[rf][g];
+#pragma unroll
+    for (int c = 0; c < NROWS / 16; ++c) {
+        int v[NREF][16];
+#pragma unroll
+        for (int rf = 0; rf < NREF; ++rf) umma::tmem_ld16(tlane + NROWS * rf + 16 * c, v[rf]);
+        umma::tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+            const int r = 16 * c + j, y = r - (TAPS - 1);   // staged row, output row
+#pragma unroll
+            for (int rf = 0; rf < NREF; ++rf) {
+                ring[rf][r % TAPS] = pack16(prev[rf], v[rf][j]);   // pair (r-1, r)
+                prev[rf] = v[rf][j];
+            }
+            if (y < 0 || y >= TROWS) continue;
+            // output row y takes the pairs ending at rows y+1, y+3, .. = slots (r + 2 + 2g) mod TAPS
+            int acc[NREF];
+#pragma unroll
+            for (int rf = 0; rf < NREF; ++rf) {
+                int a = BI ? 0 : 2048;
+#pragma unroll
+                for (int g = 0; g < TAPS / 2; ++g) a = dp2a_lo(ring[rf][(r + 2 + 2 * g) % TAPS], y2[rf][g], a);
+                acc[rf] = a;
+            }
+            int o;
+            if (BI) o = ((int)(short)(acc[0] >> 6) + (int)(short)(acc[NREF - 1] >> 6) + 64) >> 7;   // int16 wrap as in the reference's C
+            else o = acc[0] >> 12;
+            ocol[y * TCOLS] = (uint8_t)__vimin_s32_relu(o, 255);   // clip to [0, 255]: one VIMNMX
+        }
+    }
+}
+
+template <int TAPS, bool BI>
+__global__ void __launch_bounds__(Geom<TAPS, BI>::THREADS, 1) pred_umma_kernel(const __grid_constant__ Params P)
+{
+    using G = Geom<TAPS, BI>;
+    constexpr int NREF = G::NREF, NWG = G::NWG, LEFT = TAPS / 2 - 1;
+    static_assert(TROWS + TAPS - 1 <= NROWS && 16 % TAPS == 0 && NWG * G::ACC_COLS <= 512, "tile rows / TMEM columns");
+    extern __shared__ __align__(128) uint8_t us_raw[];
+    uint8_t *const us_smem = us_raw + ((1024 - (tma::smem_u32(us_raw) & 1023)) & 1023);   // the 128-byte swizzle atoms sit on 1024-byte boundaries
+    const int wg = threadIdx.x / TCOLS, tid = threadIdx.x - wg * TCOLS, warp = tid >> 5;   // warpgroup, thread and warp inside it
+    uint8_t *const sA = us_smem;
+    uint8_t *const sB = us_smem + NREF * A_BYTES + wg * G::WG_BYTES;
+    uint64_t *const full = reinterpret_cast<uint64_t *>(us_smem + G::BAR_OFF + wg * 32);   // [STAGES] of this warpgroup
+    uint64_t *const done = full + STAGES;                                                  // MMA completion of this warpgroup
+    uint32_t *const tmem_slot = reinterpret_cast<uint32_t *>(us_smem + G::BAR_OFF + NWG * 32);
+    auto wg_sync = [&]() { asm volatile("bar.sync %0, %1;" ::"r"(1 + wg), "n"(TCOLS) : "memory"); };
+
+    // Toeplitz bands: output column m reads staged bytes m + (16 - LEFT) .. + TAPS - 1
+    for (int i = threadIdx.x; i < NREF * A_BYTES; i += G::THREADS) {
+        const int rf = i / A_BYTES, j = i - rf * A_BYTES, m = j / KBYTES, k = j - m * KBYTES, t = k - m - (16 - LEFT);
+        sA[rf * A_BYTES + (k >> 4) * (TCOLS * 16) + m * 16 + (k & 15)] = (t >= 0 && t < TAPS) ? (uint8_t)P.xtap[rf][t] : 0;
+    }
+    if (tid == 0) {
+#pragma unroll
+        for (int s = 0; s < STAGES; ++s) tma::mbar_init(full + s, 1);
+        tma::mbar_init(done, 1);
+    }
+    if (threadIdx.x < 32) umma::tmem_alloc<512>(tmem_slot);
+    umma::fence_async_smem();
+    umma::fence_before();
+    __syncthreads();
+    umma::fence_after();
+    const uint32_t tm = *tmem_slot + wg * G::ACC_COLS, tlane = tm + ((uint32_t)(warp * 32) << 16);
+    constexpr uint32_t IDESC = umma::idesc_i8(true, false, false, NROWS);   // A = taps (s8), B = image (u8), both K-major
+
+    auto tile_xyf = [&](int t, int &bx, int &by, int &f) {
+        const int per = P.tiles_x * P.tiles_y;
+        f = t / per;
+        const int r = t - f * per;
+        by = r / P.tiles_x, bx = r - by * P.tiles_x;
+    };
+    auto request = [&](int t, int s) {   // thread 0 of the warpgroup: the image boxes of tile t into stage s
+        int bx, by, f;
+        tile_xyf(t, bx, by, f);
+        tma::mbar_expect_tx(full + s, NREF * (B1_BYTES + B2_BYTES));
+#pragma unroll
+        for (int rf = 0; rf < NREF; ++rf) {
+            uint8_t *b = sB + (s * NREF + rf) * B_BYTES;
+            tma::load_box_3d(b, &P.tm128[rf], bx * TCOLS, by * TROWS, f, full + s);
+            tma::load_box_3d(b + B1_BYTES, &P.tm32[rf], bx * TCOLS + 128, by * TROWS, f, full + s);
+        }
+    };
+    const int t0 = blockIdx.x * NWG + wg, tstep = gridDim.x * NWG;
+    if (tid == 0 && t0 < P.n_tiles) request(t0, 0);
+
+    int it = 0;
+#pragma unroll 1
+    for (int t = t0; t < P.n_tiles; t += tstep, ++it) {
+        const int s = it & 1;
+        int bx, by, f;
+        tile_xyf(t, bx, by, f);
+        if (tid == 0) {
+            // the other stage was read by the MMAs of the previous tile, whose completion every thread observed: refill it now,
+            // so the next tile's rows travel during this tile's MMAs and vertical pass
+            if (t + tstep < P.n_tiles) request(t + tstep, s ^ 1);
+            tma::mbar_wait(full + s, (it >> 1) & 1);
+            umma::fence_after();
+#pragma unroll
+            for (int rf = 0; rf < NREF; ++rf)
+#pragma unroll
+                for (int ks = 0; ks < KBYTES / 32; ++ks) {
+                    // A: K-major, no swizzle (LBO = distance between 16-byte k chunks, SBO = between groups of 8 rows).  B: swizzled K-major,
+                    // groups of 8 rows 1024 (256) bytes apart; a K-step advances the start address by 32 bytes inside the swizzle row
+                    const uint64_t da = umma::smem_desc(tma::smem_u32(sA + rf * A_BYTES + ks * 2 * (TCOLS * 16)), TCOLS * 16, 128);
+                    const uint32_t bb = tma::smem_u32(sB + (s * NREF + rf) * B_BYTES);
+                    const uint64_t db = ks < 4 ? umma::smem_desc(bb + ks * 32, 16, 1024, 2) : umma::smem_desc(bb + B1_BYTES, 16, 256, 6);
+                    umma::mma_i8(tm + NROWS * rf, da, db, IDESC, ks);
+                }
+            umma::commit(done);
+        }
+        tma::mbar_wait(done, it & 1);
+        umma::fence_after();
+
+        // ---- vertical pass: this thread owns output column x = bx * 128 + tid; rows arrive 16 at a time.  Output bytes go to a
+        // row-major 128-byte-pitch buffer that aliases this tile's (already consumed) image stage, then leave as 16-byte stores.
+        uint8_t *const obuf = sB + (s * NREF) * B_BYTES;
+        vertical_pass<TAPS, BI>(P, tlane, obuf + tid);
+        wg_sync();
+        {
+            const int x0 = bx * TCOLS, y0 = by * TROWS, rows = min(TROWS, P.height - y0), cols = min(TCOLS, P.width - x0);
+            uint8_t *d = P.dst + f * P.fs_dst + (ptrdiff_t)y0 * P.sd + x0;
+            if (P.dst16 && cols == TCOLS) {
+                // 8 chunks of 16 bytes per row: thread -> (row, chunk), consecutive threads consecutive chunks
+#pragma unroll 1
+                for (int i = tid; i < rows * 8; i += TCOLS) {
+                    const int r = i >> 3, ch = i & 7;
+                    *reinterpret_cast<uint4 *>(d + (ptrdiff_t)r * P.sd + 16 * ch) = *reinterpret_cast<const uint4 *>(obuf + r * TCOLS + 16 * ch);
+                }
+            } else if (tid < cols) {
+#pragma unroll 1
+                for (int r = 0; r < rows; ++r) d[(ptrdiff_t)r * P.sd + tid] = obuf[r * TCOLS + tid];
+            }
+        }
+        umma::fence_async_smem();   // generic-proxy accesses of this stage before the TMA refill two tiles on
+        umma::fence_before();       // this tile's TMEM reads are complete before the next tile's MMAs overwrite the accumulator
+        wg_sync();
+    }
+    umma::fence_before();
+    __syncthreads();
+    if (threadIdx.x < 32) umma::tmem_dealloc<512>(*tmem_slot);
+}
+
+}  // namespace um

@@ -68,6 +68,42 @@ inline int describe_u32(CUtensorMap *map, const uint8_t *first, ptrdiff_t row_st
     return describe_bytes(map, first, row_stride, frame_stride, extent_x, extent_y, n_frames, box_x, box_y, x_shift, 4);
 }
 
+// Byte planes whose boxes land in shared memory in the tensor cores' swizzled K-major form: box_x = 128 -> 128-byte swizzle
+// (destination 1024-byte aligned), box_x = 32 -> 32-byte swizzle (256-byte aligned).  `base` must be 16-byte aligned.
+inline int describe_u8_swizzled(CUtensorMap *map, const uint8_t *base, ptrdiff_t row_stride, ptrdiff_t frame_stride, long long extent_x, long long extent_y,
+                                int n_frames, int box_x, int box_y)
+{
+    if (((uintptr_t)base & 15) != 0 || (box_x != 128 && box_x != 32)) return (int)cudaErrorInvalidValue;
+    if (n_frames <= 1) frame_stride = row_stride * (ptrdiff_t)extent_y;
+    if (extent_x > (long long)row_stride) extent_x = (long long)row_stride;
+    cuuint64_t dim[3] = {(cuuint64_t)extent_x, (cuuint64_t)extent_y, (cuuint64_t)(n_frames < 1 ? 1 : n_frames)};
+    cuuint64_t stride[2] = {(cuuint64_t)row_stride, (cuuint64_t)frame_stride};
+    cuuint32_t box[3] = {(cuuint32_t)box_x, (cuuint32_t)box_y, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    const CUresult r = encoder()(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, (void *)base, dim, stride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                 box_x == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                                 CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? 0 : (int)cudaErrorInvalidValue;
+}
+
+// The same planes as a 4-D tensor (16 bytes, rows, 16-byte chunks of a row, frames): a box {16, R, C, 1} then lands in shared
+// memory as [chunk][row][16 bytes] - the tensor cores' no-swizzle K-major core-matrix layout (8 rows x 16 bytes contiguous,
+// chunks R*16 bytes apart).  `base` must be 16-byte aligned; the encoder accepts the (row stride, 16) stride order
+// (tools/umma_fir_probe.cu).
+inline int describe_u8_chunks(CUtensorMap *map, const uint8_t *base, ptrdiff_t row_stride, ptrdiff_t frame_stride, long long rows, long long chunks, int n_frames,
+                              int box_rows, int box_chunks)
+{
+    if (((uintptr_t)base & 15) != 0) return (int)cudaErrorInvalidValue;
+    if (n_frames <= 1) frame_stride = row_stride * (ptrdiff_t)rows;
+    cuuint64_t dim[4] = {16, (cuuint64_t)rows, (cuuint64_t)chunks, (cuuint64_t)(n_frames < 1 ? 1 : n_frames)};
+    cuuint64_t stride[3] = {(cuuint64_t)row_stride, 16, (cuuint64_t)frame_stride};
+    cuuint32_t box[4] = {16, (cuuint32_t)box_rows, (cuuint32_t)box_chunks, 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    const CUresult r = encoder()(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 4, (void *)base, dim, stride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                 CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? 0 : (int)cudaErrorInvalidValue;
+}
+
 // ---- device ----------------------------------------------------------------------------------------------------
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }

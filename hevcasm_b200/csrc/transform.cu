@@ -14,6 +14,7 @@
 // and for the same reason the int16 truncation inside hevcasm_clip (:350-356) is the identity.
 #include "transform.cuh"
 #include "tma.cuh"
+#include "umma.cuh"
 #include "transform_imma.cuh"
 
 #include <algorithm>

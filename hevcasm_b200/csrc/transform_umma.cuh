@@ -20,62 +20,9 @@
 // stage 1 that is row u of block b, whose N values over y are again 16-byte chunks of the stage-2 operand; in stage 2 it
 // is one row of N output samples, to which the thread adds its predictor row and which it stores as N contiguous bytes.
 // The matrix-descriptor fields were pinned with tools/umma_probe.cu before this kernel was written.
-// (included by transform.cu inside namespace hv, after BlockGrid / load_words / store_words)
+// (included by transform.cu inside namespace hv, after BlockGrid / load_words / store_words; the tcgen05 wrappers are in umma.cuh)
 #pragma once
 
-namespace umma {
-
-// shared-memory matrix descriptor, no swizzle (LBO / SBO in bytes, multiples of 16)
-//   MN-major operand: LBO = distance between groups of 8 k, SBO = distance between chunks of 16 m
-//   K-major operand : LBO = distance between chunks of 16 k, SBO = distance between groups of 8 n
-__device__ __forceinline__ uint64_t smem_desc(uint32_t addr, uint32_t lbo, uint32_t sbo)
-{
-    return (uint64_t)((addr >> 4) & 0x3fff) | ((uint64_t)((lbo >> 4) & 0x3fff) << 16) | ((uint64_t)((sbo >> 4) & 0x3fff) << 32) | ((uint64_t)1 << 46);
-}
-// instruction descriptor: D s32, A u8/s8 MN-major, B s8 K-major, M = 128, N = n
-__host__ __device__ constexpr uint32_t idesc_i8(bool a_signed, int n)
-{
-    return (2u << 4) | ((a_signed ? 1u : 0u) << 7) | (1u << 10) | (1u << 15) | ((uint32_t)(n >> 3) << 17) | ((128u >> 4) << 24);
-}
-__device__ __forceinline__ void mma_i8(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc)
-{
-    asm volatile(
-        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
-        "l"(da), "l"(db), "r"(idesc), "r"(0)
-        : "memory");
-}
-// all MMAs issued so far by this thread -> one arrival on `bar` when they have completed (implies fence::before_thread_sync)
-__device__ __forceinline__ void commit(uint64_t *bar)
-{
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(tma::smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-template <int COLS>
-__device__ __forceinline__ void tmem_alloc(uint32_t *slot)   // one whole warp
-{
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tma::smem_u32(slot)), "n"(COLS) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-}
-template <int COLS>
-__device__ __forceinline__ void tmem_dealloc(uint32_t addr)  // the same warp
-{
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "n"(COLS) : "memory");
-}
-// 16 consecutive columns of this thread's TMEM lane (warp w reads lanes 32w .. 32w+31)
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, int (&v)[16])
-{
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]),
-          "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
-        : "r"(taddr));
-}
-__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-
-}  // namespace umma
 
 constexpr int UMMA_NT = 128;
 
@@ -115,7 +62,7 @@ __global__ void __launch_bounds__(UMMA_NT, 6) umma_inv_kernel(uint8_t *__restric
     const uint32_t tm = tmem_slot, tlane = tm + ((uint32_t)(warp * 32) << 16);
     const uint64_t desc_lo = umma::smem_desc(tma::smem_u32(sA), KG, SBO), desc_hi = umma::smem_desc(tma::smem_u32(sA + A_BYTES), KG, SBO);
     const uint64_t desc_b = umma::smem_desc(tma::smem_u32(sB), 128, 256);
-    constexpr uint32_t ID_LO = umma::idesc_i8(false, N), ID_HI = umma::idesc_i8(true, N);
+    constexpr uint32_t ID_LO = umma::idesc_i8(false, true, true, N), ID_HI = umma::idesc_i8(true, true, true, N);
 
     const long long n_groups = (grid.n + BPG - 1) / BPG;
     uint32_t phase = 0;
