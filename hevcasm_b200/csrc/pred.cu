@@ -1241,7 +1241,11 @@ static bool umma_params(um::Params *u, const PredParams &p, int taps, bool bi, i
         for (int k = 0; k < 8; ++k) u->xtap[rf][k] = k < taps ? (int8_t)((c.x4[k >> 2] >> (8 * (k & 3))) & 0xff) : 0;
     }
     u->dst = p.dst, u->sd = p.sd, u->fs_dst = p.fs_dst, u->width = p.width, u->height = p.height;
-    u->dst16 = (((uintptr_t)p.dst | (uintptr_t)p.sd | (n_frames > 1 ? (uintptr_t)p.fs_dst : 0)) & 15) == 0;
+    u->dst16 = (((uintptr_t)p.dst | (uintptr_t)p.sd | (n_frames > 1 ? (uintptr_t)p.fs_dst : 0)) & 15) == 0 && p.sd > 0 && (n_frames <= 1 || p.fs_dst > 0);
+    if (u->dst16) {
+        int shift = 0;
+        if (tma::describe_u8(&u->tmdst, p.dst, p.sd, p.fs_dst, p.width, p.height, n_frames, um::TCOLS, um::TROWS, &shift) || shift) u->dst16 = 0;
+    }
     u->tiles_x = (p.width + um::TCOLS - 1) / um::TCOLS, u->tiles_y = (p.height + um::TROWS - 1) / um::TROWS;
     u->n_tiles = (int)(per * n_frames);
     return true;

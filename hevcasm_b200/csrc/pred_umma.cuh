@@ -26,38 +26,41 @@ constexpr int KBYTES = 160, KCH = KBYTES / 16;   // staged bytes per row: 16 lef
 constexpr int A_BYTES = TCOLS * KBYTES;    // 20480: Toeplitz operand, [chunk][m][16]
 constexpr int B1_BYTES = NROWS * 128, B2_BYTES = NROWS * 32;   // image operand: 128-byte-swizzled part (k < 128), 32-byte-swizzled part (k >= 128)
 constexpr int B_BYTES = 13 * 1024;         // one staged operand (12800 bytes), padded so that every one starts on a 1024-byte boundary
-constexpr int STAGES = 2;
+constexpr int O_BYTES = TROWS * TCOLS;     // one output tile, row-major
 
 struct alignas(64) Params {
     CUtensorMap tm128[2], tm32[2];   // per reference: bytes from x = -16, rows from -(TAPS/2-1), frames; boxes of 128 / 32 bytes x NROWS rows
+    CUtensorMap tmdst;               // destination planes, boxes of TCOLS bytes x TROWS rows (valid when dst16)
     uint8_t *dst;
     ptrdiff_t sd, fs_dst;
     int width, height;
-    int dst16;                // destination rows are 16-byte aligned (pointer and strides): 128-bit stores
+    int dst16;                // destination rows are 16-byte aligned (pointer and strides): tiles leave by TMA store
     int tiles_x, tiles_y, n_tiles;
     int8_t xtap[2][8];        // horizontal taps per reference
     int y2[2][4];             // vertical tap pairs per reference (PackedCoefs::y2)
 };
 
 // One CTA per SM holds NWG independent WARPGROUPS of 128 threads (6, or 3 for bi-prediction).  Each warpgroup walks over its own
-// tiles with its own image stages, barriers and accumulator columns, so the tensor-core latency of one overlaps the
-// vertical passes of the others; they share the Toeplitz operand and one 512-column TMEM allocation.
+// tiles with its own image stage, output buffers, barriers and accumulator columns, so the tensor-core and TMA latency of one
+// overlaps the vertical passes of the others; they share the Toeplitz operand and one 512-column TMEM allocation.
 template <int TAPS, bool BI>
 struct Geom {
     static constexpr int NREF = BI ? 2 : 1, NWG = BI ? 3 : 6;
-    static constexpr int WG_BYTES = STAGES * NREF * B_BYTES;       // image stages of one warpgroup
+    static constexpr int WG_BYTES = NREF * B_BYTES + 2 * O_BYTES;  // image stage + two output buffers of one warpgroup
     static constexpr int BAR_OFF = NREF * A_BYTES + NWG * WG_BYTES;
-    static constexpr int SMEM_BYTES = 1024 + BAR_OFF + NWG * 32 + 16;   // alignment slack + operands + per-warpgroup barriers + the TMEM slot
+    static constexpr int SMEM_BYTES = 1024 + BAR_OFF + NWG * 16 + 16;   // alignment slack + operands + per-warpgroup barriers + the TMEM slot
     static constexpr int ACC_COLS = BI ? 160 : 80;                 // accumulator columns per warpgroup (reference r at + 80 r)
     static constexpr int THREADS = NWG * TCOLS;
 };
 
 // The vertical pass of one tile for one thread (= one output column).  Everything about the row index is compile-time (the
-// 80 staged rows are fully unrolled), the output byte goes to shared memory at an immediate offset.
+// 80 staged rows are fully unrolled), the output byte goes to shared memory at an immediate offset.  The horizontal sums
+// arrive 8 rows per tcgen05.ld; the load of the next 8 is in flight while these 8 are consumed.
 template <int TAPS, bool BI>
 __device__ __forceinline__ void vertical_pass(const Params &P, uint32_t tlane, uint8_t *ocol /* obuf + column */)
 {
-    constexpr int NREF = BI ? 2 : 1;
+    constexpr int NREF = BI ? 2 : 1, CH = 8, NCH = NROWS / CH;
+    static_assert(CH % TAPS == 0, "ring slots must be compile-time");
     uint32_t ring[NREF][TAPS];
     int prev[NREF];
 #pragma unroll
@@ -71,19 +74,24 @@ __device__ __forceinline__ void vertical_pass(const Params &P, uint32_t tlane, u
     for (int rf = 0; rf < NREF; ++rf)
 #pragma unroll
         for (int g = 0; g < TAPS / 2; ++g) y2[rf][g] = P.y2[rf][g];
+    int v[2][NREF][CH];
 #pragma unroll
-    for (int c = 0; c < NROWS / 16; ++c) {
-        int v[NREF][16];
+    for (int rf = 0; rf < NREF; ++rf) umma::tmem_ld8(tlane + NROWS * rf, v[0][rf]);
 #pragma unroll
-        for (int rf = 0; rf < NREF; ++rf) umma::tmem_ld16(tlane + NROWS * rf + 16 * c, v[rf]);
-        umma::tmem_ld_wait();
+    for (int rf = 0; rf < NREF; ++rf) umma::tmem_ld_wait(v[0][rf]);
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-            const int r = 16 * c + j, y = r - (TAPS - 1);   // staged row, output row
+    for (int c = 0; c < NCH; ++c) {
+        if (c + 1 < NCH) {
+#pragma unroll
+            for (int rf = 0; rf < NREF; ++rf) umma::tmem_ld8(tlane + NROWS * rf + CH * (c + 1), v[(c + 1) & 1][rf]);
+        }
+#pragma unroll
+        for (int j = 0; j < CH; ++j) {
+            const int r = CH * c + j, y = r - (TAPS - 1);   // staged row, output row
 #pragma unroll
             for (int rf = 0; rf < NREF; ++rf) {
-                ring[rf][r % TAPS] = pack16(prev[rf], v[rf][j]);   // pair (r-1, r)
-                prev[rf] = v[rf][j];
+                ring[rf][r % TAPS] = pack16(prev[rf], v[c & 1][rf][j]);   // pair (r-1, r)
+                prev[rf] = v[c & 1][rf][j];
             }
             if (y < 0 || y >= TROWS) continue;
             // output row y takes the pairs ending at rows y+1, y+3, .. = slots (r + 2 + 2g) mod TAPS
@@ -100,6 +108,10 @@ __device__ __forceinline__ void vertical_pass(const Params &P, uint32_t tlane, u
             else o = acc[0] >> 12;
             ocol[y * TCOLS] = (uint8_t)__vimin_s32_relu(o, 255);   // clip to [0, 255]: one VIMNMX
         }
+        if (c + 1 < NCH) {
+#pragma unroll
+            for (int rf = 0; rf < NREF; ++rf) umma::tmem_ld_wait(v[(c + 1) & 1][rf]);
+        }
     }
 }
 
@@ -108,25 +120,31 @@ __global__ void __launch_bounds__(Geom<TAPS, BI>::THREADS, 1) pred_umma_kernel(c
 {
     using G = Geom<TAPS, BI>;
     constexpr int NREF = G::NREF, NWG = G::NWG, LEFT = TAPS / 2 - 1;
-    static_assert(TROWS + TAPS - 1 <= NROWS && 16 % TAPS == 0 && NWG * G::ACC_COLS <= 512, "tile rows / TMEM columns");
+    static_assert(TROWS + TAPS - 1 <= NROWS && NWG * G::ACC_COLS <= 512, "tile rows / TMEM columns");
     extern __shared__ __align__(128) uint8_t us_raw[];
     uint8_t *const us_smem = us_raw + ((1024 - (tma::smem_u32(us_raw) & 1023)) & 1023);   // the 128-byte swizzle atoms sit on 1024-byte boundaries
     const int wg = threadIdx.x / TCOLS, tid = threadIdx.x - wg * TCOLS, warp = tid >> 5;   // warpgroup, thread and warp inside it
     uint8_t *const sA = us_smem;
-    uint8_t *const sB = us_smem + NREF * A_BYTES + wg * G::WG_BYTES;
-    uint64_t *const full = reinterpret_cast<uint64_t *>(us_smem + G::BAR_OFF + wg * 32);   // [STAGES] of this warpgroup
-    uint64_t *const done = full + STAGES;                                                  // MMA completion of this warpgroup
-    uint32_t *const tmem_slot = reinterpret_cast<uint32_t *>(us_smem + G::BAR_OFF + NWG * 32);
+    uint8_t *const sB = us_smem + NREF * A_BYTES + wg * G::WG_BYTES;    // image stage (NREF operands), then the two output buffers
+    uint8_t *const sO = sB + NREF * B_BYTES;
+    uint64_t *const full = reinterpret_cast<uint64_t *>(us_smem + G::BAR_OFF + wg * 16);   // image boxes of this warpgroup have landed
+    uint64_t *const done = full + 1;                                                       // MMA completion of this warpgroup
+    uint32_t *const tmem_slot = reinterpret_cast<uint32_t *>(us_smem + G::BAR_OFF + NWG * 16);
     auto wg_sync = [&]() { asm volatile("bar.sync %0, %1;" ::"r"(1 + wg), "n"(TCOLS) : "memory"); };
 
-    // Toeplitz bands: output column m reads staged bytes m + (16 - LEFT) .. + TAPS - 1
-    for (int i = threadIdx.x; i < NREF * A_BYTES; i += G::THREADS) {
-        const int rf = i / A_BYTES, j = i - rf * A_BYTES, m = j / KBYTES, k = j - m * KBYTES, t = k - m - (16 - LEFT);
-        sA[rf * A_BYTES + (k >> 4) * (TCOLS * 16) + m * 16 + (k & 15)] = (t >= 0 && t < TAPS) ? (uint8_t)P.xtap[rf][t] : 0;
+    // Toeplitz bands, one 16-byte chunk per step: output column m reads staged bytes m + (16 - LEFT) .. + TAPS - 1
+    for (int i = threadIdx.x; i < NREF * KCH * TCOLS; i += G::THREADS) {
+        const int m = i % TCOLS, kc = (i / TCOLS) % KCH, rf = i / (TCOLS * KCH);
+        uint32_t w[4] = {0, 0, 0, 0};
+#pragma unroll
+        for (int b = 0; b < 16; ++b) {
+            const int t = 16 * kc + b - m - (16 - LEFT);
+            if (t >= 0 && t < TAPS) w[b >> 2] |= (uint32_t)(uint8_t)P.xtap[rf][t] << (8 * (b & 3));
+        }
+        *reinterpret_cast<uint4 *>(sA + rf * A_BYTES + kc * (TCOLS * 16) + m * 16) = make_uint4(w[0], w[1], w[2], w[3]);
     }
     if (tid == 0) {
-#pragma unroll
-        for (int s = 0; s < STAGES; ++s) tma::mbar_init(full + s, 1);
+        tma::mbar_init(full, 1);
         tma::mbar_init(done, 1);
     }
     if (threadIdx.x < 32) umma::tmem_alloc<512>(tmem_slot);
@@ -137,37 +155,38 @@ __global__ void __launch_bounds__(Geom<TAPS, BI>::THREADS, 1) pred_umma_kernel(c
     const uint32_t tm = *tmem_slot + wg * G::ACC_COLS, tlane = tm + ((uint32_t)(warp * 32) << 16);
     constexpr uint32_t IDESC = umma::idesc_i8(true, false, false, NROWS);   // A = taps (s8), B = image (u8), both K-major
 
-    auto tile_xyf = [&](int t, int &bx, int &by, int &f) {
-        const int per = P.tiles_x * P.tiles_y;
-        f = t / per;
-        const int r = t - f * per;
-        by = r / P.tiles_x, bx = r - by * P.tiles_x;
+    // tile -> (column, row, frame) of tiles: one division at the start, additions with carries afterwards
+    const int t0 = blockIdx.x * NWG + wg, tstep = gridDim.x * NWG;
+    const int per = P.tiles_x * P.tiles_y;
+    const int sf = tstep / per, sby = (tstep - sf * per) / P.tiles_x, sbx = tstep - sf * per - sby * P.tiles_x;
+    int cf = t0 / per, cy = (t0 - cf * per) / P.tiles_x, cx = t0 - cf * per - cy * P.tiles_x;   // this tile
+    auto advance = [&](int &x, int &y, int &f) {
+        x += sbx;
+        if (x >= P.tiles_x) x -= P.tiles_x, ++y;
+        y += sby;
+        if (y >= P.tiles_y) y -= P.tiles_y, ++f;
+        f += sf;
     };
-    auto request = [&](int t, int s) {   // thread 0 of the warpgroup: the image boxes of tile t into stage s
-        int bx, by, f;
-        tile_xyf(t, bx, by, f);
-        tma::mbar_expect_tx(full + s, NREF * (B1_BYTES + B2_BYTES));
+    auto request = [&](int x, int y, int f) {   // thread 0 of the warpgroup: the image boxes of tile (x, y, f) into the stage
+        tma::mbar_expect_tx(full, NREF * (B1_BYTES + B2_BYTES));
 #pragma unroll
         for (int rf = 0; rf < NREF; ++rf) {
-            uint8_t *b = sB + (s * NREF + rf) * B_BYTES;
-            tma::load_box_3d(b, &P.tm128[rf], bx * TCOLS, by * TROWS, f, full + s);
-            tma::load_box_3d(b + B1_BYTES, &P.tm32[rf], bx * TCOLS + 128, by * TROWS, f, full + s);
+            uint8_t *b = sB + rf * B_BYTES;
+            tma::load_box_3d(b, &P.tm128[rf], x * TCOLS, y * TROWS, f, full);
+            tma::load_box_3d(b + B1_BYTES, &P.tm32[rf], x * TCOLS + 128, y * TROWS, f, full);
         }
     };
-    const int t0 = blockIdx.x * NWG + wg, tstep = gridDim.x * NWG;
-    if (tid == 0 && t0 < P.n_tiles) request(t0, 0);
+    if (tid == 0 && t0 < P.n_tiles) request(cx, cy, cf);
+    // a TMA store clips rows exactly but columns only at 16-byte granularity (measured: a 200-byte-wide plane was written up to
+    // byte 207), so a partial right-hand tile of a plane whose width is not a multiple of 16 leaves by byte stores instead
+    const bool tma_all = P.dst16 && (P.width & 15) == 0;
 
     int it = 0;
 #pragma unroll 1
     for (int t = t0; t < P.n_tiles; t += tstep, ++it) {
-        const int s = it & 1;
-        int bx, by, f;
-        tile_xyf(t, bx, by, f);
+        uint8_t *const obuf = sO + (it & 1) * O_BYTES;
         if (tid == 0) {
-            // the other stage was read by the MMAs of the previous tile, whose completion every thread observed: refill it now,
-            // so the next tile's rows travel during this tile's MMAs and vertical pass
-            if (t + tstep < P.n_tiles) request(t + tstep, s ^ 1);
-            tma::mbar_wait(full + s, (it >> 1) & 1);
+            tma::mbar_wait(full, it & 1);
             umma::fence_after();
 #pragma unroll
             for (int rf = 0; rf < NREF; ++rf)
@@ -176,39 +195,48 @@ __global__ void __launch_bounds__(Geom<TAPS, BI>::THREADS, 1) pred_umma_kernel(c
                     // A: K-major, no swizzle (LBO = distance between 16-byte k chunks, SBO = between groups of 8 rows).  B: swizzled K-major,
                     // groups of 8 rows 1024 (256) bytes apart; a K-step advances the start address by 32 bytes inside the swizzle row
                     const uint64_t da = umma::smem_desc(tma::smem_u32(sA + rf * A_BYTES + ks * 2 * (TCOLS * 16)), TCOLS * 16, 128);
-                    const uint32_t bb = tma::smem_u32(sB + (s * NREF + rf) * B_BYTES);
+                    const uint32_t bb = tma::smem_u32(sB + rf * B_BYTES);
                     const uint64_t db = ks < 4 ? umma::smem_desc(bb + ks * 32, 16, 1024, 2) : umma::smem_desc(bb + B1_BYTES, 16, 256, 6);
                     umma::mma_i8(tm + NROWS * rf, da, db, IDESC, ks);
                 }
+            // the store of the tile before last has finished reading the output buffer this tile is about to fill; everybody
+            // learns that through `done`
+            tma::store_wait_read<1>();
             umma::commit(done);
         }
         tma::mbar_wait(done, it & 1);
         umma::fence_after();
+        // the MMAs have consumed the image stage: the next tile's rows travel during this tile's vertical pass
+        if (tid == 0 && t + tstep < P.n_tiles) {
+            int x = cx, y = cy, f = cf;
+            advance(x, y, f);
+            request(x, y, f);
+        }
 
-        // ---- vertical pass: this thread owns output column x = bx * 128 + tid; rows arrive 16 at a time.  Output bytes go to a
-        // row-major 128-byte-pitch buffer that aliases this tile's (already consumed) image stage, then leave as 16-byte stores.
-        uint8_t *const obuf = sB + (s * NREF) * B_BYTES;
+        // ---- vertical pass: this thread owns output column x = cx * 128 + tid.  Output bytes go to a row-major 128-byte-pitch
+        // buffer, which leaves as one TMA store (clipped to the plane by the hardware)
         vertical_pass<TAPS, BI>(P, tlane, obuf + tid);
+        umma::fence_async_smem();   // the output bytes -> visible to the TMA store
+        umma::fence_before();       // this tile's TMEM reads are complete before the next tile's MMAs overwrite the accumulator
         wg_sync();
-        {
-            const int x0 = bx * TCOLS, y0 = by * TROWS, rows = min(TROWS, P.height - y0), cols = min(TCOLS, P.width - x0);
-            uint8_t *d = P.dst + f * P.fs_dst + (ptrdiff_t)y0 * P.sd + x0;
-            if (P.dst16 && cols == TCOLS) {
-                // 8 chunks of 16 bytes per row: thread -> (row, chunk), consecutive threads consecutive chunks
-#pragma unroll 1
-                for (int i = tid; i < rows * 8; i += TCOLS) {
-                    const int r = i >> 3, ch = i & 7;
-                    *reinterpret_cast<uint4 *>(d + (ptrdiff_t)r * P.sd + 16 * ch) = *reinterpret_cast<const uint4 *>(obuf + r * TCOLS + 16 * ch);
-                }
-            } else if (tid < cols) {
+        const int x0 = cx * TCOLS, y0 = cy * TROWS;
+        if (tma_all || (P.dst16 && x0 + TCOLS <= P.width)) {
+            if (tid == 0) {
+                tma::store_box_3d(&P.tmdst, x0, y0, cf, obuf);
+                tma::store_commit();
+            }
+        } else {
+            // byte stores, a thread per column.  (The buffer is next written two tiles on, after the barrier of the tile in between.)
+            const int rows = min(TROWS, P.height - y0), cols = min(TCOLS, P.width - x0);
+            uint8_t *d = P.dst + cf * P.fs_dst + (ptrdiff_t)y0 * P.sd + x0;
+            if (tid < cols) {
 #pragma unroll 1
                 for (int r = 0; r < rows; ++r) d[(ptrdiff_t)r * P.sd + tid] = obuf[r * TCOLS + tid];
             }
         }
-        umma::fence_async_smem();   // generic-proxy accesses of this stage before the TMA refill two tiles on
-        umma::fence_before();       // this tile's TMEM reads are complete before the next tile's MMAs overwrite the accumulator
-        wg_sync();
+        advance(cx, cy, cf);
     }
+    if (tid == 0) tma::store_wait_read<0>();   // shared memory stays valid until the last stores have read it
     umma::fence_before();
     __syncthreads();
     if (threadIdx.x < 32) umma::tmem_dealloc<512>(*tmem_slot);

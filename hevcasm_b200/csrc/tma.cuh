@@ -144,6 +144,21 @@ __device__ __forceinline__ void load_box_3d(void *smem_dst, const CUtensorMap *m
                  "l"(map), "r"(x), "r"(y), "r"(z), "r"(smem_u32(bar))
                  : "memory");
 }
+// one dense box in shared memory (rows of box_x bytes) -> a 3-D tensor; the part of the box outside the tensor's extent is not written.
+// The writes of the shared-memory bytes must have been made visible to the async proxy (fence.proxy.async) before this is issued.
+__device__ __forceinline__ void store_box_3d(const CUtensorMap *map, int x, int y, int z, const void *smem_src)
+{
+    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.tile.bulk_group [%0, {%1, %2, %3}], [%4];" ::"l"(map), "r"(x), "r"(y), "r"(z),
+                 "r"(smem_u32(smem_src))
+                 : "memory");
+}
+__device__ __forceinline__ void store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// waits until at most PENDING of this thread's committed store groups are still READING their shared-memory source
+template <int PENDING>
+__device__ __forceinline__ void store_wait_read()
+{
+    asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(PENDING) : "memory");
+}
 __device__ __forceinline__ void prefetch_descriptor(const CUtensorMap *map) { asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory"); }
 
 }  // namespace tma

@@ -60,7 +60,20 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, int (&v)[16])
           "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
         : "r"(taddr));
 }
+// 8 consecutive columns
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, int (&v)[8])
+{
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+                 : "r"(taddr));
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// the same wait, tied to the registers of an earlier load so that no use of them can be scheduled above it
+__device__ __forceinline__ void tmem_ld_wait(int (&v)[8])
+{
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7])::"memory");
+}
 
 }  // namespace umma
 
