@@ -1261,6 +1261,40 @@ static int launch_umma(const um::Params &u, void *stream)
     const unsigned grid = (unsigned)std::min<long long>(u.n_tiles, (long long)sm_count());   // one persistent CTA per SM
     return launch(kern, dim3(grid), dim3(G::THREADS), (size_t)G::SMEM_BYTES, stream, u);
 }
+// one reference, vertical pass on the tensor cores (namespace uv of pred_umma.cuh)
+template <int TAPS>
+static bool vh_params(uv::Params *u, const PredParams &p, int n_frames)
+{
+    const char *pin = getenv("HEVCASM_PRED_HV");
+    if (!pin || strcmp(pin, "umma")) return false;
+    if (!tma::describable(p.sr, p.fs_ref, n_frames)) return false;
+    const int top = TAPS / 2 - 1;
+    const long long rows = (long long)p.height + TAPS - 1;
+    const long long ext_x = 16 + (long long)p.width + TAPS / 2;   // bytes of a row the filter footprints touch, from x = -16
+    u->tiles_x = (p.width + uv::TCOLS - 1) / uv::TCOLS, u->tiles_y = (p.height + uv::TROWS - 1) / uv::TROWS;
+    const long long per = (long long)u->tiles_x * u->tiles_y;
+    if (per * n_frames >= (1ll << 31)) return false;
+    if (tma::describe_u8_swizzled(&u->tmref, p.ref0 - (ptrdiff_t)top * p.sr - 16, p.sr, p.fs_ref, ext_x, rows, n_frames, 128, uv::BOXR)) return false;
+    const PackedCoefs c = pack_coefs(TAPS, p.xf0, p.yf0);
+    for (int g = 0; g < 4; ++g) u->x2[g] = c.x2e[g];
+    for (int k = 0; k < 8; ++k) u->ytap[k] = k < TAPS ? (int8_t)((c.y4s[0][k >> 2] >> (8 * (k & 3))) & 0xff) : 0;
+    u->dst = p.dst, u->sd = p.sd, u->fs_dst = p.fs_dst, u->width = p.width, u->height = p.height;
+    u->dst16 = (((uintptr_t)p.dst | (uintptr_t)p.sd | (n_frames > 1 ? (uintptr_t)p.fs_dst : 0)) & 15) == 0 && p.sd > 0 && (n_frames <= 1 || p.fs_dst > 0);
+    if (u->dst16) {
+        int shift = 0;
+        if (tma::describe_u8(&u->tmdst, p.dst, p.sd, p.fs_dst, p.width, p.height, n_frames, uv::TCOLS, uv::TROWS, &shift) || shift) u->dst16 = 0;
+    }
+    u->n_tiles = (int)(per * n_frames);
+    return true;
+}
+template <int TAPS>
+static int launch_vh(const uv::Params &u, void *stream)
+{
+    auto kern = uv::pred_vh_kernel<TAPS>;
+    if (set_max_smem(kern, uv::SMEM_BYTES)) return (int)cudaErrorInvalidValue;
+    const unsigned grid = (unsigned)std::min<long long>(u.n_tiles, (long long)sm_count());   // one persistent CTA per SM
+    return launch(kern, dim3(grid), dim3(uv::THREADS), (size_t)uv::SMEM_BYTES, stream, u);
+}
 static bool aligned8(const uint8_t *dst, ptrdiff_t sd, ptrdiff_t fs_dst, int n_frames)
 {
     uintptr_t m = (uintptr_t)dst | (uintptr_t)sd;
@@ -1284,9 +1318,8 @@ extern "C" int hevcasm_pred_uni_frames(uint8_t *dst, ptrdiff_t sd, const uint8_t
     const char *pin = getenv("HEVCASM_PRED_PATH");
     const bool tile_ok = planes_fast_ok(ref, nullptr, sr, fs_ref, n_frames) && !(pin && !strcmp(pin, "stream"));
     if (mode == HV) {
-        um::Params u;
-        if (taps == 8 ? umma_params<8, false>(&u, p, n_frames) : umma_params<4, false>(&u, p, n_frames))
-            return taps == 8 ? launch_umma<8, false>(u, stream) : launch_umma<4, false>(u, stream);
+        uv::Params u;
+        if (taps == 8 ? vh_params<8>(&u, p, n_frames) : vh_params<4>(&u, p, n_frames)) return taps == 8 ? launch_vh<8>(u, stream) : launch_vh<4>(u, stream);
     }
     if (stream_ok(dst, sd, fs_dst, ref, nullptr, sr, fs_ref, n_frames)) {
         FastParams fp{};

@@ -257,3 +257,232 @@ __global__ void __launch_bounds__(Geom<TAPS, BI>::THREADS, 1) pred_umma_kernel(c
 }
 
 }  // namespace um
+
+// ================================================================================================================================
+// The same idea with the passes swapped, for one reference: the VERTICAL pass on the tensor cores, the horizontal pass in the
+// threads.  With 8-bit input the first pass of the reference has shift 0 (pred_inter.c:182-200), so the two passes are one exact
+// separable integer convolution and their order is free (the intermediate has the same range [-6120, 22440] either way).
+//     D[m][n] = sum_k A[m][k] * B[k][n],   m = output row of the tile (128), n = staged column (256), k = staged row (160)
+//     A[m][k] = ytap[k - m]                (Toeplitz band of the vertical taps, s8, K-major, built once per CTA)
+//     B[k][n] = ref[y0 - TOP + k][x0 - 16 + n]   (u8, MN-major: image rows exactly as they lie in memory)
+// Two TMA boxes {128 bytes x 136 rows} with the 128-byte swizzle ARE the swizzled MN-major operand (descriptor pinned by
+// tools/umma_vfirst_probe.cu; a swizzled box must start on a 16-byte boundary, hence the 16-byte left margin).  Now a thread
+// = one output ROW, and what it reads from TMEM are consecutive COLUMNS: it slides the horizontal taps along its row (pairs in
+// a register ring, IDP.2A), and its output bytes are horizontally adjacent - four are clipped and packed by two cvt.pack.sat,
+// eight leave in one STS.64; no byte stores, no barrier among the consumers.  Per output sample on the CUDA cores:
+// 4 IDP.2A + 1 PRMT + 1 SHF + 0.5 I2IP + 0.125 STS.  Tile = 128 rows x 224 columns; four consumer warpgroups take 56 columns each.
+namespace uv {
+
+constexpr int TROWS = 128;                 // output rows per tile = MMA M = TMEM lanes
+constexpr int NWG = 4, CPW = 56;           // consumer warpgroups; output columns per warpgroup
+constexpr int TCOLS = NWG * CPW;           // 224 output columns per tile
+constexpr int N = 256;                     // MMA N = staged columns (16 left of the tile + 224 + 16)
+constexpr int KROWS = 160;                 // MMA K (5 steps of 32): staged rows, of which BOXR are loaded
+constexpr int BOXR = TROWS + 8;            // rows per box (>= TROWS + TAPS - 1)
+constexpr int A_BYTES = TROWS * KROWS;     // 20480: Toeplitz operand, [chunk][m][16]
+constexpr int BOX_BYTES = KROWS * 128;     // one 128-column block of a stage (BOXR rows arrive, KROWS are read)
+constexpr int STAGE_BYTES = 2 * BOX_BYTES, O_BYTES = TROWS * TCOLS;
+constexpr int B_OFF = A_BYTES, O_OFF = B_OFF + 2 * STAGE_BYTES, BAR_OFF = O_OFF + 2 * O_BYTES;
+constexpr int SMEM_BYTES = 1024 + BAR_OFF + 64;
+constexpr int CONSUMERS = NWG * 128, THREADS = CONSUMERS + 32;
+constexpr uint32_t TX_BYTES = 2 * BOXR * 128;
+
+struct alignas(64) Params {
+    CUtensorMap tmref;        // reference: bytes from x = -16, rows from -(TAPS/2-1), frames; boxes of 128 bytes x BOXR rows, 128-byte swizzle
+    CUtensorMap tmdst;        // destination planes, boxes of TCOLS bytes x TROWS rows (valid when dst16)
+    uint8_t *dst;
+    ptrdiff_t sd, fs_dst;
+    int width, height;
+    int dst16;                // destination rows are 16-byte aligned (pointer and strides): tiles leave by TMA store
+    int tiles_x, tiles_y, n_tiles;
+    int8_t ytap[8];           // vertical taps (the MMA's Toeplitz band)
+    int x2[4];                // horizontal tap pairs (PackedCoefs::x2e)
+};
+
+// The horizontal pass of one thread: output row = its TMEM lane, CPW output columns from CPW + TAPS - 1 staged ones.  Everything
+// about the column index is compile-time; 8 columns arrive per tcgen05.ld, the next 8 are in flight while these are consumed.
+template <int TAPS>
+__device__ __forceinline__ void horizontal_pass(const Params &P, uint32_t tcol /* lane, accumulator, first staged column */, uint32_t (&out)[CPW / 4])
+{
+    constexpr int CH = 8, NCH = (CPW + TAPS - 1 + CH - 1) / CH;
+    static_assert(CH % TAPS == 0, "ring slots must be compile-time");
+    uint32_t ring[TAPS];
+    int prev = 0;
+#pragma unroll
+    for (int k = 0; k < TAPS; ++k) ring[k] = 0;
+    int x2[TAPS / 2];
+#pragma unroll
+    for (int g = 0; g < TAPS / 2; ++g) x2[g] = P.x2[g];
+    int v[2][CH], o[4];
+    umma::tmem_ld8(tcol, v[0]);
+    umma::tmem_ld_wait(v[0]);
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) {
+        if (c + 1 < NCH) umma::tmem_ld8(tcol + CH * (c + 1), v[(c + 1) & 1]);
+#pragma unroll
+        for (int j = 0; j < CH; ++j) {
+            const int r = CH * c + j, x = r - (TAPS - 1);   // staged column, output column
+            if (x >= CPW) continue;
+            ring[r % TAPS] = pack16(prev, v[c & 1][j]);   // pair (r-1, r)
+            prev = v[c & 1][j];
+            if (x < 0) continue;
+            // output column x takes the pairs ending at columns x+1, x+3, .. = slots (r + 2 + 2g) mod TAPS
+            int a = 2048;
+#pragma unroll
+            for (int g = 0; g < TAPS / 2; ++g) a = dp2a_lo(ring[(r + 2 + 2 * g) % TAPS], x2[g], a);
+            o[x & 3] = a >> 12;
+            if ((x & 3) == 3) out[x >> 2] = pack_sat_u8(o[0], o[1], o[2], o[3]);   // clip to [0, 255] and pack: two cvt.pack.sat
+        }
+        if (c + 1 < NCH) umma::tmem_ld_wait(v[(c + 1) & 1]);
+    }
+}
+
+template <int TAPS>
+__global__ void __launch_bounds__(THREADS, 1) pred_vh_kernel(const __grid_constant__ Params P)
+{
+    constexpr int LEFT = TAPS / 2 - 1;
+    static_assert(TROWS + TAPS - 1 <= BOXR && BOXR <= KROWS && 16 + TCOLS + TAPS / 2 <= N && CPW % 8 == 0, "tile geometry");
+    extern __shared__ __align__(128) uint8_t us_raw[];
+    uint8_t *const us_smem = us_raw + ((1024 - (tma::smem_u32(us_raw) & 1023)) & 1023);   // the 128-byte swizzle atoms sit on 1024-byte boundaries
+    uint8_t *const sA = us_smem;
+    uint8_t *const sB = us_smem + B_OFF;         // [stage][128-column block][row][128]
+    uint8_t *const sO = us_smem + O_OFF;         // [buffer][row][TCOLS]
+    uint64_t *const full = reinterpret_cast<uint64_t *>(us_smem + BAR_OFF);   // [2] image boxes of the stage have landed
+    uint64_t *const done = full + 2;                                          // [2] the MMAs into the accumulator have completed
+    uint64_t *const consumed = full + 4;                                      // [2] every consumer has read the accumulator and written its output bytes
+    uint32_t *const tmem_slot = reinterpret_cast<uint32_t *>(full + 6);
+
+    // Toeplitz band, one 16-byte chunk per step: output row m reads staged rows m .. m + TAPS - 1
+    for (int i = threadIdx.x; i < (KROWS / 16) * TROWS; i += THREADS) {
+        const int m = i % TROWS, kc = i / TROWS;
+        uint32_t w[4] = {0, 0, 0, 0};
+#pragma unroll
+        for (int b = 0; b < 16; ++b) {
+            const int t = 16 * kc + b - m;
+            if (t >= 0 && t < TAPS) w[b >> 2] |= (uint32_t)(uint8_t)P.ytap[t] << (8 * (b & 3));
+        }
+        *reinterpret_cast<uint4 *>(sA + kc * (TROWS * 16) + m * 16) = make_uint4(w[0], w[1], w[2], w[3]);
+    }
+    // the staged rows no box writes (BOXR .. KROWS-1) only ever meet zero taps, but they are multiplied: keep them finite (they are bytes)
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int i = 0; i < 2; ++i) tma::mbar_init(full + i, 1), tma::mbar_init(done + i, 1), tma::mbar_init(consumed + i, CONSUMERS);
+    }
+    if (threadIdx.x < 32) umma::tmem_alloc<512>(tmem_slot);
+    umma::fence_async_smem();
+    umma::fence_before();
+    __syncthreads();
+    umma::fence_after();
+    const uint32_t tm = *tmem_slot;
+
+    // tile -> (column, row, frame) of tiles: one division at the start, additions with carries afterwards
+    const int t0 = blockIdx.x, tstep = gridDim.x;
+    const int per = P.tiles_x * P.tiles_y;
+    const int sf = tstep / per, sby = (tstep - sf * per) / P.tiles_x, sbx = tstep - sf * per - sby * P.tiles_x;
+    int cf = t0 / per, cy = (t0 - cf * per) / P.tiles_x, cx = t0 - cf * per - cy * P.tiles_x;
+    auto advance = [&](int &x, int &y, int &f) {
+        x += sbx;
+        if (x >= P.tiles_x) x -= P.tiles_x, ++y;
+        y += sby;
+        if (y >= P.tiles_y) y -= P.tiles_y, ++f;
+        f += sf;
+    };
+    // a TMA store clips rows exactly but columns only at 16-byte granularity (measured: a 200-byte-wide plane was written up to
+    // byte 207), so a partial right-hand tile of a plane whose width is not a multiple of 16 leaves by byte stores instead
+    const bool tma_all = P.dst16 && (P.width & 15) == 0;
+    auto by_tma = [&](int x) { return tma_all || (P.dst16 && (x + 1) * TCOLS <= P.width); };
+
+    if (threadIdx.x >= CONSUMERS) {
+        // ------------------------------------------------------------------------------------------------ producer
+        if (threadIdx.x == CONSUMERS) {
+            constexpr uint32_t IDESC = umma::idesc_i8(true, false, false, N, true);   // A = taps (s8, K-major), B = image (u8, MN-major)
+            int sx = cx, sy = cy, sfr = cf;   // tile whose output is stored next
+            auto request = [&](int s) {   // the image boxes of tile (cx, cy, cf) into stage s; then on to the next tile
+                tma::mbar_expect_tx(full + s, TX_BYTES);
+                uint8_t *b = sB + s * STAGE_BYTES;
+                tma::load_box_3d(b, &P.tmref, cx * TCOLS, cy * TROWS, cf, full + s);
+                tma::load_box_3d(b + BOX_BYTES, &P.tmref, cx * TCOLS + 128, cy * TROWS, cf, full + s);
+                advance(cx, cy, cf);
+            };
+            auto store = [&](int s) {   // the finished tile (sx, sy, sfr) out of output buffer s
+                if (by_tma(sx)) {
+                    tma::store_box_3d(&P.tmdst, sx * TCOLS, sy * TROWS, sfr, sO + s * O_BYTES);
+                    tma::store_commit();
+                }
+                advance(sx, sy, sfr);
+            };
+            if (t0 < P.n_tiles) request(0);
+            if (t0 + tstep < P.n_tiles) request(1);
+            int it = 0;
+#pragma unroll 1
+            for (int t = t0; t < P.n_tiles; t += tstep, ++it) {
+                const int s = it & 1;
+                const uint32_t ph = (it >> 1) & 1;
+                if (it >= 2) {
+                    tma::mbar_wait(consumed + s, ph ^ 1);   // tile it-2 has left this accumulator and sits in output buffer s
+                    store(s);
+                }
+                tma::mbar_wait(full + s, ph);
+                umma::fence_after();
+#pragma unroll
+                for (int ks = 0; ks < KROWS / 32; ++ks) {
+                    // A: K-major, no swizzle (LBO = distance between 16-byte k chunks, SBO = between groups of 8 rows).  B: 128-byte-swizzled
+                    // MN-major (SBO = groups of 8 k, 1024 bytes; LBO = the second 128-column block); a K-step of 32 rows is 4096 bytes
+                    const uint64_t da = umma::smem_desc(tma::smem_u32(sA + ks * 2 * (TROWS * 16)), TROWS * 16, 128);
+                    const uint64_t db = umma::smem_desc(tma::smem_u32(sB + s * STAGE_BYTES) + ks * 4096, BOX_BYTES, 1024, 2);
+                    umma::mma_i8(tm + s * N, da, db, IDESC, ks);
+                }
+                tma::store_wait_read<0>();   // output buffer s has been read by its store before the consumers of this tile learn (via `done`) that they may fill it
+                umma::commit(done + s);
+                if (t + 2 * tstep < P.n_tiles) {   // the tile after next takes this stage as soon as these MMAs have read it
+                    tma::mbar_wait(done + s, ph);
+                    request(s);
+                }
+            }
+            // the last two tiles
+            for (int k = it >= 2 ? it - 2 : 0; k < it; ++k) {
+                tma::mbar_wait(consumed + (k & 1), (k >> 1) & 1);
+                store(k & 1);
+            }
+            tma::store_wait_read<0>();
+        }
+    } else {
+        // ------------------------------------------------------------------------------------------------ consumers
+        const int wg = threadIdx.x >> 7, row = threadIdx.x & 127, warp = row >> 5;   // warpgroup; output row of the tile = TMEM lane; warp inside the warpgroup
+        const uint32_t tlane = tm + ((uint32_t)(warp * 32) << 16) + (16 - LEFT) + wg * CPW;
+        int it = 0;
+#pragma unroll 1
+        for (int t = t0; t < P.n_tiles; t += tstep, ++it) {
+            const int a = it & 1;
+            uint8_t *const obuf = sO + a * O_BYTES;
+            tma::mbar_wait(done + a, (it >> 1) & 1);
+            umma::fence_after();
+            uint32_t out[CPW / 4];
+            horizontal_pass<TAPS>(P, tlane + a * N, out);
+            uint2 *orow = reinterpret_cast<uint2 *>(obuf + row * TCOLS + wg * CPW);
+#pragma unroll
+            for (int i = 0; i < CPW / 8; ++i) orow[i] = make_uint2(out[2 * i], out[2 * i + 1]);
+            umma::fence_before();       // this thread's TMEM reads are complete before it reports the accumulator consumed
+            if (by_tma(cx)) {
+                umma::fence_async_smem();   // the output bytes -> visible to the TMA store
+            } else {
+                // byte stores (partial right-hand tile of an odd width, or a destination TMA cannot describe): all consumers, after all have written
+                asm volatile("bar.sync 1, %0;" ::"n"(CONSUMERS) : "memory");
+                const int x0 = cx * TCOLS, y0 = cy * TROWS, rows = min(TROWS, P.height - y0), cols = min(TCOLS, P.width - x0);
+                uint8_t *d = P.dst + cf * P.fs_dst + (ptrdiff_t)y0 * P.sd + x0;
+                for (int i = threadIdx.x; i < rows * cols; i += CONSUMERS) {
+                    const int r = i / cols, c = i - r * cols;
+                    d[(ptrdiff_t)r * P.sd + c] = obuf[r * TCOLS + c];
+                }
+            }
+            tma::mbar_arrive(consumed + a);
+            advance(cx, cy, cf);
+        }
+    }
+    umma::fence_before();
+    __syncthreads();
+    if (threadIdx.x < 32) umma::tmem_dealloc<512>(*tmem_slot);
+}
+
+}  // namespace uv
+

@@ -11,6 +11,9 @@ namespace umma {
 // shared-memory matrix descriptor, no swizzle (LBO / SBO in bytes, multiples of 16)
 //   MN-major operand: LBO = distance between groups of 8 k, SBO = distance between chunks of 16 m
 //   K-major operand : LBO = distance between chunks of 16 k, SBO = distance between groups of 8 n
+//   128-byte-swizzled MN-major operand (rows of 128 bytes along MN as TMA writes them with the 128-byte swizzle, one row per k):
+//   SBO = distance between groups of 8 k (1024), LBO = distance between blocks of 128 mn; a K-step of 32 advances `addr` by 4096
+//   (tools/umma_vfirst_probe.cu)
 //   swizzled K-major operand (layout 2 = 128-byte swizzle, 6 = 32-byte swizzle; atoms of 8 rows x 128 / 32 bytes written by TMA with
 //   the matching swizzle mode): SBO = distance between groups of 8 rows (1024 / 256), LBO unused; a K-step advances `addr` by 32 bytes
 __device__ __forceinline__ uint64_t smem_desc(uint32_t addr, uint32_t lbo, uint32_t sbo, uint32_t layout = 0)
@@ -19,9 +22,10 @@ __device__ __forceinline__ uint64_t smem_desc(uint32_t addr, uint32_t lbo, uint3
            ((uint64_t)layout << 61);
 }
 // instruction descriptor: D s32, A / B u8 or s8, A MN-major or K-major, B K-major, M = 128, N = n
-__host__ __device__ constexpr uint32_t idesc_i8(bool a_signed, bool b_signed, bool a_mn_major, int n)
+__host__ __device__ constexpr uint32_t idesc_i8(bool a_signed, bool b_signed, bool a_mn_major, int n, bool b_mn_major = false)
 {
-    return (2u << 4) | ((a_signed ? 1u : 0u) << 7) | ((b_signed ? 1u : 0u) << 10) | ((a_mn_major ? 1u : 0u) << 15) | ((uint32_t)(n >> 3) << 17) | ((128u >> 4) << 24);
+    return (2u << 4) | ((a_signed ? 1u : 0u) << 7) | ((b_signed ? 1u : 0u) << 10) | ((a_mn_major ? 1u : 0u) << 15) | ((b_mn_major ? 1u : 0u) << 16) |
+           ((uint32_t)(n >> 3) << 17) | ((128u >> 4) << 24);
 }
 // D = A * B (accumulate = 0) or D += A * B
 __device__ __forceinline__ void mma_i8(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, int accumulate = 0)
