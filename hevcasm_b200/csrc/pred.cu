@@ -1218,37 +1218,35 @@ static bool stream_maps(StreamMaps *sm, const PredParams &p, int taps, int mode,
     }
     return true;
 }
-// two-pass positions on the tensor cores (pred_umma.cuh): needs 16-byte aligned reference planes / strides
-template <int TAPS, bool BI>
-static bool umma_params(um::Params *u, const PredParams &p, int n_frames)
+// two-pass positions on the tensor cores (pred_umma.cuh): needs 16-byte aligned reference planes / strides (the 4-D TMA form)
+static bool umma_params(um::Params *u, const PredParams &p, int taps, bool bi, int n_frames)
 {
-    using G = um::Geom<TAPS, BI>;
     const char *pin = getenv("HEVCASM_PRED_HV");
     if (!pin || strcmp(pin, "umma")) return false;
     if (!tma::describable(p.sr, p.fs_ref, n_frames)) return false;
-    const int top = TAPS / 2 - 1;
-    const long long rows = (long long)p.height + TAPS - 1;
-    const long long ext_x = 16 + (long long)p.width + TAPS / 2;   // bytes of a row the filter footprints touch, from x = -16
-    u->tiles_x = (p.width + um::TCOLS - 1) / um::TCOLS, u->tiles_y = (p.height + G::TROWS - 1) / G::TROWS;
-    const long long per = (long long)u->tiles_x * u->tiles_y;
+    const int top = taps / 2 - 1;
+    const long long rows = (long long)p.height + taps - 1;
+    const long long ext_x = 16 + (long long)p.width + taps / 2;   // bytes of a row the filter footprints touch, from x = -16
+    const long long per = (long long)((p.width + um::TCOLS - 1) / um::TCOLS) * ((p.height + um::TROWS - 1) / um::TROWS);
     if (per * n_frames >= (1ll << 31)) return false;
     const uint8_t *refs[2] = {p.ref0, p.ref1};
     const int xf[2] = {p.xf0, p.xf1}, yf[2] = {p.yf0, p.yf1};
-    for (int rf = 0; rf < G::NREF; ++rf) {
+    for (int rf = 0; rf < (bi ? 2 : 1); ++rf) {
         const uint8_t *base = refs[rf] - (ptrdiff_t)top * p.sr - 16;
-        if (tma::describe_u8_swizzled(&u->tm128[rf], base, p.sr, p.fs_ref, ext_x, rows, n_frames, 128, G::BOXR) ||
-            tma::describe_u8_swizzled(&u->tm32[rf], base, p.sr, p.fs_ref, ext_x, rows, n_frames, 32, G::BOXR))
+        if (tma::describe_u8_swizzled(&u->tm128[rf], base, p.sr, p.fs_ref, ext_x, rows, n_frames, 128, um::NROWS) ||
+            tma::describe_u8_swizzled(&u->tm32[rf], base, p.sr, p.fs_ref, ext_x, rows, n_frames, 32, um::NROWS))
             return false;
-        const PackedCoefs c = pack_coefs(TAPS, xf[rf], yf[rf]);
+        const PackedCoefs c = pack_coefs(taps, xf[rf], yf[rf]);
         for (int g = 0; g < 4; ++g) u->y2[rf][g] = c.y2[g];
-        for (int k = 0; k < 8; ++k) u->xtap[rf][k] = k < TAPS ? (int8_t)((c.x4[k >> 2] >> (8 * (k & 3))) & 0xff) : 0;
+        for (int k = 0; k < 8; ++k) u->xtap[rf][k] = k < taps ? (int8_t)((c.x4[k >> 2] >> (8 * (k & 3))) & 0xff) : 0;
     }
     u->dst = p.dst, u->sd = p.sd, u->fs_dst = p.fs_dst, u->width = p.width, u->height = p.height;
     u->dst16 = (((uintptr_t)p.dst | (uintptr_t)p.sd | (n_frames > 1 ? (uintptr_t)p.fs_dst : 0)) & 15) == 0 && p.sd > 0 && (n_frames <= 1 || p.fs_dst > 0);
     if (u->dst16) {
         int shift = 0;
-        if (tma::describe_u8(&u->tmdst, p.dst, p.sd, p.fs_dst, p.width, p.height, n_frames, um::TCOLS, um::RPW, &shift) || shift) u->dst16 = 0;
+        if (tma::describe_u8(&u->tmdst, p.dst, p.sd, p.fs_dst, p.width, p.height, n_frames, um::TCOLS, um::TROWS, &shift) || shift) u->dst16 = 0;
     }
+    u->tiles_x = (p.width + um::TCOLS - 1) / um::TCOLS, u->tiles_y = (p.height + um::TROWS - 1) / um::TROWS;
     u->n_tiles = (int)(per * n_frames);
     return true;
 }
@@ -1258,7 +1256,7 @@ static int launch_umma(const um::Params &u, void *stream)
     using G = um::Geom<TAPS, BI>;
     auto kern = um::pred_umma_kernel<TAPS, BI>;
     if (set_max_smem(kern, G::SMEM_BYTES)) return (int)cudaErrorInvalidValue;
-    const unsigned grid = (unsigned)std::min<long long>(u.n_tiles, (long long)sm_count());   // one persistent CTA per SM
+    const unsigned grid = (unsigned)std::min<long long>((u.n_tiles + G::NWG - 1) / G::NWG, (long long)sm_count());   // one CTA of NWG warpgroups per SM
     return launch(kern, dim3(grid), dim3(G::THREADS), (size_t)G::SMEM_BYTES, stream, u);
 }
 // one reference, vertical pass on the tensor cores (namespace uv of pred_umma.cuh)
@@ -1352,8 +1350,7 @@ extern "C" int hevcasm_pred_bi_frames(uint8_t *dst, ptrdiff_t sd, const uint8_t 
     const dim3 grid((width + PTW - 1) / PTW, (height + PTH - 1) / PTH, n_frames);
     if (xFrac0 || yFrac0 || xFrac1 || yFrac1) {
         um::Params u;
-        if (taps == 8 ? umma_params<8, true>(&u, p, n_frames) : umma_params<4, true>(&u, p, n_frames))
-            return taps == 8 ? launch_umma<8, true>(u, stream) : launch_umma<4, true>(u, stream);
+        if (umma_params(&u, p, taps, true, n_frames)) return taps == 8 ? launch_umma<8, true>(u, stream) : launch_umma<4, true>(u, stream);
     }
     if (stream_ok(dst, sd, fs_dst, ref0, ref1, sr, fs_ref, n_frames)) {
         FastParams fp{};

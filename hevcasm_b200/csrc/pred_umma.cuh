@@ -19,14 +19,18 @@
 
 namespace um {
 
-constexpr int TCOLS = 128;                 // output columns per tile = MMA M = TMEM lanes = threads of a warpgroup
-constexpr int RPW = 40;                    // output rows per warpgroup and tile
+constexpr int TCOLS = 128;                 // output columns per tile = MMA M = TMEM lanes = threads
+constexpr int TROWS = 72;                  // output rows per tile
+constexpr int NROWS = 80;                  // MMA N: staged rows (TROWS + TAPS - 1 <= 80, a multiple of 16)
 constexpr int KBYTES = 160, KCH = KBYTES / 16;   // staged bytes per row: 16 left of the tile + 128 + 16
 constexpr int A_BYTES = TCOLS * KBYTES;    // 20480: Toeplitz operand, [chunk][m][16]
+constexpr int B1_BYTES = NROWS * 128, B2_BYTES = NROWS * 32;   // image operand: 128-byte-swizzled part (k < 128), 32-byte-swizzled part (k >= 128)
+constexpr int B_BYTES = 13 * 1024;         // one staged operand (12800 bytes), padded so that every one starts on a 1024-byte boundary
+constexpr int O_BYTES = TROWS * TCOLS;     // one output tile, row-major
 
 struct alignas(64) Params {
-    CUtensorMap tm128[2], tm32[2];   // per reference: bytes from x = -16, rows from -(TAPS/2-1), frames; boxes of 128 / 32 bytes x BOXR rows
-    CUtensorMap tmdst;               // destination planes, boxes of TCOLS bytes x RPW rows (valid when dst16)
+    CUtensorMap tm128[2], tm32[2];   // per reference: bytes from x = -16, rows from -(TAPS/2-1), frames; boxes of 128 / 32 bytes x NROWS rows
+    CUtensorMap tmdst;               // destination planes, boxes of TCOLS bytes x TROWS rows (valid when dst16)
     uint8_t *dst;
     ptrdiff_t sd, fs_dst;
     int width, height;
@@ -36,33 +40,26 @@ struct alignas(64) Params {
     int y2[2][4];             // vertical tap pairs per reference (PackedCoefs::y2)
 };
 
-// One CTA per SM: NWG consumer WARPGROUPS of 128 threads (thread = output column = TMEM lane; warpgroup w owns rows 40 w .. 40 w + 39 of
-// the tile) and one PRODUCER warp, whose elected thread requests the image boxes and issues the MMAs.  tcgen05.mma kind::i8 costs
-// ~134 cycles per K-step whatever N is (tools/umma_rate_probe.cu: 130-138 cycles for N = 16 .. 256), so the tile is as tall as N allows:
-// N = 256 staged rows (240 output rows) for one reference, 2 x 128 for bi-prediction.  Two accumulators (2 x 256 TMEM columns) and two
-// image stages: the MMAs of tile i+1 run while the warpgroups walk down tile i.
+// One CTA per SM holds NWG independent WARPGROUPS of 128 threads (6, or 3 for bi-prediction).  Each warpgroup walks over its own
+// tiles with its own image stage, output buffers, barriers and accumulator columns, so the tensor-core and TMA latency of one
+// overlaps the vertical passes of the others; they share the Toeplitz operand and one 512-column TMEM allocation.
 template <int TAPS, bool BI>
 struct Geom {
     static constexpr int NREF = BI ? 2 : 1, NWG = BI ? 3 : 6;
-    static constexpr int TROWS = NWG * RPW;                        // output rows per tile (240 / 120)
-    static constexpr int N = BI ? 128 : 256;                       // MMA N = accumulator columns per reference
-    static constexpr int BOXR = TROWS + 8;                         // staged rows (>= TROWS + TAPS - 1, a multiple of 8)
-    static constexpr int B1_BYTES = N * 128, B2_BYTES = N * 32;    // image operand: 128-byte-swizzled part (k < 128), 32-byte-swizzled part (k >= 128)
-    static constexpr int B_BYTES = B1_BYTES + B2_BYTES;            // one staged operand (a multiple of 1024)
-    static constexpr int STAGE_BYTES = NREF * B_BYTES, O_BYTES = TROWS * TCOLS;
-    static constexpr int O_OFF = NREF * A_BYTES + 2 * STAGE_BYTES, BAR_OFF = O_OFF + 2 * O_BYTES;
-    static constexpr int SMEM_BYTES = 1024 + BAR_OFF + 64;         // alignment slack + operands + output buffers + barriers + the TMEM slot
-    static constexpr int CONSUMERS = NWG * TCOLS, THREADS = CONSUMERS + 32;
-    static constexpr uint32_t TX_BYTES = NREF * BOXR * KBYTES;
+    static constexpr int WG_BYTES = NREF * B_BYTES + 2 * O_BYTES;  // image stage + two output buffers of one warpgroup
+    static constexpr int BAR_OFF = NREF * A_BYTES + NWG * WG_BYTES;
+    static constexpr int SMEM_BYTES = 1024 + BAR_OFF + NWG * 16 + 16;   // alignment slack + operands + per-warpgroup barriers + the TMEM slot
+    static constexpr int ACC_COLS = BI ? 160 : 80;                 // accumulator columns per warpgroup (reference r at + 80 r)
+    static constexpr int THREADS = NWG * TCOLS;
 };
 
-// The vertical pass of one warpgroup's 40 rows for one thread (= one output column).  Everything about the row index is compile-time
-// (the 48 staged rows are fully unrolled), the output byte goes to shared memory at an immediate offset.  The horizontal sums
+// The vertical pass of one tile for one thread (= one output column).  Everything about the row index is compile-time (the
+// 80 staged rows are fully unrolled), the output byte goes to shared memory at an immediate offset.  The horizontal sums
 // arrive 8 rows per tcgen05.ld; the load of the next 8 is in flight while these 8 are consumed.
-template <int TAPS, bool BI, int N>
-__device__ __forceinline__ void vertical_pass(const Params &P, uint32_t tcol /* lane, accumulator, first staged row */, uint8_t *ocol /* first output row + column */)
+template <int TAPS, bool BI>
+__device__ __forceinline__ void vertical_pass(const Params &P, uint32_t tlane, uint8_t *ocol /* obuf + column */)
 {
-    constexpr int NREF = BI ? 2 : 1, CH = 8, NCH = (RPW + TAPS - 1 + CH - 1) / CH;
+    constexpr int NREF = BI ? 2 : 1, CH = 8, NCH = NROWS / CH;
     static_assert(CH % TAPS == 0, "ring slots must be compile-time");
     uint32_t ring[NREF][TAPS];
     int prev[NREF];
@@ -79,25 +76,24 @@ __device__ __forceinline__ void vertical_pass(const Params &P, uint32_t tcol /* 
         for (int g = 0; g < TAPS / 2; ++g) y2[rf][g] = P.y2[rf][g];
     int v[2][NREF][CH];
 #pragma unroll
-    for (int rf = 0; rf < NREF; ++rf) umma::tmem_ld8(tcol + N * rf, v[0][rf]);
+    for (int rf = 0; rf < NREF; ++rf) umma::tmem_ld8(tlane + NROWS * rf, v[0][rf]);
 #pragma unroll
     for (int rf = 0; rf < NREF; ++rf) umma::tmem_ld_wait(v[0][rf]);
 #pragma unroll
     for (int c = 0; c < NCH; ++c) {
         if (c + 1 < NCH) {
 #pragma unroll
-            for (int rf = 0; rf < NREF; ++rf) umma::tmem_ld8(tcol + N * rf + CH * (c + 1), v[(c + 1) & 1][rf]);
+            for (int rf = 0; rf < NREF; ++rf) umma::tmem_ld8(tlane + NROWS * rf + CH * (c + 1), v[(c + 1) & 1][rf]);
         }
 #pragma unroll
         for (int j = 0; j < CH; ++j) {
             const int r = CH * c + j, y = r - (TAPS - 1);   // staged row, output row
-            if (y >= RPW) continue;
 #pragma unroll
             for (int rf = 0; rf < NREF; ++rf) {
                 ring[rf][r % TAPS] = pack16(prev[rf], v[c & 1][rf][j]);   // pair (r-1, r)
                 prev[rf] = v[c & 1][rf][j];
             }
-            if (y < 0) continue;
+            if (y < 0 || y >= TROWS) continue;
             // output row y takes the pairs ending at rows y+1, y+3, .. = slots (r + 2 + 2g) mod TAPS
             int acc[NREF];
 #pragma unroll
@@ -123,17 +119,18 @@ template <int TAPS, bool BI>
 __global__ void __launch_bounds__(Geom<TAPS, BI>::THREADS, 1) pred_umma_kernel(const __grid_constant__ Params P)
 {
     using G = Geom<TAPS, BI>;
-    constexpr int NREF = G::NREF, NWG = G::NWG, N = G::N, TROWS = G::TROWS, LEFT = TAPS / 2 - 1;
-    static_assert(TROWS + TAPS - 1 <= G::BOXR && G::BOXR <= N && 2 * NREF * N <= 512 && G::B_BYTES % 1024 == 0, "tile rows / TMEM columns");
+    constexpr int NREF = G::NREF, NWG = G::NWG, LEFT = TAPS / 2 - 1;
+    static_assert(TROWS + TAPS - 1 <= NROWS && NWG * G::ACC_COLS <= 512, "tile rows / TMEM columns");
     extern __shared__ __align__(128) uint8_t us_raw[];
     uint8_t *const us_smem = us_raw + ((1024 - (tma::smem_u32(us_raw) & 1023)) & 1023);   // the 128-byte swizzle atoms sit on 1024-byte boundaries
+    const int wg = threadIdx.x / TCOLS, tid = threadIdx.x - wg * TCOLS, warp = tid >> 5;   // warpgroup, thread and warp inside it
     uint8_t *const sA = us_smem;
-    uint8_t *const sB = us_smem + NREF * A_BYTES;   // [stage][reference]
-    uint8_t *const sO = us_smem + G::O_OFF;         // [buffer][row][128]
-    uint64_t *const full = reinterpret_cast<uint64_t *>(us_smem + G::BAR_OFF);   // [2] image boxes of the stage have landed
-    uint64_t *const done = full + 2;                                             // [2] the MMAs into the accumulator have completed
-    uint64_t *const empty = full + 4;                                            // [2] every consumer has finished with the accumulator (and its output buffer)
-    uint32_t *const tmem_slot = reinterpret_cast<uint32_t *>(full + 6);
+    uint8_t *const sB = us_smem + NREF * A_BYTES + wg * G::WG_BYTES;    // image stage (NREF operands), then the two output buffers
+    uint8_t *const sO = sB + NREF * B_BYTES;
+    uint64_t *const full = reinterpret_cast<uint64_t *>(us_smem + G::BAR_OFF + wg * 16);   // image boxes of this warpgroup have landed
+    uint64_t *const done = full + 1;                                                       // MMA completion of this warpgroup
+    uint32_t *const tmem_slot = reinterpret_cast<uint32_t *>(us_smem + G::BAR_OFF + NWG * 16);
+    auto wg_sync = [&]() { asm volatile("bar.sync %0, %1;" ::"r"(1 + wg), "n"(TCOLS) : "memory"); };
 
     // Toeplitz bands, one 16-byte chunk per step: output column m reads staged bytes m + (16 - LEFT) .. + TAPS - 1
     for (int i = threadIdx.x; i < NREF * KCH * TCOLS; i += G::THREADS) {
@@ -146,23 +143,23 @@ __global__ void __launch_bounds__(Geom<TAPS, BI>::THREADS, 1) pred_umma_kernel(c
         }
         *reinterpret_cast<uint4 *>(sA + rf * A_BYTES + kc * (TCOLS * 16) + m * 16) = make_uint4(w[0], w[1], w[2], w[3]);
     }
-    // the rows of a stage that no box writes (BOXR .. N-1) are read by the MMAs into accumulator columns nobody uses; they only need to exist
-    if (threadIdx.x == 0) {
-#pragma unroll
-        for (int i = 0; i < 2; ++i) tma::mbar_init(full + i, 1), tma::mbar_init(done + i, 1), tma::mbar_init(empty + i, G::CONSUMERS);
+    if (tid == 0) {
+        tma::mbar_init(full, 1);
+        tma::mbar_init(done, 1);
     }
     if (threadIdx.x < 32) umma::tmem_alloc<512>(tmem_slot);
     umma::fence_async_smem();
     umma::fence_before();
     __syncthreads();
     umma::fence_after();
-    const uint32_t tm = *tmem_slot;
+    const uint32_t tm = *tmem_slot + wg * G::ACC_COLS, tlane = tm + ((uint32_t)(warp * 32) << 16);
+    constexpr uint32_t IDESC = umma::idesc_i8(true, false, false, NROWS);   // A = taps (s8), B = image (u8), both K-major
 
     // tile -> (column, row, frame) of tiles: one division at the start, additions with carries afterwards
-    const int t0 = blockIdx.x, tstep = gridDim.x;
+    const int t0 = blockIdx.x * NWG + wg, tstep = gridDim.x * NWG;
     const int per = P.tiles_x * P.tiles_y;
     const int sf = tstep / per, sby = (tstep - sf * per) / P.tiles_x, sbx = tstep - sf * per - sby * P.tiles_x;
-    int cf = t0 / per, cy = (t0 - cf * per) / P.tiles_x, cx = t0 - cf * per - cy * P.tiles_x;
+    int cf = t0 / per, cy = (t0 - cf * per) / P.tiles_x, cx = t0 - cf * per - cy * P.tiles_x;   // this tile
     auto advance = [&](int &x, int &y, int &f) {
         x += sbx;
         if (x >= P.tiles_x) x -= P.tiles_x, ++y;
@@ -170,87 +167,76 @@ __global__ void __launch_bounds__(Geom<TAPS, BI>::THREADS, 1) pred_umma_kernel(c
         if (y >= P.tiles_y) y -= P.tiles_y, ++f;
         f += sf;
     };
+    auto request = [&](int x, int y, int f) {   // thread 0 of the warpgroup: the image boxes of tile (x, y, f) into the stage
+        tma::mbar_expect_tx(full, NREF * (B1_BYTES + B2_BYTES));
+#pragma unroll
+        for (int rf = 0; rf < NREF; ++rf) {
+            uint8_t *b = sB + rf * B_BYTES;
+            tma::load_box_3d(b, &P.tm128[rf], x * TCOLS, y * TROWS, f, full);
+            tma::load_box_3d(b + B1_BYTES, &P.tm32[rf], x * TCOLS + 128, y * TROWS, f, full);
+        }
+    };
+    if (tid == 0 && t0 < P.n_tiles) request(cx, cy, cf);
+    // a TMA store clips rows exactly but columns only at 16-byte granularity (measured: a 200-byte-wide plane was written up to
+    // byte 207), so a partial right-hand tile of a plane whose width is not a multiple of 16 leaves by byte stores instead
+    const bool tma_all = P.dst16 && (P.width & 15) == 0;
 
-    if (threadIdx.x >= G::CONSUMERS) {
-        // ------------------------------------------------------------------------------------------------ producer
-        if (threadIdx.x == G::CONSUMERS) {
-            constexpr uint32_t IDESC = umma::idesc_i8(true, false, false, N);   // A = taps (s8), B = image (u8), both K-major
-            auto request = [&](int s) {   // the image boxes of tile (cx, cy, cf) into stage s; then on to the next tile
-                tma::mbar_expect_tx(full + s, G::TX_BYTES);
-#pragma unroll
-                for (int rf = 0; rf < NREF; ++rf) {
-                    uint8_t *b = sB + (s * NREF + rf) * G::B_BYTES;
-                    tma::load_box_3d(b, &P.tm128[rf], cx * TCOLS, cy * TROWS, cf, full + s);
-                    tma::load_box_3d(b + G::B1_BYTES, &P.tm32[rf], cx * TCOLS + 128, cy * TROWS, cf, full + s);
-                }
-                advance(cx, cy, cf);
-            };
-            if (t0 < P.n_tiles) request(0);
-            if (t0 + tstep < P.n_tiles) request(1);
-            int it = 0;
+    int it = 0;
 #pragma unroll 1
-            for (int t = t0; t < P.n_tiles; t += tstep, ++it) {
-                const int s = it & 1;
-                const uint32_t ph = (it >> 1) & 1;
-                if (it >= 2) tma::mbar_wait(empty + s, ph ^ 1);   // the consumers have read tile it-2 out of this accumulator
-                tma::mbar_wait(full + s, ph);
-                umma::fence_after();
-#pragma unroll
-                for (int rf = 0; rf < NREF; ++rf)
-#pragma unroll
-                    for (int ks = 0; ks < KBYTES / 32; ++ks) {
-                        // A: K-major, no swizzle (LBO = distance between 16-byte k chunks, SBO = between groups of 8 rows).  B: swizzled K-major,
-                        // groups of 8 rows 1024 (256) bytes apart; a K-step advances the start address by 32 bytes inside the swizzle row
-                        const uint64_t da = umma::smem_desc(tma::smem_u32(sA + rf * A_BYTES + ks * 2 * (TCOLS * 16)), TCOLS * 16, 128);
-                        const uint32_t bb = tma::smem_u32(sB + (s * NREF + rf) * G::B_BYTES);
-                        const uint64_t db = ks < 4 ? umma::smem_desc(bb + ks * 32, 16, 1024, 2) : umma::smem_desc(bb + G::B1_BYTES, 16, 256, 6);
-                        umma::mma_i8(tm + (s * NREF + rf) * N, da, db, IDESC, ks);
-                    }
-                umma::commit(done + s);
-                if (t + 2 * tstep < P.n_tiles) {   // the tile after next takes this stage as soon as these MMAs have read it
-                    tma::mbar_wait(done + s, ph);
-                    request(s);
-                }
-            }
-        }
-    } else {
-        // ------------------------------------------------------------------------------------------------ consumers
-        const int wg = threadIdx.x / TCOLS, tid = threadIdx.x - wg * TCOLS, warp = tid >> 5;   // warpgroup, thread and warp inside it
-        auto wg_sync = [&]() { asm volatile("bar.sync %0, %1;" ::"r"(1 + wg), "n"(TCOLS) : "memory"); };
-        const uint32_t tlane = tm + ((uint32_t)(warp * 32) << 16) + wg * RPW;
-        // a TMA store clips rows exactly but columns only at 16-byte granularity (measured: a 200-byte-wide plane was written up to
-        // byte 207), so a partial right-hand tile of a plane whose width is not a multiple of 16 leaves by byte stores instead
-        const bool tma_all = P.dst16 && (P.width & 15) == 0;
-        int it = 0;
-#pragma unroll 1
-        for (int t = t0; t < P.n_tiles; t += tstep, ++it) {
-            const int a = it & 1;
-            uint8_t *const obuf = sO + a * G::O_BYTES + wg * (RPW * TCOLS);   // this warpgroup's rows of the tile
-            tma::mbar_wait(done + a, (it >> 1) & 1);
+    for (int t = t0; t < P.n_tiles; t += tstep, ++it) {
+        uint8_t *const obuf = sO + (it & 1) * O_BYTES;
+        if (tid == 0) {
+            tma::mbar_wait(full, it & 1);
             umma::fence_after();
-            vertical_pass<TAPS, BI, N>(P, tlane + a * (NREF * N), obuf + tid);
-            umma::fence_async_smem();   // the output bytes -> visible to the TMA store
-            umma::fence_before();       // this thread's TMEM reads are complete before it reports the accumulator free
-            wg_sync();
-            const int x0 = cx * TCOLS, y0 = cy * TROWS + wg * RPW;
-            if (tma_all || (P.dst16 && x0 + TCOLS <= P.width)) {
-                if (tid == 0 && y0 < P.height) {
-                    tma::store_box_3d(&P.tmdst, x0, y0, cf, obuf);
-                    tma::store_commit();
-                    tma::store_wait_read<0>();   // the buffer is rewritten two tiles on, once every consumer has arrived on `empty`
+#pragma unroll
+            for (int rf = 0; rf < NREF; ++rf)
+#pragma unroll
+                for (int ks = 0; ks < KBYTES / 32; ++ks) {
+                    // A: K-major, no swizzle (LBO = distance between 16-byte k chunks, SBO = between groups of 8 rows).  B: swizzled K-major,
+                    // groups of 8 rows 1024 (256) bytes apart; a K-step advances the start address by 32 bytes inside the swizzle row
+                    const uint64_t da = umma::smem_desc(tma::smem_u32(sA + rf * A_BYTES + ks * 2 * (TCOLS * 16)), TCOLS * 16, 128);
+                    const uint32_t bb = tma::smem_u32(sB + rf * B_BYTES);
+                    const uint64_t db = ks < 4 ? umma::smem_desc(bb + ks * 32, 16, 1024, 2) : umma::smem_desc(bb + B1_BYTES, 16, 256, 6);
+                    umma::mma_i8(tm + NROWS * rf, da, db, IDESC, ks);
                 }
-            } else {
-                const int rows = min(RPW, P.height - y0), cols = min(TCOLS, P.width - x0);   // byte stores, a thread per column
-                uint8_t *d = P.dst + cf * P.fs_dst + (ptrdiff_t)y0 * P.sd + x0;
-                if (tid < cols) {
-#pragma unroll 1
-                    for (int r = 0; r < rows; ++r) d[(ptrdiff_t)r * P.sd + tid] = obuf[r * TCOLS + tid];
-                }
-            }
-            tma::mbar_arrive(empty + a);
-            advance(cx, cy, cf);
+            // the store of the tile before last has finished reading the output buffer this tile is about to fill; everybody
+            // learns that through `done`
+            tma::store_wait_read<1>();
+            umma::commit(done);
         }
+        tma::mbar_wait(done, it & 1);
+        umma::fence_after();
+        // the MMAs have consumed the image stage: the next tile's rows travel during this tile's vertical pass
+        if (tid == 0 && t + tstep < P.n_tiles) {
+            int x = cx, y = cy, f = cf;
+            advance(x, y, f);
+            request(x, y, f);
+        }
+
+        // ---- vertical pass: this thread owns output column x = cx * 128 + tid.  Output bytes go to a row-major 128-byte-pitch
+        // buffer, which leaves as one TMA store (clipped to the plane by the hardware)
+        vertical_pass<TAPS, BI>(P, tlane, obuf + tid);
+        umma::fence_async_smem();   // the output bytes -> visible to the TMA store
+        umma::fence_before();       // this tile's TMEM reads are complete before the next tile's MMAs overwrite the accumulator
+        wg_sync();
+        const int x0 = cx * TCOLS, y0 = cy * TROWS;
+        if (tma_all || (P.dst16 && x0 + TCOLS <= P.width)) {
+            if (tid == 0) {
+                tma::store_box_3d(&P.tmdst, x0, y0, cf, obuf);
+                tma::store_commit();
+            }
+        } else {
+            // byte stores, a thread per column.  (The buffer is next written two tiles on, after the barrier of the tile in between.)
+            const int rows = min(TROWS, P.height - y0), cols = min(TCOLS, P.width - x0);
+            uint8_t *d = P.dst + cf * P.fs_dst + (ptrdiff_t)y0 * P.sd + x0;
+            if (tid < cols) {
+#pragma unroll 1
+                for (int r = 0; r < rows; ++r) d[(ptrdiff_t)r * P.sd + tid] = obuf[r * TCOLS + tid];
+            }
+        }
+        advance(cx, cy, cf);
     }
+    if (tid == 0) tma::store_wait_read<0>();   // shared memory stays valid until the last stores have read it
     umma::fence_before();
     __syncthreads();
     if (threadIdx.x < 32) umma::tmem_dealloc<512>(*tmem_slot);
@@ -282,7 +268,8 @@ constexpr int BOXR = TROWS + 8;            // rows per box (>= TROWS + TAPS - 1)
 constexpr int A_BYTES = TROWS * KROWS;     // 20480: Toeplitz operand, [chunk][m][16]
 constexpr int BOX_BYTES = KROWS * 128;     // one 128-column block of a stage (BOXR rows arrive, KROWS are read)
 constexpr int STAGE_BYTES = 2 * BOX_BYTES, O_BYTES = TROWS * TCOLS;
-constexpr int B_OFF = A_BYTES, O_OFF = B_OFF + 2 * STAGE_BYTES, BAR_OFF = O_OFF + 2 * O_BYTES;
+constexpr int NOBUF = 3;                   // output buffers: the store of tile i-2 may still be reading while tile i is written
+constexpr int B_OFF = A_BYTES, O_OFF = B_OFF + 2 * STAGE_BYTES, BAR_OFF = O_OFF + NOBUF * O_BYTES;
 constexpr int SMEM_BYTES = 1024 + BAR_OFF + 64;
 constexpr int CONSUMERS = NWG * 128, THREADS = CONSUMERS + 32;
 constexpr uint32_t TX_BYTES = 2 * BOXR * 128;
@@ -352,28 +339,12 @@ __global__ void __launch_bounds__(THREADS, 1) pred_vh_kernel(const __grid_consta
     uint64_t *const consumed = full + 4;                                      // [2] every consumer has read the accumulator and written its output bytes
     uint32_t *const tmem_slot = reinterpret_cast<uint32_t *>(full + 6);
 
-    // Toeplitz band, one 16-byte chunk per step: output row m reads staged rows m .. m + TAPS - 1
-    for (int i = threadIdx.x; i < (KROWS / 16) * TROWS; i += THREADS) {
-        const int m = i % TROWS, kc = i / TROWS;
-        uint32_t w[4] = {0, 0, 0, 0};
-#pragma unroll
-        for (int b = 0; b < 16; ++b) {
-            const int t = 16 * kc + b - m;
-            if (t >= 0 && t < TAPS) w[b >> 2] |= (uint32_t)(uint8_t)P.ytap[t] << (8 * (b & 3));
-        }
-        *reinterpret_cast<uint4 *>(sA + kc * (TROWS * 16) + m * 16) = make_uint4(w[0], w[1], w[2], w[3]);
-    }
-    // the staged rows no box writes (BOXR .. KROWS-1) only ever meet zero taps, but they are multiplied: keep them finite (they are bytes)
     if (threadIdx.x == 0) {
 #pragma unroll
         for (int i = 0; i < 2; ++i) tma::mbar_init(full + i, 1), tma::mbar_init(done + i, 1), tma::mbar_init(consumed + i, CONSUMERS);
     }
     if (threadIdx.x < 32) umma::tmem_alloc<512>(tmem_slot);
-    umma::fence_async_smem();
-    umma::fence_before();
-    __syncthreads();
-    umma::fence_after();
-    const uint32_t tm = *tmem_slot;
+    __syncthreads();   // barriers exist: the producer's first two requests go out before the Toeplitz operand is built
 
     // tile -> (column, row, frame) of tiles: one division at the start, additions with carries afterwards
     const int t0 = blockIdx.x, tstep = gridDim.x;
@@ -387,6 +358,37 @@ __global__ void __launch_bounds__(THREADS, 1) pred_vh_kernel(const __grid_consta
         if (y >= P.tiles_y) y -= P.tiles_y, ++f;
         f += sf;
     };
+    auto request = [&](int s) {   // producer: the image boxes of tile (cx, cy, cf) into stage s; then on to the next tile
+        tma::mbar_expect_tx(full + s, TX_BYTES);
+        uint8_t *b = sB + s * STAGE_BYTES;
+        tma::load_box_3d(b, &P.tmref, cx * TCOLS, cy * TROWS, cf, full + s);
+        tma::load_box_3d(b + BOX_BYTES, &P.tmref, cx * TCOLS + 128, cy * TROWS, cf, full + s);
+        advance(cx, cy, cf);
+    };
+    int sx = cx, sy = cy, sfr = cf;   // producer: tile whose output is stored next
+    if (threadIdx.x == CONSUMERS) {
+        if (t0 < P.n_tiles) request(0);
+        if (t0 + tstep < P.n_tiles) request(1);
+    }
+
+    // Toeplitz band, one 16-byte chunk per step: output row m reads staged rows m .. m + TAPS - 1
+    for (int i = threadIdx.x; i < (KROWS / 16) * TROWS; i += THREADS) {
+        const int m = i % TROWS, kc = i / TROWS;
+        uint32_t w[4] = {0, 0, 0, 0};
+#pragma unroll
+        for (int b = 0; b < 16; ++b) {
+            const int t = 16 * kc + b - m;
+            if (t >= 0 && t < TAPS) w[b >> 2] |= (uint32_t)(uint8_t)P.ytap[t] << (8 * (b & 3));
+        }
+        *reinterpret_cast<uint4 *>(sA + kc * (TROWS * 16) + m * 16) = make_uint4(w[0], w[1], w[2], w[3]);
+    }
+    // (the staged rows no box writes, BOXR .. KROWS-1, only ever meet zero taps)
+    umma::fence_async_smem();
+    umma::fence_before();
+    __syncthreads();
+    umma::fence_after();
+    const uint32_t tm = *tmem_slot;
+
     // a TMA store clips rows exactly but columns only at 16-byte granularity (measured: a 200-byte-wide plane was written up to
     // byte 207), so a partial right-hand tile of a plane whose width is not a multiple of 16 leaves by byte stores instead
     const bool tma_all = P.dst16 && (P.width & 15) == 0;
@@ -396,31 +398,23 @@ __global__ void __launch_bounds__(THREADS, 1) pred_vh_kernel(const __grid_consta
         // ------------------------------------------------------------------------------------------------ producer
         if (threadIdx.x == CONSUMERS) {
             constexpr uint32_t IDESC = umma::idesc_i8(true, false, false, N, true);   // A = taps (s8, K-major), B = image (u8, MN-major)
-            int sx = cx, sy = cy, sfr = cf;   // tile whose output is stored next
-            auto request = [&](int s) {   // the image boxes of tile (cx, cy, cf) into stage s; then on to the next tile
-                tma::mbar_expect_tx(full + s, TX_BYTES);
-                uint8_t *b = sB + s * STAGE_BYTES;
-                tma::load_box_3d(b, &P.tmref, cx * TCOLS, cy * TROWS, cf, full + s);
-                tma::load_box_3d(b + BOX_BYTES, &P.tmref, cx * TCOLS + 128, cy * TROWS, cf, full + s);
-                advance(cx, cy, cf);
-            };
-            auto store = [&](int s) {   // the finished tile (sx, sy, sfr) out of output buffer s
+            int ob = 0;   // output buffer of the tile stored next
+            auto store = [&]() {   // the finished tile (sx, sy, sfr) out of its output buffer
                 if (by_tma(sx)) {
-                    tma::store_box_3d(&P.tmdst, sx * TCOLS, sy * TROWS, sfr, sO + s * O_BYTES);
+                    tma::store_box_3d(&P.tmdst, sx * TCOLS, sy * TROWS, sfr, sO + ob * O_BYTES);
                     tma::store_commit();
                 }
                 advance(sx, sy, sfr);
+                ob = ob == NOBUF - 1 ? 0 : ob + 1;
             };
-            if (t0 < P.n_tiles) request(0);
-            if (t0 + tstep < P.n_tiles) request(1);
             int it = 0;
 #pragma unroll 1
             for (int t = t0; t < P.n_tiles; t += tstep, ++it) {
                 const int s = it & 1;
                 const uint32_t ph = (it >> 1) & 1;
                 if (it >= 2) {
-                    tma::mbar_wait(consumed + s, ph ^ 1);   // tile it-2 has left this accumulator and sits in output buffer s
-                    store(s);
+                    tma::mbar_wait(consumed + s, ph ^ 1);   // tile it-2 has left this accumulator and sits in its output buffer
+                    store();
                 }
                 tma::mbar_wait(full + s, ph);
                 umma::fence_after();
@@ -432,7 +426,9 @@ __global__ void __launch_bounds__(THREADS, 1) pred_vh_kernel(const __grid_consta
                     const uint64_t db = umma::smem_desc(tma::smem_u32(sB + s * STAGE_BYTES) + ks * 4096, BOX_BYTES, 1024, 2);
                     umma::mma_i8(tm + s * N, da, db, IDESC, ks);
                 }
-                tma::store_wait_read<0>();   // output buffer s has been read by its store before the consumers of this tile learn (via `done`) that they may fill it
+                // this tile's output buffer last held tile it-3, whose store was issued one iteration ago: it must have been read
+                // before the consumers learn (via `done`) that they may fill it again; the store just issued may still be reading
+                tma::store_wait_read<1>();
                 umma::commit(done + s);
                 if (t + 2 * tstep < P.n_tiles) {   // the tile after next takes this stage as soon as these MMAs have read it
                     tma::mbar_wait(done + s, ph);
@@ -442,7 +438,7 @@ __global__ void __launch_bounds__(THREADS, 1) pred_vh_kernel(const __grid_consta
             // the last two tiles
             for (int k = it >= 2 ? it - 2 : 0; k < it; ++k) {
                 tma::mbar_wait(consumed + (k & 1), (k >> 1) & 1);
-                store(k & 1);
+                store();
             }
             tma::store_wait_read<0>();
         }
@@ -450,11 +446,12 @@ __global__ void __launch_bounds__(THREADS, 1) pred_vh_kernel(const __grid_consta
         // ------------------------------------------------------------------------------------------------ consumers
         const int wg = threadIdx.x >> 7, row = threadIdx.x & 127, warp = row >> 5;   // warpgroup; output row of the tile = TMEM lane; warp inside the warpgroup
         const uint32_t tlane = tm + ((uint32_t)(warp * 32) << 16) + (16 - LEFT) + wg * CPW;
-        int it = 0;
+        int it = 0, ob = 0;
 #pragma unroll 1
         for (int t = t0; t < P.n_tiles; t += tstep, ++it) {
             const int a = it & 1;
-            uint8_t *const obuf = sO + a * O_BYTES;
+            uint8_t *const obuf = sO + ob * O_BYTES;
+            ob = ob == NOBUF - 1 ? 0 : ob + 1;
             tma::mbar_wait(done + a, (it >> 1) & 1);
             umma::fence_after();
             uint32_t out[CPW / 4];
