@@ -1218,17 +1218,31 @@ static bool stream_maps(StreamMaps *sm, const PredParams &p, int taps, int mode,
     }
     return true;
 }
-// two-pass positions on the tensor cores (pred_umma.cuh): needs 16-byte aligned reference planes / strides (the 4-D TMA form)
-static bool umma_params(um::Params *u, const PredParams &p, int taps, bool bi, int n_frames)
+// Two-pass positions on the tensor cores (pred_umma.cuh).  Default: 8-tap positions of batches that fill the chip at least once
+// (the kernels are persistent, one CTA per SM, with tiles of 128 x 224 / 128 x 72 samples); HEVCASM_PRED_HV=umma takes them for
+// every size and both filters, HEVCASM_PRED_HV=stream never (A/B runs and the parity tests of either side).
+static bool tensor_path_wanted(int taps, long long n_tiles)
 {
     const char *pin = getenv("HEVCASM_PRED_HV");
-    if (!pin || strcmp(pin, "umma")) return false;
+    if (pin && !strcmp(pin, "umma")) return true;
+    if (pin && !strcmp(pin, "stream")) return false;
+    return taps == 8 && n_tiles >= sm_count();
+}
+static unsigned tensor_grid(long long n_tiles)
+{
+    long long g = std::min<long long>(n_tiles, (long long)sm_count());   // one persistent CTA per SM
+    if (const char *e = getenv("HEVCASM_PRED_UMMA_GRID")) g = std::max(1ll, std::min<long long>(g, atoll(e)));   // test knob: more tiles per CTA
+    return (unsigned)g;
+}
+// needs 16-byte aligned reference planes / strides
+static bool umma_params(um::Params *u, const PredParams &p, int taps, bool bi, int n_frames)
+{
     if (!tma::describable(p.sr, p.fs_ref, n_frames)) return false;
     const int top = taps / 2 - 1;
     const long long rows = (long long)p.height + taps - 1;
     const long long ext_x = 16 + (long long)p.width + taps / 2;   // bytes of a row the filter footprints touch, from x = -16
     const long long per = (long long)((p.width + um::TCOLS - 1) / um::TCOLS) * ((p.height + um::TROWS - 1) / um::TROWS);
-    if (per * n_frames >= (1ll << 31)) return false;
+    if (per * n_frames >= (1ll << 31) || !tensor_path_wanted(taps, per * n_frames)) return false;
     const uint8_t *refs[2] = {p.ref0, p.ref1};
     const int xf[2] = {p.xf0, p.xf1}, yf[2] = {p.yf0, p.yf1};
     for (int rf = 0; rf < (bi ? 2 : 1); ++rf) {
@@ -1256,23 +1270,21 @@ static int launch_umma(const um::Params &u, void *stream)
     using G = um::Geom<TAPS, BI>;
     auto kern = um::pred_umma_kernel<TAPS, BI>;
     if (set_max_smem(kern, G::SMEM_BYTES)) return (int)cudaErrorInvalidValue;
-    const unsigned grid = (unsigned)std::min<long long>((u.n_tiles + G::NWG - 1) / G::NWG, (long long)sm_count());   // one CTA of NWG warpgroups per SM
+    const unsigned grid = tensor_grid((u.n_tiles + G::NWG - 1) / G::NWG);   // one CTA of NWG warpgroups per SM
     return launch(kern, dim3(grid), dim3(G::THREADS), (size_t)G::SMEM_BYTES, stream, u);
 }
 // one reference, vertical pass on the tensor cores (namespace uv of pred_umma.cuh)
 template <int TAPS>
 static bool vh_params(uv::Params *u, const PredParams &p, int n_frames)
 {
-    const char *pin = getenv("HEVCASM_PRED_HV");
-    if (!pin || strcmp(pin, "umma")) return false;
     if (!tma::describable(p.sr, p.fs_ref, n_frames)) return false;
     const int top = TAPS / 2 - 1;
     const long long rows = (long long)p.height + TAPS - 1;
     const long long ext_x = 16 + (long long)p.width + TAPS / 2;   // bytes of a row the filter footprints touch, from x = -16
     u->tiles_x = (p.width + uv::TCOLS - 1) / uv::TCOLS, u->tiles_y = (p.height + uv::TROWS - 1) / uv::TROWS;
     const long long per = (long long)u->tiles_x * u->tiles_y;
-    if (per * n_frames >= (1ll << 31)) return false;
-    if (tma::describe_u8_swizzled(&u->tmref, p.ref0 - (ptrdiff_t)top * p.sr - 16, p.sr, p.fs_ref, ext_x, rows, n_frames, 128, uv::BOXR)) return false;
+    if (per * n_frames >= (1ll << 31) || !tensor_path_wanted(TAPS, per * n_frames)) return false;
+    if (tma::describe_u32_swizzled128(&u->tmref, p.ref0 - (ptrdiff_t)top * p.sr - 16, p.sr, p.fs_ref, ext_x, rows, n_frames, uv::BOXR)) return false;
     const PackedCoefs c = pack_coefs(TAPS, p.xf0, p.yf0);
     for (int g = 0; g < 4; ++g) u->x2[g] = c.x2e[g];
     for (int k = 0; k < 8; ++k) u->ytap[k] = k < TAPS ? (int8_t)((c.y4s[0][k >> 2] >> (8 * (k & 3))) & 0xff) : 0;
@@ -1290,7 +1302,7 @@ static int launch_vh(const uv::Params &u, void *stream)
 {
     auto kern = uv::pred_vh_kernel<TAPS>;
     if (set_max_smem(kern, uv::SMEM_BYTES)) return (int)cudaErrorInvalidValue;
-    const unsigned grid = (unsigned)std::min<long long>(u.n_tiles, (long long)sm_count());   // one persistent CTA per SM
+    const unsigned grid = tensor_grid(u.n_tiles);
     return launch(kern, dim3(grid), dim3(uv::THREADS), (size_t)uv::SMEM_BYTES, stream, u);
 }
 static bool aligned8(const uint8_t *dst, ptrdiff_t sd, ptrdiff_t fs_dst, int n_frames)

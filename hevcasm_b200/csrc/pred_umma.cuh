@@ -275,7 +275,7 @@ constexpr int CONSUMERS = NWG * 128, THREADS = CONSUMERS + 32;
 constexpr uint32_t TX_BYTES = 2 * BOXR * 128;
 
 struct alignas(64) Params {
-    CUtensorMap tmref;        // reference: bytes from x = -16, rows from -(TAPS/2-1), frames; boxes of 128 bytes x BOXR rows, 128-byte swizzle
+    CUtensorMap tmref;        // reference as 32-bit words from x = -16, rows from -(TAPS/2-1), frames; boxes of 32 words x BOXR rows, 128-byte swizzle
     CUtensorMap tmdst;        // destination planes, boxes of TCOLS bytes x TROWS rows (valid when dst16)
     uint8_t *dst;
     ptrdiff_t sd, fs_dst;
@@ -361,8 +361,8 @@ __global__ void __launch_bounds__(THREADS, 1) pred_vh_kernel(const __grid_consta
     auto request = [&](int s) {   // producer: the image boxes of tile (cx, cy, cf) into stage s; then on to the next tile
         tma::mbar_expect_tx(full + s, TX_BYTES);
         uint8_t *b = sB + s * STAGE_BYTES;
-        tma::load_box_3d(b, &P.tmref, cx * TCOLS, cy * TROWS, cf, full + s);
-        tma::load_box_3d(b + BOX_BYTES, &P.tmref, cx * TCOLS + 128, cy * TROWS, cf, full + s);
+        tma::load_box_3d(b, &P.tmref, cx * (TCOLS / 4), cy * TROWS, cf, full + s);   // x in 32-bit words
+        tma::load_box_3d(b + BOX_BYTES, &P.tmref, cx * (TCOLS / 4) + 32, cy * TROWS, cf, full + s);
         advance(cx, cy, cf);
     };
     int sx = cx, sy = cy, sfr = cf;   // producer: tile whose output is stored next

@@ -86,6 +86,23 @@ inline int describe_u8_swizzled(CUtensorMap *map, const uint8_t *base, ptrdiff_t
     return r == CUDA_SUCCESS ? 0 : (int)cudaErrorInvalidValue;
 }
 
+// The 128-byte-swizzled form with the bytes described as 32-bit words (box = 32 words x box_y rows; the x coordinate of a load is in
+// words): the TMA unit moves word tensors faster than byte tensors.  The zero-fill edge is rounded up to a word.
+inline int describe_u32_swizzled128(CUtensorMap *map, const uint8_t *base, ptrdiff_t row_stride, ptrdiff_t frame_stride, long long extent_x, long long extent_y,
+                                    int n_frames, int box_y)
+{
+    if (((uintptr_t)base & 15) != 0) return (int)cudaErrorInvalidValue;
+    if (n_frames <= 1) frame_stride = row_stride * (ptrdiff_t)extent_y;
+    if (extent_x > (long long)row_stride) extent_x = (long long)row_stride;
+    cuuint64_t dim[3] = {(cuuint64_t)((extent_x + 3) / 4), (cuuint64_t)extent_y, (cuuint64_t)(n_frames < 1 ? 1 : n_frames)};
+    cuuint64_t stride[2] = {(cuuint64_t)row_stride, (cuuint64_t)frame_stride};
+    cuuint32_t box[3] = {32, (cuuint32_t)box_y, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    const CUresult r = encoder()(map, CU_TENSOR_MAP_DATA_TYPE_UINT32, 3, (void *)base, dim, stride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                 CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? 0 : (int)cudaErrorInvalidValue;
+}
+
 // The same planes as a 4-D tensor (16 bytes, rows, 16-byte chunks of a row, frames): a box {16, R, C, 1} then lands in shared
 // memory as [chunk][row][16 bytes] - the tensor cores' no-swizzle K-major core-matrix layout (8 rows x 16 bytes contiguous,
 // chunks R*16 bytes apart).  `base` must be 16-byte aligned; the encoder accepts the (row stride, 16) stride order

@@ -47,7 +47,8 @@ def test_generic_plane_kernels_all_fractions(oracle, taps, monkeypatch):
     test_bi_planes(oracle, taps)
 
 
-@pytest.mark.parametrize("env", [{"HEVCASM_PRED_STREAM": "ldg"}, {"HEVCASM_PRED_STREAM": "ldg", "HEVCASM_PRED_PATH": "stream"}, {"HEVCASM_PRED_PATH": "tile"}])
+@pytest.mark.parametrize("env", [{"HEVCASM_PRED_STREAM": "ldg"}, {"HEVCASM_PRED_STREAM": "ldg", "HEVCASM_PRED_PATH": "stream"}, {"HEVCASM_PRED_PATH": "tile"},
+                                 {"HEVCASM_PRED_HV": "stream"}])
 @pytest.mark.parametrize("taps", [8, 4])
 def test_fallback_plane_kernels_all_fractions(oracle, taps, env, monkeypatch):
     """the kernels behind the TMA-fed one: LDG-fed streaming kernel (planes the TMA unit cannot describe) and the shared-memory
@@ -57,6 +58,34 @@ def test_fallback_plane_kernels_all_fractions(oracle, taps, env, monkeypatch):
     test_uni_planes_all_fractions(oracle, taps, (200, 136))
     test_uni_planes_all_fractions(oracle, taps, (131, 37))
     test_bi_planes(oracle, taps)
+
+
+@pytest.mark.parametrize("grid", [None, "2", "1"])
+@pytest.mark.parametrize("taps", [8, 4])
+def test_tensor_core_plane_kernels(oracle, taps, grid, monkeypatch):
+    """the tcgen05 kernels (vertical pass as an int8 Toeplitz product for one reference, horizontal pass for two), pinned for
+    every plane size and both filters; with 1 or 2 CTAs each CTA walks over several tiles, which exercises the accumulator / stage /
+    output-buffer rotation of the producer-consumer pipeline.  Odd widths leave through the byte-store path of the right-hand tile."""
+    monkeypatch.setenv("HEVCASM_PRED_HV", "umma")
+    if grid:
+        monkeypatch.setenv("HEVCASM_PRED_UMMA_GRID", grid)
+    for shape in ((200, 136), (131, 37), (8, 8), (464, 400), (700, 130)):
+        width, height = shape
+        nf = 3
+        ref = _ref_planes(220 + taps, nf, width, height)
+        dr = to_dev(ref.buf)
+        nfrac = 4 if taps == 8 else 8
+        for xf, yf in ((1, 1), (2, nfrac - 1), (nfrac - 1, 2)):
+            want = synth.random_planes(221, nf, width, height, 16)
+            got = to_dev(want.buf)
+            oracle.drv("pred_uni_frames", ptr(want.buf, want.origin), want.pitch, ptr(ref.buf, ref.origin), ref.pitch, width, height, taps, xf, yf, nf,
+                       want.frame_stride, ref.frame_stride, threads=8)
+            lib.call("pred_uni_frames", dptr(got, want.origin), want.pitch, dptr(dr, ref.origin), ref.pitch, width, height, taps, xf, yf, nf, want.frame_stride,
+                     ref.frame_stride)
+            assert np.array_equal(to_host(got), want.buf), (shape, xf, yf)
+    test_bi_planes(oracle, taps)
+    if taps == 8 and grid is None:
+        test_bi_extremes(oracle)
 
 
 @pytest.mark.parametrize("taps", [8, 4])
