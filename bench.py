@@ -235,17 +235,20 @@ def kernel_table(torch, lib, synth, stream, hbm_peak):
         try:
             ms = time_on_stream(torch, lambda: lib.call("pred_uni_frames", dptr(o8, org), pitch, dptr(a, org), pitch, W4K, H4K, taps, xf, yf, NF, fs, fs,
                                                         stream=stream), 10, 3)
-            idp = {"pred_uni_luma_copy": 0, "pred_uni_luma_h": 2, "pred_uni_luma_v": 2, "pred_uni_luma_hv": 6.1, "pred_uni_chroma_hv": 3.05}[name]
+            # luma HV: vertical pass on tcgen05 (int8 Toeplitz product, 183 MAC per sample), horizontal pass 4 IDP.2A x 1.09 (tile edges)
+            idp = {"pred_uni_luma_copy": 0, "pred_uni_luma_h": 2, "pred_uni_luma_v": 2, "pred_uni_luma_hv": 4.4, "pred_uni_chroma_hv": 3.05}[name]
             # integer-pipe view (profiles/r01_pipe_peak.json: 64 IDP/clk/SM x 148 SMs x 1.965 GHz = 18.6 T IDP/s)
-            rec(name, ms, n, 2, bound="hbm" if idp < 5 else "int-pipe (IDP)",
-                extra={"idp_per_sample": idp, "idp_pipe_frac": round(n / ms / 1e6 * idp / 1e3 / 18.6, 3)})
+            extra = {"idp_per_sample": idp, "idp_pipe_frac": round(n / ms / 1e6 * idp / 1e3 / 18.6, 3)}
+            if name == "pred_uni_luma_hv":
+                extra["kernel"] = "uv::pred_vh_kernel (tcgen05.mma kind::i8 + TMA + TMEM; HEVCASM_PRED_HV=stream gives the CUDA-core kernel)"
+            rec(name, ms, n, 2, bound="hbm" if idp < 4 else "int-pipe (IDP)", extra=extra)
         except Exception as e:  # entry point not available yet
             out[name] = {"error": str(e)[:80]}
     for name, taps, fr in (("pred_bi_luma_hv", 8, (1, 2, 3, 1)), ("pred_bi_luma_copy", 8, (0, 0, 0, 0))):
         try:
             ms = time_on_stream(torch, lambda: lib.call("pred_bi_frames", dptr(o8, org), pitch, dptr(a, org), dptr(b, org), pitch, W4K, H4K, taps, *fr, NF,
                                                         fs, fs, stream=stream), 10, 3)
-            idp = 12.2 if any(fr) else 0   # two references x (horizontal + vertical pass); the all-zero position is a byte average
+            idp = 8.9 if any(fr) else 0   # two references x (horizontal pass on tcgen05, vertical pass 4 IDP.2A x 80/72); the all-zero position is a byte average
             rec(name, ms, n, 3, bound="int-pipe (IDP)" if idp else "hbm", extra={"idp_per_sample": idp, "idp_pipe_frac": round(n / ms / 1e6 * idp / 1e3 / 18.6, 3)})
         except Exception as e:
             out[name] = {"error": str(e)[:80]}
