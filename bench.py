@@ -248,7 +248,7 @@ def kernel_table(torch, lib, synth, stream, hbm_peak):
         try:
             ms = time_on_stream(torch, lambda: lib.call("pred_bi_frames", dptr(o8, org), pitch, dptr(a, org), dptr(b, org), pitch, W4K, H4K, taps, *fr, NF,
                                                         fs, fs, stream=stream), 10, 3)
-            idp = 8.9 if any(fr) else 0   # two references x (horizontal pass on tcgen05, vertical pass 4 IDP.2A x 80/72); the all-zero position is a byte average
+            idp = 9.8 if any(fr) else 0   # two references x (vertical pass on tcgen05, horizontal pass 4 IDP.2A) + 1 IDP.2A to combine, x 1.09 tile edges; the all-zero position is a byte average
             rec(name, ms, n, 3, bound="int-pipe (IDP)" if idp else "hbm", extra={"idp_per_sample": idp, "idp_pipe_frac": round(n / ms / 1e6 * idp / 1e3 / 18.6, 3)})
         except Exception as e:
             out[name] = {"error": str(e)[:80]}

@@ -1273,8 +1273,8 @@ static int launch_umma(const um::Params &u, void *stream)
     const unsigned grid = tensor_grid((u.n_tiles + G::NWG - 1) / G::NWG);   // one CTA of NWG warpgroups per SM
     return launch(kern, dim3(grid), dim3(G::THREADS), (size_t)G::SMEM_BYTES, stream, u);
 }
-// one reference, vertical pass on the tensor cores (namespace uv of pred_umma.cuh)
-template <int TAPS>
+// vertical pass on the tensor cores (namespace uv of pred_umma.cuh), one or two references
+template <int TAPS, bool BI>
 static bool vh_params(uv::Params *u, const PredParams &p, int n_frames)
 {
     if (!tma::describable(p.sr, p.fs_ref, n_frames)) return false;
@@ -1283,11 +1283,15 @@ static bool vh_params(uv::Params *u, const PredParams &p, int n_frames)
     const long long ext_x = 16 + (long long)p.width + TAPS / 2;   // bytes of a row the filter footprints touch, from x = -16
     u->tiles_x = (p.width + uv::TCOLS - 1) / uv::TCOLS, u->tiles_y = (p.height + uv::TROWS - 1) / uv::TROWS;
     const long long per = (long long)u->tiles_x * u->tiles_y;
-    if (per * n_frames >= (1ll << 31) || !tensor_path_wanted(TAPS, per * n_frames)) return false;
-    if (tma::describe_u32_swizzled128(&u->tmref, p.ref0 - (ptrdiff_t)top * p.sr - 16, p.sr, p.fs_ref, ext_x, rows, n_frames, uv::BOXR)) return false;
-    const PackedCoefs c = pack_coefs(TAPS, p.xf0, p.yf0);
-    for (int g = 0; g < 4; ++g) u->x2[g] = c.x2e[g];
-    for (int k = 0; k < 8; ++k) u->ytap[k] = k < TAPS ? (int8_t)((c.y4s[0][k >> 2] >> (8 * (k & 3))) & 0xff) : 0;
+    if (per * n_frames >= (1ll << 30) || !tensor_path_wanted(TAPS, per * n_frames)) return false;
+    const uint8_t *refs[2] = {p.ref0, p.ref1};
+    const int xf[2] = {p.xf0, p.xf1}, yf[2] = {p.yf0, p.yf1};
+    for (int rf = 0; rf < (BI ? 2 : 1); ++rf) {
+        if (tma::describe_u32_swizzled128(&u->tmref[rf], refs[rf] - (ptrdiff_t)top * p.sr - 16, p.sr, p.fs_ref, ext_x, rows, n_frames, uv::BOXR)) return false;
+        const PackedCoefs c = pack_coefs(TAPS, xf[rf], yf[rf]);
+        for (int g = 0; g < 4; ++g) u->x2[rf][g] = c.x2e[g];
+        for (int k = 0; k < 8; ++k) u->ytap[rf][k] = k < TAPS ? (int8_t)((c.y4s[0][k >> 2] >> (8 * (k & 3))) & 0xff) : 0;
+    }
     u->dst = p.dst, u->sd = p.sd, u->fs_dst = p.fs_dst, u->width = p.width, u->height = p.height;
     u->dst16 = (((uintptr_t)p.dst | (uintptr_t)p.sd | (n_frames > 1 ? (uintptr_t)p.fs_dst : 0)) & 15) == 0 && p.sd > 0 && (n_frames <= 1 || p.fs_dst > 0);
     if (u->dst16) {
@@ -1297,13 +1301,13 @@ static bool vh_params(uv::Params *u, const PredParams &p, int n_frames)
     u->n_tiles = (int)(per * n_frames);
     return true;
 }
-template <int TAPS>
+template <int TAPS, bool BI>
 static int launch_vh(const uv::Params &u, void *stream)
 {
-    auto kern = uv::pred_vh_kernel<TAPS>;
-    if (set_max_smem(kern, uv::SMEM_BYTES)) return (int)cudaErrorInvalidValue;
+    auto kern = uv::pred_vh_kernel<TAPS, BI>;
+    if (set_max_smem(kern, uv::Geom<BI>::SMEM_BYTES)) return (int)cudaErrorInvalidValue;
     const unsigned grid = tensor_grid(u.n_tiles);
-    return launch(kern, dim3(grid), dim3(uv::THREADS), (size_t)uv::SMEM_BYTES, stream, u);
+    return launch(kern, dim3(grid), dim3(uv::THREADS), (size_t)uv::Geom<BI>::SMEM_BYTES, stream, u);
 }
 static bool aligned8(const uint8_t *dst, ptrdiff_t sd, ptrdiff_t fs_dst, int n_frames)
 {
@@ -1329,7 +1333,8 @@ extern "C" int hevcasm_pred_uni_frames(uint8_t *dst, ptrdiff_t sd, const uint8_t
     const bool tile_ok = planes_fast_ok(ref, nullptr, sr, fs_ref, n_frames) && !(pin && !strcmp(pin, "stream"));
     if (mode == HV) {
         uv::Params u;
-        if (taps == 8 ? vh_params<8>(&u, p, n_frames) : vh_params<4>(&u, p, n_frames)) return taps == 8 ? launch_vh<8>(u, stream) : launch_vh<4>(u, stream);
+        if (taps == 8 ? vh_params<8, false>(&u, p, n_frames) : vh_params<4, false>(&u, p, n_frames))
+            return taps == 8 ? launch_vh<8, false>(u, stream) : launch_vh<4, false>(u, stream);
     }
     if (stream_ok(dst, sd, fs_dst, ref, nullptr, sr, fs_ref, n_frames)) {
         FastParams fp{};
@@ -1361,8 +1366,15 @@ extern "C" int hevcasm_pred_bi_frames(uint8_t *dst, ptrdiff_t sd, const uint8_t 
     p.xf0 = xFrac0, p.yf0 = yFrac0, p.xf1 = xFrac1, p.yf1 = yFrac1;
     const dim3 grid((width + PTW - 1) / PTW, (height + PTH - 1) / PTH, n_frames);
     if (xFrac0 || yFrac0 || xFrac1 || yFrac1) {
-        um::Params u;
-        if (umma_params(&u, p, taps, true, n_frames)) return taps == 8 ? launch_umma<8, true>(u, stream) : launch_umma<4, true>(u, stream);
+        const char *bk = getenv("HEVCASM_PRED_BI");   // A/B: "hfirst" = horizontal pass on the tensor cores (um), default = vertical pass (uv)
+        if (bk && !strcmp(bk, "hfirst")) {
+            um::Params u;
+            if (umma_params(&u, p, taps, true, n_frames)) return taps == 8 ? launch_umma<8, true>(u, stream) : launch_umma<4, true>(u, stream);
+        } else {
+            uv::Params u;
+            if (taps == 8 ? vh_params<8, true>(&u, p, n_frames) : vh_params<4, true>(&u, p, n_frames))
+                return taps == 8 ? launch_vh<8, true>(u, stream) : launch_vh<4, true>(u, stream);
+        }
     }
     if (stream_ok(dst, sd, fs_dst, ref0, ref1, sr, fs_ref, n_frames)) {
         FastParams fp{};

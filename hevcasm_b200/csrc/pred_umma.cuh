@@ -1,6 +1,11 @@
-// hevcasm_b200 - two-pass interpolation positions with the HORIZONTAL pass on the 5th-generation tensor cores.
-// (included by pred.cu inside namespace hv::ip, after PredParams / PackedCoefs / pack16 / dp2a_lo)
+// hevcasm_b200 - two-pass interpolation positions with one pass of the separable filter on the 5th-generation tensor cores
+// (tcgen05.mma kind::i8, operands staged by TMA, accumulators in TMEM).  Two kernels:
+//   namespace um: HORIZONTAL pass on the tensor cores, thread = output column walking down the rows  (used for two references)
+//   namespace uv: VERTICAL pass on the tensor cores, thread = output row walking along the columns     (used for one reference)
+// (included by pred.cu inside namespace hv::ip, after PredParams / PackedCoefs / pack16 / dp2a_lo; measurements and the
+// experiment series in profiles/r01_pred_umma.md)
 //
+// ---- um ----
 // The streaming kernels spend 6.1 IDP + 8 other instructions per two-pass sample and are bound by the FMA pipe and by
 // issue slots (profiles/r01_pred.md).  The horizontal pass is a banded matrix product, and int8 x int8 -> int32 is exactly
 // what tcgen05.mma kind::i8 computes:
@@ -12,7 +17,7 @@
 // form, so no thread ever touches an input byte.  (A single 4-D box (16 bytes, rows, 16-byte chunks) gives the no-swizzle
 // form and is just as exact, but its 800 16-byte pieces per tile throttle the TMA unit: 166 us per 16 4K planes.)  Five
 // K-steps of 32 accumulate the 160 input columns.  The exact horizontal sums come back from TMEM with thread = output
-// column, 16 rows per tcgen05.ld - precisely the "thread walks down its column" form the vertical pass wants: pairs of
+// column, 8 rows per tcgen05.ld - precisely the "thread walks down its column" form the vertical pass wants: pairs of
 // consecutive rows in a register ring, IDP.2A with the vertical taps, rounding shift, clip.  What remains on the CUDA
 // cores per sample is 4 IDP.2A + 1 PRMT + ~4.  tools/umma_fir_probe.cu pinned the TMA stride order and the descriptors.
 #pragma once
@@ -269,27 +274,35 @@ constexpr int A_BYTES = TROWS * KROWS;     // 20480: Toeplitz operand, [chunk][m
 constexpr int BOX_BYTES = KROWS * 128;     // one 128-column block of a stage (BOXR rows arrive, KROWS are read)
 constexpr int STAGE_BYTES = 2 * BOX_BYTES, O_BYTES = TROWS * TCOLS;
 constexpr int NOBUF = 3;                   // output buffers: the store of tile i-2 may still be reading while tile i is written
-constexpr int B_OFF = A_BYTES, O_OFF = B_OFF + 2 * STAGE_BYTES, BAR_OFF = O_OFF + NOBUF * O_BYTES;
-constexpr int SMEM_BYTES = 1024 + BAR_OFF + 64;
 constexpr int CONSUMERS = NWG * 128, THREADS = CONSUMERS + 32;
 constexpr uint32_t TX_BYTES = 2 * BOXR * 128;
+template <bool BI>
+struct Geom {
+    static constexpr int NREF = BI ? 2 : 1;
+    static constexpr int B_OFF = NREF * A_BYTES, O_OFF = B_OFF + 2 * STAGE_BYTES, BAR_OFF = O_OFF + NOBUF * O_BYTES;
+    static constexpr int SMEM_BYTES = 1024 + BAR_OFF + 64;
+};
 
 struct alignas(64) Params {
-    CUtensorMap tmref;        // reference as 32-bit words from x = -16, rows from -(TAPS/2-1), frames; boxes of 32 words x BOXR rows, 128-byte swizzle
+    CUtensorMap tmref[2];     // per reference: 32-bit words from x = -16, rows from -(TAPS/2-1), frames; boxes of 32 words x BOXR rows, 128-byte swizzle
     CUtensorMap tmdst;        // destination planes, boxes of TCOLS bytes x TROWS rows (valid when dst16)
     uint8_t *dst;
     ptrdiff_t sd, fs_dst;
     int width, height;
     int dst16;                // destination rows are 16-byte aligned (pointer and strides): tiles leave by TMA store
     int tiles_x, tiles_y, n_tiles;
-    int8_t ytap[8];           // vertical taps (the MMA's Toeplitz band)
-    int x2[4];                // horizontal tap pairs (PackedCoefs::x2e)
+    int8_t ytap[2][8];        // vertical taps per reference (the MMA's Toeplitz bands)
+    int x2[2][4];             // horizontal tap pairs per reference (PackedCoefs::x2e)
 };
 
 // The horizontal pass of one thread: output row = its TMEM lane, CPW output columns from CPW + TAPS - 1 staged ones.  Everything
 // about the column index is compile-time; 8 columns arrive per tcgen05.ld, the next 8 are in flight while these are consumed.
-template <int TAPS>
-__device__ __forceinline__ void horizontal_pass(const Params &P, uint32_t tcol /* lane, accumulator, first staged column */, uint32_t (&out)[CPW / 4])
+//   MODE 0 (one reference)      : out = clip((sum + 2048) >> 12), four neighbours per word
+//   MODE 1 (first of two)       : mid = (int16)(sum >> 6), two neighbours per word (the reference's C truncates to int16, pred_inter.c:124)
+//   MODE 2 (second of two)      : out = clip((mid + (int16)(sum >> 6) + 64) >> 7)  (pred_inter.c:490-501)
+template <int TAPS, int MODE>
+__device__ __forceinline__ void horizontal_pass(const int (&xtap2)[4], uint32_t tcol /* lane, accumulator, first staged column */, uint32_t (&out)[CPW / 4],
+                                                uint32_t (&mid)[CPW / 2])
 {
     constexpr int CH = 8, NCH = (CPW + TAPS - 1 + CH - 1) / CH;
     static_assert(CH % TAPS == 0, "ring slots must be compile-time");
@@ -299,7 +312,7 @@ __device__ __forceinline__ void horizontal_pass(const Params &P, uint32_t tcol /
     for (int k = 0; k < TAPS; ++k) ring[k] = 0;
     int x2[TAPS / 2];
 #pragma unroll
-    for (int g = 0; g < TAPS / 2; ++g) x2[g] = P.x2[g];
+    for (int g = 0; g < TAPS / 2; ++g) x2[g] = xtap2[g];
     int v[2][CH], o[4];
     umma::tmem_ld8(tcol, v[0]);
     umma::tmem_ld_wait(v[0]);
@@ -314,29 +327,42 @@ __device__ __forceinline__ void horizontal_pass(const Params &P, uint32_t tcol /
             prev = v[c & 1][j];
             if (x < 0) continue;
             // output column x takes the pairs ending at columns x+1, x+3, .. = slots (r + 2 + 2g) mod TAPS
-            int a = 2048;
+            int a = MODE == 0 ? 2048 : 0;
 #pragma unroll
             for (int g = 0; g < TAPS / 2; ++g) a = dp2a_lo(ring[(r + 2 + 2 * g) % TAPS], x2[g], a);
-            o[x & 3] = a >> 12;
-            if ((x & 3) == 3) out[x >> 2] = pack_sat_u8(o[0], o[1], o[2], o[3]);   // clip to [0, 255] and pack: two cvt.pack.sat
+            if (MODE == 0) {
+                o[x & 3] = a >> 12;
+            } else if (MODE == 1) {
+                o[x & 1] = a >> 6;
+                if (x & 1) mid[x >> 1] = pack16(o[0], o[1]);   // the low halves: int16 wrap
+            } else {
+                // (mid, this reference) as one int16 pair; IDP.2A with taps (1, 1) sign-extends and adds both halves
+                const uint32_t pr = __byte_perm(mid[x >> 1], (uint32_t)(a >> 6), (x & 1) ? 0x5432 : 0x5410);
+                o[x & 3] = dp2a_lo(pr, 0x0101, 64) >> 7;
+            }
+            if (MODE != 1 && (x & 3) == 3) out[x >> 2] = pack_sat_u8(o[0], o[1], o[2], o[3]);   // clip to [0, 255] and pack: two cvt.pack.sat
         }
         if (c + 1 < NCH) umma::tmem_ld_wait(v[(c + 1) & 1]);
     }
 }
 
-template <int TAPS>
+// Work is a sequence of MMA sets q = 0, 1, 2, ..: one per tile (one reference) or two per tile (q even: reference 0, q odd:
+// reference 1).  Set q uses image stage and accumulator q & 1, so with two references each has its own stage / accumulator and
+// the MMAs of one overlap the horizontal pass over the other.
+template <int TAPS, bool BI>
 __global__ void __launch_bounds__(THREADS, 1) pred_vh_kernel(const __grid_constant__ Params P)
 {
-    constexpr int LEFT = TAPS / 2 - 1;
+    using G = Geom<BI>;
+    constexpr int NREF = G::NREF, SPT = BI ? 2 : 1;   // MMA sets per tile
     static_assert(TROWS + TAPS - 1 <= BOXR && BOXR <= KROWS && 16 + TCOLS + TAPS / 2 <= N && CPW % 8 == 0, "tile geometry");
     extern __shared__ __align__(128) uint8_t us_raw[];
     uint8_t *const us_smem = us_raw + ((1024 - (tma::smem_u32(us_raw) & 1023)) & 1023);   // the 128-byte swizzle atoms sit on 1024-byte boundaries
-    uint8_t *const sA = us_smem;
-    uint8_t *const sB = us_smem + B_OFF;         // [stage][128-column block][row][128]
-    uint8_t *const sO = us_smem + O_OFF;         // [buffer][row][TCOLS]
-    uint64_t *const full = reinterpret_cast<uint64_t *>(us_smem + BAR_OFF);   // [2] image boxes of the stage have landed
-    uint64_t *const done = full + 2;                                          // [2] the MMAs into the accumulator have completed
-    uint64_t *const consumed = full + 4;                                      // [2] every consumer has read the accumulator and written its output bytes
+    uint8_t *const sA = us_smem;                    // [reference][chunk][m][16]
+    uint8_t *const sB = us_smem + G::B_OFF;         // [stage][128-column block][row][128]
+    uint8_t *const sO = us_smem + G::O_OFF;         // [buffer][row][TCOLS]
+    uint64_t *const full = reinterpret_cast<uint64_t *>(us_smem + G::BAR_OFF);   // [2] image boxes of the stage have landed
+    uint64_t *const done = full + 2;                                             // [2] the MMAs into the accumulator have completed
+    uint64_t *const consumed = full + 4;                                         // [2] every consumer has read the accumulator (and written its output bytes)
     uint32_t *const tmem_slot = reinterpret_cast<uint32_t *>(full + 6);
 
     if (threadIdx.x == 0) {
@@ -344,10 +370,11 @@ __global__ void __launch_bounds__(THREADS, 1) pred_vh_kernel(const __grid_consta
         for (int i = 0; i < 2; ++i) tma::mbar_init(full + i, 1), tma::mbar_init(done + i, 1), tma::mbar_init(consumed + i, CONSUMERS);
     }
     if (threadIdx.x < 32) umma::tmem_alloc<512>(tmem_slot);
-    __syncthreads();   // barriers exist: the producer's first two requests go out before the Toeplitz operand is built
+    __syncthreads();   // barriers exist: the producer's first two requests go out before the Toeplitz operands are built
 
     // tile -> (column, row, frame) of tiles: one division at the start, additions with carries afterwards
     const int t0 = blockIdx.x, tstep = gridDim.x;
+    const int n_mine = t0 < P.n_tiles ? (P.n_tiles - t0 + tstep - 1) / tstep : 0, nq = n_mine * SPT;   // this CTA's tiles, MMA sets
     const int per = P.tiles_x * P.tiles_y;
     const int sf = tstep / per, sby = (tstep - sf * per) / P.tiles_x, sbx = tstep - sf * per - sby * P.tiles_x;
     int cf = t0 / per, cy = (t0 - cf * per) / P.tiles_x, cx = t0 - cf * per - cy * P.tiles_x;
@@ -358,29 +385,30 @@ __global__ void __launch_bounds__(THREADS, 1) pred_vh_kernel(const __grid_consta
         if (y >= P.tiles_y) y -= P.tiles_y, ++f;
         f += sf;
     };
-    auto request = [&](int s) {   // producer: the image boxes of tile (cx, cy, cf) into stage s; then on to the next tile
+    auto request = [&](int s) {   // producer: the image boxes of the next MMA set into stage s (with two references, stage = reference)
         tma::mbar_expect_tx(full + s, TX_BYTES);
         uint8_t *b = sB + s * STAGE_BYTES;
-        tma::load_box_3d(b, &P.tmref, cx * (TCOLS / 4), cy * TROWS, cf, full + s);   // x in 32-bit words
-        tma::load_box_3d(b + BOX_BYTES, &P.tmref, cx * (TCOLS / 4) + 32, cy * TROWS, cf, full + s);
-        advance(cx, cy, cf);
+        const CUtensorMap *map = &P.tmref[BI ? s : 0];
+        tma::load_box_3d(b, map, cx * (TCOLS / 4), cy * TROWS, cf, full + s);   // x in 32-bit words
+        tma::load_box_3d(b + BOX_BYTES, map, cx * (TCOLS / 4) + 32, cy * TROWS, cf, full + s);
+        if (!BI || s == 1) advance(cx, cy, cf);
     };
     int sx = cx, sy = cy, sfr = cf;   // producer: tile whose output is stored next
     if (threadIdx.x == CONSUMERS) {
-        if (t0 < P.n_tiles) request(0);
-        if (t0 + tstep < P.n_tiles) request(1);
+        if (nq > 0) request(0);
+        if (nq > 1) request(1);
     }
 
-    // Toeplitz band, one 16-byte chunk per step: output row m reads staged rows m .. m + TAPS - 1
-    for (int i = threadIdx.x; i < (KROWS / 16) * TROWS; i += THREADS) {
-        const int m = i % TROWS, kc = i / TROWS;
+    // Toeplitz bands, one 16-byte chunk per step: output row m reads staged rows m .. m + TAPS - 1
+    for (int i = threadIdx.x; i < NREF * (KROWS / 16) * TROWS; i += THREADS) {
+        const int m = i % TROWS, kc = (i / TROWS) % (KROWS / 16), rf = i / (TROWS * (KROWS / 16));
         uint32_t w[4] = {0, 0, 0, 0};
 #pragma unroll
         for (int b = 0; b < 16; ++b) {
             const int t = 16 * kc + b - m;
-            if (t >= 0 && t < TAPS) w[b >> 2] |= (uint32_t)(uint8_t)P.ytap[t] << (8 * (b & 3));
+            if (t >= 0 && t < TAPS) w[b >> 2] |= (uint32_t)(uint8_t)P.ytap[rf][t] << (8 * (b & 3));
         }
-        *reinterpret_cast<uint4 *>(sA + kc * (TROWS * 16) + m * 16) = make_uint4(w[0], w[1], w[2], w[3]);
+        *reinterpret_cast<uint4 *>(sA + rf * A_BYTES + kc * (TROWS * 16) + m * 16) = make_uint4(w[0], w[1], w[2], w[3]);
     }
     // (the staged rows no box writes, BOXR .. KROWS-1, only ever meet zero taps)
     umma::fence_async_smem();
@@ -407,14 +435,13 @@ __global__ void __launch_bounds__(THREADS, 1) pred_vh_kernel(const __grid_consta
                 advance(sx, sy, sfr);
                 ob = ob == NOBUF - 1 ? 0 : ob + 1;
             };
-            int it = 0;
 #pragma unroll 1
-            for (int t = t0; t < P.n_tiles; t += tstep, ++it) {
-                const int s = it & 1;
-                const uint32_t ph = (it >> 1) & 1;
-                if (it >= 2) {
-                    tma::mbar_wait(consumed + s, ph ^ 1);   // tile it-2 has left this accumulator and sits in its output buffer
-                    store();
+            for (int q = 0; q < nq; ++q) {
+                const int s = q & 1;
+                const uint32_t ph = (q >> 1) & 1;
+                if (q >= 2) {
+                    tma::mbar_wait(consumed + s, ph ^ 1);   // set q-2 has left this accumulator; its tile (if complete) sits in its output buffer
+                    if (!BI || s == 1) store();
                 }
                 tma::mbar_wait(full + s, ph);
                 umma::fence_after();
@@ -422,40 +449,55 @@ __global__ void __launch_bounds__(THREADS, 1) pred_vh_kernel(const __grid_consta
                 for (int ks = 0; ks < KROWS / 32; ++ks) {
                     // A: K-major, no swizzle (LBO = distance between 16-byte k chunks, SBO = between groups of 8 rows).  B: 128-byte-swizzled
                     // MN-major (SBO = groups of 8 k, 1024 bytes; LBO = the second 128-column block); a K-step of 32 rows is 4096 bytes
-                    const uint64_t da = umma::smem_desc(tma::smem_u32(sA + ks * 2 * (TROWS * 16)), TROWS * 16, 128);
+                    const uint64_t da = umma::smem_desc(tma::smem_u32(sA + (BI ? s : 0) * A_BYTES + ks * 2 * (TROWS * 16)), TROWS * 16, 128);
                     const uint64_t db = umma::smem_desc(tma::smem_u32(sB + s * STAGE_BYTES) + ks * 4096, BOX_BYTES, 1024, 2);
                     umma::mma_i8(tm + s * N, da, db, IDESC, ks);
                 }
-                // this tile's output buffer last held tile it-3, whose store was issued one iteration ago: it must have been read
-                // before the consumers learn (via `done`) that they may fill it again; the store just issued may still be reading
+                // the output buffer the consumers fill next last held the tile three back, whose store was issued at least one
+                // iteration ago: it must have been read before they learn (via `done`) that they may go on; the store just issued may
+                // still be reading
                 tma::store_wait_read<1>();
                 umma::commit(done + s);
-                if (t + 2 * tstep < P.n_tiles) {   // the tile after next takes this stage as soon as these MMAs have read it
+                if (q + 2 < nq) {   // the set after next takes this stage as soon as these MMAs have read it
                     tma::mbar_wait(done + s, ph);
                     request(s);
                 }
             }
-            // the last two tiles
-            for (int k = it >= 2 ? it - 2 : 0; k < it; ++k) {
+            // the last two sets
+            for (int k = nq >= 2 ? nq - 2 : 0; k < nq; ++k) {
                 tma::mbar_wait(consumed + (k & 1), (k >> 1) & 1);
-                store();
+                if (!BI || (k & 1)) store();
             }
             tma::store_wait_read<0>();
         }
     } else {
         // ------------------------------------------------------------------------------------------------ consumers
         const int wg = threadIdx.x >> 7, row = threadIdx.x & 127, warp = row >> 5;   // warpgroup; output row of the tile = TMEM lane; warp inside the warpgroup
-        const uint32_t tlane = tm + ((uint32_t)(warp * 32) << 16) + (16 - LEFT) + wg * CPW;
-        int it = 0, ob = 0;
+        const uint32_t tlane = tm + ((uint32_t)(warp * 32) << 16) + (16 - (TAPS / 2 - 1)) + wg * CPW;
+        int ob = 0;
 #pragma unroll 1
-        for (int t = t0; t < P.n_tiles; t += tstep, ++it) {
-            const int a = it & 1;
+        for (int it = 0; it < n_mine; ++it) {
             uint8_t *const obuf = sO + ob * O_BYTES;
             ob = ob == NOBUF - 1 ? 0 : ob + 1;
-            tma::mbar_wait(done + a, (it >> 1) & 1);
-            umma::fence_after();
-            uint32_t out[CPW / 4];
-            horizontal_pass<TAPS>(P, tlane + a * N, out);
+            uint32_t out[CPW / 4], mid[CPW / 2];
+            int a;   // accumulator of the set that produces the output bytes
+            if (BI) {
+                a = 1;
+                const uint32_t ph = it & 1;
+                tma::mbar_wait(done + 0, ph);
+                umma::fence_after();
+                horizontal_pass<TAPS, 1>(P.x2[0], tlane, out, mid);
+                umma::fence_before();
+                tma::mbar_arrive(consumed + 0);   // reference 0 of the next tile may take accumulator 0
+                tma::mbar_wait(done + 1, ph);
+                umma::fence_after();
+                horizontal_pass<TAPS, 2>(P.x2[1], tlane + N, out, mid);
+            } else {
+                a = it & 1;
+                tma::mbar_wait(done + a, (it >> 1) & 1);
+                umma::fence_after();
+                horizontal_pass<TAPS, 0>(P.x2[0], tlane + a * N, out, mid);
+            }
             uint2 *orow = reinterpret_cast<uint2 *>(obuf + row * TCOLS + wg * CPW);
 #pragma unroll
             for (int i = 0; i < CPW / 8; ++i) orow[i] = make_uint2(out[2 * i], out[2 * i + 1]);
@@ -482,4 +524,3 @@ __global__ void __launch_bounds__(THREADS, 1) pred_vh_kernel(const __grid_consta
 }
 
 }  // namespace uv
-

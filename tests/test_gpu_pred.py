@@ -86,6 +86,10 @@ def test_tensor_core_plane_kernels(oracle, taps, grid, monkeypatch):
     test_bi_planes(oracle, taps)
     if taps == 8 and grid is None:
         test_bi_extremes(oracle)
+    monkeypatch.setenv("HEVCASM_PRED_BI", "hfirst")   # the other two-reference kernel: horizontal pass on the tensor cores
+    test_bi_planes(oracle, taps)
+    if taps == 8 and grid is None:
+        test_bi_extremes(oracle)
 
 
 @pytest.mark.parametrize("taps", [8, 4])
