@@ -1219,14 +1219,16 @@ static bool stream_maps(StreamMaps *sm, const PredParams &p, int taps, int mode,
     return true;
 }
 // Two-pass positions on the tensor cores (pred_umma.cuh).  Default: 8-tap positions of batches that fill the chip at least once
-// (the kernels are persistent, one CTA per SM, with tiles of 128 x 224 / 128 x 72 samples); HEVCASM_PRED_HV=umma takes them for
+// (the kernels are persistent, one CTA per SM, with tiles of 128 x 224 samples); HEVCASM_PRED_HV=umma takes them for
 // every size and both filters, HEVCASM_PRED_HV=stream never (A/B runs and the parity tests of either side).
-static bool tensor_path_wanted(int taps, long long n_tiles)
+// Measured crossover on 4K planes (us per launch, tensor / streaming): one reference 12.0 / 12.1 (1 plane), 19.3 / 23.3 (4 planes);
+// two references 18.1 / 15.1 (1), 24.6 / 23.6 (2), 36.6 / 39.8 (4): the two-reference kernel needs ~5 tiles per SM to pay off.
+static bool tensor_path_wanted(int taps, long long n_tiles, bool bi = false)
 {
     const char *pin = getenv("HEVCASM_PRED_HV");
     if (pin && !strcmp(pin, "umma")) return true;
     if (pin && !strcmp(pin, "stream")) return false;
-    return taps == 8 && n_tiles >= sm_count();
+    return taps == 8 && n_tiles >= (bi ? 5ll : 1ll) * sm_count();
 }
 static unsigned tensor_grid(long long n_tiles)
 {
@@ -1283,7 +1285,7 @@ static bool vh_params(uv::Params *u, const PredParams &p, int n_frames)
     const long long ext_x = 16 + (long long)p.width + TAPS / 2;   // bytes of a row the filter footprints touch, from x = -16
     u->tiles_x = (p.width + uv::TCOLS - 1) / uv::TCOLS, u->tiles_y = (p.height + uv::TROWS - 1) / uv::TROWS;
     const long long per = (long long)u->tiles_x * u->tiles_y;
-    if (per * n_frames >= (1ll << 30) || !tensor_path_wanted(TAPS, per * n_frames)) return false;
+    if (per * n_frames >= (1ll << 30) || !tensor_path_wanted(TAPS, per * n_frames, BI)) return false;
     const uint8_t *refs[2] = {p.ref0, p.ref1};
     const int xf[2] = {p.xf0, p.xf1}, yf[2] = {p.yf0, p.yf1};
     for (int rf = 0; rf < (BI ? 2 : 1); ++rf) {

@@ -4,7 +4,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from hevcasm_b200 import lib, synth
 
-W, H, NF, PAD = 3840, 2160, 16, 64
+W, H, NF, PAD = 3840, 2160, int(os.environ.get("RUN_ONE_NF", "16")), 64
 name = sys.argv[1]
 iters = int(sys.argv[2]) if len(sys.argv) > 2 else 3
 pitch = synth.pitch_for(W, PAD); rows = H + 2 * PAD; org = PAD * pitch + PAD; fs = rows * pitch
