@@ -524,6 +524,7 @@ __global__ void __launch_bounds__(BIG_NT) big_fwd_kernel(int16_t *__restrict__ c
 }
 
 #include "transform_umma.cuh"  // 16x16 / 32x32 inverse on tcgen05 (needs BlockGrid, load_words, store_words)
+#include "transform_fwd_umma.cuh"  // forward 32x32: first stage on tcgen05, second in registers
 
 // ================================================================================================ 16x16 / 32x32 inverse on IMMA
 
@@ -773,11 +774,38 @@ static int launch_fwd_t(int16_t *coeffs, const int16_t *res, ptrdiff_t stride, p
     return launch(big_fwd_kernel<5, PA>, (unsigned)((g.n + 7) / 8), BIG_NT, 0, stream, coeffs, res, stride, fs, g);
 }
 
+// forward 32x32 with the first stage on the tensor cores (transform_fwd_umma.cuh): regular grids over 16-byte aligned planes
+static int launch_fwd32_umma(int16_t *coeffs, const int16_t *res, ptrdiff_t stride, ptrdiff_t fs, const BlockGrid &g, void *stream, bool *taken)
+{
+    *taken = false;
+    const long long per = (long long)g.nbx * g.nby;
+    if (per <= 0 || g.n % per != 0) return 0;
+    const int n_frames = (int)(g.n / per);
+    if (!tma::describable(stride * 2, fs * 2, n_frames)) return 0;
+    ft::Params P{};
+    if (tma::describe_u8_swizzled(&P.tmres, reinterpret_cast<const uint8_t *>(res), stride * 2, fs * 2, 64ll * g.nbx, 32ll * g.nby, n_frames, 128, ft::TROWS)) return 0;
+    P.coeffs = coeffs, P.nbx = g.nbx, P.nby = g.nby;
+    P.tiles_x = (g.nbx + ft::TB - 1) / ft::TB, P.tiles_y = (g.nby + ft::TB - 1) / ft::TB;
+    const long long tiles = (long long)P.tiles_x * P.tiles_y * n_frames;
+    if (tiles >= (1ll << 30)) return 0;
+    P.n_tiles = (int)tiles;
+    if (ft::ft_tables_init() || set_max_smem(ft::fwd32_umma_kernel, ft::SMEM_BYTES)) return (int)cudaErrorInvalidValue;
+    *taken = true;
+    const unsigned grid = (unsigned)std::min<long long>(tiles, (long long)sm_count());   // one persistent CTA per SM
+    return launch(ft::fwd32_umma_kernel, dim3(grid), dim3(ft::THREADS), (size_t)ft::SMEM_BYTES, stream, P);
+}
+
 static int launch_fwd(int16_t *coeffs, const int16_t *res, ptrdiff_t stride, ptrdiff_t fs, int log2, int trType, const BlockGrid &g, void *stream)
 {
     if (g.n == 0) return 0;
     if (((uintptr_t)coeffs & 15) != 0) return HEVCASM_ERR_ARGUMENT;
     const bool pa = !g.blk_xy && aligned16(res, stride * 2, fs * 2);
+    const char *pin = getenv("HEVCASM_FWD_PATH");
+    if (log2 == 5 && pa && pin && !strcmp(pin, "umma")) {
+        bool taken = false;
+        const int e = launch_fwd32_umma(coeffs, res, stride, fs, g, stream, &taken);
+        if (taken) return e;
+    }
     return pa ? launch_fwd_t<true>(coeffs, res, stride, fs, log2, trType, g, stream) : launch_fwd_t<false>(coeffs, res, stride, fs, log2, trType, g, stream);
 }
 

@@ -1,0 +1,195 @@
+// hevcasm_b200 - forward 32x32 DCT with its FIRST stage on the 5th-generation tensor cores and the second in the threads.
+// (included by transform.cu inside namespace hv, after FwdBfly / BlockGrid; tcgen05 wrappers in umma.cuh)
+//
+// Stage 1 of the reference (residual_decode.c:795-852, shift 4) is tmp[k][j] = (sum_i T[k][i] * X[j][i] + 8) >> 4 per block
+// row j: a matrix product on int16 data.  An int16 is lo + 256 * hi, and the tensor cores take the raw bytes of the residual
+// tile unsplit: the tile row (256 bytes = 4 blocks x 32 int16) is the K dimension, and the constant operand carries T[k][i]
+// on the EVEN byte positions (2i) of its own block for the low-byte product and on the ODD positions (2i+1) for the
+// high-byte product, zeros everywhere else.  The same shared-memory bytes are read as a u8-typed operand for the first and
+// as an s8-typed operand for the second, so the bytes of the "other" half only ever meet zero coefficients:
+//     D_p[m = (block column bc, frequency k)][n = plane row r] = sum_kk A_p[m][kk] * B[kk][r],   kk = byte of the tile row
+//     A_p[(bc, k)][64 bc + 2 i + p] = T[k][i]  (s8, K-major, built once per CTA);   B = the residual tile as TMA delivers it
+// (two boxes of 128 bytes x 128 rows with the 128-byte swizzle = the swizzled K-major operand, no thread touches an input
+// sample).  16 MMAs (8 K-steps x {lo, hi}) of M = 128, N = 128 per tile of 4 x 4 blocks.  TMEM lane = (bc, k), column = plane
+// row, so the thread (block row = warpgroup, block column = warp, k = lane) finds tmp[k][0..31] of ITS block in 2 x 32 TMEM
+// columns: it recombines lo + 256 hi, rounds, truncates to int16 exactly like the reference's store, runs the second stage
+// (32-point partial butterfly over j, transform.cuh) in registers and stores coeffs[v * 32 + k] for v = 0..31 - 64
+// contiguous bytes per warp and v.  Producer / consumer structure as in pred_umma.cuh (uv): one producer warp, two
+// accumulators (2 x 256 TMEM columns), two image stages, mbarrier hand-offs, no barrier among the consumers.
+#pragma once
+
+namespace ft {
+
+constexpr int TB = 4;                          // blocks per tile side
+constexpr int TROWS = 32 * TB;                 // 128 plane rows = MMA N
+constexpr int TBYTES = 64 * TB;                // 256 bytes per tile row = MMA K (8 steps of 32)
+constexpr int A_BYTES = 128 * TBYTES;          // one constant operand: [chunk (16)][m (128)][16]
+constexpr int BOX_BYTES = 128 * TROWS;         // one box: 128 bytes x 128 rows
+constexpr int STAGE_BYTES = 2 * BOX_BYTES;
+constexpr int B_OFF = 2 * A_BYTES, BAR_OFF = B_OFF + 2 * STAGE_BYTES;
+constexpr int SMEM_BYTES = 1024 + BAR_OFF + 64;
+constexpr int CONSUMERS = 128 * TB, THREADS = CONSUMERS + 32;
+
+// the two constant operands in their shared-memory layout [lo / hi][chunk (16)][m (128)][16], built on the host once
+__device__ uint4 g_ft_A[2 * A_BYTES / 16];
+inline int ft_tables_init()
+{
+    static int done = [] {
+        static uint8_t a[2 * A_BYTES];
+        memset(a, 0, sizeof a);
+        for (int p = 0; p < 2; ++p)
+            for (int m = 0; m < 128; ++m) {
+                const int bc = m >> 5, k = m & 31;
+                for (int i = 0; i < 32; ++i) {
+                    const int kk = 64 * bc + 2 * i + p;   // byte of the tile row that holds the low (p = 0) / high (p = 1) half of sample i of block column bc
+                    a[p * A_BYTES + (kk >> 4) * (128 * 16) + m * 16 + (kk & 15)] = (uint8_t)(int8_t)dct(32, k, i);
+                }
+            }
+        return (int)cudaMemcpyToSymbol(g_ft_A, a, sizeof a);
+    }();
+    return done;
+}
+
+struct alignas(64) Params {
+    CUtensorMap tmres;        // residual planes as bytes: (2 * 32 nbx bytes, 32 nby rows, frames); boxes of 128 bytes x 128 rows, 128-byte swizzle
+    int16_t *coeffs;
+    int nbx, nby;             // blocks per plane row / column
+    int tiles_x, tiles_y, n_tiles;
+};
+
+__global__ void __launch_bounds__(THREADS, 1) fwd32_umma_kernel(const __grid_constant__ Params P)
+{
+    extern __shared__ __align__(128) uint8_t ft_raw[];
+    uint8_t *const smem = ft_raw + ((1024 - (tma::smem_u32(ft_raw) & 1023)) & 1023);
+    uint8_t *const sA = smem;                    // [lo / hi][chunk][m][16]
+    uint8_t *const sB = smem + B_OFF;            // [stage][box][row][128]
+    uint64_t *const full = reinterpret_cast<uint64_t *>(smem + BAR_OFF);   // [2] the residual boxes of the stage have landed
+    uint64_t *const done = full + 2;                                       // [2] the MMAs into the accumulator have completed
+    uint64_t *const consumed = full + 4;                                   // [2] every consumer has read the accumulator
+    uint32_t *const tmem_slot = reinterpret_cast<uint32_t *>(full + 6);
+
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int i = 0; i < 2; ++i) tma::mbar_init(full + i, 1), tma::mbar_init(done + i, 1), tma::mbar_init(consumed + i, CONSUMERS);
+    }
+    if (threadIdx.x < 32) umma::tmem_alloc<512>(tmem_slot);
+    __syncthreads();
+
+    const int t0 = blockIdx.x, tstep = gridDim.x;
+    const int n_mine = t0 < P.n_tiles ? (P.n_tiles - t0 + tstep - 1) / tstep : 0;
+    const int per = P.tiles_x * P.tiles_y;
+    const int sf = tstep / per, sby = (tstep - sf * per) / P.tiles_x, sbx = tstep - sf * per - sby * P.tiles_x;
+    int cf = t0 / per, cy = (t0 - cf * per) / P.tiles_x, cx = t0 - cf * per - cy * P.tiles_x;
+    auto advance = [&](int &x, int &y, int &f) {
+        x += sbx;
+        if (x >= P.tiles_x) x -= P.tiles_x, ++y;
+        y += sby;
+        if (y >= P.tiles_y) y -= P.tiles_y, ++f;
+        f += sf;
+    };
+    auto request = [&](int s) {   // producer: the residual boxes of tile (cx, cy, cf) into stage s; then on to the next tile
+        tma::mbar_expect_tx(full + s, 2 * BOX_BYTES);
+        uint8_t *b = sB + s * STAGE_BYTES;
+        tma::load_box_3d(b, &P.tmres, cx * TBYTES, cy * TROWS, cf, full + s);
+        tma::load_box_3d(b + BOX_BYTES, &P.tmres, cx * TBYTES + 128, cy * TROWS, cf, full + s);
+        advance(cx, cy, cf);
+    };
+    if (threadIdx.x == CONSUMERS) {
+        if (n_mine > 0) request(0);
+        if (n_mine > 1) request(1);
+    }
+
+    // constant operands: A_p[(bc, k)][64 bc + 2 i + p] = T[k][i], copied from the host-built image
+    for (int idx = threadIdx.x; idx < 2 * A_BYTES / 16; idx += THREADS) reinterpret_cast<uint4 *>(sA)[idx] = g_ft_A[idx];
+    umma::fence_async_smem();
+    umma::fence_before();
+    __syncthreads();
+    umma::fence_after();
+    const uint32_t tm = *tmem_slot;
+
+    if (threadIdx.x >= CONSUMERS) {
+        // ------------------------------------------------------------------------------------------------ producer
+        if (threadIdx.x == CONSUMERS) {
+            constexpr uint32_t ID_LO = umma::idesc_i8(true, false, false, TROWS), ID_HI = umma::idesc_i8(true, true, false, TROWS);
+#pragma unroll 1
+            for (int q = 0; q < n_mine; ++q) {
+                const int s = q & 1;
+                const uint32_t ph = (q >> 1) & 1;
+                if (q >= 2) tma::mbar_wait(consumed + s, ph ^ 1);   // tile q-2 has left this accumulator
+                tma::mbar_wait(full + s, ph);
+                umma::fence_after();
+#pragma unroll
+                for (int p = 0; p < 2; ++p)
+#pragma unroll
+                    for (int ks = 0; ks < TBYTES / 32; ++ks) {
+                        // A: K-major, no swizzle (LBO = distance between 16-byte k chunks, SBO = between groups of 8 rows).  B: swizzled K-major,
+                        // groups of 8 rows 1024 bytes apart; a K-step advances the start address by 32 bytes inside the swizzle row
+                        const uint64_t da = umma::smem_desc(tma::smem_u32(sA + p * A_BYTES + ks * 2 * (128 * 16)), 128 * 16, 128);
+                        const uint64_t db = umma::smem_desc(tma::smem_u32(sB + s * STAGE_BYTES + (ks >> 2) * BOX_BYTES) + (ks & 3) * 32, 16, 1024, 2);
+                        umma::mma_i8(tm + s * 256 + p * TROWS, da, db, p ? ID_HI : ID_LO, ks);
+                    }
+                umma::commit(done + s);
+                if (q + 2 < n_mine) {   // the tile after next takes this stage as soon as these MMAs have read it
+                    tma::mbar_wait(done + s, ph);
+                    request(s);
+                }
+            }
+        }
+    } else {
+        // ------------------------------------------------------------------------------------------------ consumers
+        const int wg = threadIdx.x >> 7, warp = (threadIdx.x >> 5) & 3, lane = threadIdx.x & 31;   // block row, block column, frequency k
+        const uint32_t tl = tm + ((uint32_t)(warp * 32) << 16) + 32 * wg;
+#pragma unroll 1
+        for (int it = 0; it < n_mine; ++it) {
+            const int a = it & 1;
+            tma::mbar_wait(done + a, (it >> 1) & 1);
+            umma::fence_after();
+            // stage 1 out of TMEM: tmp[k][j] = (lo + 256 hi + 8) >> 4, truncated to int16 (residual_decode.c:846)
+            int x[32];
+            uint32_t range = 0;   // stays below 2^15 iff every stage-1 value lies in [-16384, 16383]
+            {
+                const uint32_t t = tl + a * 256;
+                int lo[2][8], hi[2][8];
+                umma::tmem_ld8(t, lo[0]);
+                umma::tmem_ld8(t + TROWS, hi[0]);
+                umma::tmem_ld_wait(lo[0]);
+                umma::tmem_ld_wait(hi[0]);
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    if (c < 3) {
+                        umma::tmem_ld8(t + 8 * (c + 1), lo[(c + 1) & 1]);
+                        umma::tmem_ld8(t + TROWS + 8 * (c + 1), hi[(c + 1) & 1]);
+                    }
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const int t = (lo[c & 1][j] + (hi[c & 1][j] << 8) + 8 + (16384 << 4)) >> 4;   // the stage-1 value + 16384
+                        range |= (uint32_t)t;
+                        x[8 * c + j] = (int)(short)(t - 16384);
+                    }
+                    if (c < 3) {
+                        umma::tmem_ld_wait(lo[(c + 1) & 1]);
+                        umma::tmem_ld_wait(hi[(c + 1) & 1]);
+                    }
+                }
+            }
+            umma::fence_before();   // this thread's TMEM reads are complete
+            tma::mbar_arrive(consumed + a);
+            // stage 2 in registers: out[v] = (sum_j T[v][j] tmp[k][j] + 1024) >> 11 -> coeffs[v * 32 + k]  (residual_decode.c:890-892)
+            const int rb = cy * TB + wg, bcg = cx * TB + warp;
+            if (rb < P.nby && bcg < P.nbx) {
+                int o[32];
+                if ((range >> 15) == 0) FwdBflyPacked<32>::run(x, o, 1 << 10);   // odd part of the top level on IDP.2A (transform.cuh); exact for this range
+                else FwdBfly<32>::run(x, o, 1 << 10);
+                int16_t *out = P.coeffs + (((long long)cf * P.nby + rb) * P.nbx + bcg) * 1024 + lane;
+#pragma unroll
+                for (int v = 0; v < 32; ++v) out[v * 32] = (int16_t)(o[v] >> 11);
+            }
+            advance(cx, cy, cf);
+        }
+    }
+    umma::fence_before();
+    __syncthreads();
+    if (threadIdx.x < 32) umma::tmem_dealloc<512>(*tmem_slot);
+}
+
+}  // namespace ft
