@@ -774,25 +774,32 @@ static int launch_fwd_t(int16_t *coeffs, const int16_t *res, ptrdiff_t stride, p
     return launch(big_fwd_kernel<5, PA>, (unsigned)((g.n + 7) / 8), BIG_NT, 0, stream, coeffs, res, stride, fs, g);
 }
 
-// forward 32x32 with the first stage on the tensor cores (transform_fwd_umma.cuh): regular grids over 16-byte aligned planes
-static int launch_fwd32_umma(int16_t *coeffs, const int16_t *res, ptrdiff_t stride, ptrdiff_t fs, const BlockGrid &g, void *stream, bool *taken)
+// forward 16x16 / 32x32 with the first stage on the tensor cores (transform_fwd_umma.cuh): regular grids over 16-byte aligned planes.
+// Default: batches of at least 6 tiles (128 x 128 samples) per SM - measured crossover on 4K planes, us per launch, tensor / butterfly:
+// 17.1 / 15.0 (1 plane), 24.3 / 25.2 (2), 43.7 / 48.3 (4), 70.5 / 88.8 (8).  HEVCASM_FWD_PATH=umma: whenever the planes allow it;
+// =umma_only: fail instead of falling back (tests); =butterfly: never.
+template <int LOG2>
+static int launch_fwd_umma(int16_t *coeffs, const int16_t *res, ptrdiff_t stride, ptrdiff_t fs, const BlockGrid &g, void *stream, bool forced, bool *taken)
 {
     *taken = false;
+    constexpr int BS = 1 << LOG2, TB = 128 / BS;
     const long long per = (long long)g.nbx * g.nby;
     if (per <= 0 || g.n % per != 0) return 0;
     const int n_frames = (int)(g.n / per);
     if (!tma::describable(stride * 2, fs * 2, n_frames)) return 0;
     ft::Params P{};
-    if (tma::describe_u8_swizzled(&P.tmres, reinterpret_cast<const uint8_t *>(res), stride * 2, fs * 2, 64ll * g.nbx, 32ll * g.nby, n_frames, 128, ft::TROWS)) return 0;
     P.coeffs = coeffs, P.nbx = g.nbx, P.nby = g.nby;
-    P.tiles_x = (g.nbx + ft::TB - 1) / ft::TB, P.tiles_y = (g.nby + ft::TB - 1) / ft::TB;
+    P.tiles_x = (g.nbx + TB - 1) / TB, P.tiles_y = (g.nby + TB - 1) / TB;
     const long long tiles = (long long)P.tiles_x * P.tiles_y * n_frames;
-    if (tiles >= (1ll << 30)) return 0;
+    if (tiles >= (1ll << 30) || (!forced && tiles < 6ll * sm_count())) return 0;
     P.n_tiles = (int)tiles;
-    if (ft::ft_tables_init() || set_max_smem(ft::fwd32_umma_kernel, ft::SMEM_BYTES)) return (int)cudaErrorInvalidValue;
+    if (tma::describe_u8_swizzled(&P.tmres, reinterpret_cast<const uint8_t *>(res), stride * 2, fs * 2, 2ll * BS * g.nbx, (long long)BS * g.nby, n_frames, 128, ft::TROWS))
+        return 0;
+    if (ft::ft_tables_init() || set_max_smem(ft::fwd_umma_kernel<LOG2>, ft::SMEM_BYTES)) return (int)cudaErrorInvalidValue;
     *taken = true;
-    const unsigned grid = (unsigned)std::min<long long>(tiles, (long long)sm_count());   // one persistent CTA per SM
-    return launch(ft::fwd32_umma_kernel, dim3(grid), dim3(ft::THREADS), (size_t)ft::SMEM_BYTES, stream, P);
+    long long grid = std::min<long long>(tiles, (long long)sm_count());   // one persistent CTA per SM
+    if (const char *e = getenv("HEVCASM_FWD_UMMA_GRID")) grid = std::max(1ll, std::min<long long>(grid, atoll(e)));   // test knob: more tiles per CTA
+    return launch(ft::fwd_umma_kernel<LOG2>, dim3((unsigned)grid), dim3(ft::THREADS), (size_t)ft::SMEM_BYTES, stream, P);
 }
 
 static int launch_fwd(int16_t *coeffs, const int16_t *res, ptrdiff_t stride, ptrdiff_t fs, int log2, int trType, const BlockGrid &g, void *stream)
@@ -801,10 +808,12 @@ static int launch_fwd(int16_t *coeffs, const int16_t *res, ptrdiff_t stride, ptr
     if (((uintptr_t)coeffs & 15) != 0) return HEVCASM_ERR_ARGUMENT;
     const bool pa = !g.blk_xy && aligned16(res, stride * 2, fs * 2);
     const char *pin = getenv("HEVCASM_FWD_PATH");
-    if (log2 == 5 && pa && pin && !strcmp(pin, "umma")) {
+    const bool forced = pin && !strncmp(pin, "umma", 4);
+    if ((log2 == 5 || log2 == 4) && !(pin && !strcmp(pin, "butterfly"))) {
         bool taken = false;
-        const int e = launch_fwd32_umma(coeffs, res, stride, fs, g, stream, &taken);
+        const int e = !pa ? 0 : log2 == 5 ? launch_fwd_umma<5>(coeffs, res, stride, fs, g, stream, forced, &taken) : launch_fwd_umma<4>(coeffs, res, stride, fs, g, stream, forced, &taken);
         if (taken) return e;
+        if (pin && !strcmp(pin, "umma_only")) return HEVCASM_ERR_ARGUMENT;
     }
     return pa ? launch_fwd_t<true>(coeffs, res, stride, fs, log2, trType, g, stream) : launch_fwd_t<false>(coeffs, res, stride, fs, log2, trType, g, stream);
 }

@@ -1,4 +1,5 @@
-// hevcasm_b200 - forward 32x32 DCT with its FIRST stage on the 5th-generation tensor cores and the second in the threads.
+// hevcasm_b200 - forward 16x16 / 32x32 DCT with its FIRST stage on the 5th-generation tensor cores and the second in the threads.
+// (written out for 32x32; for 16x16 a tile is 8 x 8 blocks and a thread runs two 16-point second stages per tile)
 // (included by transform.cu inside namespace hv, after FwdBfly / BlockGrid; tcgen05 wrappers in umma.cuh)
 //
 // Stage 1 of the reference (residual_decode.c:795-852, shift 4) is tmp[k][j] = (sum_i T[k][i] * X[j][i] + 8) >> 4 per block
@@ -20,45 +21,50 @@
 
 namespace ft {
 
-constexpr int TB = 4;                          // blocks per tile side
-constexpr int TROWS = 32 * TB;                 // 128 plane rows = MMA N
-constexpr int TBYTES = 64 * TB;                // 256 bytes per tile row = MMA K (8 steps of 32)
+constexpr int TROWS = 128;                     // plane rows per tile = MMA N (128 / BS blocks)
+constexpr int TBYTES = 256;                    // bytes per tile row = MMA K (8 steps of 32) = 128 samples
 constexpr int A_BYTES = 128 * TBYTES;          // one constant operand: [chunk (16)][m (128)][16]
 constexpr int BOX_BYTES = 128 * TROWS;         // one box: 128 bytes x 128 rows
 constexpr int STAGE_BYTES = 2 * BOX_BYTES;
 constexpr int B_OFF = 2 * A_BYTES, BAR_OFF = B_OFF + 2 * STAGE_BYTES;
 constexpr int SMEM_BYTES = 1024 + BAR_OFF + 64;
-constexpr int CONSUMERS = 128 * TB, THREADS = CONSUMERS + 32;
+constexpr int CONSUMERS = 512, THREADS = CONSUMERS + 32;   // four consumer warpgroups (32 plane rows each) + the producer warp
 
-// the two constant operands in their shared-memory layout [lo / hi][chunk (16)][m (128)][16], built on the host once
-__device__ uint4 g_ft_A[2 * A_BYTES / 16];
+// the two constant operands in their shared-memory layout [size (16, 32)][lo / hi][chunk (16)][m (128)][16], built on the host once
+__device__ uint4 g_ft_A[2][2 * A_BYTES / 16];
 inline int ft_tables_init()
 {
     static int done = [] {
-        static uint8_t a[2 * A_BYTES];
+        static uint8_t a[2][2 * A_BYTES];
         memset(a, 0, sizeof a);
-        for (int p = 0; p < 2; ++p)
-            for (int m = 0; m < 128; ++m) {
-                const int bc = m >> 5, k = m & 31;
-                for (int i = 0; i < 32; ++i) {
-                    const int kk = 64 * bc + 2 * i + p;   // byte of the tile row that holds the low (p = 0) / high (p = 1) half of sample i of block column bc
-                    a[p * A_BYTES + (kk >> 4) * (128 * 16) + m * 16 + (kk & 15)] = (uint8_t)(int8_t)dct(32, k, i);
+        for (int sz = 0; sz < 2; ++sz) {
+            const int BS = 16 << sz;
+            for (int p = 0; p < 2; ++p)
+                for (int m = 0; m < 128; ++m) {
+                    const int bc = m / BS, k = m % BS;
+                    for (int i = 0; i < BS; ++i) {
+                        const int kk = 2 * BS * bc + 2 * i + p;   // byte of the tile row that holds the low (p = 0) / high (p = 1) half of sample i of block column bc
+                        a[sz][p * A_BYTES + (kk >> 4) * (128 * 16) + m * 16 + (kk & 15)] = (uint8_t)(int8_t)dct(BS, k, i);
+                    }
                 }
-            }
+        }
         return (int)cudaMemcpyToSymbol(g_ft_A, a, sizeof a);
     }();
     return done;
 }
 
 struct alignas(64) Params {
-    CUtensorMap tmres;        // residual planes as bytes: (2 * 32 nbx bytes, 32 nby rows, frames); boxes of 128 bytes x 128 rows, 128-byte swizzle
+    CUtensorMap tmres;        // residual planes as bytes: (2 BS nbx bytes, BS nby rows, frames); boxes of 128 bytes x 128 rows, 128-byte swizzle
     int16_t *coeffs;
     int nbx, nby;             // blocks per plane row / column
     int tiles_x, tiles_y, n_tiles;
 };
 
-__global__ void __launch_bounds__(THREADS, 1) fwd32_umma_kernel(const __grid_constant__ Params P)
+template <int LOG2>
+__global__ void __launch_bounds__(THREADS, 1) fwd_umma_kernel(const __grid_constant__ Params P)
 {
+    constexpr int BS = 1 << LOG2, TB = 128 / BS, BPT = 32 / BS;   // block size; blocks per tile side; blocks per thread and tile (one below the other)
+    constexpr int S1 = fwd_shift1(LOG2), S2 = fwd_shift2(LOG2);
     extern __shared__ __align__(128) uint8_t ft_raw[];
     uint8_t *const smem = ft_raw + ((1024 - (tma::smem_u32(ft_raw) & 1023)) & 1023);
     uint8_t *const sA = smem;                    // [lo / hi][chunk][m][16]
@@ -100,7 +106,7 @@ __global__ void __launch_bounds__(THREADS, 1) fwd32_umma_kernel(const __grid_con
     }
 
     // constant operands: A_p[(bc, k)][64 bc + 2 i + p] = T[k][i], copied from the host-built image
-    for (int idx = threadIdx.x; idx < 2 * A_BYTES / 16; idx += THREADS) reinterpret_cast<uint4 *>(sA)[idx] = g_ft_A[idx];
+    for (int idx = threadIdx.x; idx < 2 * A_BYTES / 16; idx += THREADS) reinterpret_cast<uint4 *>(sA)[idx] = g_ft_A[LOG2 - 4][idx];
     umma::fence_async_smem();
     umma::fence_before();
     __syncthreads();
@@ -137,14 +143,15 @@ __global__ void __launch_bounds__(THREADS, 1) fwd32_umma_kernel(const __grid_con
         }
     } else {
         // ------------------------------------------------------------------------------------------------ consumers
-        const int wg = threadIdx.x >> 7, warp = (threadIdx.x >> 5) & 3, lane = threadIdx.x & 31;   // block row, block column, frequency k
+        const int wg = threadIdx.x >> 7, m = threadIdx.x & 127, warp = m >> 5;   // 32 plane rows of the tile; TMEM lane = (block column, frequency k)
+        const int bc = m / BS, k = m % BS;
         const uint32_t tl = tm + ((uint32_t)(warp * 32) << 16) + 32 * wg;
 #pragma unroll 1
         for (int it = 0; it < n_mine; ++it) {
             const int a = it & 1;
             tma::mbar_wait(done + a, (it >> 1) & 1);
             umma::fence_after();
-            // stage 1 out of TMEM: tmp[k][j] = (lo + 256 hi + 8) >> 4, truncated to int16 (residual_decode.c:846)
+            // stage 1 out of TMEM: tmp[k][j] = (lo + 256 hi + round) >> S1, truncated to int16 (residual_decode.c:846)
             int x[32];
             uint32_t range = 0;   // stays below 2^15 iff every stage-1 value lies in [-16384, 16383]
             {
@@ -162,9 +169,9 @@ __global__ void __launch_bounds__(THREADS, 1) fwd32_umma_kernel(const __grid_con
                     }
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {
-                        const int t = (lo[c & 1][j] + (hi[c & 1][j] << 8) + 8 + (16384 << 4)) >> 4;   // the stage-1 value + 16384
-                        range |= (uint32_t)t;
-                        x[8 * c + j] = (int)(short)(t - 16384);
+                        const int v = (lo[c & 1][j] + (hi[c & 1][j] << 8) + (1 << (S1 - 1)) + (16384 << S1)) >> S1;   // the stage-1 value + 16384
+                        range |= (uint32_t)v;
+                        x[8 * c + j] = (int)(short)(v - 16384);
                     }
                     if (c < 3) {
                         umma::tmem_ld_wait(lo[(c + 1) & 1]);
@@ -174,15 +181,19 @@ __global__ void __launch_bounds__(THREADS, 1) fwd32_umma_kernel(const __grid_con
             }
             umma::fence_before();   // this thread's TMEM reads are complete
             tma::mbar_arrive(consumed + a);
-            // stage 2 in registers: out[v] = (sum_j T[v][j] tmp[k][j] + 1024) >> 11 -> coeffs[v * 32 + k]  (residual_decode.c:890-892)
-            const int rb = cy * TB + wg, bcg = cx * TB + warp;
-            if (rb < P.nby && bcg < P.nbx) {
-                int o[32];
-                if ((range >> 15) == 0) FwdBflyPacked<32>::run(x, o, 1 << 10);   // odd part of the top level on IDP.2A (transform.cuh); exact for this range
-                else FwdBfly<32>::run(x, o, 1 << 10);
-                int16_t *out = P.coeffs + (((long long)cf * P.nby + rb) * P.nbx + bcg) * 1024 + lane;
+            // stage 2 in registers: out[v] = (sum_j T[v][j] tmp[k][j] + round) >> S2 -> coeffs[v * BS + k]  (residual_decode.c:855-892)
+            const int bcg = cx * TB + bc;
 #pragma unroll
-                for (int v = 0; v < 32; ++v) out[v * 32] = (int16_t)(o[v] >> 11);
+            for (int h = 0; h < BPT; ++h) {
+                const int rb = cy * TB + wg * BPT + h;
+                if (rb < P.nby && bcg < P.nbx) {
+                    int o[BS];
+                    if (BS == 32 && (range >> 15) == 0) FwdBflyPacked<BS>::run(x + h * BS, o, 1 << (S2 - 1));   // odd part of the top level on IDP.2A; exact for this range
+                    else FwdBfly<BS>::run(x + h * BS, o, 1 << (S2 - 1));
+                    int16_t *out = P.coeffs + (((long long)cf * P.nby + rb) * P.nbx + bcg) * (BS * BS) + k;
+#pragma unroll
+                    for (int v = 0; v < BS; ++v) out[v * BS] = (int16_t)(o[v] >> S2);
+                }
             }
             advance(cx, cy, cf);
         }

@@ -31,6 +31,29 @@ def test_forward_frames(oracle, trType, log2, rng):
     assert np.array_equal(to_host(got), want)
 
 
+@pytest.mark.parametrize("grid", [None, "2", "1"])
+@pytest.mark.parametrize("rng", [(-256, 255), (-32768, 32767), (-20000, -12000)])
+@pytest.mark.parametrize("log2", [5, 4])
+def test_forward_tensor_core(oracle, log2, rng, grid, monkeypatch):
+    """forward 16x16 / 32x32 with the first stage on tcgen05 (transform_fwd_umma.cuh): 16-byte aligned planes, block counts that leave
+    partial 4x4-block tiles, several frames; "umma_only" makes the call fail rather than fall back, so a pass is the tensor
+    path.  Full-range and all-negative inputs exercise the high-byte product and the unpacked second-stage butterfly; with
+    1 or 2 CTAs each CTA walks over several tiles (accumulator / stage rotation)."""
+    monkeypatch.setenv("HEVCASM_FWD_PATH", "umma_only")
+    if grid:
+        monkeypatch.setenv("HEVCASM_FWD_UMMA_GRID", grid)
+    n = 1 << log2
+    for width, height, nf in ((224, 160, 3), (32, 32, 1), (416, 300, 2)):
+        res = _res_planes(160 + width, nf, width, height, *rng, pad=8)
+        nb = (width // n) * (height // n)
+        want = np.zeros(nf * nb * n * n, np.int16)
+        oracle.drv("transform_frames", ptr(want), ptr(res.buf, res.origin), res.pitch, width, height, log2, 0, nf, res.frame_stride, threads=8)
+        dres = to_dev(res.buf)
+        got = dev_full(want.shape, np.int16, 0x5a5a)
+        lib.call("transform_frames", dptr(got), dptr(dres, res.origin), res.pitch, width, height, log2, 0, nf, res.frame_stride)
+        assert np.array_equal(to_host(got), want), (width, height, nf)
+
+
 @pytest.mark.parametrize("trType,log2", TR)
 def test_forward_list_unaligned(oracle, trType, log2):
     width, height, n = 160, 96, 1 << log2
