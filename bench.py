@@ -262,7 +262,9 @@ def kernel_table(torch, lib, synth, stream, hbm_peak):
     for log2 in (2, 3, 4, 5):
         N = 1 << log2
         ms = time_on_stream(torch, lambda: lib.call("transform_frames", dptr(co), dptr(res), rp, W4K, H4K, log2, 0, NF, H4K * rp, stream=stream), 10, 3)
-        rec(f"fwd_dct_{N}x{N}", ms, NF * (W4K // N * N) * (H4K // N * N), 4)
+        extra = {"kernel": "ft::fwd_umma_kernel: first stage on tcgen05 (kind::i8 on the raw int16 tile, TMEM), second stage in registers; "
+                           "HEVCASM_FWD_PATH=butterfly gives the CUDA-core kernel"} if log2 >= 4 else None
+        rec(f"fwd_dct_{N}x{N}", ms, NF * (W4K // N * N) * (H4K // N * N), 4, extra=extra)
     lib.call("transform_frames", dptr(co), dptr(res), rp, W4K, H4K, 3, 0, NF, H4K * rp, stream=stream)
     ms = time_on_stream(torch, lambda: lib.call("quantize_batch", dptr(co2), dptr(co), 26214, 18, 171 << 7, 64, n // 64, dptr(cbf), stream=stream), 10, 3)
     rec("quantize", ms, n, 4 + 4 / 64)
