@@ -525,6 +525,7 @@ __global__ void __launch_bounds__(BIG_NT) big_fwd_kernel(int16_t *__restrict__ c
 
 #include "transform_umma.cuh"  // 16x16 / 32x32 inverse on tcgen05 (needs BlockGrid, load_words, store_words)
 #include "transform_fwd_umma.cuh"  // forward 32x32: first stage on tcgen05, second in registers
+#include "transform_inv_umma.cuh"  // inverse 16x16 / 32x32: first stage in registers, second on tcgen05
 
 // ================================================================================================ 16x16 / 32x32 inverse on IMMA
 
@@ -846,12 +847,45 @@ static int launch_inv_t(uint8_t *dst, ptrdiff_t sd, const uint8_t *pred, ptrdiff
     return launch(big_inv_kernel<5, PA>, (unsigned)((g.n + 7) / 8), BIG_NT, 0, stream, dst, sd, pred, sp, fs_dst, fs_pred, coeffs, g);
 }
 
+// inverse 16x16 / 32x32 with the second stage on the tensor cores (transform_inv_umma.cuh): regular grids over 16-byte aligned planes
+template <int LOG2>
+static int launch_inv_umma(uint8_t *dst, ptrdiff_t sd, const uint8_t *pred, ptrdiff_t sp, ptrdiff_t fs_dst, ptrdiff_t fs_pred, const int16_t *coeffs,
+                           const BlockGrid &g, void *stream, bool forced, bool *taken)
+{
+    *taken = false;
+    constexpr int BS = 1 << LOG2, TB = 128 / BS;
+    const long long per = (long long)g.nbx * g.nby;
+    if (per <= 0 || g.n % per != 0) return 0;
+    const int n_frames = (int)(g.n / per);
+    fi::Params P{};
+    P.dst = dst, P.pred = pred, P.coeffs = coeffs, P.sd = sd, P.sp = sp, P.fs_dst = fs_dst, P.fs_pred = fs_pred, P.nbx = g.nbx, P.nby = g.nby;
+    P.tiles_x = (g.nbx + TB - 1) / TB, P.tiles_y = (g.nby + TB - 1) / TB;
+    const long long tiles = (long long)P.tiles_x * P.tiles_y * n_frames;
+    if (tiles >= (1ll << 30) || (!forced && tiles < 6ll * sm_count())) return 0;
+    P.n_tiles = (int)tiles;
+    if (fi::fi_tables_init() || set_max_smem(fi::inv_umma_kernel<LOG2>, fi::SMEM_BYTES)) return (int)cudaErrorInvalidValue;
+    *taken = true;
+    long long grid = std::min<long long>(tiles, (long long)sm_count());   // one persistent CTA per SM
+    if (const char *e = getenv("HEVCASM_INV_UMMA_GRID")) grid = std::max(1ll, std::min<long long>(grid, atoll(e)));   // test knob: more tiles per CTA
+    return launch(fi::inv_umma_kernel<LOG2>, dim3((unsigned)grid), dim3(fi::THREADS), (size_t)fi::SMEM_BYTES, stream, P);
+}
+
 static int launch_inv(uint8_t *dst, ptrdiff_t sd, const uint8_t *pred, ptrdiff_t sp, ptrdiff_t fs_dst, ptrdiff_t fs_pred, const int16_t *coeffs, int log2,
                       int trType, const BlockGrid &g, void *stream)
 {
     if (g.n == 0) return 0;
     if (((uintptr_t)coeffs & 15) != 0) return HEVCASM_ERR_ARGUMENT;
     const bool pa = !g.blk_xy && aligned16(dst, sd, fs_dst, pred, sp, fs_pred);
+    // HEVCASM_INV_PATH=hybrid: 16x16 / 32x32 with the second stage on tcgen05 whenever the planes allow it; =hybrid_only: fail instead of
+    // falling back (tests)
+    const char *ipin = getenv("HEVCASM_INV_PATH");
+    if ((log2 == 5 || log2 == 4) && ipin && !strncmp(ipin, "hybrid", 6)) {
+        bool taken = false;
+        const int e = !pa ? 0 : log2 == 5 ? launch_inv_umma<5>(dst, sd, pred, sp, fs_dst, fs_pred, coeffs, g, stream, true, &taken)
+                                          : launch_inv_umma<4>(dst, sd, pred, sp, fs_dst, fs_pred, coeffs, g, stream, true, &taken);
+        if (taken) return e;
+        if (!strcmp(ipin, "hybrid_only")) return HEVCASM_ERR_ARGUMENT;
+    }
     return pa ? launch_inv_t<true>(dst, sd, pred, sp, fs_dst, fs_pred, coeffs, log2, trType, g, stream)
               : launch_inv_t<false>(dst, sd, pred, sp, fs_dst, fs_pred, coeffs, log2, trType, g, stream);
 }

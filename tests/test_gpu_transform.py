@@ -114,6 +114,30 @@ def test_inverse_frames_imma_variant(oracle, log2, path, monkeypatch):
     assert np.array_equal(to_host(got), want.buf)
 
 
+@pytest.mark.parametrize("grid", [None, "2", "1"])
+@pytest.mark.parametrize("rng", [(-600, 600), (-32768, 32767)])
+@pytest.mark.parametrize("log2", [5, 4])
+def test_inverse_tensor_core(oracle, log2, rng, grid, monkeypatch):
+    """inverse 16x16 / 32x32 with the SECOND stage on tcgen05 (transform_inv_umma.cuh): stage 1 in the threads writes the int16
+    intermediate into shared memory in the swizzled operand layout.  16-byte aligned planes, block counts that leave partial
+    tiles, several frames, full-range coefficients (stage-1 clip, high-byte product); "hybrid_only" fails rather than fall back."""
+    monkeypatch.setenv("HEVCASM_INV_PATH", "hybrid_only")
+    if grid:
+        monkeypatch.setenv("HEVCASM_INV_UMMA_GRID", grid)
+    n = 1 << log2
+    for width, height, nf in ((224, 160, 3), (32, 32, 1), (416, 300, 2)):
+        pred = synth.random_planes(185 + width, nf, width, height, 16)
+        co = synth.random_int16(186 + log2, nf * (width // n) * (height // n) * n * n, *rng)
+        want = synth.random_planes(187, nf, width, height, 16)
+        got = to_dev(want.buf)
+        oracle.drv("inverse_transform_add_frames", ptr(want.buf, want.origin), want.pitch, ptr(pred.buf, pred.origin), pred.pitch, ptr(co), width, height, log2, 0,
+                   nf, want.frame_stride, pred.frame_stride, threads=8)
+        dp, dc = to_dev(pred.buf), to_dev(co)
+        lib.call("inverse_transform_add_frames", dptr(got, want.origin), want.pitch, dptr(dp, pred.origin), pred.pitch, dptr(dc), width, height, log2, 0, nf,
+                 want.frame_stride, pred.frame_stride)
+        assert np.array_equal(to_host(got), want.buf), (width, height, nf)
+
+
 @pytest.mark.parametrize("trType,log2", TR)
 def test_inverse_list_unaligned(oracle, trType, log2):
     width, height, n = 160, 96, 1 << log2
