@@ -127,8 +127,11 @@ __global__ void __launch_bounds__(THREADS, 1) inv_umma_kernel(const Params P)
             uint8_t *const stage = sA + (it & 1) * STAGE_BYTES;
             const int bc = m / BS, u = m % BS, bcg = tx * TB + bc;
             const int kk = 2 * BS * bc + 2 * u;                                  // byte of the tile row
-            uint8_t *const col = stage + (kk >> 7) * HALF_BYTES + (kk & 15);     // + row terms below
             const int chunk = (kk & 127) >> 4;
+            // tile row r = 32 wg + BS h + y: r & 7 = y & 7, so the eight swizzled chunk positions are per-thread constants
+            uint8_t *rowbase[8];
+#pragma unroll
+            for (int y7 = 0; y7 < 8; ++y7) rowbase[y7] = stage + (kk >> 7) * HALF_BYTES + (kk & 15) + (4 * wg) * 1024 + y7 * 128 + ((chunk ^ y7) << 4);
 #pragma unroll 1
             for (int h = 0; h < BPT; ++h) {
                 const int rb = ty * TB + wg * BPT + h;
@@ -145,11 +148,8 @@ __global__ void __launch_bounds__(THREADS, 1) inv_umma_kernel(const Params P)
                     int o[BS];
                     InvBfly<BS>::run(p, o, 64);
 #pragma unroll
-                    for (int y = 0; y < BS; ++y) {
-                        const int r = 32 * wg + BS * h + y;   // tile row
-                        const int v = min(max(o[y] >> 7, -32768), 32767);   // the clip to int16 of residual_decode.c stage 1
-                        *reinterpret_cast<int16_t *>(col + (r >> 3) * 1024 + (r & 7) * 128 + ((chunk ^ (r & 7)) << 4)) = (int16_t)v;
-                    }
+                    for (int y = 0; y < BS; ++y)   // the clip to int16 of residual_decode.c stage 1: one cvt.pack.sat; rows 8 apart are 1024 bytes apart
+                        *reinterpret_cast<int16_t *>(rowbase[y & 7] + ((BS * h + y) >> 3) * 1024) = (int16_t)pack_sat_s16(o[y] >> 7, 0);
                 }
             }
             umma::fence_async_smem();   // the operand bytes -> visible to the tensor cores
@@ -161,9 +161,7 @@ __global__ void __launch_bounds__(THREADS, 1) inv_umma_kernel(const Params P)
         for (int it = 0; it < n_mine; ++it) {
             if (it + 1 < n_mine) stage1(it + 1);   // its stage was last read by the MMAs of tile it-1, whose completion this thread has observed
             const int a = it & 1;
-            tma::mbar_wait(done + a, (it >> 1) & 1);
-            umma::fence_after();
-            // stage 2 out of TMEM: tile row r = 32 warp + lane, tile columns 32 wg .. 32 wg + 31
+            // stage 2 out of TMEM: tile row r = 32 warp + lane, tile columns 32 wg .. 32 wg + 31 (the predictor row is requested before the wait)
             int tx, ty, tf;
             tile_xyf(it, tx, ty, tf);
             const int r = 32 * warp + lane, yg = ty * TROWS + r, xg = tx * 128 + 32 * wg;
@@ -177,6 +175,8 @@ __global__ void __launch_bounds__(THREADS, 1) inv_umma_kernel(const Params P)
                 ok[g] = row_ok && (xg + 16 * g) / BS < P.nbx;
                 if (ok[g]) pw[g] = __ldg(reinterpret_cast<const uint4 *>(pp) + g);
             }
+            tma::mbar_wait(done + a, (it >> 1) & 1);
+            umma::fence_after();
             const uint32_t t = tm + ((uint32_t)(warp * 32) << 16) + a * 256 + 32 * wg;
             uint32_t ow[8];
             {
