@@ -34,7 +34,14 @@ constexpr int CONSUMERS = 512, THREADS = CONSUMERS + 32;   // four consumer warp
 __device__ uint4 g_ft_A[2][2 * A_BYTES / 16];
 inline int ft_tables_init()
 {
-    static int done = [] {
+    // one copy per device of this process (the symbol lives in each device's module image)
+    static std::mutex mu;
+    static bool ready[64] = {};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return (int)cudaErrorInvalidDevice;
+    std::lock_guard<std::mutex> lock(mu);
+    if (ready[dev]) return 0;
+    const int done = [] {
         static uint8_t a[2][2 * A_BYTES];
         memset(a, 0, sizeof a);
         for (int sz = 0; sz < 2; ++sz) {
@@ -50,6 +57,7 @@ inline int ft_tables_init()
         }
         return (int)cudaMemcpyToSymbol(g_ft_A, a, sizeof a);
     }();
+    ready[dev] = done == 0;
     return done;
 }
 

@@ -30,7 +30,14 @@ constexpr int CONSUMERS = 512, THREADS = CONSUMERS + 32;
 __device__ uint4 g_fi_B[2][2 * C_BYTES / 16];
 inline int fi_tables_init()
 {
-    static int done = [] {
+    // one copy per device of this process (the symbol lives in each device's module image)
+    static std::mutex mu;
+    static bool ready[64] = {};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return (int)cudaErrorInvalidDevice;
+    std::lock_guard<std::mutex> lock(mu);
+    if (ready[dev]) return 0;
+    const int done = [] {
         static uint8_t a[2][2 * C_BYTES];
         memset(a, 0, sizeof a);
         for (int sz = 0; sz < 2; ++sz) {
@@ -46,6 +53,7 @@ inline int fi_tables_init()
         }
         return (int)cudaMemcpyToSymbol(g_fi_B, a, sizeof a);
     }();
+    ready[dev] = done == 0;
     return done;
 }
 
@@ -61,19 +69,19 @@ struct Params {
 template <int LOG2>
 __global__ void __launch_bounds__(THREADS, 1) inv_umma_kernel(const Params P)
 {
-    constexpr int BS = 1 << LOG2, TB = 128 / BS, BPT = 32 / BS;   // block size; blocks per tile side; blocks per thread and tile in stage 1
+    constexpr int BS = 1 << LOG2, TB = 128 / BS;   // block size; blocks per tile side
     extern __shared__ __align__(128) uint8_t fi_raw[];
     uint8_t *const smem = fi_raw + ((1024 - (tma::smem_u32(fi_raw) & 1023)) & 1023);
     uint8_t *const sC = smem;                    // [lo / hi][chunk][n][16]
     uint8_t *const sA = smem + A_OFF;            // [stage][half][row][128], 128-byte swizzle
-    uint64_t *const filled = reinterpret_cast<uint64_t *>(smem + BAR_OFF);   // [2] every consumer has written its part of the operand stage
+    uint64_t *const filled = reinterpret_cast<uint64_t *>(smem + BAR_OFF);   // [2] the warpgroup pair in charge has written the operand stage
     uint64_t *const done = filled + 2;                                       // [2] the MMAs into the accumulator have completed
     uint64_t *const consumed = filled + 4;                                   // [2] every consumer has read the accumulator
     uint32_t *const tmem_slot = reinterpret_cast<uint32_t *>(filled + 6);
 
     if (threadIdx.x == 0) {
 #pragma unroll
-        for (int i = 0; i < 2; ++i) tma::mbar_init(filled + i, CONSUMERS), tma::mbar_init(done + i, 1), tma::mbar_init(consumed + i, CONSUMERS);
+        for (int i = 0; i < 2; ++i) tma::mbar_init(filled + i, CONSUMERS / 2), tma::mbar_init(done + i, 1), tma::mbar_init(consumed + i, CONSUMERS);
     }
     if (threadIdx.x < 32) umma::tmem_alloc<512>(tmem_slot);
     for (int idx = threadIdx.x; idx < 2 * C_BYTES / 16; idx += THREADS) reinterpret_cast<uint4 *>(sC)[idx] = g_fi_B[LOG2 - 4][idx];
@@ -120,42 +128,48 @@ __global__ void __launch_bounds__(THREADS, 1) inv_umma_kernel(const Params P)
             const int r = t - tf * per;
             ty = r / P.tiles_x, tx = r - ty * P.tiles_x;
         };
-        // stage 1 of tile `it` into operand stage it & 1: this thread owns coefficient column u of block column bc, BPT blocks one below the other
+        // stage 1 of tile `it` into operand stage it & 1.  A work item = two adjacent coefficient columns (2 uw, 2 uw + 1) of one block,
+        // loaded as 32-bit words (coalesced rows), two IDP.2A butterflies, one clipped int16 pair stored per row.  A tile has
+        // (128 / BS)^2 * BS / 2 = 256 (32x32) or 512 (16x16) items; the two warpgroup pairs take the tiles' first stages alternately
+        // (pair it & 1 fills tile it), so each thread runs one or two items every other tile.
         auto stage1 = [&](int it) {
+            if ((wg >> 1) != (it & 1)) return;
             int tx, ty, tf;
             tile_xyf(it, tx, ty, tf);
             uint8_t *const stage = sA + (it & 1) * STAGE_BYTES;
-            const int bc = m / BS, u = m % BS, bcg = tx * TB + bc;
-            const int kk = 2 * BS * bc + 2 * u;                                  // byte of the tile row
-            const int chunk = (kk & 127) >> 4;
-            // tile row r = 32 wg + BS h + y: r & 7 = y & 7, so the eight swizzled chunk positions are per-thread constants
-            uint8_t *rowbase[8];
-#pragma unroll
-            for (int y7 = 0; y7 < 8; ++y7) rowbase[y7] = stage + (kk >> 7) * HALF_BYTES + (kk & 15) + (4 * wg) * 1024 + y7 * 128 + ((chunk ^ y7) << 4);
+            constexpr int HW = BS / 2, ITEMS = TB * TB * HW;
 #pragma unroll 1
-            for (int h = 0; h < BPT; ++h) {
-                const int rb = ty * TB + wg * BPT + h;
+            for (int j = (wg & 1) * 128 + m; j < ITEMS; j += 256) {
+                const int b = j / HW, uw = j % HW, br = b / TB, bc = b % TB;
+                const int rb = ty * TB + br, bcg = tx * TB + bc;
                 if (rb < P.nby && bcg < P.nbx) {
-                    const int16_t *c = P.coeffs + (((long long)tf * P.nby + rb) * P.nbx + bcg) * (BS * BS) + u;
-                    int cv[BS];
+                    const uint32_t *cw = reinterpret_cast<const uint32_t *>(P.coeffs + (((long long)tf * P.nby + rb) * P.nbx + bcg) * (BS * BS)) + uw;
+                    uint32_t W[BS];
 #pragma unroll
-                    for (int v = 0; v < BS; ++v) cv[v] = __ldg(c + v * BS);
-                    uint32_t p[BS / 2];
-                    static_for<0, BS / 2>([&](auto kq) {
+                    for (int v = 0; v < BS; ++v) W[v] = __ldg(cw + v * HW);
+                    uint32_t p[HW];
+                    int o0[BS], o1[BS];
+                    static_for<0, HW>([&](auto kq) {
                         constexpr int k = HV_V(kq);
-                        p[k] = pack16(cv[pair_row(BS, k, 0)], cv[pair_row(BS, k, 1)]);
+                        p[k] = lolo(W[pair_row(BS, k, 0)], W[pair_row(BS, k, 1)]);
                     });
-                    int o[BS];
-                    InvBfly<BS>::run(p, o, 64);
+                    InvBfly<BS>::run(p, o0, 64);
+                    static_for<0, HW>([&](auto kq) {
+                        constexpr int k = HV_V(kq);
+                        p[k] = hihi(W[pair_row(BS, k, 0)], W[pair_row(BS, k, 1)]);
+                    });
+                    InvBfly<BS>::run(p, o1, 64);
+                    // tile row r = BS br + y: r & 7 = y & 7, so the swizzled position of this item's word depends on y & 7 only
+                    const int kk = 2 * BS * bc + 4 * uw, chunk = (kk & 127) >> 4;   // byte of the tile row
+                    uint8_t *const base = stage + (kk >> 7) * HALF_BYTES + (kk & 15) + ((BS * br) >> 3) * 1024;
 #pragma unroll
-                    for (int y = 0; y < BS; ++y)   // the clip to int16 of residual_decode.c stage 1: one cvt.pack.sat; rows 8 apart are 1024 bytes apart
-                        *reinterpret_cast<int16_t *>(rowbase[y & 7] + ((BS * h + y) >> 3) * 1024) = (int16_t)pack_sat_s16(o[y] >> 7, 0);
+                    for (int y = 0; y < BS; ++y)   // the clip to int16 of residual_decode.c stage 1 = cvt.pack.sat
+                        *reinterpret_cast<uint32_t *>(base + (y >> 3) * 1024 + (y & 7) * 128 + ((chunk ^ (y & 7)) << 4)) = pack_sat_s16(o0[y] >> 7, o1[y] >> 7);
                 }
             }
             umma::fence_async_smem();   // the operand bytes -> visible to the tensor cores
             tma::mbar_arrive(filled + (it & 1));
         };
-
         if (n_mine > 0) stage1(0);
 #pragma unroll 1
         for (int it = 0; it < n_mine; ++it) {
