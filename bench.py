@@ -159,7 +159,7 @@ def run_reference(args):
         t += dt
     value = args.steps * nf * W4K * H4K / t / 1e9
     sample = f"{nf} 4K frames per step, all four PU sizes, 64 candidates as 16 four-way calls per PU"
-    print(json.dumps({
+    emit({
         "impl": "reference", "metric": METRIC, "value": value, "unit": "Gsamples/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "u8", "data": "synthetic",
@@ -168,7 +168,7 @@ def run_reference(args):
         "cpu_baseline": {"value": value, "unit": "Gsamples/s", "cores": threads, "kind": kind, "sample": sample,
                          "note": "reference C path at -O3 -mavx2 (+ libvpx AVX2 intrinsics for 32x32/64x64); the x86 asm needs yasm/nasm, absent here"},
         "e2e": {"value": value, "unit": "Gsamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-    }))
+    })
 
 
 # ---------------------------------------------------------------------------------------------- GPU arm
@@ -435,14 +435,28 @@ def run_gpu(args):
                                     "gpu_output_matches": ok}
         if world == 1 and not args.no_kernels:
             line["kernels"] = kernel_table(torch, lib, synth, stream, hbm_peak)
-        print(json.dumps(line))
+        emit(line)
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
 
 
+_JSON_OUT = None   # the process's real stdout; fd 1 itself is pointed at stderr so that only the JSON line reaches stdout
+
+
+def emit(line):
+    (_JSON_OUT or sys.stdout).write(json.dumps(line) + "\n")
+    (_JSON_OUT or sys.stdout).flush()
+
+
 def main():
+    global _JSON_OUT
     args = parse()
+    # libraries print to fd 1 behind Python's back (NCCL's version banner precedes the JSON line under torchrun): keep a private
+    # copy of stdout for the one JSON line and send everything else to stderr
+    sys.stdout.flush()
+    _JSON_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     if args.impl == "reference":
         run_reference(args)
     else:
