@@ -176,6 +176,13 @@ __device__ __forceinline__ void store_wait_read()
 {
     asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(PENDING) : "memory");
 }
+// `bytes` contiguous bytes of global memory -> shared memory (both 16-byte aligned, bytes a multiple of 16); completion on `bar`
+__device__ __forceinline__ void bulk_load_1d(void *smem_dst, const void *src, uint32_t bytes, uint64_t *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(smem_dst)), "l"(src), "r"(bytes),
+                 "r"(smem_u32(bar))
+                 : "memory");
+}
 __device__ __forceinline__ void prefetch_descriptor(const CUtensorMap *map) { asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory"); }
 
 }  // namespace tma

@@ -864,6 +864,9 @@ static int launch_inv_umma(uint8_t *dst, ptrdiff_t sd, const uint8_t *pred, ptrd
     const long long tiles = (long long)P.tiles_x * P.tiles_y * n_frames;
     if (tiles >= (1ll << 30) || (!forced && tiles < 6ll * sm_count())) return 0;
     P.n_tiles = (int)tiles;
+    if (!tma::describable(sp, fs_pred, n_frames) ||
+        tma::describe_u8_swizzled(&P.tmpred, pred, sp, fs_pred, (long long)BS * g.nbx, (long long)BS * g.nby, n_frames, 128, fi::TROWS))
+        return 0;
     if (fi::fi_tables_init() || set_max_smem(fi::inv_umma_kernel<LOG2>, fi::SMEM_BYTES)) return (int)cudaErrorInvalidValue;
     *taken = true;
     long long grid = std::min<long long>(tiles, (long long)sm_count());   // one persistent CTA per SM

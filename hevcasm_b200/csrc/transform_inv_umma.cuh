@@ -22,9 +22,11 @@ constexpr int TROWS = 128, TBYTES = 256;       // tile: 128 rows x 128 samples (
 constexpr int C_BYTES = 128 * TBYTES;          // one constant operand (lo or hi): [chunk (16)][n (128)][16]
 constexpr int HALF_BYTES = 128 * TROWS;        // one 128-byte-wide half of the data operand: 16 groups of 8 rows x 1024 bytes
 constexpr int STAGE_BYTES = 2 * HALF_BYTES;
-constexpr int A_OFF = 2 * C_BYTES, BAR_OFF = A_OFF + 2 * STAGE_BYTES;
-constexpr int SMEM_BYTES = 1024 + BAR_OFF + 64;
-constexpr int CONSUMERS = 512, THREADS = CONSUMERS + 32;
+constexpr int CO_BYTES = TROWS * TBYTES;       // the tile's coefficient blocks (block rows one after the other, as in memory)
+constexpr int PR_BYTES = TROWS * 128;          // the tile's predictor rows (128 bytes x 128 rows, 128-byte swizzle)
+constexpr int A_OFF = 2 * C_BYTES, CO_OFF = A_OFF + 2 * STAGE_BYTES, PR_OFF = CO_OFF + 2 * CO_BYTES, BAR_OFF = PR_OFF + 2 * PR_BYTES;
+constexpr int SMEM_BYTES = 1024 + BAR_OFF + 96;
+constexpr int CONSUMERS = 512, THREADS = CONSUMERS + 64;   // + the MMA warp and the loader warp
 
 // the constant operands in their shared-memory layout [size (16, 32)][lo / hi][chunk (16)][n (128)][16], built on the host once
 __device__ uint4 g_fi_B[2][2 * C_BYTES / 16];
@@ -57,7 +59,8 @@ inline int fi_tables_init()
     return done;
 }
 
-struct Params {
+struct alignas(64) Params {
+    CUtensorMap tmpred;       // predictor planes: (BS nbx bytes, BS nby rows, frames); boxes of 128 bytes x 128 rows, 128-byte swizzle
     uint8_t *dst;
     const uint8_t *pred;
     const int16_t *coeffs;
@@ -67,7 +70,7 @@ struct Params {
 };
 
 template <int LOG2>
-__global__ void __launch_bounds__(THREADS, 1) inv_umma_kernel(const Params P)
+__global__ void __launch_bounds__(THREADS, 1) inv_umma_kernel(const __grid_constant__ Params P)
 {
     constexpr int BS = 1 << LOG2, TB = 128 / BS;   // block size; blocks per tile side
     extern __shared__ __align__(128) uint8_t fi_raw[];
@@ -76,12 +79,15 @@ __global__ void __launch_bounds__(THREADS, 1) inv_umma_kernel(const Params P)
     uint8_t *const sA = smem + A_OFF;            // [stage][half][row][128], 128-byte swizzle
     uint64_t *const filled = reinterpret_cast<uint64_t *>(smem + BAR_OFF);   // [2] the warpgroup pair in charge has written the operand stage
     uint64_t *const done = filled + 2;                                       // [2] the MMAs into the accumulator have completed
-    uint64_t *const consumed = filled + 4;                                   // [2] every consumer has read the accumulator
-    uint32_t *const tmem_slot = reinterpret_cast<uint32_t *>(filled + 6);
+    uint64_t *const consumed = filled + 4;                                   // [2] every consumer has read the accumulator (and its predictor rows)
+    uint64_t *const loaded_c = filled + 6;                                   // [2] the tile's coefficient blocks have landed
+    uint64_t *const loaded_p = filled + 8;                                   // [2] the tile's predictor rows have landed
+    uint32_t *const tmem_slot = reinterpret_cast<uint32_t *>(filled + 10);
+    uint8_t *const sCo = smem + CO_OFF, *const sPr = smem + PR_OFF;
 
     if (threadIdx.x == 0) {
 #pragma unroll
-        for (int i = 0; i < 2; ++i) tma::mbar_init(filled + i, CONSUMERS / 2), tma::mbar_init(done + i, 1), tma::mbar_init(consumed + i, CONSUMERS);
+        for (int i = 0; i < 2; ++i) tma::mbar_init(filled + i, CONSUMERS / 2), tma::mbar_init(done + i, 1), tma::mbar_init(consumed + i, CONSUMERS), tma::mbar_init(loaded_c + i, 1), tma::mbar_init(loaded_p + i, 1);
     }
     if (threadIdx.x < 32) umma::tmem_alloc<512>(tmem_slot);
     for (int idx = threadIdx.x; idx < 2 * C_BYTES / 16; idx += THREADS) reinterpret_cast<uint4 *>(sC)[idx] = g_fi_B[LOG2 - 4][idx];
@@ -93,6 +99,13 @@ __global__ void __launch_bounds__(THREADS, 1) inv_umma_kernel(const Params P)
 
     const int t0 = blockIdx.x, tstep = gridDim.x;
     const int n_mine = t0 < P.n_tiles ? (P.n_tiles - t0 + tstep - 1) / tstep : 0;
+    const int per = P.tiles_x * P.tiles_y;
+    auto tile_xyf = [&](int it, int &tx, int &ty, int &tf) {
+        const int t = t0 + it * tstep;
+        tf = t / per;
+        const int r = t - tf * per;
+        ty = r / P.tiles_x, tx = r - ty * P.tiles_x;
+    };
 
     if (threadIdx.x >= CONSUMERS) {
         // ------------------------------------------------------------------------------------------------ producer (MMA issue only)
@@ -117,17 +130,29 @@ __global__ void __launch_bounds__(THREADS, 1) inv_umma_kernel(const Params P)
                     }
                 umma::commit(done + s);
             }
+        } else if (threadIdx.x == CONSUMERS + 32) {
+            // ---------------------------------------------------------------------------------------------- loader: coefficient blocks (one bulk
+            // copy per block row: the tile's blocks of a row are contiguous) and predictor rows (one TMA box) of tile q into stage q & 1
+#pragma unroll 1
+            for (int q = 0; q < n_mine; ++q) {
+                const int s = q & 1;
+                const uint32_t ph = (q >> 1) & 1;
+                int tx, ty, tf;
+                tile_xyf(q, tx, ty, tf);
+                const int nb = min(TB, P.nbx - tx * TB), rows = min(TB, P.nby - ty * TB);
+                if (q >= 2) tma::mbar_wait(filled + s, ph ^ 1);     // the first stage of the stage's previous tile has read the coefficients
+                tma::mbar_expect_tx(loaded_c + s, (uint32_t)(rows * nb * BS * BS * 2));
+                for (int br = 0; br < rows; ++br)
+                    tma::bulk_load_1d(sCo + s * CO_BYTES + br * (TB * BS * BS * 2),
+                                      P.coeffs + (((long long)tf * P.nby + ty * TB + br) * P.nbx + tx * TB) * (BS * BS), (uint32_t)(nb * BS * BS * 2), loaded_c + s);
+                if (q >= 2) tma::mbar_wait(consumed + s, ph ^ 1);   // .. and its epilogue the predictor rows (an iteration later)
+                tma::mbar_expect_tx(loaded_p + s, PR_BYTES);
+                tma::load_box_3d(sPr + s * PR_BYTES, &P.tmpred, tx * 128, ty * TROWS, tf, loaded_p + s);
+            }
         }
     } else {
         // ------------------------------------------------------------------------------------------------ consumers
         const int wg = threadIdx.x >> 7, m = threadIdx.x & 127, warp = m >> 5, lane = m & 31;
-        const int per = P.tiles_x * P.tiles_y;
-        auto tile_xyf = [&](int it, int &tx, int &ty, int &tf) {
-            const int t = t0 + it * tstep;
-            tf = t / per;
-            const int r = t - tf * per;
-            ty = r / P.tiles_x, tx = r - ty * P.tiles_x;
-        };
         // stage 1 of tile `it` into operand stage it & 1.  A work item = two adjacent coefficient columns (2 uw, 2 uw + 1) of one block,
         // loaded as 32-bit words (coalesced rows), two IDP.2A butterflies, one clipped int16 pair stored per row.  A tile has
         // (128 / BS)^2 * BS / 2 = 256 (32x32) or 512 (16x16) items; the two warpgroup pairs take the tiles' first stages alternately
@@ -137,16 +162,17 @@ __global__ void __launch_bounds__(THREADS, 1) inv_umma_kernel(const Params P)
             int tx, ty, tf;
             tile_xyf(it, tx, ty, tf);
             uint8_t *const stage = sA + (it & 1) * STAGE_BYTES;
+            tma::mbar_wait(loaded_c + (it & 1), (it >> 1) & 1);
             constexpr int HW = BS / 2, ITEMS = TB * TB * HW;
 #pragma unroll 1
             for (int j = (wg & 1) * 128 + m; j < ITEMS; j += 256) {
                 const int b = j / HW, uw = j % HW, br = b / TB, bc = b % TB;
                 const int rb = ty * TB + br, bcg = tx * TB + bc;
                 if (rb < P.nby && bcg < P.nbx) {
-                    const uint32_t *cw = reinterpret_cast<const uint32_t *>(P.coeffs + (((long long)tf * P.nby + rb) * P.nbx + bcg) * (BS * BS)) + uw;
+                    const uint32_t *cw = reinterpret_cast<const uint32_t *>(sCo + (it & 1) * CO_BYTES) + b * (BS * HW) + uw;   // block b of the staged tile
                     uint32_t W[BS];
 #pragma unroll
-                    for (int v = 0; v < BS; ++v) W[v] = __ldg(cw + v * HW);
+                    for (int v = 0; v < BS; ++v) W[v] = cw[v * HW];
                     uint32_t p[HW];
                     int o0[BS], o1[BS];
                     static_for<0, HW>([&](auto kq) {
@@ -180,15 +206,14 @@ __global__ void __launch_bounds__(THREADS, 1) inv_umma_kernel(const Params P)
             tile_xyf(it, tx, ty, tf);
             const int r = 32 * warp + lane, yg = ty * TROWS + r, xg = tx * 128 + 32 * wg;
             const bool row_ok = yg < P.nby * BS;
-            const uint8_t *pp = P.pred + tf * P.fs_pred + (ptrdiff_t)yg * P.sp + xg;
             uint8_t *dp = P.dst + tf * P.fs_dst + (ptrdiff_t)yg * P.sd + xg;
-            uint4 pw[2] = {make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0)};
             bool ok[2];
 #pragma unroll
-            for (int g = 0; g < 2; ++g) {
-                ok[g] = row_ok && (xg + 16 * g) / BS < P.nbx;
-                if (ok[g]) pw[g] = __ldg(reinterpret_cast<const uint4 *>(pp) + g);
-            }
+            for (int g = 0; g < 2; ++g) ok[g] = row_ok && (xg + 16 * g) / BS < P.nbx;
+            tma::mbar_wait(loaded_p + a, (it >> 1) & 1);
+            uint4 pw[2];   // this row's 32 predictor bytes: 16-byte chunks 2 wg, 2 wg + 1 of the swizzled row
+#pragma unroll
+            for (int g = 0; g < 2; ++g) pw[g] = *reinterpret_cast<const uint4 *>(sPr + a * PR_BYTES + (r >> 3) * 1024 + (r & 7) * 128 + (((2 * wg + g) ^ (r & 7)) << 4));
             tma::mbar_wait(done + a, (it >> 1) & 1);
             umma::fence_after();
             const uint32_t t = tm + ((uint32_t)(warp * 32) << 16) + a * 256 + 32 * wg;
@@ -217,7 +242,8 @@ __global__ void __launch_bounds__(THREADS, 1) inv_umma_kernel(const Params P)
                     }
                 }
             }
-            umma::fence_before();   // this thread's TMEM reads are complete
+            umma::fence_before();       // this thread's TMEM reads are complete
+            umma::fence_async_smem();   // .. and its reads of the predictor stage precede the loader's next box
             tma::mbar_arrive(consumed + a);
 #pragma unroll
             for (int g = 0; g < 2; ++g)
