@@ -133,21 +133,29 @@ __global__ void __launch_bounds__(THREADS, 1) inv_umma_kernel(const __grid_const
         } else if (threadIdx.x == CONSUMERS + 32) {
             // ---------------------------------------------------------------------------------------------- loader: coefficient blocks (one bulk
             // copy per block row: the tile's blocks of a row are contiguous) and predictor rows (one TMA box) of tile q into stage q & 1
+            // The coefficient stage of tile q is free once the first stage of tile q-2 has run (an iteration before that tile's epilogue
+            // frees the predictor stage), so the coefficients run one tile ahead of the predictor rows: neither wait holds the other up.
 #pragma unroll 1
-            for (int q = 0; q < n_mine; ++q) {
-                const int s = q & 1;
-                const uint32_t ph = (q >> 1) & 1;
-                int tx, ty, tf;
-                tile_xyf(q, tx, ty, tf);
-                const int nb = min(TB, P.nbx - tx * TB), rows = min(TB, P.nby - ty * TB);
-                if (q >= 2) tma::mbar_wait(filled + s, ph ^ 1);     // the first stage of the stage's previous tile has read the coefficients
-                tma::mbar_expect_tx(loaded_c + s, (uint32_t)(rows * nb * BS * BS * 2));
-                for (int br = 0; br < rows; ++br)
-                    tma::bulk_load_1d(sCo + s * CO_BYTES + br * (TB * BS * BS * 2),
-                                      P.coeffs + (((long long)tf * P.nby + ty * TB + br) * P.nbx + tx * TB) * (BS * BS), (uint32_t)(nb * BS * BS * 2), loaded_c + s);
-                if (q >= 2) tma::mbar_wait(consumed + s, ph ^ 1);   // .. and its epilogue the predictor rows (an iteration later)
-                tma::mbar_expect_tx(loaded_p + s, PR_BYTES);
-                tma::load_box_3d(sPr + s * PR_BYTES, &P.tmpred, tx * 128, ty * TROWS, tf, loaded_p + s);
+            for (int q = 0; q <= n_mine; ++q) {
+                if (q < n_mine) {
+                    const int s = q & 1;
+                    int tx, ty, tf;
+                    tile_xyf(q, tx, ty, tf);
+                    const int nb = min(TB, P.nbx - tx * TB), rows = min(TB, P.nby - ty * TB);
+                    if (q >= 2) tma::mbar_wait(filled + s, ((q >> 1) & 1) ^ 1);
+                    tma::mbar_expect_tx(loaded_c + s, (uint32_t)(rows * nb * BS * BS * 2));
+                    for (int br = 0; br < rows; ++br)
+                        tma::bulk_load_1d(sCo + s * CO_BYTES + br * (TB * BS * BS * 2),
+                                          P.coeffs + (((long long)tf * P.nby + ty * TB + br) * P.nbx + tx * TB) * (BS * BS), (uint32_t)(nb * BS * BS * 2), loaded_c + s);
+                }
+                if (q >= 1) {
+                    const int t = q - 1, s = t & 1;
+                    int tx, ty, tf;
+                    tile_xyf(t, tx, ty, tf);
+                    if (t >= 2) tma::mbar_wait(consumed + s, ((t >> 1) & 1) ^ 1);
+                    tma::mbar_expect_tx(loaded_p + s, PR_BYTES);
+                    tma::load_box_3d(sPr + s * PR_BYTES, &P.tmpred, tx * 128, ty * TROWS, tf, loaded_p + s);
+                }
             }
         }
     } else {
