@@ -80,11 +80,13 @@ __global__ void __launch_bounds__(THREADS, 1) fwd_umma_kernel(const __grid_const
     uint64_t *const full = reinterpret_cast<uint64_t *>(smem + BAR_OFF);   // [2] the residual boxes of the stage have landed
     uint64_t *const done = full + 2;                                       // [2] the MMAs into the accumulator have completed
     uint64_t *const consumed = full + 4;                                   // [2] every consumer has read the accumulator
-    uint32_t *const tmem_slot = reinterpret_cast<uint32_t *>(full + 6);
+    uint64_t *const cready = full + 6;                                     // the constant operands have landed
+    uint32_t *const tmem_slot = reinterpret_cast<uint32_t *>(full + 7);
 
     if (threadIdx.x == 0) {
 #pragma unroll
         for (int i = 0; i < 2; ++i) tma::mbar_init(full + i, 1), tma::mbar_init(done + i, 1), tma::mbar_init(consumed + i, CONSUMERS);
+        tma::mbar_init(cready, 1);
     }
     if (threadIdx.x < 32) umma::tmem_alloc<512>(tmem_slot);
     __syncthreads();
@@ -109,13 +111,13 @@ __global__ void __launch_bounds__(THREADS, 1) fwd_umma_kernel(const __grid_const
         advance(cx, cy, cf);
     };
     if (threadIdx.x == CONSUMERS) {
+        // constant operands A_p[(bc, k)][64 bc + 2 i + p] = T[k][i]: the host-built image arrives by bulk copies while the first tiles load
+        tma::mbar_expect_tx(cready, 2 * A_BYTES);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) tma::bulk_load_1d(sA + i * (A_BYTES / 2), reinterpret_cast<const uint8_t *>(g_ft_A[LOG2 - 4]) + i * (A_BYTES / 2), A_BYTES / 2, cready);
         if (n_mine > 0) request(0);
         if (n_mine > 1) request(1);
     }
-
-    // constant operands: A_p[(bc, k)][64 bc + 2 i + p] = T[k][i], copied from the host-built image
-    for (int idx = threadIdx.x; idx < 2 * A_BYTES / 16; idx += THREADS) reinterpret_cast<uint4 *>(sA)[idx] = g_ft_A[LOG2 - 4][idx];
-    umma::fence_async_smem();
     umma::fence_before();
     __syncthreads();
     umma::fence_after();
@@ -125,6 +127,7 @@ __global__ void __launch_bounds__(THREADS, 1) fwd_umma_kernel(const __grid_const
         // ------------------------------------------------------------------------------------------------ producer
         if (threadIdx.x == CONSUMERS) {
             constexpr uint32_t ID_LO = umma::idesc_i8(true, false, false, TROWS), ID_HI = umma::idesc_i8(true, true, false, TROWS);
+            tma::mbar_wait(cready, 0);
 #pragma unroll 1
             for (int q = 0; q < n_mine; ++q) {
                 const int s = q & 1;
