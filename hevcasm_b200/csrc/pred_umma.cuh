@@ -45,7 +45,7 @@ struct alignas(64) Params {
     int y2[2][4];             // vertical tap pairs per reference (PackedCoefs::y2)
 };
 
-// One CTA per SM holds NWG independent WARPGROUPS of 128 threads (6, or 3 for bi-prediction).  Each warpgroup walks over its own
+// One CTA per SM holds NWG independent WARPGROUPS of 128 threads (6 for one reference, 3 for two; only the two-reference form is still instantiated - HEVCASM_PRED_BI=hfirst).  Each warpgroup walks over its own
 // tiles with its own image stage, output buffers, barriers and accumulator columns, so the tensor-core and TMA latency of one
 // overlaps the vertical passes of the others; they share the Toeplitz operand and one 512-column TMEM allocation.
 template <int TAPS, bool BI>

@@ -9,14 +9,14 @@
 // high-byte product, zeros everywhere else.  The same shared-memory bytes are read as a u8-typed operand for the first and
 // as an s8-typed operand for the second, so the bytes of the "other" half only ever meet zero coefficients:
 //     D_p[m = (block column bc, frequency k)][n = plane row r] = sum_kk A_p[m][kk] * B[kk][r],   kk = byte of the tile row
-//     A_p[(bc, k)][64 bc + 2 i + p] = T[k][i]  (s8, K-major, built once per CTA);   B = the residual tile as TMA delivers it
+//     A_p[(bc, k)][64 bc + 2 i + p] = T[k][i]  (s8, K-major, host-built image, copied per CTA by cp.async.bulk);   B = the residual tile as TMA delivers it
 // (two boxes of 128 bytes x 128 rows with the 128-byte swizzle = the swizzled K-major operand, no thread touches an input
 // sample).  16 MMAs (8 K-steps x {lo, hi}) of M = 128, N = 128 per tile of 4 x 4 blocks.  TMEM lane = (bc, k), column = plane
 // row, so the thread (block row = warpgroup, block column = warp, k = lane) finds tmp[k][0..31] of ITS block in 2 x 32 TMEM
 // columns: it recombines lo + 256 hi, rounds, truncates to int16 exactly like the reference's store, runs the second stage
 // (32-point partial butterfly over j, transform.cuh) in registers and stores coeffs[v * 32 + k] for v = 0..31 - 64
 // contiguous bytes per warp and v.  Producer / consumer structure as in pred_umma.cuh (uv): one producer warp, two
-// accumulators (2 x 256 TMEM columns), two image stages, mbarrier hand-offs, no barrier among the consumers.
+// accumulators (2 x 256 TMEM columns), two residual stages, mbarrier hand-offs, no barrier among the consumers.
 #pragma once
 
 namespace ft {
