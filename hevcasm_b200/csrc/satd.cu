@@ -9,10 +9,15 @@
 // the plane accesses of a warp are contiguous.  Linear SSD: one warp per run, |a-b| per byte (VABSDIFF4) squared and
 // summed with IDP.4A.
 #include "common.cuh"
+#include "tma.cuh"
+#include "umma.cuh"
 
+#include <algorithm>
 #include <cstdlib>
+#include <cstring>
 
 namespace hv {
+#include "satd_umma.cuh"   // 4x4 / 8x8: horizontal Hadamard pass on tcgen05
 
 // unsigned 32-bit division by a run-time constant as multiply-high + shifts (exact for every 32-bit numerator)
 struct SatdDiv {
@@ -215,10 +220,45 @@ __global__ void __launch_bounds__(256) ssd_linear_kernel(const uint8_t *__restri
 
 using namespace hv;
 
+// 4x4 / 8x8 on the tensor cores (satd_umma.cuh): regular grids over 16-byte aligned planes
+template <int LOG2>
+static int launch_satd_umma(const uint8_t *a, ptrdiff_t sa, const uint8_t *b, ptrdiff_t sb, ptrdiff_t fs_a, ptrdiff_t fs_b, const SatdGrid &g, int32_t *out,
+                            void *stream, bool *taken)
+{
+    *taken = false;
+    constexpr int N = 1 << LOG2;
+    const long long per = (long long)g.nbx * g.nby;
+    if (g.blk_xy || per <= 0 || g.n % per != 0) return 0;
+    const int n_frames = (int)(g.n / per);
+    if (!tma::describable(sa, fs_a, n_frames) || !tma::describable(sb, fs_b, n_frames)) return 0;
+    su::Params P{};
+    if (tma::describe_u32_swizzled128(&P.tm[0], a, sa, fs_a, (long long)N * g.nbx, (long long)N * g.nby, n_frames, su::TROWS) ||
+        tma::describe_u32_swizzled128(&P.tm[1], b, sb, fs_b, (long long)N * g.nbx, (long long)N * g.nby, n_frames, su::TROWS))
+        return 0;
+    P.out = out, P.nbx = g.nbx, P.nby = g.nby;
+    P.tiles_x = (g.nbx * N + su::TCOLS - 1) / su::TCOLS, P.tiles_y = (g.nby * N + su::TROWS - 1) / su::TROWS;
+    const long long tiles = (long long)P.tiles_x * P.tiles_y * n_frames;
+    if (tiles >= (1ll << 30)) return 0;
+    P.n_tiles = (int)tiles;
+    if (set_max_smem(su::satd_umma_kernel<LOG2>, su::SMEM_BYTES)) return (int)cudaErrorInvalidValue;
+    *taken = true;
+    long long grid = std::min<long long>(tiles, (long long)sm_count());   // one persistent CTA per SM
+    if (const char *e = getenv("HEVCASM_SATD_UMMA_GRID")) grid = std::max(1ll, std::min<long long>(grid, atoll(e)));   // test knob: more tiles per CTA
+    return launch(su::satd_umma_kernel<LOG2>, dim3((unsigned)grid), dim3(su::THREADS), (size_t)su::SMEM_BYTES, stream, P);
+}
+
 static int launch_satd(const uint8_t *a, ptrdiff_t sa, const uint8_t *b, ptrdiff_t sb, ptrdiff_t fs_a, ptrdiff_t fs_b, int log2size, const SatdGrid &g,
                        int32_t *out, void *stream)
 {
     if (g.n == 0) return 0;
+    // HEVCASM_SATD_PATH=umma: 4x4 / 8x8 on the tensor-core kernel when the planes allow it; =umma_only: fail instead of falling back (tests)
+    const char *pin = getenv("HEVCASM_SATD_PATH");
+    if (log2size >= 2 && pin && !strncmp(pin, "umma", 4)) {
+        bool taken = false;
+        const int e = log2size == 3 ? launch_satd_umma<3>(a, sa, b, sb, fs_a, fs_b, g, out, stream, &taken) : launch_satd_umma<2>(a, sa, b, sb, fs_a, fs_b, g, out, stream, &taken);
+        if (taken) return e;
+        if (!strcmp(pin, "umma_only")) return HEVCASM_ERR_ARGUMENT;
+    }
     const unsigned grid = (unsigned)((g.n + 127) / 128);
     // byte-wise kernels: every row of every block starts on a 4-byte boundary (regular grids of 4x4 / 8x8 blocks on 4-byte aligned planes)
     uintptr_t m = (uintptr_t)a | (uintptr_t)b | (uintptr_t)sa | (uintptr_t)sb;

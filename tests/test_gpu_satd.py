@@ -34,12 +34,35 @@ def test_satd_frames_and_lists(oracle, log2, shape):
     assert np.array_equal(to_host(got2), want2)
 
 
-def test_satd_extremes_and_full_size():
+@pytest.mark.parametrize("grid", [None, "1"])
+@pytest.mark.parametrize("log2", [2, 3])
+def test_satd_tensor_core(oracle, log2, grid, monkeypatch):
+    """4x4 / 8x8 SATD with the horizontal Hadamard pass on tcgen05 (satd_umma.cuh): 16-byte aligned planes, block counts that
+    leave partial 128 x 256 tiles, several frames; extreme planes (0 vs 255); "umma_only" fails rather than fall back."""
+    monkeypatch.setenv("HEVCASM_SATD_PATH", "umma_only")
+    if grid:
+        monkeypatch.setenv("HEVCASM_SATD_UMMA_GRID", grid)
+    n = 1 << log2
+    for width, height, nf in ((200, 136, 3), (8, 8, 1), (416, 600, 2)):
+        a = synth.random_planes(520 + width, nf, width, height, 16)
+        b = synth.smooth_planes(521, nf, width, height, 16)
+        nb = (width // n) * (height // n)
+        want = np.zeros((nf, nb), np.int32)
+        oracle.drv("hadamard_satd_frames", ptr(a.buf, a.origin), a.pitch, ptr(b.buf, b.origin), b.pitch, width, height, log2, nf, a.frame_stride, b.frame_stride,
+                   ptr(want), threads=4)
+        da, db = to_dev(a.buf), to_dev(b.buf)
+        got = dev_full(want.shape, np.int32, -1)
+        lib.call("hadamard_satd_frames", dptr(da, a.origin), a.pitch, dptr(db, b.origin), b.pitch, width, height, log2, nf, a.frame_stride, b.frame_stride, dptr(got))
+        assert np.array_equal(to_host(got), want), (width, height, nf)
+    test_satd_extremes_and_full_size(min_log2=2)
+
+
+def test_satd_extremes_and_full_size(min_log2=1):
     """all-0 vs all-255 8x8 blocks: (2 + 64*255) / 4; identical planes: 0 for 2x2 and N/4/(N/2) = 0 otherwise; on a 4K frame"""
     width, height = 3840, 2160
     z = synth.Planes(synth.aligned_copy(np.zeros((1, height, 3840), np.uint8)), width, height, 0)
     dz, do = to_dev(z.buf), to_dev(np.full_like(z.buf, 255))
-    for log2 in (1, 2, 3):
+    for log2 in range(min_log2, 4):
         n = 1 << log2
         out = dev_full(((width // n) * (height // n),), np.int32, -1)
         lib.call("hadamard_satd_frames", dptr(dz), 3840, dptr(do), 3840, width, height, log2, 1, 0, 0, dptr(out))
