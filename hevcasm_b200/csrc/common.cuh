@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stddef.h>
+#include <stdlib.h>
 
 #include "hevcasm_batch.h"
 
@@ -42,6 +43,19 @@ inline int set_max_smem(K kernel, size_t bytes)
 {
     return (int)cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
 }
+
+// ---- A/B switches ---------------------------------------------------------------------------------
+// The product library chooses every kernel from the call's arguments alone: tune::knob() is a constant there, so the branches
+// that test it fold away and no entry point reads the environment.  The experiments build (-DHEVCASM_EXPERIMENTS ->
+// libhevcasm_b200_exp.so: the measured-but-not-adopted kernel variants plus these switches, used by tools/ and by the parity
+// tests that pin one path) reads HEVCASM_* environment variables here.
+namespace tune {
+#ifdef HEVCASM_EXPERIMENTS
+inline const char *knob(const char *name) { return getenv(name); }
+#else
+constexpr const char *knob(const char *) { return nullptr; }
+#endif
+}  // namespace tune
 
 // SMs of the current device (148 on a B200); grids are sized against it
 inline int sm_count()

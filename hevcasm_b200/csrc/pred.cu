@@ -953,7 +953,7 @@ int launch_stream_tma(const FastParams &fp, const StreamMaps &sm, int n_frames, 
     // one-pass positions and copies are bound by memory: short strips, whose two or three boxes are all requested at once,
     // measured best (32 rows: 45-46 us per 16 4K planes; 64: 47-48; 120: 50-53).  Two-pass positions: see pick_strip.
     int strip = (MODE == HV) ? pick_strip(fp.p.height, cols * n_frames, per_sm * sm_count()) : 32;
-    if (const char *e = getenv("HEVCASM_PRED_STRIP")) {   // tuning knob: rows per CTA (rounded to a multiple of 8)
+    if (const char *e = tune::knob("HEVCASM_PRED_STRIP")) {   // tuning knob: rows per CTA (rounded to a multiple of 8)
         const int v = atoi(e) & ~7;
         if (v >= 8 && v <= 1024) strip = v;
     }
@@ -1177,7 +1177,7 @@ static PackedCoefs pack_coefs(int taps, int xFrac, int yFrac)
 // 15 bytes right of the reference's own footprint - hevcasm_batch.h documents the padding this needs)
 static bool planes_fast_ok(const uint8_t *ref0, const uint8_t *ref1, ptrdiff_t sr, ptrdiff_t fs_ref, int n_frames)
 {
-    if (getenv("HEVCASM_PRED_GENERIC")) return false;
+    if (tune::knob("HEVCASM_PRED_GENERIC")) return false;
     uintptr_t m = (uintptr_t)ref0 | (uintptr_t)sr | (ref1 ? (uintptr_t)ref1 : 0);
     if (n_frames > 1) m |= (uintptr_t)fs_ref;
     return (m & 15) == 0;
@@ -1185,8 +1185,8 @@ static bool planes_fast_ok(const uint8_t *ref0, const uint8_t *ref1, ptrdiff_t s
 // the streaming kernels issue aligned 32-bit loads / stores: everything 4-byte aligned (HEVCASM_PRED_PATH=tile pins the tile kernels)
 static bool stream_ok(const uint8_t *dst, ptrdiff_t sd, ptrdiff_t fs_dst, const uint8_t *ref0, const uint8_t *ref1, ptrdiff_t sr, ptrdiff_t fs_ref, int n_frames)
 {
-    const char *pin = getenv("HEVCASM_PRED_PATH");
-    if (getenv("HEVCASM_PRED_GENERIC") || (pin && strcmp(pin, "stream"))) return false;
+    const char *pin = tune::knob("HEVCASM_PRED_PATH");
+    if (tune::knob("HEVCASM_PRED_GENERIC") || (pin && strcmp(pin, "stream"))) return false;
     uintptr_t m = (uintptr_t)dst | (uintptr_t)sd | (uintptr_t)ref0 | (uintptr_t)sr | (ref1 ? (uintptr_t)ref1 : 0);
     if (n_frames > 1) m |= (uintptr_t)fs_dst | (uintptr_t)fs_ref;
     return (m & 3) == 0;
@@ -1195,8 +1195,8 @@ static bool stream_ok(const uint8_t *dst, ptrdiff_t sd, ptrdiff_t fs_dst, const 
 // kernel reads exactly the reference's footprint per position while the streaming one always reads the two-pass footprint)
 static bool list_stream_ok()
 {
-    const char *pin = getenv("HEVCASM_PRED_PATH");
-    return !getenv("HEVCASM_PRED_GENERIC") && !(pin && strcmp(pin, "stream"));
+    const char *pin = tune::knob("HEVCASM_PRED_PATH");
+    return !tune::knob("HEVCASM_PRED_GENERIC") && !(pin && strcmp(pin, "stream"));
 }
 // TMA-fed streaming kernel: describes each reference as a (x, y, frame) byte tensor starting at the first byte the filter
 // footprint touches (x = -4 with a horizontal pass, y = -(taps/2-1) with a vertical one).  Not possible (-> LDG streaming kernel)
@@ -1204,7 +1204,7 @@ static bool list_stream_ok()
 // lie in the next row, outside the declared row).  HEVCASM_PRED_STREAM=ldg / =tma pin one kernel (A/B runs).
 static bool stream_maps(StreamMaps *sm, const PredParams &p, int taps, int mode, bool bi, int n_frames)
 {
-    const char *pin = getenv("HEVCASM_PRED_STREAM");
+    const char *pin = tune::knob("HEVCASM_PRED_STREAM");
     if (pin && !strcmp(pin, "ldg")) return false;
     if (!tma::describable(p.sr, p.fs_ref, n_frames)) return false;
     const bool need_h = (bi && mode != COPY) || (mode & 1), need_v = (bi && mode != COPY) || (mode & 2);
@@ -1225,7 +1225,7 @@ static bool stream_maps(StreamMaps *sm, const PredParams &p, int taps, int mode,
 // two references 18.1 / 15.1 (1), 24.6 / 23.6 (2), 36.6 / 39.8 (4): the two-reference kernel needs ~5 tiles per SM to pay off.
 static bool tensor_path_wanted(int taps, long long n_tiles, bool bi = false)
 {
-    const char *pin = getenv("HEVCASM_PRED_HV");
+    const char *pin = tune::knob("HEVCASM_PRED_HV");
     if (pin && !strcmp(pin, "umma")) return true;
     if (pin && !strcmp(pin, "stream")) return false;
     return taps == 8 && n_tiles >= (bi ? 5ll : 1ll) * sm_count();
@@ -1233,9 +1233,10 @@ static bool tensor_path_wanted(int taps, long long n_tiles, bool bi = false)
 static unsigned tensor_grid(long long n_tiles)
 {
     long long g = std::min<long long>(n_tiles, (long long)sm_count());   // one persistent CTA per SM
-    if (const char *e = getenv("HEVCASM_PRED_UMMA_GRID")) g = std::max(1ll, std::min<long long>(g, atoll(e)));   // test knob: more tiles per CTA
+    if (const char *e = tune::knob("HEVCASM_PRED_UMMA_GRID")) g = std::max(1ll, std::min<long long>(g, atoll(e)));   // test knob: more tiles per CTA
     return (unsigned)g;
 }
+#ifdef HEVCASM_EXPERIMENTS
 // needs 16-byte aligned reference planes / strides
 static bool umma_params(um::Params *u, const PredParams &p, int taps, bool bi, int n_frames)
 {
@@ -1275,6 +1276,7 @@ static int launch_umma(const um::Params &u, void *stream)
     const unsigned grid = tensor_grid((u.n_tiles + G::NWG - 1) / G::NWG);   // one CTA of NWG warpgroups per SM
     return launch(kern, dim3(grid), dim3(G::THREADS), (size_t)G::SMEM_BYTES, stream, u);
 }
+#endif
 // vertical pass on the tensor cores (namespace uv of pred_umma.cuh), one or two references
 template <int TAPS, bool BI>
 static bool vh_params(uv::Params *u, const PredParams &p, int n_frames)
@@ -1331,7 +1333,7 @@ extern "C" int hevcasm_pred_uni_frames(uint8_t *dst, ptrdiff_t sd, const uint8_t
     // every position: the TMA-fed streaming kernel when the planes can be described to the TMA unit (strides multiples
     // of 16, 4-byte aligned rows).  Otherwise: two-pass positions -> LDG streaming kernel; one-pass positions -> tile kernels on
     // 16-byte aligned planes (2.2-2.4 vs 2.0 Tsamples/s), LDG streaming kernel on 4-byte aligned ones; copies -> tile kernels.
-    const char *pin = getenv("HEVCASM_PRED_PATH");
+    const char *pin = tune::knob("HEVCASM_PRED_PATH");
     const bool tile_ok = planes_fast_ok(ref, nullptr, sr, fs_ref, n_frames) && !(pin && !strcmp(pin, "stream"));
     if (mode == HV) {
         uv::Params u;
@@ -1368,11 +1370,14 @@ extern "C" int hevcasm_pred_bi_frames(uint8_t *dst, ptrdiff_t sd, const uint8_t 
     p.xf0 = xFrac0, p.yf0 = yFrac0, p.xf1 = xFrac1, p.yf1 = yFrac1;
     const dim3 grid((width + PTW - 1) / PTW, (height + PTH - 1) / PTH, n_frames);
     if (xFrac0 || yFrac0 || xFrac1 || yFrac1) {
-        const char *bk = getenv("HEVCASM_PRED_BI");   // A/B: "hfirst" = horizontal pass on the tensor cores (um), default = vertical pass (uv)
+#ifdef HEVCASM_EXPERIMENTS
+        const char *bk = tune::knob("HEVCASM_PRED_BI");   // A/B: "hfirst" = horizontal pass on the tensor cores (um), default = vertical pass (uv)
         if (bk && !strcmp(bk, "hfirst")) {
             um::Params u;
             if (umma_params(&u, p, taps, true, n_frames)) return taps == 8 ? launch_umma<8, true>(u, stream) : launch_umma<4, true>(u, stream);
-        } else {
+        } else
+#endif
+        {
             uv::Params u;
             if (taps == 8 ? vh_params<8, true>(&u, p, n_frames) : vh_params<4, true>(&u, p, n_frames))
                 return taps == 8 ? launch_vh<8, true>(u, stream) : launch_vh<4, true>(u, stream);

@@ -22,6 +22,7 @@
 // cores per sample is 4 IDP.2A + 1 PRMT + ~4.  tools/umma_fir_probe.cu pinned the TMA stride order and the descriptors.
 #pragma once
 
+#ifdef HEVCASM_EXPERIMENTS   // the horizontal-pass-first kernel is measured-but-not-adopted (126 vs 110 us): experiments build only
 namespace um {
 
 constexpr int TCOLS = 128;                 // output columns per tile = MMA M = TMEM lanes = threads
@@ -248,6 +249,7 @@ __global__ void __launch_bounds__(Geom<TAPS, BI>::THREADS, 1) pred_umma_kernel(c
 }
 
 }  // namespace um
+#endif  // HEVCASM_EXPERIMENTS
 
 // ================================================================================================================================
 // The same idea with the passes swapped, for one reference: the VERTICAL pass on the tensor cores, the horizontal pass in the

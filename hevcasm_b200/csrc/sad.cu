@@ -833,7 +833,7 @@ using namespace hv;
 // realignment shifts on the FMA pipe unless HEVCASM_SAD_SHIFT=alu (A/B switch)
 static void fill_shc(uint32_t (&shc)[3])
 {
-    const char *e = getenv("HEVCASM_SAD_SHIFT");
+    const char *e = tune::knob("HEVCASM_SAD_SHIFT");
     const bool alu = e && !strcmp(e, "alu");
     shc[0] = alu ? 0u : 1u << 24, shc[1] = 1u << 16, shc[2] = 1u << 8;
 }
@@ -880,7 +880,7 @@ extern "C" int hevcasm_sad_sweep_frames(const uint8_t *src, ptrdiff_t ss, const 
     if (p.npx == 0 || p.npy == 0 || n_frames == 0) return 0;
     // sides of 8, 16, 32, 64 with TMA-describable planes: the TMA-staged kernel, one launch per 8 x 8 tile of the candidate window
     {
-        const char *pin = getenv("HEVCASM_SAD_PATH");
+        const char *pin = tune::knob("HEVCASM_SAD_PATH");
         auto pow2_8_64 = [](int v) { return v == 8 || v == 16 || v == 32 || v == 64; };
         if ((!pin || !strcmp(pin, "tma")) && pow2_8_64(w) && pow2_8_64(h) && ((uintptr_t)src & 15) == 0 && ((uintptr_t)sad & 15) == 0 &&
             tma::describable(ss, fs_src, n_frames) && tma::describable(sr, fs_ref, n_frames)) {
@@ -956,7 +956,7 @@ extern "C" int hevcasm_sad_sweep_pyramid_frames(const uint8_t *src, ptrdiff_t ss
     int full_x = 0;
     // path selection: TMA staged (any byte alignment, needs 16-byte strides) > LDG fast (4-byte aligned window) > generic.
     // HEVCASM_SAD_PATH=tma|fast|generic pins one for A/B profiling.
-    const char *pin = getenv("HEVCASM_SAD_PATH");
+    const char *pin = tune::knob("HEVCASM_SAD_PATH");
     const bool all_levels = sad8 && sad16 && sad32 && sad64;
     const bool want_tma = !pin || !strcmp(pin, "tma"), want_fast = !pin || !strcmp(pin, "fast");
     if (want_tma && all_levels && ((uintptr_t)src & 15) == 0 && tma::describable(ss, fs_src, n_frames) && tma::describable(sr, fs_ref, n_frames)) {

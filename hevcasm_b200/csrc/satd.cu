@@ -17,7 +17,9 @@
 #include <cstring>
 
 namespace hv {
-#include "satd_umma.cuh"   // 4x4 / 8x8: horizontal Hadamard pass on tcgen05
+#ifdef HEVCASM_EXPERIMENTS
+#include "satd_umma.cuh"   // 4x4 / 8x8: horizontal Hadamard pass on tcgen05 (measured, not adopted: profiles/r01_satd.md)
+#endif
 
 // unsigned 32-bit division by a run-time constant as multiply-high + shifts (exact for every 32-bit numerator)
 struct SatdDiv {
@@ -221,6 +223,7 @@ __global__ void __launch_bounds__(256) ssd_linear_kernel(const uint8_t *__restri
 using namespace hv;
 
 // 4x4 / 8x8 on the tensor cores (satd_umma.cuh): regular grids over 16-byte aligned planes
+#ifdef HEVCASM_EXPERIMENTS
 template <int LOG2>
 static int launch_satd_umma(const uint8_t *a, ptrdiff_t sa, const uint8_t *b, ptrdiff_t sb, ptrdiff_t fs_a, ptrdiff_t fs_b, const SatdGrid &g, int32_t *out,
                             void *stream, bool *taken)
@@ -243,27 +246,30 @@ static int launch_satd_umma(const uint8_t *a, ptrdiff_t sa, const uint8_t *b, pt
     if (set_max_smem(su::satd_umma_kernel<LOG2>, su::SMEM_BYTES)) return (int)cudaErrorInvalidValue;
     *taken = true;
     long long grid = std::min<long long>(tiles, (long long)sm_count());   // one persistent CTA per SM
-    if (const char *e = getenv("HEVCASM_SATD_UMMA_GRID")) grid = std::max(1ll, std::min<long long>(grid, atoll(e)));   // test knob: more tiles per CTA
+    if (const char *e = tune::knob("HEVCASM_SATD_UMMA_GRID")) grid = std::max(1ll, std::min<long long>(grid, atoll(e)));   // test knob: more tiles per CTA
     return launch(su::satd_umma_kernel<LOG2>, dim3((unsigned)grid), dim3(su::THREADS), (size_t)su::SMEM_BYTES, stream, P);
 }
+#endif
 
 static int launch_satd(const uint8_t *a, ptrdiff_t sa, const uint8_t *b, ptrdiff_t sb, ptrdiff_t fs_a, ptrdiff_t fs_b, int log2size, const SatdGrid &g,
                        int32_t *out, void *stream)
 {
     if (g.n == 0) return 0;
+#ifdef HEVCASM_EXPERIMENTS
     // HEVCASM_SATD_PATH=umma: 4x4 / 8x8 on the tensor-core kernel when the planes allow it; =umma_only: fail instead of falling back (tests)
-    const char *pin = getenv("HEVCASM_SATD_PATH");
+    const char *pin = tune::knob("HEVCASM_SATD_PATH");
     if (log2size >= 2 && pin && !strncmp(pin, "umma", 4)) {
         bool taken = false;
         const int e = log2size == 3 ? launch_satd_umma<3>(a, sa, b, sb, fs_a, fs_b, g, out, stream, &taken) : launch_satd_umma<2>(a, sa, b, sb, fs_a, fs_b, g, out, stream, &taken);
         if (taken) return e;
         if (!strcmp(pin, "umma_only")) return HEVCASM_ERR_ARGUMENT;
     }
+#endif
     const unsigned grid = (unsigned)((g.n + 127) / 128);
     // byte-wise kernels: every row of every block starts on a 4-byte boundary (regular grids of 4x4 / 8x8 blocks on 4-byte aligned planes)
     uintptr_t m = (uintptr_t)a | (uintptr_t)b | (uintptr_t)sa | (uintptr_t)sb;
     if (g.n > g.nbx * (long long)g.nby) m |= (uintptr_t)fs_a | (uintptr_t)fs_b;
-    const bool bytewise = !g.blk_xy && (m & 3) == 0 && !getenv("HEVCASM_SATD_GENERIC");
+    const bool bytewise = !g.blk_xy && (m & 3) == 0 && !tune::knob("HEVCASM_SATD_GENERIC");
     if (log2size == 1) return launch(satd_generic_kernel<1>, grid, 128, 0, stream, a, sa, b, sb, fs_a, fs_b, g, out);
     if (log2size == 2)
         return bytewise ? launch(satd_kernel<2>, grid, 128, 0, stream, a, sa, b, sb, fs_a, fs_b, g, out)

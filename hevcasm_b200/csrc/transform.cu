@@ -15,7 +15,9 @@
 #include "transform.cuh"
 #include "tma.cuh"
 #include "umma.cuh"
+#ifdef HEVCASM_EXPERIMENTS
 #include "transform_imma.cuh"
+#endif
 
 #include <algorithm>
 #include <cstdlib>
@@ -524,8 +526,10 @@ __global__ void __launch_bounds__(BIG_NT) big_fwd_kernel(int16_t *__restrict__ c
     }
 }
 
-#include "transform_umma.cuh"  // 16x16 / 32x32 inverse on tcgen05 (needs BlockGrid, load_words, store_words)
-#include "transform_fwd_umma.cuh"  // forward 32x32: first stage on tcgen05, second in registers
+#include "transform_fwd_umma.cuh"  // forward 16x16 / 32x32: first stage on tcgen05, second in registers (the default for batches that fill the chip)
+#ifdef HEVCASM_EXPERIMENTS
+// measured, not adopted (profiles/r01_transforms.md); compiled into libhevcasm_b200_exp.so only
+#include "transform_umma.cuh"      // 16x16 / 32x32 inverse, both stages on tcgen05 (needs BlockGrid, load_words, store_words)
 #include "transform_inv_umma.cuh"  // inverse 16x16 / 32x32: first stage in registers, second on tcgen05
 
 // ================================================================================================ 16x16 / 32x32 inverse on IMMA
@@ -662,6 +666,8 @@ __global__ void __launch_bounds__(IMMA_NT) imma_inv_kernel(uint8_t *__restrict__
         __syncwarp();  // the tile is overwritten by the next block
     }
 }
+
+#endif  // HEVCASM_EXPERIMENTS
 
 // ================================================================================================ fused residual pipeline
 //
@@ -800,7 +806,7 @@ static int launch_fwd_umma(int16_t *coeffs, const int16_t *res, ptrdiff_t stride
     if (ft::ft_tables_init() || set_max_smem(ft::fwd_umma_kernel<LOG2>, ft::SMEM_BYTES)) return (int)cudaErrorInvalidValue;
     *taken = true;
     long long grid = std::min<long long>(tiles, (long long)sm_count());   // one persistent CTA per SM
-    if (const char *e = getenv("HEVCASM_FWD_UMMA_GRID")) grid = std::max(1ll, std::min<long long>(grid, atoll(e)));   // test knob: more tiles per CTA
+    if (const char *e = tune::knob("HEVCASM_FWD_UMMA_GRID")) grid = std::max(1ll, std::min<long long>(grid, atoll(e)));   // test knob: more tiles per CTA
     return launch(ft::fwd_umma_kernel<LOG2>, dim3((unsigned)grid), dim3(ft::THREADS), (size_t)ft::SMEM_BYTES, stream, P);
 }
 
@@ -809,7 +815,7 @@ static int launch_fwd(int16_t *coeffs, const int16_t *res, ptrdiff_t stride, ptr
     if (g.n == 0) return 0;
     if (((uintptr_t)coeffs & 15) != 0) return HEVCASM_ERR_ARGUMENT;
     const bool pa = !g.blk_xy && aligned16(res, stride * 2, fs * 2);
-    const char *pin = getenv("HEVCASM_FWD_PATH");
+    const char *pin = tune::knob("HEVCASM_FWD_PATH");
     const bool forced = pin && !strncmp(pin, "umma", 4);
     if ((log2 == 5 || log2 == 4) && !(pin && !strcmp(pin, "butterfly"))) {
         bool taken = false;
@@ -828,10 +834,11 @@ static int launch_inv_t(uint8_t *dst, ptrdiff_t sd, const uint8_t *pred, ptrdiff
     if (log2 == 2 && trType) return launch(small_inv_kernel<2, true, PA>, small_grid, SMALL_NT, 0, stream, dst, sd, pred, sp, fs_dst, fs_pred, coeffs, g);
     if (log2 == 2) return launch(small_inv_kernel<2, false, PA>, small_grid, SMALL_NT, 0, stream, dst, sd, pred, sp, fs_dst, fs_pred, coeffs, g);
     if (log2 == 3) return launch(small_inv_kernel<3, false, PA>, small_grid, SMALL_NT, 0, stream, dst, sd, pred, sp, fs_dst, fs_pred, coeffs, g);
+#ifdef HEVCASM_EXPERIMENTS
     // The tensor-core formulation is exact and tested, but NOT adopted: on B200 legacy mma.sync s8 issues at 512 MAC/clk/SM and
     // the kernel runs 178 us vs 145 us (32x32) / 200 vs 119 us (16x16) for the butterfly (profiles/r01_transforms.md).
     // HEVCASM_INV_PATH=imma selects it for A/B profiling.
-    const char *pin = getenv("HEVCASM_INV_PATH");
+    const char *pin = tune::knob("HEVCASM_INV_PATH");
     if (pin && !strcmp(pin, "imma") && imma_tables_init() == 0) {
         const unsigned blocks = (unsigned)std::min<long long>((g.n + IMMA_NT / 32 - 1) / (IMMA_NT / 32), 148 * 8);  // persistent warps, 8 CTAs per SM
         if (log2 == 4) return launch(imma_inv_kernel<4, PA>, blocks, IMMA_NT, 0, stream, dst, sd, pred, sp, fs_dst, fs_pred, coeffs, g);
@@ -844,10 +851,12 @@ static int launch_inv_t(uint8_t *dst, ptrdiff_t sd, const uint8_t *pred, ptrdiff
         if (log2 == 4) return launch(umma_inv_kernel<4, PA>, blocks, UMMA_NT, 0, stream, dst, sd, pred, sp, fs_dst, fs_pred, coeffs, g);
         return launch(umma_inv_kernel<5, PA>, blocks, UMMA_NT, 0, stream, dst, sd, pred, sp, fs_dst, fs_pred, coeffs, g);
     }
+#endif
     if (log2 == 4) return launch(big_inv_kernel<4, PA>, (unsigned)((g.n + 15) / 16), BIG_NT, 0, stream, dst, sd, pred, sp, fs_dst, fs_pred, coeffs, g);
     return launch(big_inv_kernel<5, PA>, (unsigned)((g.n + 7) / 8), BIG_NT, 0, stream, dst, sd, pred, sp, fs_dst, fs_pred, coeffs, g);
 }
 
+#ifdef HEVCASM_EXPERIMENTS
 // inverse 16x16 / 32x32 with the second stage on the tensor cores (transform_inv_umma.cuh): regular grids over 16-byte aligned planes
 template <int LOG2>
 static int launch_inv_umma(uint8_t *dst, ptrdiff_t sd, const uint8_t *pred, ptrdiff_t sp, ptrdiff_t fs_dst, ptrdiff_t fs_pred, const int16_t *coeffs,
@@ -870,9 +879,10 @@ static int launch_inv_umma(uint8_t *dst, ptrdiff_t sd, const uint8_t *pred, ptrd
     if (fi::fi_tables_init() || set_max_smem(fi::inv_umma_kernel<LOG2>, fi::SMEM_BYTES)) return (int)cudaErrorInvalidValue;
     *taken = true;
     long long grid = std::min<long long>(tiles, (long long)sm_count());   // one persistent CTA per SM
-    if (const char *e = getenv("HEVCASM_INV_UMMA_GRID")) grid = std::max(1ll, std::min<long long>(grid, atoll(e)));   // test knob: more tiles per CTA
+    if (const char *e = tune::knob("HEVCASM_INV_UMMA_GRID")) grid = std::max(1ll, std::min<long long>(grid, atoll(e)));   // test knob: more tiles per CTA
     return launch(fi::inv_umma_kernel<LOG2>, dim3((unsigned)grid), dim3(fi::THREADS), (size_t)fi::SMEM_BYTES, stream, P);
 }
+#endif
 
 static int launch_inv(uint8_t *dst, ptrdiff_t sd, const uint8_t *pred, ptrdiff_t sp, ptrdiff_t fs_dst, ptrdiff_t fs_pred, const int16_t *coeffs, int log2,
                       int trType, const BlockGrid &g, void *stream)
@@ -880,9 +890,10 @@ static int launch_inv(uint8_t *dst, ptrdiff_t sd, const uint8_t *pred, ptrdiff_t
     if (g.n == 0) return 0;
     if (((uintptr_t)coeffs & 15) != 0) return HEVCASM_ERR_ARGUMENT;
     const bool pa = !g.blk_xy && aligned16(dst, sd, fs_dst, pred, sp, fs_pred);
+#ifdef HEVCASM_EXPERIMENTS
     // HEVCASM_INV_PATH=hybrid: 16x16 / 32x32 with the second stage on tcgen05 whenever the planes allow it; =hybrid_only: fail instead of
     // falling back (tests)
-    const char *ipin = getenv("HEVCASM_INV_PATH");
+    const char *ipin = tune::knob("HEVCASM_INV_PATH");
     if ((log2 == 5 || log2 == 4) && ipin && !strncmp(ipin, "hybrid", 6)) {
         bool taken = false;
         const int e = !pa ? 0 : log2 == 5 ? launch_inv_umma<5>(dst, sd, pred, sp, fs_dst, fs_pred, coeffs, g, stream, true, &taken)
@@ -890,6 +901,7 @@ static int launch_inv(uint8_t *dst, ptrdiff_t sd, const uint8_t *pred, ptrdiff_t
         if (taken) return e;
         if (!strcmp(ipin, "hybrid_only")) return HEVCASM_ERR_ARGUMENT;
     }
+#endif
     return pa ? launch_inv_t<true>(dst, sd, pred, sp, fs_dst, fs_pred, coeffs, log2, trType, g, stream)
               : launch_inv_t<false>(dst, sd, pred, sp, fs_dst, fs_pred, coeffs, log2, trType, g, stream);
 }

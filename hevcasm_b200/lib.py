@@ -7,23 +7,40 @@ from .abi import BATCH_ABI, GPU_ONLY_ABI, HOST_ABI, P
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libhevcasm_b200.so")
+# the same sources built with -DHEVCASM_EXPERIMENTS: measured-but-not-adopted kernel variants + HEVCASM_* environment switches.
+# Only tools/ and the parity tests that pin one code path load it (use_experiments()); bench.py and smoke() never do.
+EXP_LIB_PATH = os.path.join(_HERE, "libhevcasm_b200_exp.so")
 
 _lib = None
+_libs = {}
 
 
 class HevcasmError(RuntimeError):
     pass
 
 
+def use_experiments(on=True):
+    """Route lib.call() through libhevcasm_b200_exp.so (on) or back through the product library (off)."""
+    global _lib
+    _lib = _bind(EXP_LIB_PATH if on else LIB_PATH)
+    return _lib
+
+
 def load():
     global _lib
-    if _lib is not None:
-        return _lib
-    if not os.path.exists(LIB_PATH):
+    if _lib is None:
+        _lib = _bind(LIB_PATH)
+    return _lib
+
+
+def _bind(path):
+    if path in _libs:
+        return _libs[path]
+    if not os.path.exists(path):
         raise HevcasmError(
-            f"{LIB_PATH} is missing: build it with `make -C hevcasm_b200/csrc` (or __graft_entry__.build()). "
+            f"{path} is missing: build it with `make -C hevcasm_b200/csrc` (or __graft_entry__.build()). "
             "hevcasm_b200 has no CPU fallback.")
-    lib = C.CDLL(LIB_PATH)
+    lib = C.CDLL(path)
     for table in (BATCH_ABI, GPU_ONLY_ABI):
         for name, args in table.items():
             fn = getattr(lib, "hevcasm_" + name)  # AttributeError if the symbol is missing: fail loudly
@@ -49,7 +66,7 @@ def load():
     lib.hevcasm_cuda_launch_count.restype = C.c_ulonglong
     lib.hevcasm_instruction_set_support.argtypes = []
     lib.hevcasm_instruction_set_support.restype = C.c_int
-    _lib = lib
+    _libs[path] = lib
     return lib
 
 
@@ -91,29 +108,19 @@ class Context:
 
 
 def pinned_array(shape, dtype):
-    """numpy array over page-locked host memory from hevcasm_cuda_host_alloc (kept alive by the array's base)."""
+    """numpy array over page-locked host memory from hevcasm_cuda_host_alloc; the allocation is released when the array (and
+    every view of it) has been garbage-collected."""
+    import weakref
+
     import numpy as np
     n = int(np.prod(shape)) * np.dtype(dtype).itemsize
-    p = load().hevcasm_cuda_host_alloc(max(n, 1))
+    lib = load()
+    p = lib.hevcasm_cuda_host_alloc(max(n, 1))
     if not p:
         raise HevcasmError(f"hevcasm_cuda_host_alloc({n}) failed")
     buf = (C.c_uint8 * max(n, 1)).from_address(p)
-
-    class _Owner:
-        def __init__(self, ptr, keep):
-            self.ptr, self.keep = ptr, keep
-
-        def __del__(self):
-            try:
-                load().hevcasm_cuda_host_free(self.ptr)
-            except Exception:
-                pass
-    arr = np.frombuffer(buf, dtype=np.uint8, count=n).view(dtype).reshape(shape)
-    _PINNED[arr.ctypes.data] = _Owner(p, buf)
-    return arr
-
-
-_PINNED = {}
+    weakref.finalize(buf, lib.hevcasm_cuda_host_free, p)   # views keep `buf` alive through their .base chain
+    return np.frombuffer(buf, dtype=np.uint8, count=n).view(dtype).reshape(shape)
 
 
 def launch_count():

@@ -26,3 +26,14 @@ def reference():
     if ref is None:
         pytest.skip("oracle/_ref not built (no /root/reference in this environment)")
     return ref
+
+
+@pytest.fixture
+def experiments():
+    """Routes lib.call() through libhevcasm_b200_exp.so for the duration of one test: the same sources built with
+    -DHEVCASM_EXPERIMENTS, i.e. with the HEVCASM_* switches that pin one code path (the product library has none) and the
+    measured-but-not-adopted kernel variants."""
+    from hevcasm_b200 import lib
+    lib.use_experiments(True)
+    yield
+    lib.use_experiments(False)

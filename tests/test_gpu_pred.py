@@ -40,7 +40,7 @@ def test_uni_planes_all_fractions(oracle, taps, shape):
 
 
 @pytest.mark.parametrize("taps", [8, 4])
-def test_generic_plane_kernels_all_fractions(oracle, taps, monkeypatch):
+def test_generic_plane_kernels_all_fractions(oracle, taps, monkeypatch, experiments):
     """the alignment-agnostic plane kernels (taken when reference rows are not 16-byte aligned), forced on aligned planes"""
     monkeypatch.setenv("HEVCASM_PRED_GENERIC", "1")
     test_uni_planes_all_fractions(oracle, taps, (200, 136))
@@ -50,7 +50,7 @@ def test_generic_plane_kernels_all_fractions(oracle, taps, monkeypatch):
 @pytest.mark.parametrize("env", [{"HEVCASM_PRED_STREAM": "ldg"}, {"HEVCASM_PRED_STREAM": "ldg", "HEVCASM_PRED_PATH": "stream"}, {"HEVCASM_PRED_PATH": "tile"},
                                  {"HEVCASM_PRED_HV": "stream"}])
 @pytest.mark.parametrize("taps", [8, 4])
-def test_fallback_plane_kernels_all_fractions(oracle, taps, env, monkeypatch):
+def test_fallback_plane_kernels_all_fractions(oracle, taps, env, monkeypatch, experiments):
     """the kernels behind the TMA-fed one: LDG-fed streaming kernel (planes the TMA unit cannot describe) and the shared-memory
     tile kernels, each forced on planes the default dispatch would hand to the TMA kernel"""
     for k, v in env.items():
@@ -62,7 +62,7 @@ def test_fallback_plane_kernels_all_fractions(oracle, taps, env, monkeypatch):
 
 @pytest.mark.parametrize("grid", [None, "2", "1"])
 @pytest.mark.parametrize("taps", [8, 4])
-def test_tensor_core_plane_kernels(oracle, taps, grid, monkeypatch):
+def test_tensor_core_plane_kernels(oracle, taps, grid, monkeypatch, experiments):
     """the tcgen05 kernels (vertical pass as an int8 Toeplitz product for one reference, horizontal pass for two), pinned for
     every plane size and both filters; with 1 or 2 CTAs each CTA walks over several tiles, which exercises the accumulator / stage /
     output-buffer rotation of the producer-consumer pipeline.  Odd widths leave through the byte-store path of the right-hand tile."""

@@ -36,7 +36,7 @@ def test_satd_frames_and_lists(oracle, log2, shape):
 
 @pytest.mark.parametrize("grid", [None, "1"])
 @pytest.mark.parametrize("log2", [2, 3])
-def test_satd_tensor_core(oracle, log2, grid, monkeypatch):
+def test_satd_tensor_core(oracle, log2, grid, monkeypatch, experiments):
     """4x4 / 8x8 SATD with the horizontal Hadamard pass on tcgen05 (satd_umma.cuh): 16-byte aligned planes, block counts that
     leave partial 128 x 256 tiles, several frames; extreme planes (0 vs 255); "umma_only" fails rather than fall back."""
     monkeypatch.setenv("HEVCASM_SATD_PATH", "umma_only")

@@ -34,7 +34,7 @@ def test_forward_frames(oracle, trType, log2, rng):
 @pytest.mark.parametrize("grid", [None, "2", "1"])
 @pytest.mark.parametrize("rng", [(-256, 255), (-32768, 32767), (-20000, -12000)])
 @pytest.mark.parametrize("log2", [5, 4])
-def test_forward_tensor_core(oracle, log2, rng, grid, monkeypatch):
+def test_forward_tensor_core(oracle, log2, rng, grid, monkeypatch, experiments):
     """forward 16x16 / 32x32 with the first stage on tcgen05 (transform_fwd_umma.cuh): 16-byte aligned planes, block counts that leave
     partial 4x4-block tiles, several frames; "umma_only" makes the call fail rather than fall back, so a pass is the tensor
     path.  Full-range and all-negative inputs exercise the high-byte product and the unpacked second-stage butterfly; with
@@ -96,7 +96,7 @@ def test_inverse_frames(oracle, trType, log2):
 
 @pytest.mark.parametrize("path", ["imma", "umma"])
 @pytest.mark.parametrize("log2", [4, 5])
-def test_inverse_frames_imma_variant(oracle, log2, path, monkeypatch):
+def test_inverse_frames_imma_variant(oracle, log2, path, monkeypatch, experiments):
     """the exact tensor-core formulations of the 16x16 / 32x32 inverse: legacy mma.sync s8/u8 -> s32 ("imma", kept for A/B
     profiling) and tcgen05 kind::i8 with TMEM accumulators ("umma")"""
     monkeypatch.setenv("HEVCASM_INV_PATH", path)
@@ -117,7 +117,7 @@ def test_inverse_frames_imma_variant(oracle, log2, path, monkeypatch):
 @pytest.mark.parametrize("grid", [None, "2", "1"])
 @pytest.mark.parametrize("rng", [(-600, 600), (-32768, 32767)])
 @pytest.mark.parametrize("log2", [5, 4])
-def test_inverse_tensor_core(oracle, log2, rng, grid, monkeypatch):
+def test_inverse_tensor_core(oracle, log2, rng, grid, monkeypatch, experiments):
     """inverse 16x16 / 32x32 with the SECOND stage on tcgen05 (transform_inv_umma.cuh): stage 1 in the threads writes the int16
     intermediate into shared memory in the swizzled operand layout.  16-byte aligned planes, block counts that leave partial
     tiles, several frames, full-range coefficients (stage-1 clip, high-byte product); "hybrid_only" fails rather than fall back."""

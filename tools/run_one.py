@@ -3,6 +3,8 @@ import ctypes as C, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from hevcasm_b200 import lib, synth
+if os.environ.get("RUN_ONE_EXP"):   # experiments build: HEVCASM_* switches and the not-adopted kernel variants
+    lib.use_experiments()
 
 W, H, NF, PAD = 3840, 2160, int(os.environ.get("RUN_ONE_NF", "16")), 64
 name = sys.argv[1]
