@@ -25,6 +25,7 @@
 #include <algorithm>
 #include <cstdlib>
 #include <cstring>
+#include <cstdio>
 
 namespace hv {
 namespace ip {
@@ -1219,7 +1220,7 @@ static bool stream_maps(StreamMaps *sm, const PredParams &p, int taps, int mode,
     return true;
 }
 // Two-pass positions on the tensor cores (pred_umma.cuh).  Default: 8-tap positions of batches that fill the chip at least once
-// (the kernels are persistent, one CTA per SM, with tiles of 128 x 224 samples); HEVCASM_PRED_HV=umma takes them for
+// (the kernels are persistent, one CTA per SM, with tiles of 128 x 192 samples); HEVCASM_PRED_HV=umma takes them for
 // every size and both filters, HEVCASM_PRED_HV=stream never (A/B runs and the parity tests of either side).
 // Measured crossover on 4K planes (us per launch, tensor / streaming): one reference 12.0 / 12.1 (1 plane), 19.3 / 23.3 (4 planes);
 // two references 18.1 / 15.1 (1), 24.6 / 23.6 (2), 36.6 / 39.8 (4): the two-reference kernel needs ~5 tiles per SM to pay off.
@@ -1293,24 +1294,44 @@ static bool vh_params(uv::Params *u, const PredParams &p, int n_frames)
     for (int rf = 0; rf < (BI ? 2 : 1); ++rf) {
         if (tma::describe_u32_swizzled128(&u->tmref[rf], refs[rf] - (ptrdiff_t)top * p.sr - 16, p.sr, p.fs_ref, ext_x, rows, n_frames, uv::BOXR)) return false;
         const PackedCoefs c = pack_coefs(TAPS, xf[rf], yf[rf]);
-        for (int g = 0; g < 4; ++g) u->x2[rf][g] = c.x2e[g];
+        for (int g = 0; g < 4; ++g) u->x2[rf][g] = c.x2e[g], u->x2o[rf][g] = g < 3 ? c.x2o[g + 1] : 0;
+        u->xfrac[rf] = xf[rf];
         for (int k = 0; k < 8; ++k) u->ytap[rf][k] = k < TAPS ? (int8_t)((c.y4s[0][k >> 2] >> (8 * (k & 3))) & 0xff) : 0;
     }
     u->dst = p.dst, u->sd = p.sd, u->fs_dst = p.fs_dst, u->width = p.width, u->height = p.height;
     u->dst16 = (((uintptr_t)p.dst | (uintptr_t)p.sd | (n_frames > 1 ? (uintptr_t)p.fs_dst : 0)) & 15) == 0 && p.sd > 0 && (n_frames <= 1 || p.fs_dst > 0);
-    if (u->dst16) {
-        int shift = 0;
-        if (tma::describe_u8(&u->tmdst, p.dst, p.sd, p.fs_dst, p.width, p.height, n_frames, uv::TCOLS, uv::TROWS, &shift) || shift) u->dst16 = 0;
-    }
+    if (u->dst16 && (tma::describe_u8_swizzled(&u->tmdst[0], p.dst, p.sd, p.fs_dst, p.width, p.height, n_frames, 128, uv::TROWS) ||
+                     tma::describe_u8_swizzled(&u->tmdst[1], p.dst, p.sd, p.fs_dst, p.width, p.height, n_frames, 64, uv::TROWS)))
+        u->dst16 = 0;
     u->n_tiles = (int)(per * n_frames);
     return true;
 }
 template <int TAPS, bool BI>
-static int launch_vh(const uv::Params &u, void *stream)
+static int launch_vh(uv::Params &u, void *stream)
 {
     auto kern = uv::pred_vh_kernel<TAPS, BI>;
     if (set_max_smem(kern, uv::Geom<BI>::SMEM_BYTES)) return (int)cudaErrorInvalidValue;
     const unsigned grid = tensor_grid(u.n_tiles);
+    u.prof = nullptr;
+#ifdef HEVCASM_EXPERIMENTS
+    if (tune::knob("HEVCASM_PRED_PROF")) {   // per-phase clock totals of CTA 0, printed after a synchronous launch (development aid)
+        static long long *buf = nullptr;
+        if (!buf) cudaMalloc(&buf, 32 * sizeof(long long));
+        cudaMemset(buf, 0, 32 * sizeof(long long));
+        u.prof = buf;
+        const int e = launch(kern, dim3(grid), dim3(uv::THREADS), (size_t)uv::Geom<BI>::SMEM_BYTES, stream, u);
+        long long h[32];
+        cudaStreamSynchronize((cudaStream_t)stream);
+        cudaMemcpy(h, buf, sizeof(h), cudaMemcpyDeviceToHost);
+        const int tiles = (u.n_tiles + (int)grid - 1) / (int)grid;
+        fprintf(stderr, "pred_vh prof, cycles per tile (%d tiles): loader wait_empty %lld request %lld | mma wait_ofree+full %lld wait_consumed %lld issue+commit %lld (%lld) | "
+                        "storer wait_ready %lld issue %lld wait_read %lld | consumer", tiles, h[0] / tiles, h[1] / tiles, h[8] / tiles, h[9] / tiles, h[10] / tiles, h[11] / tiles,
+                h[16] / tiles, h[17] / tiles, h[18] / tiles);
+        for (int k = 0; k < 5; ++k) fprintf(stderr, " %lld", h[24 + k] / tiles);
+        fprintf(stderr, "\n");
+        return e;
+    }
+#endif
     return launch(kern, dim3(grid), dim3(uv::THREADS), (size_t)uv::Geom<BI>::SMEM_BYTES, stream, u);
 }
 static bool aligned8(const uint8_t *dst, ptrdiff_t sd, ptrdiff_t fs_dst, int n_frames)

@@ -45,7 +45,7 @@ __global__ void __launch_bounds__(THREADS, 1) satd_umma_kernel(const __grid_cons
 
     if (threadIdx.x == 0) {
 #pragma unroll
-        for (int i = 0; i < 2; ++i) tma::mbar_init(full + i, 1), tma::mbar_init(done + i, 1), tma::mbar_init(consumed + i, CONSUMERS);
+        for (int i = 0; i < 2; ++i) tma::mbar_init(full + i, 1), tma::mbar_init(done + i, 1), tma::mbar_init(consumed + i, CONSUMERS / 32);
     }
     if (threadIdx.x < 32) umma::tmem_alloc<512>(tmem_slot);
     __syncthreads();
@@ -164,7 +164,7 @@ __global__ void __launch_bounds__(THREADS, 1) satd_umma_kernel(const __grid_cons
                 }
             }
             umma::fence_before();   // this thread's TMEM reads are complete
-            tma::mbar_arrive(consumed + a);
+            tma::mbar_arrive_warp(consumed + a);
             // the N lanes (k) of a block add up; lane k = 0 writes (N/4 + sum) / (N/2)
             const int bx = tx * BPR + bc;
 #pragma unroll

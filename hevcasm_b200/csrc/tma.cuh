@@ -69,11 +69,12 @@ inline int describe_u32(CUtensorMap *map, const uint8_t *first, ptrdiff_t row_st
 }
 
 // Byte planes whose boxes land in shared memory in the tensor cores' swizzled K-major form: box_x = 128 -> 128-byte swizzle
-// (destination 1024-byte aligned), box_x = 32 -> 32-byte swizzle (256-byte aligned).  `base` must be 16-byte aligned.
+// (destination 1024-byte aligned), box_x = 64 -> 64-byte swizzle (512-byte aligned), box_x = 32 -> 32-byte swizzle (256-byte aligned).
+// `base` must be 16-byte aligned.  (Also used for TMA STORES out of a swizzled staging buffer, which threads can fill without bank conflicts.)
 inline int describe_u8_swizzled(CUtensorMap *map, const uint8_t *base, ptrdiff_t row_stride, ptrdiff_t frame_stride, long long extent_x, long long extent_y,
                                 int n_frames, int box_x, int box_y)
 {
-    if (((uintptr_t)base & 15) != 0 || (box_x != 128 && box_x != 32)) return (int)cudaErrorInvalidValue;
+    if (((uintptr_t)base & 15) != 0 || (box_x != 128 && box_x != 64 && box_x != 32)) return (int)cudaErrorInvalidValue;
     if (n_frames <= 1) frame_stride = row_stride * (ptrdiff_t)extent_y;
     if (extent_x > (long long)row_stride) extent_x = (long long)row_stride;
     cuuint64_t dim[3] = {(cuuint64_t)extent_x, (cuuint64_t)extent_y, (cuuint64_t)(n_frames < 1 ? 1 : n_frames)};
@@ -81,7 +82,7 @@ inline int describe_u8_swizzled(CUtensorMap *map, const uint8_t *base, ptrdiff_t
     cuuint32_t box[3] = {(cuuint32_t)box_x, (cuuint32_t)box_y, 1};
     cuuint32_t estr[3] = {1, 1, 1};
     const CUresult r = encoder()(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, (void *)base, dim, stride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                                 box_x == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                                 box_x == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : box_x == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     return r == CUDA_SUCCESS ? 0 : (int)cudaErrorInvalidValue;
 }
@@ -135,14 +136,32 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
 __device__ __forceinline__ void mbar_arrive(uint64_t *bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory"); }
+// One arrival for the whole (converged) warp: the barrier's count is the number of WARPS.  Every arrival is a serialised
+// shared-memory atomic - with one per thread, the 512 consumers of a tensor-core kernel spent ~1300 cycles per tile just arriving
+// (measured with every other stage of the kernel switched off, profiles/r02_pred.md).  __syncwarp orders the lanes' earlier
+// shared-memory writes and fences before lane 0's release-arrive.
+__device__ __forceinline__ void mbar_arrive_warp(uint64_t *bar)
+{
+    __syncwarp();
+    if ((threadIdx.x & 31) == 0) mbar_arrive(bar);
+}
 // Waits for the phase with the given parity.  A descriptor / coordinate error would leave the barrier incomplete for ever;
 // rather than hang the GPU the wait gives up after ~1 s worth of polls and traps, which surfaces as a launch failure.
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
 {
     const uint32_t addr = smem_u32(bar);
+    uint32_t done;
+    // fast path: the phase has usually completed long before the wait (pipelines run ahead); test_wait never suspends the warp
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(addr), "r"(parity)
+        : "memory");
+    if (done) return;
 #pragma unroll 1
     for (int spin = 0; spin < (1 << 22); ++spin) {
-        uint32_t done;
         asm volatile(
             "{\n\t.reg .pred p;\n\t"
             "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"

@@ -85,7 +85,7 @@ __global__ void __launch_bounds__(THREADS, 1) fwd_umma_kernel(const __grid_const
 
     if (threadIdx.x == 0) {
 #pragma unroll
-        for (int i = 0; i < 2; ++i) tma::mbar_init(full + i, 1), tma::mbar_init(done + i, 1), tma::mbar_init(consumed + i, CONSUMERS);
+        for (int i = 0; i < 2; ++i) tma::mbar_init(full + i, 1), tma::mbar_init(done + i, 1), tma::mbar_init(consumed + i, CONSUMERS / 32);
         tma::mbar_init(cready, 1);
     }
     if (threadIdx.x < 32) umma::tmem_alloc<512>(tmem_slot);
@@ -188,7 +188,7 @@ __global__ void __launch_bounds__(THREADS, 1) fwd_umma_kernel(const __grid_const
                 }
             }
             umma::fence_before();   // this thread's TMEM reads are complete
-            tma::mbar_arrive(consumed + a);
+            tma::mbar_arrive_warp(consumed + a);
             // stage 2 in registers: out[v] = (sum_j T[v][j] tmp[k][j] + round) >> S2 -> coeffs[v * BS + k]  (residual_decode.c:855-892)
             const int bcg = cx * TB + bc;
 #pragma unroll

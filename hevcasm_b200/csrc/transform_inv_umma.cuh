@@ -87,7 +87,7 @@ __global__ void __launch_bounds__(THREADS, 1) inv_umma_kernel(const __grid_const
 
     if (threadIdx.x == 0) {
 #pragma unroll
-        for (int i = 0; i < 2; ++i) tma::mbar_init(filled + i, CONSUMERS / 2), tma::mbar_init(done + i, 1), tma::mbar_init(consumed + i, CONSUMERS), tma::mbar_init(loaded_c + i, 1), tma::mbar_init(loaded_p + i, 1);
+        for (int i = 0; i < 2; ++i) tma::mbar_init(filled + i, CONSUMERS / 2 / 32), tma::mbar_init(done + i, 1), tma::mbar_init(consumed + i, CONSUMERS / 32), tma::mbar_init(loaded_c + i, 1), tma::mbar_init(loaded_p + i, 1);
     }
     if (threadIdx.x < 32) umma::tmem_alloc<512>(tmem_slot);
     for (int idx = threadIdx.x; idx < 2 * C_BYTES / 16; idx += THREADS) reinterpret_cast<uint4 *>(sC)[idx] = g_fi_B[LOG2 - 4][idx];
@@ -202,7 +202,7 @@ __global__ void __launch_bounds__(THREADS, 1) inv_umma_kernel(const __grid_const
                 }
             }
             umma::fence_async_smem();   // the operand bytes -> visible to the tensor cores
-            tma::mbar_arrive(filled + (it & 1));
+            tma::mbar_arrive_warp(filled + (it & 1));
         };
         if (n_mine > 0) stage1(0);
 #pragma unroll 1
@@ -252,7 +252,7 @@ __global__ void __launch_bounds__(THREADS, 1) inv_umma_kernel(const __grid_const
             }
             umma::fence_before();       // this thread's TMEM reads are complete
             umma::fence_async_smem();   // .. and its reads of the predictor stage precede the loader's next box
-            tma::mbar_arrive(consumed + a);
+            tma::mbar_arrive_warp(consumed + a);
 #pragma unroll
             for (int g = 0; g < 2; ++g)
                 if (ok[g]) reinterpret_cast<uint4 *>(dp)[g] = make_uint4(ow[4 * g], ow[4 * g + 1], ow[4 * g + 2], ow[4 * g + 3]);

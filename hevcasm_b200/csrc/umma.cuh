@@ -71,7 +71,19 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, int (&v)[8])
                  : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
                  : "r"(taddr));
 }
+// 8 consecutive columns (the address must be EVEN) as 4 words: the low 16 bits of columns 2i and 2i+1 in the low / high half of word i -
+// int16 pairs straight out of TMEM, no PRMT (semantics and alignment pinned by tools/tmem_probe.cu: an odd column address faults)
+__device__ __forceinline__ void tmem_ld8_pack16(uint32_t taddr, uint32_t (&v)[4])
+{
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.pack::16b.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]) : "r"(taddr));
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// the wait tied to the registers of a packed + a plain load of the same 8 columns
+__device__ __forceinline__ void tmem_ld_wait(uint32_t (&p)[4], int (&v)[8])
+{
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(p[0]), "+r"(p[1]), "+r"(p[2]), "+r"(p[3]), "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7])::"memory");
+}
 // the same wait, tied to the registers of an earlier load so that no use of them can be scheduled above it
 __device__ __forceinline__ void tmem_ld_wait(int (&v)[8])
 {

@@ -7,7 +7,7 @@
 using namespace hv;
 
 // layoutA / layoutB: 0 = no swizzle (K-major, 16-byte chunks [chunk][row][16]), 2 = 128-byte swizzle, 6 = 32-byte swizzle
-__global__ void __launch_bounds__(128, 1) rate(long long *out, int n, int layoutA, int layoutB, int rounds, int ksteps, int kind_f8)
+__global__ void __launch_bounds__(128, 1) rate(long long *out, int n, int layoutA, int layoutB, int rounds, int ksteps, int b_mn)
 {
     extern __shared__ __align__(128) uint8_t raw[];
     uint8_t *smem = raw + ((1024 - (tma::smem_u32(raw) & 1023)) & 1023);
@@ -23,7 +23,7 @@ __global__ void __launch_bounds__(128, 1) rate(long long *out, int n, int layout
     umma::fence_after();
     const uint32_t tm = slot;
     uint8_t *sA = smem, *sB = smem + 48 * 1024;
-    const uint32_t idesc = umma::idesc_i8(true, false, false, n);
+    const uint32_t idesc = umma::idesc_i8(true, false, false, n, b_mn != 0);
     if (tid == 0) {
         long long best = 1ll << 60;
         for (int rep = 0; rep < 4; ++rep) {
@@ -32,7 +32,7 @@ __global__ void __launch_bounds__(128, 1) rate(long long *out, int n, int layout
                 for (int ks = 0; ks < ksteps; ++ks) {
                     const uint64_t da = layoutA == 0 ? umma::smem_desc(tma::smem_u32(sA) + ks * 2 * 2048, 2048, 128)
                                                      : umma::smem_desc(tma::smem_u32(sA) + (ks & 3) * 32, 16, layoutA == 2 ? 1024 : 256, layoutA);
-                    const uint64_t db = layoutB == 0 ? umma::smem_desc(tma::smem_u32(sB) + ks * 2 * (n * 16), n * 16, 128)
+                    const uint64_t db = b_mn ? umma::smem_desc(tma::smem_u32(sB) + ks * 4096, 20480, 1024, 2) : layoutB == 0 ? umma::smem_desc(tma::smem_u32(sB) + ks * 2 * (n * 16), n * 16, 128)
                                                      : umma::smem_desc(tma::smem_u32(sB) + (ks & 3) * 32, 16, layoutB == 2 ? 1024 : 256, layoutB);
                     umma::mma_i8(tm + (r & 1) * 256, da, db, idesc, ks);
                 }
@@ -67,5 +67,14 @@ int main()
             printf("layoutA %d layoutB %d N %3d: %.1f cycles per MMA (min SM; max SM %.1f) = %.0f MAC/clk/SM\n", l[0], l[1], n, per, (double)mx / (rounds * ksteps),
                    128.0 * n * 32 / per);
         }
+    // the image operand of the vertical-pass-first interpolation kernel: MN-major, 128-byte swizzle, two blocks of 128 columns
+    for (int n : {128, 192, 216, 256}) {
+        rate<<<148, 128, 100 * 1024>>>(d, n, 0, 2, rounds, ksteps, 1);
+        if (cudaDeviceSynchronize() != cudaSuccess) { printf("launch failed: %s\n", cudaGetErrorString(cudaGetLastError())); return 1; }
+        cudaMemcpy(h, d, sizeof(h), cudaMemcpyDeviceToHost);
+        long long mn = 1ll << 60;
+        for (long long v : h) mn = v < mn ? v : mn;
+        printf("A K-major no swizzle, B MN-major 128-byte swizzle, N %3d: %.1f cycles per MMA\n", n, (double)mn / (rounds * ksteps));
+    }
     return 0;
 }
