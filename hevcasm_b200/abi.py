@@ -40,13 +40,17 @@ BATCH_ABI = {
 GPU_ONLY_ABI = {
     "sad_sweep_pyramid_frames": [P, PD, P, PD, I, I, I, I, I, PD, PD, P, P, P, P],
     "sad_sweep_pyramid_best_frames": [P, PD, P, PD, I, I, I, I, I, PD, PD, P, P, P, P],
+    "sad_sweep_pyramid_packed_frames": [P, PD, P, PD, I, I, I, I, I, PD, PD, P, P, P, P],
     "residual_pipeline_frames": [P, PD, P, P, P, PD, P, PD, I, I, I, I, I, I, I, I, I, I, PD, PD, PD],
+    "pred_uni_frames_bounded": [P, PD, P, PD, I, I, I, I, I, I, PD, PD, PD, PD],
+    "pred_bi_frames_bounded": [P, PD, P, P, PD, I, I, I, I, I, I, I, I, PD, PD, PD, PD],
 }
 
 # host-memory forms: hevcasm_<name>(hevcasm_cuda_context *ctx, ...host pointers...) - no stream argument
 HOST_ABI = {
     "sad_sweep_pyramid_frames_host": [P, P, PD, P, PD, I, I, I, I, I, I, PD, PD, P, P, P, P],
     "sad_sweep_pyramid_best_frames_host": [P, P, PD, P, PD, I, I, I, I, I, I, PD, PD, P, P, P, P],
+    "sad_sweep_pyramid_packed_frames_host": [P, P, PD, P, PD, I, I, I, I, I, I, PD, PD, P, P, P, P],
     "pred_uni_frames_host": [P, P, PD, P, PD, I, I, I, I, I, I, I, PD, PD],
     "residual_pipeline_frames_host": [P, P, PD, P, P, P, PD, P, PD, I, I, I, I, I, I, I, I, I, I, PD, PD, PD],
 }

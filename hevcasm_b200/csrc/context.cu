@@ -10,8 +10,16 @@
 #include "common.cuh"
 
 #include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <mutex>
 #include <new>
 #include <vector>
+
+#include <sys/mman.h>
+#include <sys/syscall.h>
+#include <unistd.h>
 
 struct hevcasm_cuda_context {
     int device = 0;
@@ -109,29 +117,33 @@ int run_pipeline(hevcasm_cuda_context *ctx, int n_frames, size_t bytes_per_frame
     const size_t slot_bytes = (size_t)chunk * per_frame;
     ctx->next_event = 0;
     std::vector<cudaEvent_t> done_out(n_chunks, nullptr);
-    for (int c = 0; c < n_chunks; ++c) {
-        const int f0 = c * chunk, nf = std::min(chunk, n_frames - f0);
-        uint8_t *slot = ctx->arena + (size_t)(c % n_slots) * slot_bytes;
-        if (c >= n_slots) HV_CUDA(cudaStreamWaitEvent(ctx->s_in, done_out[c - n_slots], 0));  // slot is free again
-        int e = in(slot, f0, nf, ctx->s_in);
-        if (e) return e;
-        cudaEvent_t ev_in = ctx->event(), ev_run = ctx->event(), ev_out = ctx->event();
-        if (!ev_in || !ev_run || !ev_out) return (int)cudaErrorMemoryAllocation;
-        HV_CUDA(cudaEventRecord(ev_in, ctx->s_in));
-        HV_CUDA(cudaStreamWaitEvent(ctx->s_run, ev_in, 0));
-        e = run(slot, f0, nf, ctx->s_run);
-        if (e) return e;
-        HV_CUDA(cudaEventRecord(ev_run, ctx->s_run));
-        HV_CUDA(cudaStreamWaitEvent(ctx->s_out, ev_run, 0));
-        e = out(slot, f0, nf, ctx->s_out);
-        if (e) return e;
-        HV_CUDA(cudaEventRecord(ev_out, ctx->s_out));
-        done_out[c] = ev_out;
-    }
-    HV_CUDA(cudaStreamSynchronize(ctx->s_out));
-    HV_CUDA(cudaStreamSynchronize(ctx->s_run));
-    HV_CUDA(cudaStreamSynchronize(ctx->s_in));
-    return 0;
+    auto enqueue = [&]() -> int {
+        for (int c = 0; c < n_chunks; ++c) {
+            const int f0 = c * chunk, nf = std::min(chunk, n_frames - f0);
+            uint8_t *slot = ctx->arena + (size_t)(c % n_slots) * slot_bytes;
+            if (c >= n_slots) HV_CUDA(cudaStreamWaitEvent(ctx->s_in, done_out[c - n_slots], 0));  // slot is free again
+            int e = in(slot, f0, nf, ctx->s_in);
+            if (e) return e;
+            cudaEvent_t ev_in = ctx->event(), ev_run = ctx->event(), ev_out = ctx->event();
+            if (!ev_in || !ev_run || !ev_out) return (int)cudaErrorMemoryAllocation;
+            HV_CUDA(cudaEventRecord(ev_in, ctx->s_in));
+            HV_CUDA(cudaStreamWaitEvent(ctx->s_run, ev_in, 0));
+            e = run(slot, f0, nf, ctx->s_run);
+            if (e) return e;
+            HV_CUDA(cudaEventRecord(ev_run, ctx->s_run));
+            HV_CUDA(cudaStreamWaitEvent(ctx->s_out, ev_run, 0));
+            e = out(slot, f0, nf, ctx->s_out);
+            if (e) return e;
+            HV_CUDA(cudaEventRecord(ev_out, ctx->s_out));
+            done_out[c] = ev_out;
+        }
+        return 0;
+    };
+    const int e = enqueue();
+    // success or not, nothing may still be reading or writing the caller's buffers (or be waiting on this call's events) when we return
+    const cudaError_t s1 = cudaStreamSynchronize(ctx->s_in), s2 = cudaStreamSynchronize(ctx->s_run), s3 = cudaStreamSynchronize(ctx->s_out);
+    if (e) return e;
+    return s1 != cudaSuccess ? (int)s1 : s2 != cudaSuccess ? (int)s2 : (int)s3;
 }
 
 }  // namespace
@@ -168,43 +180,111 @@ extern "C" void hevcasm_cuda_context_destroy(hevcasm_cuda_context *ctx)
 
 extern "C" void *hevcasm_cuda_context_stream(hevcasm_cuda_context *ctx) { return ctx ? (void *)ctx->s_run : nullptr; }
 
+// ---- page-locked host memory --------------------------------------------------------------------------------
+// hevcasm_cuda_host_alloc: cudaHostAlloc.  hevcasm_cuda_host_alloc_near(bytes, device): pages bound to the NUMA node the GPU hangs off
+// (sysfs numa_node of its PCI function; mbind) and then registered with the driver - on a two-socket 8-GPU box the D2H result streams
+// of the ranks otherwise all land on whichever node the allocating thread happened to run on, and the end-to-end figure stops scaling
+// at that node's memory bandwidth (SCALE_r01: 0.20 efficiency at 8 GPUs).  Falls back to cudaHostAlloc when the node is unknown.
+namespace {
+std::mutex g_host_mu;
+std::map<void *, size_t> g_mapped;   // regions from mmap + cudaHostRegister: pointer -> mapped bytes
+
+int gpu_numa_node(int device)
+{
+    char bus[32] = {0};
+    if (cudaDeviceGetPCIBusId(bus, sizeof bus, device) != cudaSuccess) return -1;
+    for (char *c = bus; *c; ++c)
+        if (*c >= 'A' && *c <= 'F') *c = (char)(*c - 'A' + 'a');   // sysfs spells the address in lower case
+    char path[96];
+    snprintf(path, sizeof path, "/sys/bus/pci/devices/%s/numa_node", bus);
+    FILE *f = fopen(path, "r");
+    if (!f) return -1;
+    int node = -1;
+    if (fscanf(f, "%d", &node) != 1) node = -1;
+    fclose(f);
+    return node;
+}
+}  // namespace
+
 extern "C" void *hevcasm_cuda_host_alloc(size_t bytes)
 {
     void *p = nullptr;
     return cudaHostAlloc(&p, bytes, cudaHostAllocDefault) == cudaSuccess ? p : nullptr;
 }
 
+extern "C" void *hevcasm_cuda_host_alloc_near(size_t bytes, int device)
+{
+    const int node = gpu_numa_node(device);
+    if (node < 0 || node >= 64 || bytes == 0) return hevcasm_cuda_host_alloc(bytes);
+    const size_t page = (size_t)sysconf(_SC_PAGESIZE), len = round_up(bytes, page);
+    void *p = mmap(nullptr, len, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS, -1, 0);
+    if (p == MAP_FAILED) return hevcasm_cuda_host_alloc(bytes);
+    const unsigned long mask = 1ul << node;
+#ifdef SYS_mbind
+    const long rc = syscall(SYS_mbind, p, len, 2 /* MPOL_BIND */, &mask, 64ul + 1, 0u);
+#else
+    const long rc = -1;
+#endif
+    if (rc != 0) {   // no NUMA policy available (container without CAP_SYS_NICE, single node): plain page-locked memory
+        munmap(p, len);
+        return hevcasm_cuda_host_alloc(bytes);
+    }
+    memset(p, 0, len);   // fault the pages in on the bound node before the driver pins them
+    if (cudaHostRegister(p, len, cudaHostRegisterPortable) != cudaSuccess) {
+        (void)cudaGetLastError();
+        munmap(p, len);
+        return hevcasm_cuda_host_alloc(bytes);
+    }
+    std::lock_guard<std::mutex> lock(g_host_mu);
+    g_mapped[p] = len;
+    return p;
+}
+
 extern "C" void hevcasm_cuda_host_free(void *p)
 {
-    if (p) cudaFreeHost(p);
+    if (!p) return;
+    {
+        std::lock_guard<std::mutex> lock(g_host_mu);
+        auto it = g_mapped.find(p);
+        if (it != g_mapped.end()) {
+            cudaHostUnregister(p);
+            munmap(p, it->second);
+            g_mapped.erase(it);
+            return;
+        }
+    }
+    cudaFreeHost(p);
 }
 
 // ------------------------------------------------------------------------------------------------ SAD pyramid
 
-// full = 64 SADs per PU (hevcasm_sad_sweep_pyramid_frames), !full = {min SAD, candidate} per PU (..._best_frames)
-static int sad_pyramid_host(bool full, hevcasm_cuda_context *ctx, const uint8_t *src, ptrdiff_t ss, const uint8_t *ref, ptrdiff_t sr, int width, int height, int pad,
-                            int dx0, int dy0, int n_frames, ptrdiff_t fs_src, ptrdiff_t fs_ref, int32_t *const host_out[4])
+// mode 0: 64 int32 SADs per PU (hevcasm_sad_sweep_pyramid_frames); 1: {min SAD, candidate} per PU (..._best_frames);
+// 2: 64 SADs per PU, uint16 for the 8x8 and 16x16 levels (..._packed_frames)
+static int sad_pyramid_host(int mode, hevcasm_cuda_context *ctx, const uint8_t *src, ptrdiff_t ss, const uint8_t *ref, ptrdiff_t sr, int width, int height, int pad,
+                            int dx0, int dy0, int n_frames, ptrdiff_t fs_src, ptrdiff_t fs_ref, void *const host_out[4])
 {
     if (!ctx || width < 8 || height < 8 || n_frames < 0 || pad < 0) return HEVCASM_ERR_ARGUMENT;
     // the window [dx0, dx0+8) x [dy0, dy0+8) must lie inside the padding that travels with the frames
     if (dx0 < -pad || dy0 < -pad || dx0 + 7 > pad || dy0 + 7 > pad) return HEVCASM_ERR_ARGUMENT;
+    if (mode != 0 && !(host_out[0] && host_out[1] && host_out[2] && host_out[3])) return HEVCASM_ERR_ARGUMENT;
     const DevPlanes d = plan_planes(width, height, pad, 1);
-    const size_t per_pu = full ? 64 : 2;
-    size_t out_elems[4];  // per frame
-    for (int l = 0; l < 4; ++l) out_elems[l] = host_out[l] ? (size_t)(width >> (3 + l)) * (height >> (3 + l)) * per_pu : 0;
+    const size_t per_pu = mode == 1 ? 2 : 64;
+    size_t out_bytes[4];  // per frame
+    for (int l = 0; l < 4; ++l)
+        out_bytes[l] = host_out[l] ? (size_t)(width >> (3 + l)) * (height >> (3 + l)) * per_pu * ((mode == 2 && l < 2) ? 2 : 4) : 0;
     size_t per_frame = 2 * (d.frame_elems + kAlign);
-    for (int l = 0; l < 4; ++l) per_frame += out_elems[l] * 4 + kAlign;
+    for (int l = 0; l < 4; ++l) per_frame += out_bytes[l] + kAlign;
 
     struct Slot {
         uint8_t *src, *ref;
-        int32_t *out[4];
+        uint8_t *out[4];
     };
     auto carve = [&](uint8_t *slot, int nf) {
         Carver c{slot};
         Slot s;
         s.src = c.take<uint8_t>(d.bytes(nf));
         s.ref = c.take<uint8_t>(d.bytes(nf));
-        for (int l = 0; l < 4; ++l) s.out[l] = out_elems[l] ? c.take<int32_t>(out_elems[l] * 4 * nf) : nullptr;
+        for (int l = 0; l < 4; ++l) s.out[l] = out_bytes[l] ? c.take<uint8_t>(out_bytes[l] * nf) : nullptr;
         return s;
     };
     return run_pipeline(
@@ -216,16 +296,22 @@ static int sad_pyramid_host(bool full, hevcasm_cuda_context *ctx, const uint8_t 
         },
         [&](uint8_t *slot, int, int nf, cudaStream_t s) {
             const Slot k = carve(slot, nf);
-            return full ? hevcasm_sad_sweep_pyramid_frames(k.src + d.origin(), d.pitch_elems, k.ref + d.origin(), d.pitch_elems, width, height, dx0, dy0, nf,
-                                                           d.frame_elems, d.frame_elems, k.out[0], k.out[1], k.out[2], k.out[3], s)
-                        : hevcasm_sad_sweep_pyramid_best_frames(k.src + d.origin(), d.pitch_elems, k.ref + d.origin(), d.pitch_elems, width, height, dx0, dy0, nf,
-                                                                d.frame_elems, d.frame_elems, k.out[0], k.out[1], k.out[2], k.out[3], s);
+            const uint8_t *a = k.src + d.origin(), *b = k.ref + d.origin();
+            const ptrdiff_t pitch = (ptrdiff_t)d.pitch_elems, fs = (ptrdiff_t)d.frame_elems;
+            if (mode == 0)
+                return hevcasm_sad_sweep_pyramid_frames(a, pitch, b, pitch, width, height, dx0, dy0, nf, fs, fs, (int32_t *)k.out[0], (int32_t *)k.out[1],
+                                                        (int32_t *)k.out[2], (int32_t *)k.out[3], s);
+            if (mode == 1)
+                return hevcasm_sad_sweep_pyramid_best_frames(a, pitch, b, pitch, width, height, dx0, dy0, nf, fs, fs, (int32_t *)k.out[0], (int32_t *)k.out[1],
+                                                             (int32_t *)k.out[2], (int32_t *)k.out[3], s);
+            return hevcasm_sad_sweep_pyramid_packed_frames(a, pitch, b, pitch, width, height, dx0, dy0, nf, fs, fs, (uint16_t *)k.out[0], (uint16_t *)k.out[1],
+                                                           (int32_t *)k.out[2], (int32_t *)k.out[3], s);
         },
         [&](uint8_t *slot, int f0, int nf, cudaStream_t s) {
             const Slot k = carve(slot, nf);
             for (int l = 0; l < 4; ++l)
-                if (host_out[l] && out_elems[l])
-                    HV_CUDA(cudaMemcpyAsync(host_out[l] + (size_t)f0 * out_elems[l], k.out[l], out_elems[l] * 4 * nf, cudaMemcpyDeviceToHost, s));
+                if (host_out[l] && out_bytes[l])
+                    HV_CUDA(cudaMemcpyAsync((uint8_t *)host_out[l] + (size_t)f0 * out_bytes[l], k.out[l], out_bytes[l] * nf, cudaMemcpyDeviceToHost, s));
             return 0;
         });
 }
@@ -234,17 +320,24 @@ extern "C" int hevcasm_sad_sweep_pyramid_frames_host(hevcasm_cuda_context *ctx, 
                                                      int width, int height, int pad, int dx0, int dy0, int n_frames, ptrdiff_t fs_src,
                                                      ptrdiff_t fs_ref, int32_t *sad8, int32_t *sad16, int32_t *sad32, int32_t *sad64)
 {
-    int32_t *const out[4] = {sad8, sad16, sad32, sad64};
-    return sad_pyramid_host(true, ctx, src, ss, ref, sr, width, height, pad, dx0, dy0, n_frames, fs_src, fs_ref, out);
+    void *const out[4] = {sad8, sad16, sad32, sad64};
+    return sad_pyramid_host(0, ctx, src, ss, ref, sr, width, height, pad, dx0, dy0, n_frames, fs_src, fs_ref, out);
 }
 
 extern "C" int hevcasm_sad_sweep_pyramid_best_frames_host(hevcasm_cuda_context *ctx, const uint8_t *src, ptrdiff_t ss, const uint8_t *ref, ptrdiff_t sr,
                                                           int width, int height, int pad, int dx0, int dy0, int n_frames, ptrdiff_t fs_src,
                                                           ptrdiff_t fs_ref, int32_t *best8, int32_t *best16, int32_t *best32, int32_t *best64)
 {
-    if (!best8 || !best16 || !best32 || !best64) return HEVCASM_ERR_ARGUMENT;
-    int32_t *const out[4] = {best8, best16, best32, best64};
-    return sad_pyramid_host(false, ctx, src, ss, ref, sr, width, height, pad, dx0, dy0, n_frames, fs_src, fs_ref, out);
+    void *const out[4] = {best8, best16, best32, best64};
+    return sad_pyramid_host(1, ctx, src, ss, ref, sr, width, height, pad, dx0, dy0, n_frames, fs_src, fs_ref, out);
+}
+
+extern "C" int hevcasm_sad_sweep_pyramid_packed_frames_host(hevcasm_cuda_context *ctx, const uint8_t *src, ptrdiff_t ss, const uint8_t *ref, ptrdiff_t sr,
+                                                            int width, int height, int pad, int dx0, int dy0, int n_frames, ptrdiff_t fs_src,
+                                                            ptrdiff_t fs_ref, uint16_t *sad8, uint16_t *sad16, int32_t *sad32, int32_t *sad64)
+{
+    void *const out[4] = {sad8, sad16, sad32, sad64};
+    return sad_pyramid_host(2, ctx, src, ss, ref, sr, width, height, pad, dx0, dy0, n_frames, fs_src, fs_ref, out);
 }
 
 // ------------------------------------------------------------------------------------------------ inter prediction planes

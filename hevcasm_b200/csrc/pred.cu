@@ -1341,8 +1341,10 @@ static bool aligned8(const uint8_t *dst, ptrdiff_t sd, ptrdiff_t fs_dst, int n_f
     return (m & 7) == 0;
 }
 
-extern "C" int hevcasm_pred_uni_frames(uint8_t *dst, ptrdiff_t sd, const uint8_t *ref, ptrdiff_t sr, int width, int height, int taps, int xFrac, int yFrac,
-                                       int n_frames, ptrdiff_t fs_dst, ptrdiff_t fs_ref, void *stream)
+// `exact`: only the kernel that stays inside the reference's own footprint (rounded out to aligned 32-bit words) may run - the caller
+// has not promised the 16 readable bytes around it that the aligned, TMA and tensor-core kernels assume (hevcasm_batch.h)
+static int pred_uni_frames_impl(uint8_t *dst, ptrdiff_t sd, const uint8_t *ref, ptrdiff_t sr, int width, int height, int taps, int xFrac, int yFrac,
+                                int n_frames, ptrdiff_t fs_dst, ptrdiff_t fs_ref, bool exact, void *stream)
 {
     if ((taps != 8 && taps != 4) || !frac_ok(taps, xFrac) || !frac_ok(taps, yFrac) || width < 0 || height < 0 || n_frames < 0) return HEVCASM_ERR_ARGUMENT;
     if (width == 0 || height == 0 || n_frames == 0) return 0;
@@ -1351,6 +1353,7 @@ extern "C" int hevcasm_pred_uni_frames(uint8_t *dst, ptrdiff_t sd, const uint8_t
     p.xf0 = xFrac, p.yf0 = yFrac;
     const dim3 grid((width + PTW - 1) / PTW, (height + PTH - 1) / PTH, n_frames);
     const int mode = (xFrac ? 1 : 0) | (yFrac ? 2 : 0);
+    if (exact) return taps == 8 ? launch_uni_planes<8>(p, grid, mode, stream) : launch_uni_planes<4>(p, grid, mode, stream);
     // every position: the TMA-fed streaming kernel when the planes can be described to the TMA unit (strides multiples
     // of 16, 4-byte aligned rows).  Otherwise: two-pass positions -> LDG streaming kernel; one-pass positions -> tile kernels on
     // 16-byte aligned planes (2.2-2.4 vs 2.0 Tsamples/s), LDG streaming kernel on 4-byte aligned ones; copies -> tile kernels.
@@ -1379,8 +1382,22 @@ extern "C" int hevcasm_pred_uni_frames(uint8_t *dst, ptrdiff_t sd, const uint8_t
     return taps == 8 ? launch_uni_planes<8>(p, grid, mode, stream) : launch_uni_planes<4>(p, grid, mode, stream);
 }
 
-extern "C" int hevcasm_pred_bi_frames(uint8_t *dst, ptrdiff_t sd, const uint8_t *ref0, const uint8_t *ref1, ptrdiff_t sr, int width, int height, int taps,
-                                      int xFrac0, int yFrac0, int xFrac1, int yFrac1, int n_frames, ptrdiff_t fs_dst, ptrdiff_t fs_ref, void *stream)
+extern "C" int hevcasm_pred_uni_frames(uint8_t *dst, ptrdiff_t sd, const uint8_t *ref, ptrdiff_t sr, int width, int height, int taps, int xFrac, int yFrac,
+                                       int n_frames, ptrdiff_t fs_dst, ptrdiff_t fs_ref, void *stream)
+{
+    return pred_uni_frames_impl(dst, sd, ref, sr, width, height, taps, xFrac, yFrac, n_frames, fs_dst, fs_ref, false, stream);
+}
+
+extern "C" int hevcasm_pred_uni_frames_bounded(uint8_t *dst, ptrdiff_t sd, const uint8_t *ref, ptrdiff_t sr, int width, int height, int taps, int xFrac,
+                                               int yFrac, int n_frames, ptrdiff_t fs_dst, ptrdiff_t fs_ref, ptrdiff_t slack_before, ptrdiff_t slack_after,
+                                               void *stream)
+{
+    if (slack_before < 0 || slack_after < 0) return HEVCASM_ERR_ARGUMENT;
+    return pred_uni_frames_impl(dst, sd, ref, sr, width, height, taps, xFrac, yFrac, n_frames, fs_dst, fs_ref, slack_before < 16 || slack_after < 16, stream);
+}
+
+static int pred_bi_frames_impl(uint8_t *dst, ptrdiff_t sd, const uint8_t *ref0, const uint8_t *ref1, ptrdiff_t sr, int width, int height, int taps,
+                               int xFrac0, int yFrac0, int xFrac1, int yFrac1, int n_frames, ptrdiff_t fs_dst, ptrdiff_t fs_ref, bool exact, void *stream)
 {
     if ((taps != 8 && taps != 4) || !frac_ok(taps, xFrac0) || !frac_ok(taps, yFrac0) || !frac_ok(taps, xFrac1) || !frac_ok(taps, yFrac1) || width < 0 ||
         height < 0 || n_frames < 0)
@@ -1390,6 +1407,7 @@ extern "C" int hevcasm_pred_bi_frames(uint8_t *dst, ptrdiff_t sd, const uint8_t 
     p.dst = dst, p.ref0 = ref0, p.ref1 = ref1, p.sd = sd, p.sr = sr, p.fs_dst = fs_dst, p.fs_ref = fs_ref, p.width = width, p.height = height;
     p.xf0 = xFrac0, p.yf0 = yFrac0, p.xf1 = xFrac1, p.yf1 = yFrac1;
     const dim3 grid((width + PTW - 1) / PTW, (height + PTH - 1) / PTH, n_frames);
+    if (exact) return taps == 8 ? launch_pred<8, PTW, PTH, true, RUNTIME>(p, grid, stream) : launch_pred<4, PTW, PTH, true, RUNTIME>(p, grid, stream);
     if (xFrac0 || yFrac0 || xFrac1 || yFrac1) {
 #ifdef HEVCASM_EXPERIMENTS
         const char *bk = tune::knob("HEVCASM_PRED_BI");   // A/B: "hfirst" = horizontal pass on the tensor cores (um), default = vertical pass (uv)
@@ -1425,6 +1443,21 @@ extern "C" int hevcasm_pred_bi_frames(uint8_t *dst, ptrdiff_t sd, const uint8_t 
         return taps == 8 ? launch_plane_fast<8, HV, true>(fp, fgrid, dst8, stream) : launch_plane_fast<4, HV, true>(fp, fgrid, dst8, stream);
     }
     return taps == 8 ? launch_pred<8, PTW, PTH, true, RUNTIME>(p, grid, stream) : launch_pred<4, PTW, PTH, true, RUNTIME>(p, grid, stream);
+}
+
+extern "C" int hevcasm_pred_bi_frames(uint8_t *dst, ptrdiff_t sd, const uint8_t *ref0, const uint8_t *ref1, ptrdiff_t sr, int width, int height, int taps,
+                                      int xFrac0, int yFrac0, int xFrac1, int yFrac1, int n_frames, ptrdiff_t fs_dst, ptrdiff_t fs_ref, void *stream)
+{
+    return pred_bi_frames_impl(dst, sd, ref0, ref1, sr, width, height, taps, xFrac0, yFrac0, xFrac1, yFrac1, n_frames, fs_dst, fs_ref, false, stream);
+}
+
+extern "C" int hevcasm_pred_bi_frames_bounded(uint8_t *dst, ptrdiff_t sd, const uint8_t *ref0, const uint8_t *ref1, ptrdiff_t sr, int width, int height,
+                                              int taps, int xFrac0, int yFrac0, int xFrac1, int yFrac1, int n_frames, ptrdiff_t fs_dst, ptrdiff_t fs_ref,
+                                              ptrdiff_t slack_before, ptrdiff_t slack_after, void *stream)
+{
+    if (slack_before < 0 || slack_after < 0) return HEVCASM_ERR_ARGUMENT;
+    return pred_bi_frames_impl(dst, sd, ref0, ref1, sr, width, height, taps, xFrac0, yFrac0, xFrac1, yFrac1, n_frames, fs_dst, fs_ref,
+                               slack_before < 16 || slack_after < 16, stream);
 }
 
 extern "C" int hevcasm_pred_uni_batch(uint8_t *dst, ptrdiff_t sd, const uint8_t *ref, ptrdiff_t sr, int taps, const int16_t *pus, int n_pu, void *stream)

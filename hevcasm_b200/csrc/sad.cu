@@ -401,8 +401,13 @@ __device__ __forceinline__ uint32_t best_reduce16(uint32_t k)
 }
 __device__ __forceinline__ void best_store(int32_t *out, size_t pu, uint32_t key) { reinterpret_cast<int2 *>(out)[pu] = make_int2((int)(key >> 6), (int)(key & 63)); }
 
-// BEST = false: out[l] receive the 64 SADs of every PU.  BEST = true: out[l] receive {min SAD, candidate index} per PU.
-template <int LEVEL_MASK, int WO1, bool BS, bool BEST, bool FS>
+// the four SADs of an int4 as uint16 (8x8 and 16x16 PUs: at most 8*8*255 = 16 320 resp. 16*16*255 = 65 280, so nothing is lost)
+__device__ __forceinline__ uint2 pack_u16x4(int4 v) { return make_uint2(__byte_perm((uint32_t)v.x, (uint32_t)v.y, 0x5410), __byte_perm((uint32_t)v.z, (uint32_t)v.w, 0x5410)); }
+
+// OUT = 0: out[l] receive the 64 SADs of every PU as int32.  OUT = 1: out[l] receive {min SAD, candidate index} per PU.
+// OUT = 2: as 0, but the 8x8 and 16x16 levels are written as uint16 (half the bytes that have to cross PCIe in the host forms).
+constexpr int OUT_FULL = 0, OUT_BEST = 1, OUT_PACKED = 2;
+template <int LEVEL_MASK, int WO1, bool BS, int OUT, bool FS>
 __global__ void __launch_bounds__(pyr::NT, 5) sad_pyramid_tma_kernel(const __grid_constant__ PyramidTmaParams p)
 {
     using namespace pyr;
@@ -439,7 +444,7 @@ __global__ void __launch_bounds__(pyr::NT, 5) sad_pyramid_tma_kernel(const __gri
     __syncthreads();
 
     const int g = tid & 15, hi = tid >> 4;
-    if (BEST) {
+    if (OUT == OUT_BEST) {
         // level 0: every thread reduces its own cell straight from the accumulators
         if ((LEVEL_MASK & 1) && cx < vcx && cy < vcy) {
             uint32_t k = 0xffffffffu;
@@ -482,20 +487,26 @@ __global__ void __launch_bounds__(pyr::NT, 5) sad_pyramid_tma_kernel(const __gri
         }
         return;
     }
+    // (the element index of a PU's 4-candidate group is the same for both output widths: int4 index = uint2 index)
+    auto put = [](int32_t *base, size_t idx, int4 v, bool packed) {
+        if (packed) reinterpret_cast<uint2 *>(base)[idx] = pack_u16x4(v);
+        else reinterpret_cast<int4 *>(base)[idx] = v;
+    };
+    constexpr bool PK = OUT == OUT_PACKED;
     if (LEVEL_MASK & 1) {
-        int4 *o = reinterpret_cast<int4 *>(p.out[0]) + ((size_t)f * npy8 + cy0) * npx8 * 16 + (size_t)(cx0 + hi) * 16 + g;
+        const size_t o = ((size_t)f * npy8 + cy0) * npx8 * 16 + (size_t)(cx0 + hi) * 16 + g;
         const int s0 = g ^ hi, s1 = g ^ (hi + 8);
         const bool ok0 = hi < vcx, ok1 = hi + 8 < vcx;
 #pragma unroll
         for (int k = 0; k < 16; ++k) {
             const int ccy = k >> 1, c = hi + 8 * k;
             const int4 v = cb[c * 16 + ((k & 1) ? s1 : s0)];
-            if (ccy < vcy && ((k & 1) ? ok1 : ok0)) o[(size_t)ccy * npx8 * 16 + (k & 1) * 128] = v;
+            if (ccy < vcy && ((k & 1) ? ok1 : ok0)) put(p.out[0], o + (size_t)ccy * npx8 * 16 + (k & 1) * 128, v, PK);
         }
     }
     {
         const int npx = p.width >> 4, npy = p.height >> 4, py0 = cy0 >> 1;
-        int4 *o = (LEVEL_MASK & 2) ? reinterpret_cast<int4 *>(p.out[1]) + ((size_t)f * npy + py0) * npx * 16 + (size_t)((cx0 >> 1) + hi) * 16 + g : nullptr;
+        const size_t o = ((size_t)f * npy + py0) * npx * 16 + (size_t)((cx0 >> 1) + hi) * 16 + g;
         const int sa = g ^ (2 * hi), sb = g ^ (2 * hi + 1);
         const bool okx = (cx0 >> 1) + hi < npx;
 #pragma unroll
@@ -503,7 +514,7 @@ __global__ void __launch_bounds__(pyr::NT, 5) sad_pyramid_tma_kernel(const __gri
             const int c00 = (2 * k) * CX + 2 * hi;
             const int4 v = add4(add4(cb[c00 * 16 + sa], cb[(c00 + 1) * 16 + sb]), add4(cb[(c00 + CX) * 16 + sa], cb[(c00 + CX + 1) * 16 + sb]));
             l16[tid + k * NT] = v;
-            if ((LEVEL_MASK & 2) && okx && py0 + k < npy) o[(size_t)k * npx * 16] = v;
+            if ((LEVEL_MASK & 2) && okx && py0 + k < npy) put(p.out[1], o + (size_t)k * npx * 16, v, PK);
         }
     }
     __syncthreads();
@@ -872,7 +883,7 @@ extern "C" int hevcasm_sad_sweep_frames(const uint8_t *src, ptrdiff_t ss, const 
                                         ptrdiff_t fs_ref, int32_t *sad, void *stream)
 {
     int w, h;
-    if (!rect_ok(rect, w, h) || ncx < 1 || ncy < 1 || n_frames < 0 || width < 0 || height < 0) return HEVCASM_ERR_ARGUMENT;
+    if (!rect_ok(rect, w, h) || ncx < 1 || ncy < 1 || (long long)ncx * ncy > 256 || n_frames < 0 || width < 0 || height < 0) return HEVCASM_ERR_ARGUMENT;
     SweepParams p;
     p.src = src, p.ref = ref, p.ss = ss, p.sr = sr, p.fs_src = fs_src, p.fs_ref = fs_ref;
     p.w = w, p.h = h, p.npx = width / w, p.npy = height / h;
@@ -977,11 +988,11 @@ extern "C" int hevcasm_sad_sweep_pyramid_frames(const uint8_t *src, ptrdiff_t ss
 #define HV_TMA(WO1_, BS_)                                                 \
     do {                                                                  \
         if (t.shc[0]) {                                                   \
-            auto kern = sad_pyramid_tma_kernel<15, WO1_, BS_, false, true>;  \
+            auto kern = sad_pyramid_tma_kernel<15, WO1_, BS_, OUT_FULL, true>;  \
             HV_CUDA((cudaError_t)set_max_smem(kern, smem_bytes));         \
             HV_LAUNCH(kern, grid, pyr::NT, smem_bytes, stream, t);        \
         } else {                                                          \
-            auto kern = sad_pyramid_tma_kernel<15, WO1_, BS_, false, false>; \
+            auto kern = sad_pyramid_tma_kernel<15, WO1_, BS_, OUT_FULL, false>; \
             HV_CUDA((cudaError_t)set_max_smem(kern, smem_bytes));         \
             HV_LAUNCH(kern, grid, pyr::NT, smem_bytes, stream, t);        \
         }                                                                 \
@@ -1013,19 +1024,21 @@ extern "C" int hevcasm_sad_sweep_pyramid_frames(const uint8_t *src, ptrdiff_t ss
     return 0;
 }
 
-extern "C" int hevcasm_sad_sweep_pyramid_best_frames(const uint8_t *src, ptrdiff_t ss, const uint8_t *ref, ptrdiff_t sr, int width, int height, int dx0, int dy0,
-                                                     int n_frames, ptrdiff_t fs_src, ptrdiff_t fs_ref, int32_t *best8, int32_t *best16, int32_t *best32,
-                                                     int32_t *best64, void *stream)
+// the TMA-staged pyramid kernel in one of its compact output modes (all four outputs required, TMA-describable planes)
+template <int OUT>
+static int launch_pyramid_compact(const uint8_t *src, ptrdiff_t ss, const uint8_t *ref, ptrdiff_t sr, int width, int height, int dx0, int dy0, int n_frames,
+                                  ptrdiff_t fs_src, ptrdiff_t fs_ref, void *o8, void *o16, void *o32, void *o64, void *stream)
 {
-    if (width < 8 || height < 8 || n_frames < 0 || !best8 || !best16 || !best32 || !best64) return HEVCASM_ERR_ARGUMENT;
+    if (width < 8 || height < 8 || n_frames < 0 || !o8 || !o16 || !o32 || !o64) return HEVCASM_ERR_ARGUMENT;
     if (n_frames == 0) return 0;
     // TMA staged only: needs a 16-byte aligned source origin and 16-byte multiples for all strides
     if (((uintptr_t)src & 15) != 0 || !tma::describable(ss, fs_src, n_frames) || !tma::describable(sr, fs_ref, n_frames)) return HEVCASM_ERR_ARGUMENT;
+    if (OUT == OUT_PACKED && ((((uintptr_t)o8 | (uintptr_t)o16) & 7) != 0 || (((uintptr_t)o32 | (uintptr_t)o64) & 15) != 0)) return HEVCASM_ERR_ARGUMENT;
     const int npx8 = width >> 3, npy8 = height >> 3;
     PyramidTmaParams t;
     t.width = width, t.height = height;
     fill_shc(t.shc);
-    t.out[0] = best8, t.out[1] = best16, t.out[2] = best32, t.out[3] = best64;
+    t.out[0] = (int32_t *)o8, t.out[1] = (int32_t *)o16, t.out[2] = (int32_t *)o32, t.out[3] = (int32_t *)o64;
     int xs_src = 0;
     int e = tma::describe_u8(&t.tm_src, src, ss, fs_src, (long long)npx8 * 8, (long long)npy8 * 8, n_frames, pyr::TW, pyr::TH, &xs_src);
     if (!e)
@@ -1035,24 +1048,38 @@ extern "C" int hevcasm_sad_sweep_pyramid_best_frames(const uint8_t *src, ptrdiff
     const dim3 grid((npx8 + pyr::CX - 1) / pyr::CX, (npy8 + pyr::CY - 1) / pyr::CY, n_frames);
     const size_t smem_bytes = pyr::SMEM_BYTES + 16;
     const int wo1 = (t.win_shift >> 2) & 1, bs = t.win_shift & 3;
-#define HV_TMA_BEST(WO1_, BS_)                                            \
+#define HV_TMA_COMPACT(WO1_, BS_)                                         \
     do {                                                                  \
         if (t.shc[0]) {                                                   \
-            auto kern = sad_pyramid_tma_kernel<15, WO1_, BS_, true, true>;   \
+            auto kern = sad_pyramid_tma_kernel<15, WO1_, BS_, OUT, true>;    \
             HV_CUDA((cudaError_t)set_max_smem(kern, smem_bytes));         \
             HV_LAUNCH(kern, grid, pyr::NT, smem_bytes, stream, t);        \
         } else {                                                          \
-            auto kern = sad_pyramid_tma_kernel<15, WO1_, BS_, true, false>;  \
+            auto kern = sad_pyramid_tma_kernel<15, WO1_, BS_, OUT, false>;   \
             HV_CUDA((cudaError_t)set_max_smem(kern, smem_bytes));         \
             HV_LAUNCH(kern, grid, pyr::NT, smem_bytes, stream, t);        \
         }                                                                 \
     } while (0)
-    if (wo1 && bs) HV_TMA_BEST(1, true);
-    else if (wo1) HV_TMA_BEST(1, false);
-    else if (bs) HV_TMA_BEST(0, true);
-    else HV_TMA_BEST(0, false);
-#undef HV_TMA_BEST
+    if (wo1 && bs) HV_TMA_COMPACT(1, true);
+    else if (wo1) HV_TMA_COMPACT(1, false);
+    else if (bs) HV_TMA_COMPACT(0, true);
+    else HV_TMA_COMPACT(0, false);
+#undef HV_TMA_COMPACT
     return 0;
+}
+
+extern "C" int hevcasm_sad_sweep_pyramid_best_frames(const uint8_t *src, ptrdiff_t ss, const uint8_t *ref, ptrdiff_t sr, int width, int height, int dx0, int dy0,
+                                                     int n_frames, ptrdiff_t fs_src, ptrdiff_t fs_ref, int32_t *best8, int32_t *best16, int32_t *best32,
+                                                     int32_t *best64, void *stream)
+{
+    return launch_pyramid_compact<OUT_BEST>(src, ss, ref, sr, width, height, dx0, dy0, n_frames, fs_src, fs_ref, best8, best16, best32, best64, stream);
+}
+
+extern "C" int hevcasm_sad_sweep_pyramid_packed_frames(const uint8_t *src, ptrdiff_t ss, const uint8_t *ref, ptrdiff_t sr, int width, int height, int dx0, int dy0,
+                                                       int n_frames, ptrdiff_t fs_src, ptrdiff_t fs_ref, uint16_t *sad8, uint16_t *sad16, int32_t *sad32,
+                                                       int32_t *sad64, void *stream)
+{
+    return launch_pyramid_compact<OUT_PACKED>(src, ss, ref, sr, width, height, dx0, dy0, n_frames, fs_src, fs_ref, sad8, sad16, sad32, sad64, stream);
 }
 
 extern "C" int hevcasm_ssd_batch(const uint8_t *a, ptrdiff_t sa, const uint8_t *b, ptrdiff_t sb, int log2size, const int16_t *blk_xy, int n,

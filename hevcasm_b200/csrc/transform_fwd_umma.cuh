@@ -26,9 +26,10 @@ constexpr int TBYTES = 256;                    // bytes per tile row = MMA K (8 
 constexpr int A_BYTES = 128 * TBYTES;          // one constant operand: [chunk (16)][m (128)][16]
 constexpr int BOX_BYTES = 128 * TROWS;         // one box: 128 bytes x 128 rows
 constexpr int STAGE_BYTES = 2 * BOX_BYTES;
-constexpr int B_OFF = 2 * A_BYTES, BAR_OFF = B_OFF + 2 * STAGE_BYTES;
-constexpr int SMEM_BYTES = 1024 + BAR_OFF + 64;
-constexpr int CONSUMERS = 512, THREADS = CONSUMERS + 32;   // four consumer warpgroups (32 plane rows each) + the producer warp
+constexpr int NST = 4;                         // residual stages in flight
+constexpr int B_OFF = 2 * A_BYTES, BAR_OFF = B_OFF + NST * STAGE_BYTES;
+constexpr int SMEM_BYTES = 1024 + BAR_OFF + 128;
+constexpr int CONSUMERS = 512, THREADS = CONSUMERS + 64;   // four consumer warpgroups (32 plane rows each) + the loader warp + the MMA warp (one thread of each works)
 
 // the two constant operands in their shared-memory layout [size (16, 32)][lo / hi][chunk (16)][m (128)][16], built on the host once
 __device__ uint4 g_ft_A[2][2 * A_BYTES / 16];
@@ -77,15 +78,18 @@ __global__ void __launch_bounds__(THREADS, 1) fwd_umma_kernel(const __grid_const
     uint8_t *const smem = ft_raw + ((1024 - (tma::smem_u32(ft_raw) & 1023)) & 1023);
     uint8_t *const sA = smem;                    // [lo / hi][chunk][m][16]
     uint8_t *const sB = smem + B_OFF;            // [stage][box][row][128]
-    uint64_t *const full = reinterpret_cast<uint64_t *>(smem + BAR_OFF);   // [2] the residual boxes of the stage have landed
-    uint64_t *const done = full + 2;                                       // [2] the MMAs into the accumulator have completed
-    uint64_t *const consumed = full + 4;                                   // [2] every consumer has read the accumulator
-    uint64_t *const cready = full + 6;                                     // the constant operands have landed
-    uint32_t *const tmem_slot = reinterpret_cast<uint32_t *>(full + 7);
+    uint64_t *const full = reinterpret_cast<uint64_t *>(smem + BAR_OFF);   // [NST] the residual boxes of the stage have landed
+    uint64_t *const empty = full + NST;                                    // [NST] the MMAs reading the stage have completed
+    uint64_t *const done = empty + NST;                                    // [2] the MMAs into the accumulator have completed
+    uint64_t *const consumed = done + 2;                                   // [2] every consumer warp has read the accumulator
+    uint64_t *const cready = consumed + 2;                                 // the constant operands have landed
+    uint32_t *const tmem_slot = reinterpret_cast<uint32_t *>(cready + 1);
 
     if (threadIdx.x == 0) {
 #pragma unroll
-        for (int i = 0; i < 2; ++i) tma::mbar_init(full + i, 1), tma::mbar_init(done + i, 1), tma::mbar_init(consumed + i, CONSUMERS / 32);
+        for (int i = 0; i < NST; ++i) tma::mbar_init(full + i, 1), tma::mbar_init(empty + i, 1);
+#pragma unroll
+        for (int i = 0; i < 2; ++i) tma::mbar_init(done + i, 1), tma::mbar_init(consumed + i, CONSUMERS / 32);
         tma::mbar_init(cready, 1);
     }
     if (threadIdx.x < 32) umma::tmem_alloc<512>(tmem_slot);
@@ -103,20 +107,28 @@ __global__ void __launch_bounds__(THREADS, 1) fwd_umma_kernel(const __grid_const
         if (y >= P.tiles_y) y -= P.tiles_y, ++f;
         f += sf;
     };
-    auto request = [&](int s) {   // producer: the residual boxes of tile (cx, cy, cf) into stage s; then on to the next tile
-        tma::mbar_expect_tx(full + s, 2 * BOX_BYTES);
-        uint8_t *b = sB + s * STAGE_BYTES;
-        tma::load_box_3d(b, &P.tmres, cx * TBYTES, cy * TROWS, cf, full + s);
-        tma::load_box_3d(b + BOX_BYTES, &P.tmres, cx * TBYTES + 128, cy * TROWS, cf, full + s);
+    // Service work is split over two single-thread warps (as in pred_umma.cuh: one thread doing requests AND MMA issue was the critical
+    // path): the loader waits `empty[stage]` and requests the residual boxes, the MMA thread waits `full[stage]` / `consumed[acc]`,
+    // issues the 16 MMAs and commits `done[acc]` + `empty[stage]`.
+    int lq = 0, lst = 0;   // loader: next tile to request, its stage, the parity to wait for on `empty` (a fresh barrier passes a wait for parity 1)
+    uint32_t eph = 1;
+    auto request = [&]() {
+        tma::mbar_expect_tx(full + lst, 2 * BOX_BYTES);
+        uint8_t *b = sB + lst * STAGE_BYTES;
+        tma::load_box_3d(b, &P.tmres, cx * TBYTES, cy * TROWS, cf, full + lst);
+        tma::load_box_3d(b + BOX_BYTES, &P.tmres, cx * TBYTES + 128, cy * TROWS, cf, full + lst);
         advance(cx, cy, cf);
+        ++lq;
+        if (++lst == NST) lst = 0, eph ^= 1;
     };
     if (threadIdx.x == CONSUMERS) {
+        // ------------------------------------------------------------------------------------------------ loader (prologue)
         // constant operands A_p[(bc, k)][64 bc + 2 i + p] = T[k][i]: the host-built image arrives by bulk copies while the first tiles load
         tma::mbar_expect_tx(cready, 2 * A_BYTES);
 #pragma unroll
         for (int i = 0; i < 4; ++i) tma::bulk_load_1d(sA + i * (A_BYTES / 2), reinterpret_cast<const uint8_t *>(g_ft_A[LOG2 - 4]) + i * (A_BYTES / 2), A_BYTES / 2, cready);
-        if (n_mine > 0) request(0);
-        if (n_mine > 1) request(1);
+#pragma unroll 1
+        while (lq < NST && lq < n_mine) request();   // the first NST tiles travel during the rest of the prologue
     }
     umma::fence_before();
     __syncthreads();
@@ -124,32 +136,37 @@ __global__ void __launch_bounds__(THREADS, 1) fwd_umma_kernel(const __grid_const
     const uint32_t tm = *tmem_slot;
 
     if (threadIdx.x >= CONSUMERS) {
-        // ------------------------------------------------------------------------------------------------ producer
         if (threadIdx.x == CONSUMERS) {
+            // ------------------------------------------------------------------------------------------------ loader
+#pragma unroll 1
+            while (lq < n_mine) {
+                tma::mbar_wait(empty + lst, eph);
+                request();
+            }
+        } else if (threadIdx.x == CONSUMERS + 32) {
+            // ------------------------------------------------------------------------------------------------ MMA issue
             constexpr uint32_t ID_LO = umma::idesc_i8(true, false, false, TROWS), ID_HI = umma::idesc_i8(true, true, false, TROWS);
+            // A: K-major, no swizzle (LBO = distance between 16-byte k chunks, SBO = between groups of 8 rows).  B: swizzled K-major,
+            // groups of 8 rows 1024 bytes apart; a K-step advances the start address by 32 bytes inside the swizzle row
+            const uint64_t da0 = umma::smem_desc(tma::smem_u32(sA), 128 * 16, 128), db0 = umma::smem_desc(tma::smem_u32(sB), 16, 1024, 2);
             tma::mbar_wait(cready, 0);
+            int st = 0;
+            uint32_t fph = 0;
 #pragma unroll 1
             for (int q = 0; q < n_mine; ++q) {
                 const int s = q & 1;
-                const uint32_t ph = (q >> 1) & 1;
-                if (q >= 2) tma::mbar_wait(consumed + s, ph ^ 1);   // tile q-2 has left this accumulator
-                tma::mbar_wait(full + s, ph);
+                tma::mbar_wait(full + st, fph);
+                if (q >= 2) tma::mbar_wait(consumed + s, ((q >> 1) & 1) ^ 1);   // tile q-2 has left this accumulator
                 umma::fence_after();
 #pragma unroll
                 for (int p = 0; p < 2; ++p)
 #pragma unroll
-                    for (int ks = 0; ks < TBYTES / 32; ++ks) {
-                        // A: K-major, no swizzle (LBO = distance between 16-byte k chunks, SBO = between groups of 8 rows).  B: swizzled K-major,
-                        // groups of 8 rows 1024 bytes apart; a K-step advances the start address by 32 bytes inside the swizzle row
-                        const uint64_t da = umma::smem_desc(tma::smem_u32(sA + p * A_BYTES + ks * 2 * (128 * 16)), 128 * 16, 128);
-                        const uint64_t db = umma::smem_desc(tma::smem_u32(sB + s * STAGE_BYTES + (ks >> 2) * BOX_BYTES) + (ks & 3) * 32, 16, 1024, 2);
-                        umma::mma_i8(tm + s * 256 + p * TROWS, da, db, p ? ID_HI : ID_LO, ks);
-                    }
+                    for (int ks = 0; ks < TBYTES / 32; ++ks)   // (descriptor arithmetic on the 14-bit address field, 16-byte units)
+                        umma::mma_i8(tm + s * 256 + p * TROWS, da0 + (uint64_t)((p * A_BYTES + ks * 2 * (128 * 16)) >> 4),
+                                     db0 + (uint64_t)((st * STAGE_BYTES + (ks >> 2) * BOX_BYTES + (ks & 3) * 32) >> 4), p ? ID_HI : ID_LO, ks);
                 umma::commit(done + s);
-                if (q + 2 < n_mine) {   // the tile after next takes this stage as soon as these MMAs have read it
-                    tma::mbar_wait(done + s, ph);
-                    request(s);
-                }
+                umma::commit(empty + st);
+                if (++st == NST) st = 0, fph ^= 1;
             }
         }
     } else {

@@ -58,6 +58,8 @@ def _bind(path):
     lib.hevcasm_cuda_context_stream.restype = P
     lib.hevcasm_cuda_host_alloc.argtypes = [C.c_size_t]
     lib.hevcasm_cuda_host_alloc.restype = P
+    lib.hevcasm_cuda_host_alloc_near.argtypes = [C.c_size_t, C.c_int]
+    lib.hevcasm_cuda_host_alloc_near.restype = P
     lib.hevcasm_cuda_host_free.argtypes = [P]
     lib.hevcasm_cuda_host_free.restype = None
     lib.hevcasm_cuda_error_string.argtypes = [C.c_int]
@@ -107,15 +109,15 @@ class Context:
         self.close()
 
 
-def pinned_array(shape, dtype):
-    """numpy array over page-locked host memory from hevcasm_cuda_host_alloc; the allocation is released when the array (and
-    every view of it) has been garbage-collected."""
+def pinned_array(shape, dtype, device=None):
+    """numpy array over page-locked host memory from hevcasm_cuda_host_alloc (device=None) or, bound to the NUMA node of a GPU,
+    hevcasm_cuda_host_alloc_near; the allocation is released when the array (and every view of it) has been garbage-collected."""
     import weakref
 
     import numpy as np
     n = int(np.prod(shape)) * np.dtype(dtype).itemsize
     lib = load()
-    p = lib.hevcasm_cuda_host_alloc(max(n, 1))
+    p = lib.hevcasm_cuda_host_alloc(max(n, 1)) if device is None else lib.hevcasm_cuda_host_alloc_near(max(n, 1), int(device))
     if not p:
         raise HevcasmError(f"hevcasm_cuda_host_alloc({n}) failed")
     buf = (C.c_uint8 * max(n, 1)).from_address(p)

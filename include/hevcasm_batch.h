@@ -16,9 +16,14 @@
  *   - "_batch" variants take an explicit list of block positions, "_frames" variants process every block of
  *     a regular grid over `n_frames` planes laid out `frame stride` elements apart (one launch for the lot -
  *     that is how a 4K/8K batch reaches HBM speed);
- *   - frames must be padded like the reference's test buffers (reference pred_inter.c:468-471): interpolation
- *     reads taps/2-1 samples left/above and taps/2 right/below the block, the SAD entry points read the
- *     candidate window around each PU;
+ *   - frames must be padded like the reference's test buffers (reference pred_inter.c:468-471): the interpolation
+ *     FOOTPRINT is taps/2-1 samples left/above and taps/2 right/below the block or plane, the SAD entry points read the
+ *     candidate window around each PU.  The interpolation plane entry points (hevcasm_pred_*_frames) and the PU-list entry
+ *     points additionally require 16 READABLE bytes before the first and after the last byte of that footprint: their
+ *     aligned, TMA and tensor-core kernels move whole 16-byte chunks (up to 16 bytes left and 15 bytes right of a row's
+ *     footprint - inside the plane these are neighbouring samples), and the list kernels always read the two-pass footprint,
+ *     full-sample motion vectors included.  Any frame store with >= 16 samples and >= 4 rows of padding satisfies this; a
+ *     caller who cannot promise it uses the *_bounded plane forms, which then stay inside the footprint;
  *   - position lists are int16_t pairs {x, y} (an 8K plane fits), candidate / motion vectors int16_t {dx, dy}.
  *
  * Host-memory convenience forms (host pointers, H2D/D2H inside) live behind hevcasm_cuda_context at the end.
@@ -60,7 +65,8 @@ int HEVCASM_API hevcasm_sad_sweep_frames(const uint8_t *src, ptrdiff_t stride_sr
 
 /* The same sweep for the four square PU sizes 8, 16, 32, 64 in ONE pass over the frames (the 8x8 partial sums are
  * composed on chip into the larger PUs).  Window fixed at 8 x 8 candidates: dx in [dx0, dx0+8), dy in [dy0, dy0+8).
- * width and height must be multiples of 64.  Any of the four outputs may be NULL.  Each output has the layout
+ * width and height >= 8; a level covers the floor(width/s) x floor(height/s) whole PUs of its size s (so all four levels tile the
+ * same area only when both are multiples of 64).  Any of the four outputs may be NULL.  Each output has the layout
  * hevcasm_sad_sweep_frames would produce for that size. */
 int HEVCASM_API hevcasm_sad_sweep_pyramid_frames(const uint8_t *src, ptrdiff_t stride_src, const uint8_t *ref, ptrdiff_t stride_ref,
                                                  int width, int height, int dx0, int dy0, int n_frames,
@@ -76,6 +82,16 @@ int HEVCASM_API hevcasm_sad_sweep_pyramid_best_frames(const uint8_t *src, ptrdif
                                                       int width, int height, int dx0, int dy0, int n_frames,
                                                       ptrdiff_t frame_stride_src, ptrdiff_t frame_stride_ref, int32_t *best8,
                                                       int32_t *best16, int32_t *best32, int32_t *best64, void *stream);
+
+/* The full pyramid sweep with the two small levels packed: sad8 and sad16 are uint16_t - exact, an 8x8 SAD is at most 8*8*255 = 16 320 and
+ * a 16x16 SAD at most 16*16*255 = 65 280 - while sad32 and sad64 stay int32_t.  Same layout and values as
+ * hevcasm_sad_sweep_pyramid_frames, 2.81 instead of 5.31 output bytes per sample (what matters when the results cross PCIe).
+ * All four outputs are required; src 16-byte aligned, strides multiples of 16 bytes, sad8 / sad16 8-byte and sad32 / sad64 16-byte
+ * aligned (HEVCASM_ERR_ARGUMENT otherwise). */
+int HEVCASM_API hevcasm_sad_sweep_pyramid_packed_frames(const uint8_t *src, ptrdiff_t stride_src, const uint8_t *ref, ptrdiff_t stride_ref,
+                                                        int width, int height, int dx0, int dy0, int n_frames,
+                                                        ptrdiff_t frame_stride_src, ptrdiff_t frame_stride_ref, uint16_t *sad8,
+                                                        uint16_t *sad16, int32_t *sad32, int32_t *sad64, void *stream);
 
 /* ------------------------------------------------------------------------------------------------ SSD
  * element semantics: reference ssd.h:53 / ssd.c:43-55, square blocks of size 1<<log2size (2..6) */
@@ -112,6 +128,17 @@ int HEVCASM_API hevcasm_pred_bi_frames(uint8_t *dst, ptrdiff_t stride_dst, const
                                        ptrdiff_t stride_ref, int width, int height, int taps, int xFrac0, int yFrac0, int xFrac1,
                                        int yFrac1, int n_frames, ptrdiff_t frame_stride_dst, ptrdiff_t frame_stride_ref,
                                        void *stream);
+
+/* The same with the readable bytes around the footprint stated: slack_before / slack_after = bytes the caller guarantees to be readable
+ * before the first byte (row -(taps/2-1), column -(taps/2-1) of frame 0) and after the last byte of the reference's own footprint.
+ * With either below 16 only the kernels that stay inside the footprint run (slower; bit-identical results). */
+int HEVCASM_API hevcasm_pred_uni_frames_bounded(uint8_t *dst, ptrdiff_t stride_dst, const uint8_t *ref, ptrdiff_t stride_ref, int width,
+                                                int height, int taps, int xFrac, int yFrac, int n_frames, ptrdiff_t frame_stride_dst,
+                                                ptrdiff_t frame_stride_ref, ptrdiff_t slack_before, ptrdiff_t slack_after, void *stream);
+int HEVCASM_API hevcasm_pred_bi_frames_bounded(uint8_t *dst, ptrdiff_t stride_dst, const uint8_t *ref0, const uint8_t *ref1,
+                                               ptrdiff_t stride_ref, int width, int height, int taps, int xFrac0, int yFrac0, int xFrac1,
+                                               int yFrac1, int n_frames, ptrdiff_t frame_stride_dst, ptrdiff_t frame_stride_ref,
+                                               ptrdiff_t slack_before, ptrdiff_t slack_after, void *stream);
 
 /* prediction-unit lists.  Uni descriptor = 6 x int16 {x, y, w, h, mvx, mvy}; bi descriptor = 8 x int16
  * {x, y, w, h, mvx0, mvy0, mvx1, mvy1}.  Motion vectors are in 1/4 (taps 8) or 1/8 (taps 4) sample units:
@@ -176,8 +203,10 @@ typedef struct hevcasm_cuda_context hevcasm_cuda_context;
 hevcasm_cuda_context HEVCASM_API *hevcasm_cuda_context_create(int device, size_t arena_bytes);
 void HEVCASM_API hevcasm_cuda_context_destroy(hevcasm_cuda_context *ctx);
 void HEVCASM_API *hevcasm_cuda_context_stream(hevcasm_cuda_context *ctx);
-/* page-locked host memory, so that the copies of the *_host forms overlap with compute */
+/* page-locked host memory, so that the copies of the *_host forms overlap with compute.  The _near form binds the pages to the NUMA node
+ * of `device` (falls back to the plain form when the platform does not say which node that is); both are released by hevcasm_cuda_host_free */
 void HEVCASM_API *hevcasm_cuda_host_alloc(size_t bytes);
+void HEVCASM_API *hevcasm_cuda_host_alloc_near(size_t bytes, int device);
 void HEVCASM_API hevcasm_cuda_host_free(void *p);
 
 /* plane-level host forms: each frame is a tightly described plane {pointer to sample (0,0), stride}; `pad` = the number
@@ -192,6 +221,11 @@ int HEVCASM_API hevcasm_sad_sweep_pyramid_best_frames_host(hevcasm_cuda_context 
                                                            int dx0, int dy0, int n_frames, ptrdiff_t frame_stride_src,
                                                            ptrdiff_t frame_stride_ref, int32_t *best8, int32_t *best16, int32_t *best32,
                                                            int32_t *best64);
+int HEVCASM_API hevcasm_sad_sweep_pyramid_packed_frames_host(hevcasm_cuda_context *ctx, const uint8_t *src, ptrdiff_t stride_src,
+                                                             const uint8_t *ref, ptrdiff_t stride_ref, int width, int height, int pad,
+                                                             int dx0, int dy0, int n_frames, ptrdiff_t frame_stride_src,
+                                                             ptrdiff_t frame_stride_ref, uint16_t *sad8, uint16_t *sad16, int32_t *sad32,
+                                                             int32_t *sad64);
 int HEVCASM_API hevcasm_pred_uni_frames_host(hevcasm_cuda_context *ctx, uint8_t *dst, ptrdiff_t stride_dst, const uint8_t *ref,
                                              ptrdiff_t stride_ref, int width, int height, int pad, int taps, int xFrac, int yFrac,
                                              int n_frames, ptrdiff_t frame_stride_dst, ptrdiff_t frame_stride_ref);

@@ -5,7 +5,7 @@ import pytest
 
 from hevcasm_b200 import lib, synth
 from oracle.binding import ptr
-from gpu_util import to_dev, dptr, to_host
+from gpu_util import to_dev, dev_full, dptr, to_host
 
 pytestmark = pytest.mark.gpu
 
@@ -234,3 +234,34 @@ def test_full_size_properties():
     ha = to_host(o_a)[0, pad:pad + n, pad:pad + n]
     vt = to_host(o_t)[0, pad:pad + n, pad:pad + n]
     assert np.array_equal(ha, vt.T)
+
+
+@pytest.mark.parametrize("taps", [8, 4])
+def test_bounded_forms_stay_inside_the_footprint(oracle, taps):
+    """hevcasm_pred_*_frames_bounded with no slack: the reference planes sit at the very start and end of their device allocation, padded by
+    exactly the filter footprint (taps/2-1 before, taps/2 after) - a kernel that read whole 16-byte chunks around it would leave the
+    allocation (compute-sanitizer memcheck runs this test).  Results equal the unbounded forms' and the oracle's."""
+    import torch
+    width, height, nf = 120, 72, 2
+    lo, hi = taps // 2 - 1, taps // 2
+    pitch, rows = width + lo + hi, height + lo + hi           # tight: no alignment padding at all
+    n = nf * rows * pitch
+    host = synth.random_bytes(300 + taps, n).reshape(nf, rows, pitch)
+    host1 = synth.random_bytes(301 + taps, n).reshape(nf, rows, pitch)
+    d0 = torch.from_numpy(host.copy()).cuda()   # exactly n bytes: the footprint ends with the allocation
+    d1 = torch.from_numpy(host1.copy()).cuda()
+    org = lo * pitch + lo
+    nfrac = 4 if taps == 8 else 8
+    for xf, yf in ((0, 0), (1, 0), (0, nfrac - 1), (2, 1)):
+        want = np.zeros((nf, height, width), np.uint8)
+        oracle.drv("pred_uni_frames", ptr(want), width, ptr(host, org), pitch, width, height, taps, xf, yf, nf, width * height, rows * pitch, threads=4)
+        got = dev_full(want.shape, np.uint8, 9)
+        lib.call("pred_uni_frames_bounded", dptr(got), width, dptr(d0, org), pitch, width, height, taps, xf, yf, nf, width * height, rows * pitch, 0, 0)
+        assert np.array_equal(to_host(got), want), (xf, yf)
+    want = np.zeros((nf, height, width), np.uint8)
+    oracle.drv("pred_bi_frames", ptr(want), width, ptr(host, org), ptr(host1, org), pitch, width, height, taps, 1, 2, nfrac - 1, 0, nf, width * height,
+               rows * pitch, threads=4)
+    got = dev_full(want.shape, np.uint8, 9)
+    lib.call("pred_bi_frames_bounded", dptr(got), width, dptr(d0, org), dptr(d1, org), pitch, width, height, taps, 1, 2, nfrac - 1, 0, nf, width * height,
+             rows * pitch, 0, 0)
+    assert np.array_equal(to_host(got), want)

@@ -213,3 +213,26 @@ def test_pyramid_best_rejects_unaligned():
     with pytest.raises(lib.HevcasmError):
         lib.call("sad_sweep_pyramid_best_frames", dptr(ds, src.origin + 1), src.pitch, dptr(dr, ref.origin), ref.pitch, 32, 32, -4, -4, 1, src.frame_stride,
                  ref.frame_stride, dptr(o), dptr(o), dptr(o), dptr(o))
+
+
+@pytest.mark.parametrize("shape", [(256, 128), (200, 136), (3840, 2160)])
+def test_pyramid_packed_matches_full(shape):
+    """hevcasm_sad_sweep_pyramid_packed_frames = the int32 pyramid with the 8x8 / 16x16 levels narrowed to uint16 (exact), at ragged and
+    at full 4K size; the full form is checked against the oracle above"""
+    width, height = shape
+    nf = 2
+    src = synth.smooth_planes(61, nf, width, height, 16)
+    ref = synth.smooth_planes(61, nf, width, height, 16, shift=(2, -1), noise=5)
+    src.buf[1][:] = 255   # a frame of extreme differences: every 16x16 SAD is 65 280
+    ref.buf[1][:] = 0
+    ds, dr = to_dev(src.buf), to_dev(ref.buf)
+    full = [dev_full((nf * (width // s) * (height // s) * 64,), np.int32, -1) for s in (8, 16, 32, 64)]
+    lib.call("sad_sweep_pyramid_frames", dptr(ds, src.origin), src.pitch, dptr(dr, ref.origin), ref.pitch, width, height, -4, -4, nf, src.frame_stride,
+             ref.frame_stride, *[dptr(o) for o in full])
+    import torch
+    pk = [torch.full((nf * (width // s) * (height // s) * 64,), 3, dtype=torch.uint16 if s < 32 else torch.int32, device="cuda") for s in (8, 16, 32, 64)]
+    lib.call("sad_sweep_pyramid_packed_frames", dptr(ds, src.origin), src.pitch, dptr(dr, ref.origin), ref.pitch, width, height, -4, -4, nf, src.frame_stride,
+             ref.frame_stride, *[dptr(o) for o in pk])
+    for s, a, b in zip((8, 16, 32, 64), full, pk):
+        assert np.array_equal(to_host(a), to_host(b).astype(np.int32)), s
+    assert int(to_host(pk[1]).max()) == 65280
