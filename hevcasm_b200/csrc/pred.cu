@@ -161,6 +161,7 @@ struct PredParams {
     int xf0, yf0, xf1, yf1;
     const int16_t *pus;          // list form: one CTA per descriptor
     int n_pu;
+    int desc_frame;              // list form: 1 = every descriptor ends with a frame index (planes fs_dst / fs_ref apart), 0 = one plane
 };
 
 constexpr int NT = 128;
@@ -986,16 +987,18 @@ int launch_uni_stream_tma(const FastParams &fp, const StreamMaps &sm, int mode, 
 template <int TAPS, bool BI>
 __global__ void __launch_bounds__(NT) pred_list_stream_kernel(PredParams p)
 {
-    constexpr int G = 32, NREF = BI ? 2 : 1, DW = BI ? 8 : 6, LEFT = TAPS / 2 - 1, FB = TAPS == 8 ? 2 : 3, FM = (1 << FB) - 1;
+    constexpr int G = 32, NREF = BI ? 2 : 1, DW0 = BI ? 8 : 6, LEFT = TAPS / 2 - 1, FB = TAPS == 8 ? 2 : 3, FM = (1 << FB) - 1;
+    const int DW = DW0 + p.desc_frame;   // a trailing frame index makes one launch cover the PU lists of a whole batch of frames
     __shared__ int s_prefix[G + 1];
-    __shared__ short s_desc[G][8];
+    __shared__ short s_desc[G][10];
     const int tid = threadIdx.x, lane = tid & 31, first = blockIdx.x * G;
     if (tid < 32) {
         int nq = 0;
         if (first + lane < p.n_pu) {
             const int16_t *dsc = p.pus + (size_t)(first + lane) * DW;
 #pragma unroll
-            for (int j = 0; j < DW; ++j) s_desc[lane][j] = dsc[j];
+            for (int j = 0; j < DW0; ++j) s_desc[lane][j] = dsc[j];
+            s_desc[lane][DW0] = p.desc_frame ? dsc[DW0] : (short)0;
             const int w = dsc[2], h = dsc[3];
             if (w > 0 && h > 0 && w <= 64 && h <= 64) nq = (w + 3) >> 2;
         }
@@ -1019,14 +1022,14 @@ __global__ void __launch_bounds__(NT) pred_list_stream_kernel(PredParams p)
             if (s_prefix[pu + step] <= item) pu += step;
         const int q = item - s_prefix[pu];
         const int x = s_desc[pu][0], y = s_desc[pu][1], w = s_desc[pu][2], h = s_desc[pu][3];
-        const int nvalid = w - 4 * q, rows_in = h + TAPS - 1;
-        uint8_t *d = p.dst + (ptrdiff_t)y * p.sd + x + 4 * q;
+        const int nvalid = w - 4 * q, rows_in = h + TAPS - 1, frame = s_desc[pu][DW0];
+        uint8_t *d = p.dst + frame * p.fs_dst + (ptrdiff_t)y * p.sd + x + 4 * q;
         const uint8_t *src[NREF];
         int cx4[NREF][TAPS / 4], cy2[NREF][TAPS / 2];
 #pragma unroll
         for (int rf = 0; rf < NREF; ++rf) {
             const int mvx = s_desc[pu][4 + 2 * rf], mvy = s_desc[pu][5 + 2 * rf];
-            src[rf] = (rf ? p.ref1 : p.ref0) + (ptrdiff_t)(y + (mvy >> FB) - LEFT) * p.sr + x + (mvx >> FB) + 4 * q - 4;
+            src[rf] = (rf ? p.ref1 : p.ref0) + frame * p.fs_ref + (ptrdiff_t)(y + (mvy >> FB) - LEFT) * p.sr + x + (mvx >> FB) + 4 * q - 4;
             Coefs<TAPS> c;
             c.load(mvx & FM);
 #pragma unroll
@@ -1485,4 +1488,27 @@ extern "C" int hevcasm_pred_bi_batch(uint8_t *dst, ptrdiff_t sd, const uint8_t *
         return taps == 8 ? launch(pred_list_stream_kernel<8, true>, grid, dim3(NT), 0, stream, p) : launch(pred_list_stream_kernel<4, true>, grid, dim3(NT), 0, stream, p);
     }
     return taps == 8 ? launch_pred<8, LTW, LTH, true, RUNTIME>(p, dim3(n_pu), stream) : launch_pred<4, LTW, LTH, true, RUNTIME>(p, dim3(n_pu), stream);
+}
+
+// PU lists over a batch of frames in one launch: descriptors carry a trailing frame index
+extern "C" int hevcasm_pred_uni_list_frames(uint8_t *dst, ptrdiff_t sd, const uint8_t *ref, ptrdiff_t sr, int taps, const int16_t *pus, int n_pu, ptrdiff_t fs_dst,
+                                            ptrdiff_t fs_ref, void *stream)
+{
+    if ((taps != 8 && taps != 4) || n_pu < 0 || (n_pu > 0 && !pus)) return HEVCASM_ERR_ARGUMENT;
+    if (n_pu == 0) return 0;
+    PredParams p{};
+    p.dst = dst, p.ref0 = ref, p.sd = sd, p.sr = sr, p.fs_dst = fs_dst, p.fs_ref = fs_ref, p.pus = pus, p.n_pu = n_pu, p.desc_frame = 1;
+    const dim3 grid((n_pu + 31) / 32, 4);
+    return taps == 8 ? launch(pred_list_stream_kernel<8, false>, grid, dim3(NT), 0, stream, p) : launch(pred_list_stream_kernel<4, false>, grid, dim3(NT), 0, stream, p);
+}
+
+extern "C" int hevcasm_pred_bi_list_frames(uint8_t *dst, ptrdiff_t sd, const uint8_t *ref0, const uint8_t *ref1, ptrdiff_t sr, int taps, const int16_t *pus, int n_pu,
+                                           ptrdiff_t fs_dst, ptrdiff_t fs_ref, void *stream)
+{
+    if ((taps != 8 && taps != 4) || n_pu < 0 || (n_pu > 0 && !pus)) return HEVCASM_ERR_ARGUMENT;
+    if (n_pu == 0) return 0;
+    PredParams p{};
+    p.dst = dst, p.ref0 = ref0, p.ref1 = ref1, p.sd = sd, p.sr = sr, p.fs_dst = fs_dst, p.fs_ref = fs_ref, p.pus = pus, p.n_pu = n_pu, p.desc_frame = 1;
+    const dim3 grid((n_pu + 31) / 32, 4);
+    return taps == 8 ? launch(pred_list_stream_kernel<8, true>, grid, dim3(NT), 0, stream, p) : launch(pred_list_stream_kernel<4, true>, grid, dim3(NT), 0, stream, p);
 }

@@ -149,6 +149,16 @@ int HEVCASM_API hevcasm_pred_uni_batch(uint8_t *dst, ptrdiff_t stride_dst, const
 int HEVCASM_API hevcasm_pred_bi_batch(uint8_t *dst, ptrdiff_t stride_dst, const uint8_t *ref0, const uint8_t *ref1,
                                       ptrdiff_t stride_ref, int taps, const int16_t *pus, int n_pu, void *stream);
 
+/* The PU lists of a whole batch of frames (a GOP) in ONE launch: each descriptor carries a trailing frame index - 7 x int16
+ * {x, y, w, h, mvx, mvy, frame} resp. 9 x int16 {x, y, w, h, mvx0, mvy0, mvx1, mvy1, frame} - and frame f's planes start
+ * frame_stride elements after frame f-1's.  PUs of any sizes and frames may be mixed in any order. */
+int HEVCASM_API hevcasm_pred_uni_list_frames(uint8_t *dst, ptrdiff_t stride_dst, const uint8_t *ref, ptrdiff_t stride_ref, int taps,
+                                             const int16_t *pus, int n_pu, ptrdiff_t frame_stride_dst, ptrdiff_t frame_stride_ref,
+                                             void *stream);
+int HEVCASM_API hevcasm_pred_bi_list_frames(uint8_t *dst, ptrdiff_t stride_dst, const uint8_t *ref0, const uint8_t *ref1,
+                                            ptrdiff_t stride_ref, int taps, const int16_t *pus, int n_pu, ptrdiff_t frame_stride_dst,
+                                            ptrdiff_t frame_stride_ref, void *stream);
+
 /* ------------------------------------------------------------------------------------------------ transforms
  * element semantics: reference residual_decode.h:82 (hevcasm_transform; residual_decode.c:592-893) and
  * residual_decode.h:54 (hevcasm_inverse_transform_add; residual_decode.c:69-413).  log2size 2..5; trType 1 selects

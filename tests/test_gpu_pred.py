@@ -265,3 +265,37 @@ def test_bounded_forms_stay_inside_the_footprint(oracle, taps):
     lib.call("pred_bi_frames_bounded", dptr(got), width, dptr(d0, org), dptr(d1, org), pitch, width, height, taps, 1, 2, nfrac - 1, 0, nf, width * height,
              rows * pitch, 0, 0)
     assert np.array_equal(to_host(got), want)
+
+
+@pytest.mark.parametrize("taps", [8, 4])
+def test_pu_lists_over_frames(oracle, taps):
+    """hevcasm_pred_*_list_frames: the PU lists of several frames in one launch (descriptors with a trailing frame index, frames
+    interleaved in the list) = the per-frame list forms of the oracle on each frame"""
+    width, height, nf = 512, 420, 3
+    r0 = _ref_planes(270 + taps, nf, width, height, pad=32)
+    r1 = _ref_planes(271 + taps, nf, width, height, pad=32, kind="smooth")
+    per_frame = [_pu_list(taps, width, height, 272 + f) for f in range(nf)]
+    for bi in (False, True):
+        want = synth.random_planes(273, nf, width, height, 32)
+        got = to_dev(want.buf)
+        rows = []
+        for f, pus in enumerate(per_frame):
+            d = np.ascontiguousarray(pus if bi else pus[:, :6])
+            wf, rf0, rf1 = want.buf[f], r0.buf[f], r1.buf[f]
+            org = want.origin
+            if bi:
+                oracle.drv("pred_bi_batch", ptr(wf, org), want.pitch, ptr(rf0, r0.origin), ptr(rf1, r1.origin), r0.pitch, taps, ptr(d), len(d), threads=4)
+            else:
+                oracle.drv("pred_uni_batch", ptr(wf, org), want.pitch, ptr(rf0, r0.origin), r0.pitch, taps, ptr(d), len(d), threads=4)
+            rows.append(np.concatenate([d, np.full((len(d), 1), f, np.int16)], axis=1))
+        # interleave the frames' lists: PU i of frame 0, PU i of frame 1, ...
+        n = min(len(r) for r in rows)
+        mixed = np.ascontiguousarray(np.concatenate([np.stack([r[:n] for r in rows], 1).reshape(-1, rows[0].shape[1])] + [r[n:] for r in rows]))
+        d0, d1, dp = to_dev(r0.buf), to_dev(r1.buf), to_dev(mixed)
+        if bi:
+            lib.call("pred_bi_list_frames", dptr(got, want.origin), want.pitch, dptr(d0, r0.origin), dptr(d1, r1.origin), r0.pitch, taps, dptr(dp), len(mixed),
+                     want.frame_stride, r0.frame_stride)
+        else:
+            lib.call("pred_uni_list_frames", dptr(got, want.origin), want.pitch, dptr(d0, r0.origin), r0.pitch, taps, dptr(dp), len(mixed), want.frame_stride,
+                     r0.frame_stride)
+        assert np.array_equal(to_host(got), want.buf), bi
