@@ -42,6 +42,8 @@ GPU_ONLY_ABI = {
     "sad_sweep_pyramid_best_frames": [P, PD, P, PD, I, I, I, I, I, PD, PD, P, P, P, P],
     "sad_sweep_pyramid_packed_frames": [P, PD, P, PD, I, I, I, I, I, PD, PD, P, P, P, P],
     "residual_pipeline_frames": [P, PD, P, P, P, PD, P, PD, I, I, I, I, I, I, I, I, I, I, PD, PD, PD],
+    "transform_from_planes_frames": [P, P, PD, P, PD, I, I, I, I, I, PD, PD],
+    "residual_from_planes_pipeline_frames": [P, PD, P, P, P, PD, P, PD, I, I, I, I, I, I, I, I, I, I, PD, PD, PD],
     "pred_uni_list_frames": [P, PD, P, PD, I, P, I, PD, PD],
     "pred_bi_list_frames": [P, PD, P, P, PD, I, P, I, PD, PD],
     "pred_uni_frames_bounded": [P, PD, P, PD, I, I, I, I, I, I, PD, PD, PD, PD],

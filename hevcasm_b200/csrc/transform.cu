@@ -265,6 +265,36 @@ __device__ __forceinline__ void small_fwd_core(const int16_t *src, ptrdiff_t str
     }
 }
 
+// The same with the residual formed on the fly from two 8-bit blocks (src - pred): stage 1 runs on the bytes themselves (IDP.4A with T
+// for src and -T for pred), so the 9-bit difference never exists and the instruction count equals the int16 form's.  This is the batched
+// counterpart of f265_lbd_dct_8_avx2 (reference f265/dct.asm:561), which also takes two 8-bit blocks.  pw = the predictor block's rows.
+template <int LOG2, bool DST, bool PA>
+__device__ __forceinline__ void small_fwd_core_planes(const uint8_t *src, ptrdiff_t ss, const uint32_t (&pw)[1 << LOG2][(1 << LOG2) / 4],
+                                                      uint32_t (&Yw)[1 << LOG2][(1 << LOG2) / 2])
+{
+    constexpr int N = 1 << LOG2, HW = N / 2, S1 = fwd_shift1(LOG2), S2 = fwd_shift2(LOG2);
+    uint32_t S[N][N / 4];
+#pragma unroll
+    for (int r = 0; r < N; ++r) load_words<N / 4, PA>(src + (ptrdiff_t)r * ss, S[r]);
+    uint32_t Aw[N][HW];
+#pragma unroll
+    for (int r = 0; r < N; r += 2) {
+        int a0[N], a1[N];
+        fwd_matrix_bytes<N, DST>(S[r], pw[r], a0, 1 << (S1 - 1));
+        fwd_matrix_bytes<N, DST>(S[r + 1], pw[r + 1], a1, 1 << (S1 - 1));
+#pragma unroll
+        for (int u = 0; u < N; ++u) Aw[u][r / 2] = lolo((uint32_t)(a0[u] >> S1), (uint32_t)(a1[u] >> S1));
+    }
+#pragma unroll
+    for (int u = 0; u < N; u += 2) {
+        int b0[N], b1[N];
+        fwd_matrix<N, DST>(Aw[u], b0, 1 << (S2 - 1));
+        fwd_matrix<N, DST>(Aw[u + 1], b1, 1 << (S2 - 1));
+#pragma unroll
+        for (int v = 0; v < N; ++v) Yw[v][u / 2] = lolo((uint32_t)(b0[v] >> S2), (uint32_t)(b1[v] >> S2));
+    }
+}
+
 template <int LOG2, bool DST, bool PA>
 __global__ void __launch_bounds__(SMALL_NT) small_fwd_kernel(int16_t *__restrict__ coeffs, const int16_t *__restrict__ res, ptrdiff_t stride,
                                                              ptrdiff_t fs, BlockGrid g)
@@ -291,6 +321,27 @@ __device__ __forceinline__ void load_pred(const uint8_t *pp, ptrdiff_t sp, uint3
 {
 #pragma unroll
     for (int r = 0; r < N; ++r) load_words<N / 4, PA>(pp + (ptrdiff_t)r * sp, pw[r]);
+}
+
+template <int LOG2, bool DST, bool PA>
+__global__ void __launch_bounds__(SMALL_NT) small_fwd_planes_kernel(int16_t *__restrict__ coeffs, const uint8_t *__restrict__ src, ptrdiff_t ss, ptrdiff_t fs_src,
+                                                                    const uint8_t *__restrict__ pred, ptrdiff_t sp, ptrdiff_t fs_pred, BlockGrid g)
+{
+    using Io = SmallIo<LOG2>;
+    constexpr int N = 1 << LOG2, HW = N / 2;
+    __shared__ __align__(16) int4 io[SMALL_NT / 32][Io::WARP_CHUNKS];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const long long i = (long long)blockIdx.x * SMALL_NT + threadIdx.x, first = i - lane;
+    if (first >= g.n) return;  // whole warp out of range
+    uint32_t Yw[N][HW];
+    if (i < g.n) {
+        int x, y, f;
+        g.locate(i, LOG2, x, y, f);
+        uint32_t pw[N][N / 4];
+        load_pred<N, PA>(pred + f * fs_pred + (ptrdiff_t)y * sp + x, sp, pw);
+        small_fwd_core_planes<LOG2, DST, PA>(src + f * fs_src + (ptrdiff_t)y * ss + x, ss, pw, Yw);
+    }
+    Io::store(coeffs, first, g.n, lane, io[warp], Yw);
 }
 
 template <int LOG2, bool DST, bool PA>
@@ -695,6 +746,8 @@ __device__ __forceinline__ uint32_t quant_dequant_word(uint32_t w, const QuantPa
 struct PipelineParams {
     uint8_t *rec;
     const uint8_t *pred;
+    const uint8_t *src;          // "from planes" form: residual = src - pred, formed on the fly (res is null then)
+    ptrdiff_t s_src, fs_src;
     const int16_t *res;
     int16_t *levels;
     int32_t *cbf;
@@ -702,7 +755,7 @@ struct PipelineParams {
     QuantParams q;
 };
 
-template <int LOG2, bool DST, bool PA>
+template <int LOG2, bool DST, bool PA, bool PLANES = false>
 __global__ void __launch_bounds__(SMALL_NT) small_pipeline_kernel(PipelineParams p, BlockGrid g)
 {
     using Io = SmallIo<LOG2>;
@@ -718,7 +771,8 @@ __global__ void __launch_bounds__(SMALL_NT) small_pipeline_kernel(PipelineParams
     if (valid) {
         g.locate(i, LOG2, x, y, f);
         load_pred<N, PA>(p.pred + f * p.fs_pred + (ptrdiff_t)y * p.s_pred + x, p.s_pred, pw);
-        small_fwd_core<LOG2, DST, PA>(p.res + f * p.fs_res + (ptrdiff_t)y * p.s_res + x, p.s_res, Yw);
+        if (PLANES) small_fwd_core_planes<LOG2, DST, PA>(p.src + f * p.fs_src + (ptrdiff_t)y * p.s_src + x, p.s_src, pw, Yw);
+        else small_fwd_core<LOG2, DST, PA>(p.res + f * p.fs_res + (ptrdiff_t)y * p.s_res + x, p.s_res, Yw);
 #pragma unroll
         for (int v = 0; v < N; ++v)
 #pragma unroll
@@ -970,10 +1024,59 @@ extern "C" int hevcasm_residual_pipeline_frames(uint8_t *rec, ptrdiff_t s_rec, i
     g.n = (long long)g.nbx * g.nby * n_frames;
     g.finish();
     if (g.n == 0) return 0;
-    PipelineParams p;
+    PipelineParams p{};
     p.rec = rec, p.pred = pred, p.res = residual, p.levels = levels, p.cbf = cbf;
     p.s_rec = s_rec, p.s_pred = s_pred, p.s_res = s_res, p.fs_rec = fs_rec, p.fs_pred = fs_pred, p.fs_res = fs_res;
     p.q = QuantParams{q_scale, q_shift, q_offset << (q_shift - 16), iq_scale, iq_shift};
     const bool pa = aligned16(rec, s_rec, fs_rec, pred, s_pred, fs_pred) && aligned16(residual, s_res * 2, fs_res * 2);
     return pa ? launch_pipeline_t<true>(p, g, log2size, trType, stream) : launch_pipeline_t<false>(p, g, log2size, trType, stream);
+}
+
+// ------------------------------------------------------------------------------------------------ residual formed on the fly (src - pred)
+
+extern "C" int hevcasm_transform_from_planes_frames(int16_t *coeffs, const uint8_t *src, ptrdiff_t s_src, const uint8_t *pred, ptrdiff_t s_pred, int width,
+                                                    int height, int log2size, int trType, int n_frames, ptrdiff_t fs_src, ptrdiff_t fs_pred, void *stream)
+{
+    // 4x4 (DCT, DST) and 8x8: the block sizes whose first stage runs on bytes.  (f265_lbd_dct_8_avx2 is the 8x8 case.)
+    if (!tr_args_ok(log2size, trType) || log2size > 3 || n_frames < 0 || width < 0 || height < 0 || ((uintptr_t)coeffs & 15)) return HEVCASM_ERR_ARGUMENT;
+    BlockGrid g{nullptr, width >> log2size, height >> log2size, 0};
+    g.n = (long long)g.nbx * g.nby * n_frames;
+    g.finish();
+    if (g.n == 0) return 0;
+    const unsigned grid = (unsigned)((g.n + SMALL_NT - 1) / SMALL_NT);
+    const bool pa = aligned16(src, s_src, fs_src, pred, s_pred, fs_pred);
+#define HV_FP(L_, D_)                                                                                                                              \
+    return pa ? launch(small_fwd_planes_kernel<L_, D_, true>, grid, SMALL_NT, 0, stream, coeffs, src, s_src, fs_src, pred, s_pred, fs_pred, g)      \
+              : launch(small_fwd_planes_kernel<L_, D_, false>, grid, SMALL_NT, 0, stream, coeffs, src, s_src, fs_src, pred, s_pred, fs_pred, g)
+    if (log2size == 2 && trType) HV_FP(2, true);
+    if (log2size == 2) HV_FP(2, false);
+    HV_FP(3, false);
+#undef HV_FP
+}
+
+extern "C" int hevcasm_residual_from_planes_pipeline_frames(uint8_t *rec, ptrdiff_t s_rec, int16_t *levels, int32_t *cbf, const uint8_t *src, ptrdiff_t s_src,
+                                                            const uint8_t *pred, ptrdiff_t s_pred, int width, int height, int log2size, int trType, int q_scale,
+                                                            int q_shift, int q_offset, int iq_scale, int iq_shift, int n_frames, ptrdiff_t fs_rec, ptrdiff_t fs_src,
+                                                            ptrdiff_t fs_pred, void *stream)
+{
+    if (!tr_args_ok(log2size, trType) || log2size > 3 || n_frames < 0 || width < 0 || height < 0 || q_shift < 16 || q_shift > 27 || q_scale < 0 ||
+        q_scale >= 0x8000 || q_offset < 0 || q_offset >= 0x8000 || iq_shift < 1 || iq_shift > 30 || ((uintptr_t)levels & 15))
+        return HEVCASM_ERR_ARGUMENT;
+    BlockGrid g{nullptr, width >> log2size, height >> log2size, 0};
+    g.n = (long long)g.nbx * g.nby * n_frames;
+    g.finish();
+    if (g.n == 0) return 0;
+    PipelineParams p{};
+    p.rec = rec, p.pred = pred, p.src = src, p.res = nullptr, p.levels = levels, p.cbf = cbf;
+    p.s_rec = s_rec, p.s_pred = s_pred, p.s_src = s_src, p.s_res = 0, p.fs_rec = fs_rec, p.fs_pred = fs_pred, p.fs_src = fs_src, p.fs_res = 0;
+    p.q = QuantParams{q_scale, q_shift, q_offset << (q_shift - 16), iq_scale, iq_shift};
+    const bool pa = aligned16(rec, s_rec, fs_rec, pred, s_pred, fs_pred) && aligned16(src, s_src, fs_src);
+    const unsigned grid = (unsigned)((g.n + SMALL_NT - 1) / SMALL_NT);
+#define HV_PP(L_, D_)                                                                                       \
+    return pa ? launch(small_pipeline_kernel<L_, D_, true, true>, grid, SMALL_NT, 0, stream, p, g)           \
+              : launch(small_pipeline_kernel<L_, D_, false, true>, grid, SMALL_NT, 0, stream, p, g)
+    if (log2size == 2 && trType) HV_PP(2, true);
+    if (log2size == 2) HV_PP(2, false);
+    HV_PP(3, false);
+#undef HV_PP
 }

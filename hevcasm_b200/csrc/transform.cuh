@@ -82,6 +82,30 @@ constexpr FwdTab make_fwd_tab()
 }
 __constant__ FwdTab c_fwd = make_fwd_tab();
 
+// the same matrices for BYTE inputs (dp4a: four u8 samples x four s8 coefficients): [u][j] = (T[u][4j] .. T[u][4j+3]); `neg` holds the negated
+// coefficients, so that a row of src - pred is transformed as sum T*src + sum (-T)*pred without ever forming the 9-bit difference
+struct FwdByteTab {
+    int dct4[4], dst4[4], dct8[8][2], ndct4[4], ndst4[4], ndct8[8][2];
+};
+__host__ __device__ constexpr int cquad(int a, int b, int c, int d) { return (a & 0xff) | ((b & 0xff) << 8) | ((c & 0xff) << 16) | ((d & 0xff) << 24); }
+constexpr FwdByteTab make_fwd_byte_tab()
+{
+    FwdByteTab t{};
+    for (int u = 0; u < 4; ++u) {
+        t.dct4[u] = cquad(dct(4, u, 0), dct(4, u, 1), dct(4, u, 2), dct(4, u, 3));
+        t.ndct4[u] = cquad(-dct(4, u, 0), -dct(4, u, 1), -dct(4, u, 2), -dct(4, u, 3));
+        t.dst4[u] = cquad(dst4(u, 0), dst4(u, 1), dst4(u, 2), dst4(u, 3));
+        t.ndst4[u] = cquad(-dst4(u, 0), -dst4(u, 1), -dst4(u, 2), -dst4(u, 3));
+    }
+    for (int u = 0; u < 8; ++u)
+        for (int j = 0; j < 2; ++j) {
+            t.dct8[u][j] = cquad(dct(8, u, 4 * j), dct(8, u, 4 * j + 1), dct(8, u, 4 * j + 2), dct(8, u, 4 * j + 3));
+            t.ndct8[u][j] = cquad(-dct(8, u, 4 * j), -dct(8, u, 4 * j + 1), -dct(8, u, 4 * j + 2), -dct(8, u, 4 * j + 3));
+        }
+    return t;
+}
+__constant__ FwdByteTab c_fwd_byte = make_fwd_byte_tab();
+
 #define HV_V(ic) (decltype(ic)::value)
 
 template <int I>
@@ -153,6 +177,21 @@ __device__ __forceinline__ void fwd_matrix(const uint32_t *w, int *out, int roun
         static_for<0, N / 2>([&](auto j) {
             const int c = DST ? c_fwd.dst4[HV_V(u) & 3][HV_V(j) & 1] : (N == 4 ? c_fwd.dct4[HV_V(u) & 3][HV_V(j) & 1] : c_fwd.dct8[HV_V(u) & 7][HV_V(j) & 3]);
             a = dp2a_lo(w[HV_V(j)], c, a);
+        });
+        out[HV_V(u)] = a;
+    });
+}
+
+// ---- forward, matrix form on the BYTES of two 8-bit rows: out[u] = round + sum_x T[u][x] * (s[x] - p[x]) --------------
+template <int N, bool DST>
+__device__ __forceinline__ void fwd_matrix_bytes(const uint32_t *sw, const uint32_t *pw, int *out, int round)
+{
+    static_for<0, N>([&](auto u) {
+        int a = round;
+        static_for<0, N / 4>([&](auto j) {
+            const int c = DST ? c_fwd_byte.dst4[HV_V(u) & 3] : (N == 4 ? c_fwd_byte.dct4[HV_V(u) & 3] : c_fwd_byte.dct8[HV_V(u) & 7][HV_V(j) & 1]);
+            const int nc = DST ? c_fwd_byte.ndst4[HV_V(u) & 3] : (N == 4 ? c_fwd_byte.ndct4[HV_V(u) & 3] : c_fwd_byte.ndct8[HV_V(u) & 7][HV_V(j) & 1]);
+            a = dp4a_us(pw[HV_V(j)], nc, dp4a_us(sw[HV_V(j)], c, a));
         });
         out[HV_V(u)] = a;
     });

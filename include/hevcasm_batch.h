@@ -203,6 +203,21 @@ int HEVCASM_API hevcasm_residual_pipeline_frames(uint8_t *rec, ptrdiff_t stride_
                                                  ptrdiff_t frame_stride_rec, ptrdiff_t frame_stride_residual,
                                                  ptrdiff_t frame_stride_pred, void *stream);
 
+/* The residual formed on the fly from two 8-bit planes, residual = src - pred, as the encoder-side f265_lbd_dct_8_avx2 (reference
+ * f265/dct.asm:561) takes its input: the forward transform alone, and the whole fused pipeline (then the predictor is read once for the
+ * residual AND the reconstruction: 5.06 instead of 6.06 bytes per sample, and no int16 residual plane is ever written).  Block sizes
+ * 4x4 (DCT or DST) and 8x8, whose first stage runs directly on the bytes.  Element semantics: hevcasm_transform resp. the pipeline above
+ * applied to the int16 differences. */
+int HEVCASM_API hevcasm_transform_from_planes_frames(int16_t *coeffs, const uint8_t *src, ptrdiff_t stride_src, const uint8_t *pred,
+                                                     ptrdiff_t stride_pred, int width, int height, int log2size, int trType, int n_frames,
+                                                     ptrdiff_t frame_stride_src, ptrdiff_t frame_stride_pred, void *stream);
+int HEVCASM_API hevcasm_residual_from_planes_pipeline_frames(uint8_t *rec, ptrdiff_t stride_rec, int16_t *levels, int32_t *cbf,
+                                                             const uint8_t *src, ptrdiff_t stride_src, const uint8_t *pred,
+                                                             ptrdiff_t stride_pred, int width, int height, int log2size, int trType,
+                                                             int q_scale, int q_shift, int q_offset, int iq_scale, int iq_shift,
+                                                             int n_frames, ptrdiff_t frame_stride_rec, ptrdiff_t frame_stride_src,
+                                                             ptrdiff_t frame_stride_pred, void *stream);
+
 /* ------------------------------------------------------------------------------------------------ host-memory forms
  * A context owns one CUDA stream and a device staging arena on one device.  The *_host entry points take HOST
  * pointers with the same meaning as the device forms, copy inputs in, run, copy results out and synchronise

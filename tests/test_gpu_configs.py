@@ -111,37 +111,89 @@ def test_config3_4k_residual_pipeline(oracle):
         assert np.array_equal(to_host(got), want.buf), log2
 
 
-def test_config4_8k_frames_sharded(oracle):
-    """configs[4] at reduced frame count: 8K frames dealt to ranks by hevcasm_b200.shard; every shard's SAD + HV interpolation +
-    8x8 forward DCT equals the unsharded result (per-frame digests), and frame 0 equals the oracle"""
-    W, H, NF = 7680, 4320, 3
+def test_config4_8k_64_frames_sharded(oracle):
+    """configs[4] at its full frame count: 64 8K frames dealt to ranks by hevcasm_b200.shard.  Every frame goes through the SAD sweep (argmin
+    form), one two-pass luma interpolation and the 8x8 forward DCT, in batched calls of 8 frames, and EVERY frame's outputs are compared with
+    the oracle's by digest; the per-frame digests of a 2-rank deal equal those of the 1-rank run (no result depends on which rank, or
+    which position in a batch, a frame had)."""
+    W, H, NF, CH = 7680, 4320, 64, 8
+
+    def frames(fs):   # every frame is generated from its own seed, as a rank would
+        src = synth.Planes(np.concatenate([synth.random_planes(740 + f, 1, W, H, 16).buf for f in fs]), W, H, 16)
+        ref = synth.Planes(np.concatenate([synth.random_planes(860 + f, 1, W, H, 16).buf for f in fs]), W, H, 16)
+        res = synth.Planes(np.concatenate([synth.residual_planes(980 + f, 1, W, H).buf for f in fs]), W, H, 0)
+        return src, ref, res
+
+    def gpu_digests(src, ref, res):
+        n = src.n_frames
+        ds, dr, dres = to_dev(src.buf), to_dev(ref.buf), to_dev(res.buf)
+        best = [dev_full((n, (W // s) * (H // s), 2), np.int32, -1) for s in (8, 16, 32, 64)]
+        lib.call("sad_sweep_pyramid_best_frames", dptr(ds, src.origin), src.pitch, dptr(dr, ref.origin), ref.pitch, W, H, -4, -4, n, src.frame_stride,
+                 ref.frame_stride, *[dptr(o) for o in best])
+        pr = to_dev(np.zeros_like(src.buf))
+        lib.call("pred_uni_frames", dptr(pr, src.origin), src.pitch, dptr(dr, ref.origin), ref.pitch, W, H, 8, 2, 1, n, src.frame_stride, ref.frame_stride)
+        co = dev_full((n, (W // 8) * (H // 8) * 64), np.int16, 0)
+        lib.call("transform_frames", dptr(co), dptr(dres, res.origin), res.pitch, W, H, 3, 0, n, res.frame_stride)
+        b, p, c = [to_host(o) for o in best], to_host(pr), to_host(co)
+        return [shard.frame_digest(*[x[k] for x in b], p[k], c[k]) for k in range(n)]
+
+    def oracle_digests(src, ref, res):
+        n = src.n_frames
+        b = []
+        for s in (8, 16, 32, 64):
+            sad = np.zeros((n, (W // s) * (H // s), 64), np.int32)
+            oracle.drv("sad_sweep_frames", ptr(src.buf, src.origin), src.pitch, ptr(ref.buf, ref.origin), ref.pitch, W, H, HEVCASM_RECT(s, s), -4, -4, 8, 8, n,
+                       src.frame_stride, ref.frame_stride, ptr(sad), threads=T)
+            b.append(np.stack([sad.min(-1), sad.argmin(-1).astype(np.int32)], -1).astype(np.int32))
+        wp = np.zeros_like(src.buf)
+        oracle.drv("pred_uni_frames", ptr(wp, src.origin), src.pitch, ptr(ref.buf, ref.origin), ref.pitch, W, H, 8, 2, 1, n, src.frame_stride, ref.frame_stride, threads=T)
+        co = np.zeros((n, (W // 8) * (H // 8) * 64), np.int16)
+        oracle.drv("transform_frames", ptr(co), ptr(res.buf, res.origin), res.pitch, W, H, 3, 0, n, res.frame_stride, threads=T)
+        return [shard.frame_digest(*[x[k] for x in b], wp[k], co[k]) for k in range(n)]
+
+    want = [None] * NF
     digests = {}
     for world in (1, 2):
         per_frame = [None] * NF
         for rank in range(world):
             f0, f1 = shard.frame_range(NF, rank, world)
-            for f in range(f0, f1):                      # every frame is generated from its own seed, as a rank would
-                src = synth.random_planes(740 + f, 1, W, H, 16)
-                ref = synth.random_planes(760 + f, 1, W, H, 16)
-                res = synth.residual_planes(780 + f, 1, W, H)
-                ds, dr, dres = to_dev(src.buf), to_dev(ref.buf), to_dev(res.buf)
-                best = [dev_full(((W // s) * (H // s), 2), np.int32, -1) for s in (8, 16, 32, 64)]
-                lib.call("sad_sweep_pyramid_best_frames", dptr(ds, src.origin), src.pitch, dptr(dr, ref.origin), ref.pitch, W, H, -4, -4, 1, src.frame_stride,
-                         ref.frame_stride, *[dptr(o) for o in best])
-                pr = to_dev(np.zeros_like(src.buf))
-                lib.call("pred_uni_frames", dptr(pr, src.origin), src.pitch, dptr(dr, ref.origin), ref.pitch, W, H, 8, 2, 1, 1, src.frame_stride, ref.frame_stride)
-                co = dev_full(((W // 8) * (H // 8) * 64,), np.int16, 0)
-                lib.call("transform_frames", dptr(co), dptr(dres, res.origin), res.pitch, W, H, 3, 0, 1, res.frame_stride)
-                per_frame[f] = shard.frame_digest(*[to_host(o) for o in best], to_host(pr), to_host(co))
-                if world == 1 and f == 0:
-                    want = np.zeros(((W // 64) * (H // 64), 64), np.int32)
-                    oracle.drv("sad_sweep_frames", ptr(src.buf, src.origin), src.pitch, ptr(ref.buf, ref.origin), ref.pitch, W, H, HEVCASM_RECT(64, 64), -4, -4, 8,
-                               8, 1, src.frame_stride, ref.frame_stride, ptr(want), threads=T)
-                    b = to_host(best[3])
-                    assert np.array_equal(b[:, 0], want.min(-1)) and np.array_equal(b[:, 1], want.argmin(-1))
-                    wp = synth.Planes(np.zeros_like(src.buf), W, H, 16)
-                    oracle.drv("pred_uni_frames", ptr(wp.buf, wp.origin), wp.pitch, ptr(ref.buf, ref.origin), ref.pitch, W, H, 8, 2, 1, 1, wp.frame_stride,
-                               ref.frame_stride, threads=T)
-                    assert np.array_equal(to_host(pr), wp.buf)
+            first = f0 + (3 if world == 2 else 0)     # the second deal also cuts its batches at different frames
+            cuts = [f0] + list(range(first, f1, CH)) + [f1]
+            for a, b_ in zip(cuts[:-1], cuts[1:]):
+                if a == b_:
+                    continue
+                src, ref, res = frames(range(a, b_))
+                per_frame[a:b_] = gpu_digests(src, ref, res)
+                if world == 1:
+                    want[a:b_] = oracle_digests(src, ref, res)
         digests[world] = shard.gather_frame_digests(per_frame, 0, NF)
+    assert digests[1] == want, [i for i, (g, w) in enumerate(zip(digests[1], want)) if g != w]
     assert digests[1] == digests[2] and len(set(digests[1])) == NF
+
+
+def test_default_dispatch_reaches_the_tensor_core_kernels_at_full_size(oracle):
+    """The sizes bench.py runs, through the DEFAULT dispatch of the product library (no switches exist there): forward 16x16 / 32x32 over
+    16 4K frames (>= 6 tiles per SM -> ft::fwd_umma_kernel), two-reference luma interpolation over 3 4K frames (>= 5 tiles per SM ->
+    uv::pred_vh_kernel<8, true>) and two-reference chroma over 16 1080p planes, every output sample compared with the oracle"""
+    W, H, NF = 3840, 2160, 16
+    res = synth.residual_planes(990, NF, W, H)
+    dres = to_dev(res.buf)
+    for log2 in (4, 5):
+        n = 1 << log2
+        nb = (W // n) * (H // n) * NF
+        want = np.zeros(nb * n * n, np.int16)
+        oracle.drv("transform_frames", ptr(want), ptr(res.buf, res.origin), res.pitch, W, H, log2, 0, NF, res.frame_stride, threads=T)
+        got = dev_full(want.shape, np.int16, 0x5a5a)
+        lib.call("transform_frames", dptr(got), dptr(dres, res.origin), res.pitch, W, H, log2, 0, NF, res.frame_stride)
+        assert np.array_equal(to_host(got), want), log2
+    del dres
+    for taps, w, h, nf, fr in ((8, 3840, 2160, 3, (1, 2, 3, 1)), (8, 3840, 2160, 3, (2, 0, 0, 3)), (4, 1920, 1080, 16, (3, 5, 6, 1))):
+        r0 = synth.random_planes(991 + taps, nf, w, h, 16)
+        r1 = synth.smooth_planes(992 + taps, nf, w, h, 16)
+        want = synth.Planes(np.zeros_like(r0.buf), w, h, 16)
+        oracle.drv("pred_bi_frames", ptr(want.buf, want.origin), want.pitch, ptr(r0.buf, r0.origin), ptr(r1.buf, r1.origin), r0.pitch, w, h, taps, *fr, nf,
+                   want.frame_stride, r0.frame_stride, threads=T)
+        got, d0, d1 = to_dev(np.zeros_like(r0.buf)), to_dev(r0.buf), to_dev(r1.buf)
+        lib.call("pred_bi_frames", dptr(got, want.origin), want.pitch, dptr(d0, r0.origin), dptr(d1, r1.origin), r0.pitch, w, h, taps, *fr, nf, want.frame_stride,
+                 r0.frame_stride)
+        assert np.array_equal(to_host(got), want.buf), (taps, fr)

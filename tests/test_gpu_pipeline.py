@@ -80,3 +80,34 @@ def test_pipeline_full_size_properties():
              pred.frame_stride, pred.frame_stride)
     assert np.array_equal(to_host(lv), to_host(lv2)) and np.array_equal(to_host(cbf), to_host(cbf2)) and np.array_equal(to_host(rec), to_host(rec2))
     assert to_host(cbf).any()
+
+
+@pytest.mark.parametrize("log2,tr", [(2, 0), (2, 1), (3, 0)])
+@pytest.mark.parametrize("shape", [(200, 104), (256, 128)])
+def test_from_planes_forms(oracle, log2, tr, shape):
+    """residual = src - pred formed on the fly from two 8-bit planes (the input form of f265_lbd_dct_8_avx2): the forward transform and the fused
+    pipeline equal the int16-residual forms applied to the differences, extreme differences (+-255) included"""
+    width, height = shape
+    nf, n = 3, 1 << log2
+    src = synth.random_planes(610 + log2, nf, width, height, 8)
+    pred = synth.random_planes(611 + log2, nf, width, height, 8)
+    src.buf[0][:] = 255
+    pred.buf[0][:] = 0
+    src.buf[1, :, ::2] = 0
+    pred.buf[1, :, ::2] = 255
+    res = synth.Planes((src.buf.astype(np.int16) - pred.buf.astype(np.int16)), width, height, 8)
+    nb = (width // n) * (height // n) * nf
+    want = np.zeros(nb * n * n, np.int16)
+    oracle.drv("transform_frames", ptr(want), ptr(res.buf, res.origin), res.pitch, width, height, log2, tr, nf, res.frame_stride, threads=4)
+    ds, dp = to_dev(src.buf), to_dev(pred.buf)
+    got = dev_full(want.shape, np.int16, 0x5a5a)
+    lib.call("transform_from_planes_frames", dptr(got), dptr(ds, src.origin), src.pitch, dptr(dp, pred.origin), pred.pitch, width, height, log2, tr, nf, src.frame_stride,
+             pred.frame_stride)
+    assert np.array_equal(to_host(got), want)
+    for qp in QP[:2]:
+        lv_w, cbf_w, rec_w = oracle_pipeline(oracle, res, pred, width, height, log2, tr, qp, nf)
+        rec = to_dev(synth.random_planes(301, nf, width, height, 8).buf)
+        lv, cbf = dev_full(lv_w.shape, np.int16, 1), dev_full(cbf_w.shape, np.int32, 1)
+        lib.call("residual_from_planes_pipeline_frames", dptr(rec, rec_w.origin), rec_w.pitch, dptr(lv), dptr(cbf), dptr(ds, src.origin), src.pitch, dptr(dp, pred.origin),
+                 pred.pitch, width, height, log2, tr, *qp, nf, rec_w.frame_stride, src.frame_stride, pred.frame_stride)
+        assert np.array_equal(to_host(lv), lv_w) and np.array_equal(to_host(cbf), cbf_w) and np.array_equal(to_host(rec), rec_w.buf), qp
