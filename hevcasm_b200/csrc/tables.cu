@@ -36,10 +36,12 @@ struct Scratch {
     cudaStream_t s = nullptr;
     uint8_t *dev = nullptr;
     bool ready = false;
+    int device = 0;   // the device the stream and the staging area belong to: whichever was current at the first slot call
 
     void init()
     {
         if (ready) return;
+        check(cudaGetDevice(&device), "cudaGetDevice");
         check(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking), "cudaStreamCreate");
         check(cudaMalloc((void **)&dev, kRegion * kRegions), "cudaMalloc");
         check(cudaMemsetAsync(dev, 0, kRegion * kRegions, s), "cudaMemset");
@@ -75,10 +77,25 @@ struct Scratch {
 
 Scratch g_scratch;
 
+// Holds the scratch lock and makes the scratch's device current for the duration of one slot call (a caller thread may have another
+// device current; launching on a foreign stream would fail), restoring the caller's device afterwards.
 struct Locked {
     std::lock_guard<std::mutex> lock;
     Scratch &sc;
-    Locked() : lock(g_scratch.mu), sc(g_scratch) { sc.init(); }
+    int caller_device = -1;
+    Locked() : lock(g_scratch.mu), sc(g_scratch)
+    {
+        sc.init();
+        int cur = 0;
+        if (cudaGetDevice(&cur) == cudaSuccess && cur != sc.device) {
+            caller_device = cur;
+            Scratch::check(cudaSetDevice(sc.device), "cudaSetDevice");
+        }
+    }
+    ~Locked()
+    {
+        if (caller_device >= 0) cudaSetDevice(caller_device);
+    }
 };
 
 // region roles
@@ -161,8 +178,8 @@ int hadamard_satd_cuda(const uint8_t *a, ptrdiff_t sa, const uint8_t *b, ptrdiff
 int ssd_linear_cuda(const uint8_t *p0, const uint8_t *p1, int size)
 {
     if (size <= 0) return 0;
-    if ((size_t)size > kRegion) {
-        fprintf(stderr, "hevcasm_b200: ssd_linear slot serves size <= %zu (got %d)\n", kRegion, size);
+    if (size > 33025) {   // the limit of hevcasm_ssd_linear_batch: 255^2 * size must fit the reference's int accumulator (and the staging region)
+        fprintf(stderr, "hevcasm_b200: ssd_linear slot serves size <= 33025 (got %d)\n", size);
         abort();
     }
     Locked l;

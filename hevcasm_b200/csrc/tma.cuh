@@ -7,6 +7,7 @@
 #pragma once
 
 #include <cuda.h>  // CUtensorMap and enums only; the encoder is fetched from the driver at run time (no -lcuda)
+#include <string.h>
 
 #include "common.cuh"
 
@@ -27,6 +28,42 @@ inline EncodeTiledFn encoder()
         return (EncodeTiledFn)p;
     }();
     return fn;
+}
+
+// cuTensorMapEncodeTiled behind a small per-thread cache: a codec calls the same entry point on the same frame stores over and over,
+// and re-encoding two or three descriptors on every call was measurable host overhead per launch.  Direct-mapped, keyed by every
+// argument of the encoder; a hit copies 128 bytes.
+struct EncodeKey {
+    uint64_t base, dim[4], stride[3];
+    uint32_t box[4], dtype, rank, swizzle, pad;
+    bool operator==(const EncodeKey &o) const { return memcmp(this, &o, sizeof *this) == 0; }
+};
+inline CUresult encode_cached(CUtensorMap *map, CUtensorMapDataType dtype, cuuint32_t rank, void *base, const cuuint64_t *dim, const cuuint64_t *stride,
+                              const cuuint32_t *box, const cuuint32_t *estr, CUtensorMapSwizzle swizzle)
+{
+    struct Slot {
+        EncodeKey key;
+        CUtensorMap map;
+        bool valid;
+    };
+    constexpr int SLOTS = 64;
+    static thread_local Slot cache[SLOTS];
+    EncodeKey k;
+    memset(&k, 0, sizeof k);
+    k.base = (uint64_t)(uintptr_t)base, k.dtype = (uint32_t)dtype, k.rank = rank, k.swizzle = (uint32_t)swizzle;
+    for (cuuint32_t i = 0; i < rank; ++i) k.dim[i] = dim[i], k.box[i] = box[i];
+    for (cuuint32_t i = 0; i + 1 < rank; ++i) k.stride[i] = stride[i];
+    uint64_t h = 1469598103934665603ull;
+    for (size_t i = 0; i < sizeof k / 8; ++i) h = (h ^ reinterpret_cast<const uint64_t *>(&k)[i]) * 1099511628211ull;
+    Slot &s = cache[(h >> 20) % SLOTS];
+    if (s.valid && s.key == k) {
+        *map = s.map;
+        return CUDA_SUCCESS;
+    }
+    const CUresult r = encoder()(map, dtype, rank, base, dim, stride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                                 CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r == CUDA_SUCCESS) s.key = k, s.map = *map, s.valid = true;
+    return r;
 }
 
 // can a plane batch with these byte strides be described at all?  (row / frame strides must be multiples of 16 bytes)
@@ -51,8 +88,8 @@ inline int describe_bytes(CUtensorMap *map, const uint8_t *first, ptrdiff_t row_
     cuuint64_t stride[2] = {(cuuint64_t)row_stride, (cuuint64_t)frame_stride};
     cuuint32_t box[3] = {(cuuint32_t)(box_x / elem), (cuuint32_t)box_y, 1};
     cuuint32_t estr[3] = {1, 1, 1};
-    const CUresult r = encoder()(map, elem == 4 ? CU_TENSOR_MAP_DATA_TYPE_UINT32 : CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, (void *)(a - shift), dim, stride, box, estr,
-                                 CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    const CUresult r = encode_cached(map, elem == 4 ? CU_TENSOR_MAP_DATA_TYPE_UINT32 : CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, (void *)(a - shift), dim, stride, box, estr,
+                                     CU_TENSOR_MAP_SWIZZLE_NONE);
     return r == CUDA_SUCCESS ? 0 : (int)cudaErrorInvalidValue;
 }
 inline int describe_u8(CUtensorMap *map, const uint8_t *first, ptrdiff_t row_stride, ptrdiff_t frame_stride, long long extent_x, long long extent_y,
@@ -81,9 +118,8 @@ inline int describe_u8_swizzled(CUtensorMap *map, const uint8_t *base, ptrdiff_t
     cuuint64_t stride[2] = {(cuuint64_t)row_stride, (cuuint64_t)frame_stride};
     cuuint32_t box[3] = {(cuuint32_t)box_x, (cuuint32_t)box_y, 1};
     cuuint32_t estr[3] = {1, 1, 1};
-    const CUresult r = encoder()(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, (void *)base, dim, stride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                                 box_x == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : box_x == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                                 CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    const CUresult r = encode_cached(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, (void *)base, dim, stride, box, estr,
+                                     box_x == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : box_x == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
     return r == CUDA_SUCCESS ? 0 : (int)cudaErrorInvalidValue;
 }
 
@@ -99,8 +135,7 @@ inline int describe_u32_swizzled128(CUtensorMap *map, const uint8_t *base, ptrdi
     cuuint64_t stride[2] = {(cuuint64_t)row_stride, (cuuint64_t)frame_stride};
     cuuint32_t box[3] = {32, (cuuint32_t)box_y, 1};
     cuuint32_t estr[3] = {1, 1, 1};
-    const CUresult r = encoder()(map, CU_TENSOR_MAP_DATA_TYPE_UINT32, 3, (void *)base, dim, stride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                                 CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    const CUresult r = encode_cached(map, CU_TENSOR_MAP_DATA_TYPE_UINT32, 3, (void *)base, dim, stride, box, estr, CU_TENSOR_MAP_SWIZZLE_128B);
     return r == CUDA_SUCCESS ? 0 : (int)cudaErrorInvalidValue;
 }
 
@@ -117,8 +152,7 @@ inline int describe_u8_chunks(CUtensorMap *map, const uint8_t *base, ptrdiff_t r
     cuuint64_t stride[3] = {(cuuint64_t)row_stride, 16, (cuuint64_t)frame_stride};
     cuuint32_t box[4] = {16, (cuuint32_t)box_rows, (cuuint32_t)box_chunks, 1};
     cuuint32_t estr[4] = {1, 1, 1, 1};
-    const CUresult r = encoder()(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 4, (void *)base, dim, stride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                                 CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    const CUresult r = encode_cached(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 4, (void *)base, dim, stride, box, estr, CU_TENSOR_MAP_SWIZZLE_NONE);
     return r == CUDA_SUCCESS ? 0 : (int)cudaErrorInvalidValue;
 }
 
