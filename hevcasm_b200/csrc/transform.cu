@@ -432,18 +432,14 @@ __device__ __forceinline__ void big_inv_core(uint32_t *tmp, int b, int uw, bool 
         asm volatile("prefetch.global.L1 [%0];" ::"l"(pp + (ptrdiff_t)(uw + HW) * sp));
     }
     if (valid) {  // stage 1: columns 2*uw and 2*uw+1
-        uint32_t p[HW];
+        uint32_t p0[HW], p1[HW];
         int o0[N], o1[N];
         static_for<0, HW>([&](auto kk) {
             constexpr int k = HV_V(kk);
-            p[k] = lolo(W[pair_row(N, k, 0)], W[pair_row(N, k, 1)]);
+            p0[k] = lolo(W[pair_row(N, k, 0)], W[pair_row(N, k, 1)]);
+            p1[k] = hihi(W[pair_row(N, k, 0)], W[pair_row(N, k, 1)]);
         });
-        InvBfly<N>::run(p, o0, 64);
-        static_for<0, HW>([&](auto kk) {
-            constexpr int k = HV_V(kk);
-            p[k] = hihi(W[pair_row(N, k, 0)], W[pair_row(N, k, 1)]);
-        });
-        InvBfly<N>::run(p, o1, 64);
+        InvBfly2<N>::run(p0, p1, o0, o1, 64);   // both columns against each coefficient pair
 #pragma unroll
         for (int r = 0; r < N; ++r) tmp[b * G::BLK_STRIDE + r * G::PITCH + uw] = pack_sat_s16(o0[r] >> 7, o1[r] >> 7);
     }
@@ -485,6 +481,9 @@ __device__ __forceinline__ void big_inv_core(uint32_t *tmp, int b, int uw, bool 
     }
 }
 
+// (A persistent variant with the coefficient blocks prefetched into shared memory by cp.async.bulk, two stages per warp, was measured in
+//  round 2: 165 vs 130 us (32x32) and 136 vs 118 us (16x16) - 128 registers and 16 warps per SM lose more than the prefetch gains; capping
+//  this kernel at 80 registers for 6 CTAs per SM changes nothing either (130.0 us, 20 bytes of spills): it is bound by its pipes.)
 template <int LOG2, bool PA>
 __global__ void __launch_bounds__(BIG_NT) big_inv_kernel(uint8_t *__restrict__ dst, ptrdiff_t sd, const uint8_t *__restrict__ pred, ptrdiff_t sp,
                                                          ptrdiff_t fs_dst, ptrdiff_t fs_pred, const int16_t *__restrict__ coeffs, BlockGrid g)

@@ -162,6 +162,35 @@ struct InvBfly<2> {
     }
 };
 
+// Two transforms at once with the SAME coefficients (the two coefficient columns a thread owns): every coefficient pair is fetched once
+// (LDCU + R2UR per IDP were 11 % of the 32x32 inverse's instructions, profiles/r02_transforms.md) and feeds two IDP.2A.
+template <int N>
+struct InvBfly2 {
+    __device__ static __forceinline__ void run(const uint32_t *p0, const uint32_t *p1, int *out0, int *out1, int round)
+    {
+        int E0[N / 2], E1[N / 2];
+        InvBfly2<N / 2>::run(p0 + N / 4, p1 + N / 4, E0, E1, round);
+        static_for<0, N / 2>([&](auto k) {
+            int a = 0, b = 0;
+            static_for<0, N / 4>([&](auto j) {
+                const int c = c_inv.v[inv_tab_offset(N) + HV_V(k) * (N / 4) + HV_V(j)];
+                a = dp2a_lo(p0[HV_V(j)], c, a);
+                b = dp2a_lo(p1[HV_V(j)], c, b);
+            });
+            out0[HV_V(k)] = E0[HV_V(k)] + a, out0[N - 1 - HV_V(k)] = E0[HV_V(k)] - a;
+            out1[HV_V(k)] = E1[HV_V(k)] + b, out1[N - 1 - HV_V(k)] = E1[HV_V(k)] - b;
+        });
+    }
+};
+template <>
+struct InvBfly2<2> {
+    __device__ static __forceinline__ void run(const uint32_t *p0, const uint32_t *p1, int *out0, int *out1, int round)
+    {
+        out0[0] = dp2a_lo(p0[0], c_inv.two[0], round), out0[1] = dp2a_lo(p0[0], c_inv.two[1], round);
+        out1[0] = dp2a_lo(p1[0], c_inv.two[0], round), out1[1] = dp2a_lo(p1[0], c_inv.two[1], round);
+    }
+};
+
 // inverse 4-point DST: out[x] = round + sum_k M[k][x] * in[k]; p = natural pairs (in0,in1), (in2,in3)
 __device__ __forceinline__ void inv_dst4(const uint32_t *p, int *out, int round)
 {
