@@ -175,4 +175,23 @@ __device__ __forceinline__ void stage_tile_u8(uint32_t *s, int s_pitch_words, co
     }
 }
 
+// The same staging with a readable byte range [lo, hi): an aligned word is loaded only if it contains at least one byte of the range
+// (such a word cannot fault), anything else is staged as zero - those bytes only ever meet positions no tap reads.  Used by the
+// interpolation kernels of the *_bounded entry points, which must stay inside the reference's own footprint.
+__device__ __forceinline__ void stage_tile_u8_bounded(uint32_t *s, int s_pitch_words, const uint8_t *g, ptrdiff_t g_pitch, int row_words, int rows, int tid,
+                                                      int nthreads, const uint8_t *lo, const uint8_t *hi)
+{
+    const int total = row_words * rows;
+    const uintptr_t l = (uintptr_t)lo, h = (uintptr_t)hi;
+    for (int i = tid; i < total; i += nthreads) {
+        const int r = i / row_words, j = i - r * row_words;
+        const uint8_t *p = g + (ptrdiff_t)r * g_pitch + 4 * j;
+        const int a = (int)((uintptr_t)p & 3);
+        const uintptr_t pa = (uintptr_t)(p - a);
+        uint32_t w0 = (pa + 4 > l && pa < h) ? __ldg((const uint32_t *)pa) : 0u;
+        if (a) w0 = shr_bytes(w0, (pa + 8 > l && pa + 4 < h) ? __ldg((const uint32_t *)(pa + 4)) : 0u, a);
+        s[r * s_pitch_words + j] = w0;
+    }
+}
+
 }  // namespace hv

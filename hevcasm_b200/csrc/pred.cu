@@ -162,6 +162,7 @@ struct PredParams {
     const int16_t *pus;          // list form: one CTA per descriptor
     int n_pu;
     int desc_frame;              // list form: 1 = every descriptor ends with a frame index (planes fs_dst / fs_ref apart), 0 = one plane
+    const uint8_t *lo[2], *hi[2];   // *_bounded plane forms: the readable bytes of each reference, [lo, hi) = its own footprint; null = unbounded
 };
 
 constexpr int NT = 128;
@@ -182,13 +183,15 @@ struct Geom {
 //   others  : results have been written to dst
 // Returns nothing; the caller runs the horizontal pass (it differs between uni and bi).
 template <int TAPS, int TW, int TH>
-__device__ __forceinline__ void stage_source(uint32_t *src_s, const uint8_t *ref, ptrdiff_t sr, int w, int h, bool need_h, bool need_v, int tid)
+__device__ __forceinline__ void stage_source(uint32_t *src_s, const uint8_t *ref, ptrdiff_t sr, int w, int h, bool need_h, bool need_v, int tid,
+                                             const uint8_t *lo = nullptr, const uint8_t *hi = nullptr)
 {
     using G = Geom<TAPS, TW, TH>;
     const int xoff = need_h ? 4 : 0, top = need_v ? G::LEFT : 0;
     const int bytes = w + xoff + (need_h ? G::RIGHT : 0);
     const int rows = h + (need_v ? TAPS - 1 : 0);
-    stage_tile_u8(src_s, G::SP, ref - (ptrdiff_t)top * sr - xoff, sr, (bytes + 3) >> 2, rows, tid, NT);
+    if (hi) stage_tile_u8_bounded(src_s, G::SP, ref - (ptrdiff_t)top * sr - xoff, sr, (bytes + 3) >> 2, rows, tid, NT, lo, hi);
+    else stage_tile_u8(src_s, G::SP, ref - (ptrdiff_t)top * sr - xoff, sr, (bytes + 3) >> 2, rows, tid, NT);
 }
 
 // vertical pass of a whole tile into `mid` (exact sums as int16); quads cover staged columns 0 .. ncols-1
@@ -244,7 +247,7 @@ __global__ void __launch_bounds__(NT) pred_kernel(PredParams p)
     if (!BI) {
         const int mode = FIXED_MODE != RUNTIME ? FIXED_MODE : ((xf[0] ? 1 : 0) | (yf[0] ? 2 : 0));
         const bool need_h = mode & 1, need_v = mode & 2;
-        stage_source<TAPS, TW, TH>(src_s, ref[0], p.sr, w, h, need_h, need_v, tid);
+        stage_source<TAPS, TW, TH>(src_s, ref[0], p.sr, w, h, need_h, need_v, tid, p.lo[0], p.hi[0]);
         __syncthreads();
         if (mode == COPY) {
             const int nw = (w + 3) >> 2;
@@ -305,7 +308,7 @@ __global__ void __launch_bounds__(NT) pred_kernel(PredParams p)
             cx.load(xf[r]);
             cy.load(yf[r]);
             if (r) __syncthreads();  // everyone is done reading the first reference's intermediate
-            stage_source<TAPS, TW, TH>(src_s, ref[r], p.sr, w, h, true, true, tid);
+            stage_source<TAPS, TW, TH>(src_s, ref[r], p.sr, w, h, true, true, tid, p.lo[r], p.hi[r]);
             __syncthreads();
             vertical_to_mid<TAPS, TW, TH>(mid, src_s, cy, w + 4 + G::RIGHT, h, tid);
             __syncthreads();
@@ -1232,7 +1235,8 @@ static bool tensor_path_wanted(int taps, long long n_tiles, bool bi = false)
     const char *pin = tune::knob("HEVCASM_PRED_HV");
     if (pin && !strcmp(pin, "umma")) return true;
     if (pin && !strcmp(pin, "stream")) return false;
-    return taps == 8 && n_tiles >= (bi ? 5ll : 1ll) * sm_count();
+    // two references: both filters (chroma 84.8 vs 105.3 us per 16 4K planes); one reference: 8-tap only (chroma 54.4 vs 52.9 us on the streaming kernel)
+    return (taps == 8 || bi) && n_tiles >= (bi ? 5ll : 1ll) * sm_count();
 }
 static unsigned tensor_grid(long long n_tiles)
 {
@@ -1356,7 +1360,13 @@ static int pred_uni_frames_impl(uint8_t *dst, ptrdiff_t sd, const uint8_t *ref, 
     p.xf0 = xFrac, p.yf0 = yFrac;
     const dim3 grid((width + PTW - 1) / PTW, (height + PTH - 1) / PTH, n_frames);
     const int mode = (xFrac ? 1 : 0) | (yFrac ? 2 : 0);
-    if (exact) return taps == 8 ? launch_uni_planes<8>(p, grid, mode, stream) : launch_uni_planes<4>(p, grid, mode, stream);
+    if (exact) {   // the reference's own footprint over the whole batch: rows -(taps/2-1) .. height+taps/2-1, columns likewise, of every frame
+        // (a pass that is not run reads no halo: reference pred_inter.c:141-228 picks copy / H / V / HV by the fractions)
+        const int bx = xFrac ? taps / 2 - 1 : 0, ax = xFrac ? taps / 2 : 0, by = yFrac ? taps / 2 - 1 : 0, ay = yFrac ? taps / 2 : 0;
+        p.lo[0] = ref - (ptrdiff_t)by * sr - bx;
+        p.hi[0] = ref + (ptrdiff_t)(n_frames - 1) * fs_ref + (ptrdiff_t)(height - 1 + ay) * sr + width + ax;
+        return taps == 8 ? launch_uni_planes<8>(p, grid, mode, stream) : launch_uni_planes<4>(p, grid, mode, stream);
+    }
     // every position: the TMA-fed streaming kernel when the planes can be described to the TMA unit (strides multiples
     // of 16, 4-byte aligned rows).  Otherwise: two-pass positions -> LDG streaming kernel; one-pass positions -> tile kernels on
     // 16-byte aligned planes (2.2-2.4 vs 2.0 Tsamples/s), LDG streaming kernel on 4-byte aligned ones; copies -> tile kernels.
@@ -1410,7 +1420,15 @@ static int pred_bi_frames_impl(uint8_t *dst, ptrdiff_t sd, const uint8_t *ref0, 
     p.dst = dst, p.ref0 = ref0, p.ref1 = ref1, p.sd = sd, p.sr = sr, p.fs_dst = fs_dst, p.fs_ref = fs_ref, p.width = width, p.height = height;
     p.xf0 = xFrac0, p.yf0 = yFrac0, p.xf1 = xFrac1, p.yf1 = yFrac1;
     const dim3 grid((width + PTW - 1) / PTW, (height + PTH - 1) / PTH, n_frames);
-    if (exact) return taps == 8 ? launch_pred<8, PTW, PTH, true, RUNTIME>(p, grid, stream) : launch_pred<4, PTW, PTH, true, RUNTIME>(p, grid, stream);
+    if (exact) {
+        const int b = taps / 2 - 1, a = taps / 2;
+        const uint8_t *refs[2] = {ref0, ref1};
+        for (int r = 0; r < 2; ++r) {
+            p.lo[r] = refs[r] - (ptrdiff_t)b * sr - b;
+            p.hi[r] = refs[r] + (ptrdiff_t)(n_frames - 1) * fs_ref + (ptrdiff_t)(height - 1 + a) * sr + width + a;
+        }
+        return taps == 8 ? launch_pred<8, PTW, PTH, true, RUNTIME>(p, grid, stream) : launch_pred<4, PTW, PTH, true, RUNTIME>(p, grid, stream);
+    }
     if (xFrac0 || yFrac0 || xFrac1 || yFrac1) {
 #ifdef HEVCASM_EXPERIMENTS
         const char *bk = tune::knob("HEVCASM_PRED_BI");   // A/B: "hfirst" = horizontal pass on the tensor cores (um), default = vertical pass (uv)

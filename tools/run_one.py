@@ -31,6 +31,8 @@ calls = {
     "pred_chroma_hv": lambda: lib.call("pred_uni_frames", d(o8, org), pitch, d(a, org), pitch, W, H, 4, 3, 5, NF, fs, fs),
     "pred_bi_avg": lambda: lib.call("pred_bi_frames", d(o8, org), pitch, d(a, org), d(b, org), pitch, W, H, 8, 0, 0, 0, 0, NF, fs, fs),
     "pred_bi": lambda: lib.call("pred_bi_frames", d(o8, org), pitch, d(a, org), d(b, org), pitch, W, H, 8, 1, 2, 3, 1, NF, fs, fs),
+    "pred_bi_chroma": lambda: lib.call("pred_bi_frames", d(o8, org), pitch, d(a, org), d(b, org), pitch, W, H, 4, 3, 5, 6, 1, NF, fs, fs),
+    "pipe8p": lambda: lib.call("residual_from_planes_pipeline_frames", d(o8, org), pitch, d(co2), d(cbf), d(b, org), pitch, d(a, org), pitch, W, H, 3, 0, 26214, 18, 171 << 7, 18432, 6, NF, fs, fs, fs),
     "fwd8": lambda: lib.call("transform_frames", d(co2), d(res), rp, W, H, 3, 0, NF, H * rp),
     "fwd4": lambda: lib.call("transform_frames", d(co2), d(res), rp, W, H, 2, 0, NF, H * rp),
     "fwd16": lambda: lib.call("transform_frames", d(co2), d(res), rp, W, H, 4, 0, NF, H * rp),
