@@ -33,7 +33,7 @@ constexpr int CONSUMERS = 512, THREADS = CONSUMERS + 64;   // four consumer warp
 
 // the two constant operands in their shared-memory layout [size (16, 32)][lo / hi][chunk (16)][m (128)][16], built on the host once
 __device__ uint4 g_ft_A[2][2 * A_BYTES / 16];
-inline int ft_tables_init()
+static int ft_tables_init()   // internal linkage: the statics of an INLINE function are process-unique (STB_GNU_UNIQUE) and would be shared with the experiments library, whose copy of the table would then never be filled
 {
     // one copy per device of this process (the symbol lives in each device's module image)
     static std::mutex mu;

@@ -29,7 +29,7 @@ namespace tr {
 __constant__ int8_t c_T32[32][32];   // filled by imma_tables_init(): T_32[k][x]
 __constant__ int8_t c_T16[16][16];
 
-inline int imma_tables_init()
+static int imma_tables_init()
 {
     static int done = [] {
         int8_t t32[32][32], t16[16][16];

@@ -30,7 +30,7 @@ constexpr int CONSUMERS = 512, THREADS = CONSUMERS + 64;   // + the MMA warp and
 
 // the constant operands in their shared-memory layout [size (16, 32)][lo / hi][chunk (16)][n (128)][16], built on the host once
 __device__ uint4 g_fi_B[2][2 * C_BYTES / 16];
-inline int fi_tables_init()
+static int fi_tables_init()
 {
     // one copy per device of this process (the symbol lives in each device's module image)
     static std::mutex mu;

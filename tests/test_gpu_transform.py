@@ -51,7 +51,9 @@ def test_forward_tensor_core(oracle, log2, rng, grid, monkeypatch, experiments):
         dres = to_dev(res.buf)
         got = dev_full(want.shape, np.int16, 0x5a5a)
         lib.call("transform_frames", dptr(got), dptr(dres, res.origin), res.pitch, width, height, log2, 0, nf, res.frame_stride)
-        assert np.array_equal(to_host(got), want), (width, height, nf)
+        g = to_host(got)
+        bad = np.flatnonzero(g != want)
+        assert bad.size == 0, (width, height, nf, int(bad.size), [int(b) // (n * n) for b in bad[:8]], [int(b) % (n * n) for b in bad[:8]], g[bad[:4]], want[bad[:4]])
 
 
 @pytest.mark.parametrize("trType,log2", TR)
