@@ -987,31 +987,47 @@ int launch_uni_stream_tma(const FastParams &fp, const StreamMaps &sm, int mode, 
 // 8x8 PUs).  Every PU runs the two-pass arithmetic; a zero fraction is the {64} filter, for which the two-pass rounding
 // (sum + 2048) >> 12 reduces exactly to the one-pass (sum + 32) >> 6 and to a copy, so one code path serves all positions
 // without divergence.  Reference rows may have any alignment (a funnel shift per loaded word re-aligns them).
+// descriptors per CTA: 64 PUs of 8x8 are 128 four-column items - one per thread.  (With 32, half of the threads of a CTA had nothing to
+// do on 8x8 lists and three of the four CTAs of a group found no item at all: 438 us per 16 4K frames of 8x8 PUs.)
+constexpr int LIST_G = 64;
+// blockIdx.y slices a group's item list; enough slices that a short list of large PUs (32 groups for a 4K frame of 64x64 PUs, 1024 items each)
+// still spreads over the chip, one slice when there are groups enough (empty slices of small-PU groups only cost launches)
+static unsigned list_slices(int n_pu)
+{
+    const int groups = (n_pu + LIST_G - 1) / LIST_G, want = 4 * sm_count();
+    return (unsigned)std::max(1, std::min(8, (want + groups - 1) / groups));
+}
 template <int TAPS, bool BI>
 __global__ void __launch_bounds__(NT) pred_list_stream_kernel(PredParams p)
 {
-    constexpr int G = 32, NREF = BI ? 2 : 1, DW0 = BI ? 8 : 6, LEFT = TAPS / 2 - 1, FB = TAPS == 8 ? 2 : 3, FM = (1 << FB) - 1;
+    constexpr int G = LIST_G, NREF = BI ? 2 : 1, DW0 = BI ? 8 : 6, LEFT = TAPS / 2 - 1, FB = TAPS == 8 ? 2 : 3, FM = (1 << FB) - 1;
     const int DW = DW0 + p.desc_frame;   // a trailing frame index makes one launch cover the PU lists of a whole batch of frames
     __shared__ int s_prefix[G + 1];
     __shared__ short s_desc[G][10];
     const int tid = threadIdx.x, lane = tid & 31, first = blockIdx.x * G;
     if (tid < 32) {
-        int nq = 0;
-        if (first + lane < p.n_pu) {
-            const int16_t *dsc = p.pus + (size_t)(first + lane) * DW;
+        // lane l owns descriptors 2l and 2l+1: inclusive scan over the lanes' pair sums
+        int nq[2] = {0, 0};
 #pragma unroll
-            for (int j = 0; j < DW0; ++j) s_desc[lane][j] = dsc[j];
-            s_desc[lane][DW0] = p.desc_frame ? dsc[DW0] : (short)0;
-            const int w = dsc[2], h = dsc[3];
-            if (w > 0 && h > 0 && w <= 64 && h <= 64) nq = (w + 3) >> 2;
+        for (int k = 0; k < 2; ++k) {
+            const int i = 2 * lane + k;
+            if (first + i < p.n_pu) {
+                const int16_t *dsc = p.pus + (size_t)(first + i) * DW;
+#pragma unroll
+                for (int j = 0; j < DW0; ++j) s_desc[i][j] = dsc[j];
+                s_desc[i][DW0] = p.desc_frame ? dsc[DW0] : (short)0;
+                const int w = dsc[2], h = dsc[3];
+                if (w > 0 && h > 0 && w <= 64 && h <= 64) nq[k] = (w + 3) >> 2;
+            }
         }
-        int incl = nq;
+        int incl = nq[0] + nq[1];
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
             const int v = __shfl_up_sync(0xffffffffu, incl, o);
             if (lane >= o) incl += v;
         }
-        s_prefix[lane + 1] = incl;
+        s_prefix[2 * lane + 1] = incl - nq[1];
+        s_prefix[2 * lane + 2] = incl;
         if (lane == 0) s_prefix[0] = 0;
     }
     __syncthreads();
@@ -1488,7 +1504,7 @@ extern "C" int hevcasm_pred_uni_batch(uint8_t *dst, ptrdiff_t sd, const uint8_t 
     PredParams p{};
     p.dst = dst, p.ref0 = ref, p.sd = sd, p.sr = sr, p.pus = pus, p.n_pu = n_pu;
     if (list_stream_ok()) {
-        const dim3 grid((n_pu + 31) / 32, 4);
+        const dim3 grid((n_pu + LIST_G - 1) / LIST_G, list_slices(n_pu));
         return taps == 8 ? launch(pred_list_stream_kernel<8, false>, grid, dim3(NT), 0, stream, p) : launch(pred_list_stream_kernel<4, false>, grid, dim3(NT), 0, stream, p);
     }
     return taps == 8 ? launch_pred<8, LTW, LTH, false, RUNTIME>(p, dim3(n_pu), stream) : launch_pred<4, LTW, LTH, false, RUNTIME>(p, dim3(n_pu), stream);
@@ -1502,7 +1518,7 @@ extern "C" int hevcasm_pred_bi_batch(uint8_t *dst, ptrdiff_t sd, const uint8_t *
     PredParams p{};
     p.dst = dst, p.ref0 = ref0, p.ref1 = ref1, p.sd = sd, p.sr = sr, p.pus = pus, p.n_pu = n_pu;
     if (list_stream_ok()) {
-        const dim3 grid((n_pu + 31) / 32, 4);
+        const dim3 grid((n_pu + LIST_G - 1) / LIST_G, list_slices(n_pu));
         return taps == 8 ? launch(pred_list_stream_kernel<8, true>, grid, dim3(NT), 0, stream, p) : launch(pred_list_stream_kernel<4, true>, grid, dim3(NT), 0, stream, p);
     }
     return taps == 8 ? launch_pred<8, LTW, LTH, true, RUNTIME>(p, dim3(n_pu), stream) : launch_pred<4, LTW, LTH, true, RUNTIME>(p, dim3(n_pu), stream);
@@ -1516,7 +1532,7 @@ extern "C" int hevcasm_pred_uni_list_frames(uint8_t *dst, ptrdiff_t sd, const ui
     if (n_pu == 0) return 0;
     PredParams p{};
     p.dst = dst, p.ref0 = ref, p.sd = sd, p.sr = sr, p.fs_dst = fs_dst, p.fs_ref = fs_ref, p.pus = pus, p.n_pu = n_pu, p.desc_frame = 1;
-    const dim3 grid((n_pu + 31) / 32, 4);
+    const dim3 grid((n_pu + LIST_G - 1) / LIST_G, list_slices(n_pu));
     return taps == 8 ? launch(pred_list_stream_kernel<8, false>, grid, dim3(NT), 0, stream, p) : launch(pred_list_stream_kernel<4, false>, grid, dim3(NT), 0, stream, p);
 }
 
@@ -1527,6 +1543,6 @@ extern "C" int hevcasm_pred_bi_list_frames(uint8_t *dst, ptrdiff_t sd, const uin
     if (n_pu == 0) return 0;
     PredParams p{};
     p.dst = dst, p.ref0 = ref0, p.ref1 = ref1, p.sd = sd, p.sr = sr, p.fs_dst = fs_dst, p.fs_ref = fs_ref, p.pus = pus, p.n_pu = n_pu, p.desc_frame = 1;
-    const dim3 grid((n_pu + 31) / 32, 4);
+    const dim3 grid((n_pu + LIST_G - 1) / LIST_G, list_slices(n_pu));
     return taps == 8 ? launch(pred_list_stream_kernel<8, true>, grid, dim3(NT), 0, stream, p) : launch(pred_list_stream_kernel<4, true>, grid, dim3(NT), 0, stream, p);
 }

@@ -726,21 +726,31 @@ __global__ void __launch_bounds__(IMMA_NT) imma_inv_kernel(uint8_t *__restrict__
 // hevcasm_quantize (quantize.c:160-186), hevcasm_quantize_inverse (quantize.c:53-62) and hevcasm_inverse_transform_add.
 
 struct QuantParams {
-    int q_scale, q_shift, q_off /* offset << (shift-16) */, iq_scale, iq_shift;
+    int q_scale, q_shift, q_off /* offset << (shift-16) */, q_offn /* 2^shift - 1 - q_off */, iq_scale, iq_shift;
 };
+inline QuantParams make_quant_params(int q_scale, int q_shift, int q_offset, int iq_scale, int iq_shift)
+{
+    const int off = q_offset << (q_shift - 16);
+    return QuantParams{q_scale, q_shift, off, (1 << q_shift) - 1 - off, iq_scale, iq_shift};
+}
 
-// quantise then dequantise one word (two coefficients); the level word goes to `lv`, the OR of the levels into cbf
-__device__ __forceinline__ uint32_t quant_dequant_word(uint32_t w, const QuantParams &q, uint32_t &lv, int &cbf)
+// Quantise then dequantise one word (two coefficients); the level word goes to `lv`, the OR of the level WORDS into cbf2 (cbf_fold turns
+// it into the reference's return value).  Same integers as quantize.c:160-186 / :53-62 with fewer instructions:
+//   * sign(x) * ((|x| * s + off) >> sh)  =  (x * s + (x < 0 ? 2^sh - 1 - off : off)) >> sh      (-floor(a / b) = floor((-a + b - 1) / b)),
+//     which replaces abs, compare and negate by one select;
+//   * in the quantiser's domain (|x| <= 2^15, s < 2^15, sh >= 16, off < 2^(sh-1), checked by the entry point) |level| <= 2^14, so the
+//     reference's clip to int16 cannot bind and the levels feed the dequantiser without being re-extracted from the packed word;
+//   * the OR of sign-extended levels is the sign extension of the OR of their 16-bit patterns, so one LOP3 per word does for cbf.
+__device__ __forceinline__ uint32_t quant_dequant_word(uint32_t w, const QuantParams &q, uint32_t &lv, uint32_t &cbf2)
 {
     const int x0 = s16lo(w), x1 = s16hi(w);
-    int l0 = (abs(x0) * q.q_scale + q.q_off) >> q.q_shift, l1 = (abs(x1) * q.q_scale + q.q_off) >> q.q_shift;
-    l0 = x0 < 0 ? -l0 : l0, l1 = x1 < 0 ? -l1 : l1;
-    lv = pack_sat_s16(l0, l1);
-    const int c0 = s16lo(lv), c1 = s16hi(lv);
-    cbf |= c0 | c1;
+    const int l0 = (x0 * q.q_scale + (x0 < 0 ? q.q_offn : q.q_off)) >> q.q_shift, l1 = (x1 * q.q_scale + (x1 < 0 ? q.q_offn : q.q_off)) >> q.q_shift;
+    lv = pack16(l0, l1);
+    cbf2 |= lv;
     const int add = 1 << (q.iq_shift - 1);
-    return pack_sat_s16((c0 * q.iq_scale + add) >> q.iq_shift, (c1 * q.iq_scale + add) >> q.iq_shift);
+    return pack_sat_s16((l0 * q.iq_scale + add) >> q.iq_shift, (l1 * q.iq_scale + add) >> q.iq_shift);
 }
+__device__ __forceinline__ int cbf_fold(uint32_t cbf2) { return (int)(short)((cbf2 & 0xffffu) | (cbf2 >> 16)); }
 
 struct PipelineParams {
     uint8_t *rec;
@@ -766,7 +776,7 @@ __global__ void __launch_bounds__(SMALL_NT) small_pipeline_kernel(PipelineParams
     const bool valid = i < g.n;
     int x = 0, y = 0, f = 0;
     uint32_t Yw[N][HW], L[N][HW], pw[N][N / 4];
-    int cbf = 0;
+    uint32_t cbf = 0;
     if (valid) {
         g.locate(i, LOG2, x, y, f);
         load_pred<N, PA>(p.pred + f * p.fs_pred + (ptrdiff_t)y * p.s_pred + x, p.s_pred, pw);
@@ -776,7 +786,7 @@ __global__ void __launch_bounds__(SMALL_NT) small_pipeline_kernel(PipelineParams
         for (int v = 0; v < N; ++v)
 #pragma unroll
             for (int k = 0; k < HW; ++k) Yw[v][k] = quant_dequant_word(Yw[v][k], p.q, L[v][k], cbf);
-        if (p.cbf) p.cbf[i] = cbf;
+        if (p.cbf) p.cbf[i] = cbf_fold(cbf);
     }
     Io::store(p.levels, first, g.n, lane, io[warp], L);
     if (valid) small_inv_core<LOG2, DST, PA>(Yw, p.rec + f * p.fs_rec + (ptrdiff_t)y * p.s_rec + x, p.s_rec, pw);
@@ -796,7 +806,7 @@ __global__ void __launch_bounds__(BIG_NT) big_pipeline_kernel(PipelineParams p, 
     if (valid) g.locate(gb, LOG2, x, y, f);
     uint32_t W[N];
     big_fwd_core<LOG2, PA>(tmp_all[warp], b, uw, valid, p.res + f * p.fs_res + (ptrdiff_t)y * p.s_res + x, p.s_res, W);
-    int cbf = 0;
+    uint32_t cbf = 0;
     if (valid) {
         uint32_t *lv = reinterpret_cast<uint32_t *>(p.levels + gb * (N * N)) + uw;
 #pragma unroll
@@ -809,7 +819,7 @@ __global__ void __launch_bounds__(BIG_NT) big_pipeline_kernel(PipelineParams p, 
     // OR across the HW lanes that share the block (HW = 8 or 16: groups are aligned, xor stays inside the group)
 #pragma unroll
     for (int o = 1; o < HW; o <<= 1) cbf |= __shfl_xor_sync(0xffffffffu, cbf, o);
-    if (valid && uw == 0 && p.cbf) p.cbf[gb] = cbf;
+    if (valid && uw == 0 && p.cbf) p.cbf[gb] = cbf_fold(cbf);
     big_inv_core<LOG2, PA>(tmp_all[warp], b, uw, valid, W, p.rec + f * p.fs_rec + (ptrdiff_t)y * p.s_rec + x, p.s_rec,
                        p.pred + f * p.fs_pred + (ptrdiff_t)y * p.s_pred + x, p.s_pred);
 }
@@ -1026,7 +1036,7 @@ extern "C" int hevcasm_residual_pipeline_frames(uint8_t *rec, ptrdiff_t s_rec, i
     PipelineParams p{};
     p.rec = rec, p.pred = pred, p.res = residual, p.levels = levels, p.cbf = cbf;
     p.s_rec = s_rec, p.s_pred = s_pred, p.s_res = s_res, p.fs_rec = fs_rec, p.fs_pred = fs_pred, p.fs_res = fs_res;
-    p.q = QuantParams{q_scale, q_shift, q_offset << (q_shift - 16), iq_scale, iq_shift};
+    p.q = make_quant_params(q_scale, q_shift, q_offset, iq_scale, iq_shift);
     const bool pa = aligned16(rec, s_rec, fs_rec, pred, s_pred, fs_pred) && aligned16(residual, s_res * 2, fs_res * 2);
     return pa ? launch_pipeline_t<true>(p, g, log2size, trType, stream) : launch_pipeline_t<false>(p, g, log2size, trType, stream);
 }
@@ -1068,7 +1078,7 @@ extern "C" int hevcasm_residual_from_planes_pipeline_frames(uint8_t *rec, ptrdif
     PipelineParams p{};
     p.rec = rec, p.pred = pred, p.src = src, p.res = nullptr, p.levels = levels, p.cbf = cbf;
     p.s_rec = s_rec, p.s_pred = s_pred, p.s_src = s_src, p.s_res = 0, p.fs_rec = fs_rec, p.fs_pred = fs_pred, p.fs_src = fs_src, p.fs_res = 0;
-    p.q = QuantParams{q_scale, q_shift, q_offset << (q_shift - 16), iq_scale, iq_shift};
+    p.q = make_quant_params(q_scale, q_shift, q_offset, iq_scale, iq_shift);
     const bool pa = aligned16(rec, s_rec, fs_rec, pred, s_pred, fs_pred) && aligned16(src, s_src, fs_src);
     const unsigned grid = (unsigned)((g.n + SMALL_NT - 1) / SMALL_NT);
 #define HV_PP(L_, D_)                                                                                       \

@@ -13,7 +13,7 @@ import subprocess
 import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-OUT = os.path.join(ROOT, "profiles", "r02_kernel_counters.json")
+OUT = os.environ.get("NCU_COUNTERS_OUT", os.path.join(ROOT, "profiles", "r02_kernel_counters.json"))
 
 
 def distil(rep, samples, frames):
@@ -39,7 +39,7 @@ def distil(rep, samples, frames):
         ops[op] += int(r[ti])
     total = sum(ops.values())
     dram = val("dram__bytes_read.sum") + val("dram__bytes_write.sum")
-    out = {"kernel": d["Kernel Name"][:80], "source": os.path.relpath(rep, ROOT), "duration_us_under_ncu": round(val("gpu__time_duration.sum"), 2),
+    out = {"kernel": d["Kernel Name"][:80], "source": os.environ.get("NCU_COUNTERS_SOURCE", os.path.relpath(rep, ROOT)), "duration_us_under_ncu": round(val("gpu__time_duration.sum"), 2),
            "dram_bytes_per_launch": dram, "dram_bytes_per_sample": round(dram / samples, 4), "thread_instructions_per_sample": round(total / samples, 2),
            "idp_per_sample": round(ops["IDP"] / samples, 3), "registers": int(float(d["launch__registers_per_thread"])),
            "top_ops_per_sample": {k: round(v / samples, 3) for k, v in ops.most_common(8)}}
