@@ -34,6 +34,7 @@ sys.path.insert(0, ROOT)
 import numpy as np  # noqa: E402
 
 W4K, H4K, W8K, H8K, PAD = 3840, 2160, 7680, 4320, 64
+PAD_TRAVEL = 16   # samples of padding the host forms copy with each plane: the window [-4, 3] needs 4, the interpolation kernels 16
 SAD_OUT_BYTES = 4.0 * 64 * (1 / 64 + 1 / 256 + 1 / 1024 + 1 / 4096)            # int32 outputs of the 4 levels, per sample
 SAD_OUT_BYTES_PACKED = 64 * (2 / 64 + 2 / 256 + 4 / 1024 + 4 / 4096)           # uint16 for 8x8 / 16x16, int32 for 32x32 / 64x64
 SAD_BYTES_PER_SAMPLE = 2.0 + SAD_OUT_BYTES                                      # + src + ref
@@ -527,13 +528,13 @@ def run_gpu_4k(args):
         ref_p = lib.pinned_array(ref_h.buf.shape, np.uint8, device=local)
         src_p[...] = src_h.buf
         ref_p[...] = ref_h.buf
-        h2d = 2 * NF * (H4K + 2 * PAD) * (W4K + 2 * PAD)
+        h2d = 2 * NF * (H4K + 2 * PAD_TRAVEL) * (W4K + 2 * PAD_TRAVEL)
         e2e_steps = max(3, min(args.steps, 10))
 
         def run_host(api, outs, arena):
             with lib.Context(local, arena_bytes=arena) as ctx:
                 def one():
-                    lib.call_host(api, ctx.handle, hptr(src_p, org), pitch, hptr(ref_p, org), pitch, W4K, H4K, PAD, -4, -4, NF, fs, fs, *[hptr(o) for o in outs])
+                    lib.call_host(api, ctx.handle, hptr(src_p, org), pitch, hptr(ref_p, org), pitch, W4K, H4K, PAD_TRAVEL, -4, -4, NF, fs, fs, *[hptr(o) for o in outs])
                 one()
                 barrier()
                 t0 = time.perf_counter()
@@ -550,7 +551,7 @@ def run_gpu_4k(args):
         same = all(bool(np.array_equal(p.astype(np.int32), d)) for p, d in zip(pk_p, dev))
         e2e = {"value": samples_per_step * e2e_steps / dt / 1e9, "unit": "Gsamples/s", "h2d_bytes_per_step": h2d * world,
                "d2h_bytes_per_step": sum(o.nbytes for o in pk_p) * world, "steps": e2e_steps, "api": "hevcasm_sad_sweep_pyramid_packed_frames_host",
-               "matches_device_path": same, "compared": "every SAD of every PU of every frame", "host_buffers": "page-locked, bound to the GPU's NUMA node (hevcasm_cuda_host_alloc_near)"}
+               "matches_device_path": same, "compared": "every SAD of every PU of every frame", "host_buffers": "page-locked, bound to the GPU's NUMA node (hevcasm_cuda_host_alloc_near)", "numa_node_rank0": int(lib.load().hevcasm_cuda_device_numa_node(local))}
         del pk_p
         outs_p = [lib.pinned_array((e,), np.int32, device=local) for e in out_elems]
         dt = run_host("sad_sweep_pyramid_frames_host", outs_p, 3 << 30)
@@ -667,13 +668,14 @@ def run_gpu_8k(args):
             hlv = lib.pinned_array((ne * W8K * H8K,), np.int16, device=local)
             hcbf = lib.pinned_array((ne * (W8K // 8) * (H8K // 8),), np.int32, device=local)
             P0 = hp[0]
-            h2d = hsrc.nbytes + 2 * href.nbytes + hres.nbytes + hpred.nbytes
+            padded = ne * (H8K + 2 * PAD_TRAVEL) * (W8K + 2 * PAD_TRAVEL)
+            h2d = 3 * padded + ne * W8K * H8K * 3   # src + ref (SAD), ref (interpolation), residual (int16) + predictor
             d2h = sum(o.nbytes for o in hsad) + 2 * ne * W8K * H8K + hlv.nbytes + hcbf.nbytes
             with lib.Context(local, arena_bytes=3 << 30) as ctx:
                 def one():
-                    lib.call_host("sad_sweep_pyramid_packed_frames_host", ctx.handle, hptr(hsrc, P0.origin), P0.pitch, hptr(href, P0.origin), P0.pitch, W8K, H8K, PAD, -4, -4,
+                    lib.call_host("sad_sweep_pyramid_packed_frames_host", ctx.handle, hptr(hsrc, P0.origin), P0.pitch, hptr(href, P0.origin), P0.pitch, W8K, H8K, PAD_TRAVEL, -4, -4,
                                   ne, P0.frame_stride, P0.frame_stride, *[hptr(o) for o in hsad])
-                    lib.call_host("pred_uni_frames_host", ctx.handle, hptr(hipl, P0.origin), P0.pitch, hptr(href, P0.origin), P0.pitch, W8K, H8K, PAD, 8, 1, 3, ne,
+                    lib.call_host("pred_uni_frames_host", ctx.handle, hptr(hipl, P0.origin), P0.pitch, hptr(href, P0.origin), P0.pitch, W8K, H8K, PAD_TRAVEL, 8, 1, 3, ne,
                                   P0.frame_stride, P0.frame_stride)
                     lib.call_host("residual_pipeline_frames_host", ctx.handle, hptr(hrec, P0.origin), P0.pitch, hptr(hlv), hptr(hcbf), hptr(hres, hp[2].origin), hp[2].pitch,
                                   hptr(hpred, P0.origin), P0.pitch, W8K, H8K, 3, 0, *QP, ne, P0.frame_stride, hp[2].frame_stride, P0.frame_stride)

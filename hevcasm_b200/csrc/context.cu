@@ -212,6 +212,9 @@ extern "C" void *hevcasm_cuda_host_alloc(size_t bytes)
     return cudaHostAlloc(&p, bytes, cudaHostAllocDefault) == cudaSuccess ? p : nullptr;
 }
 
+// the NUMA node hevcasm_cuda_host_alloc_near binds to for `device`, or -1 (unknown: plain page-locked memory is used)
+extern "C" int hevcasm_cuda_device_numa_node(int device) { return gpu_numa_node(device); }
+
 extern "C" void *hevcasm_cuda_host_alloc_near(size_t bytes, int device)
 {
     const int node = gpu_numa_node(device);

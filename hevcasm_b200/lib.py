@@ -60,6 +60,8 @@ def _bind(path):
     lib.hevcasm_cuda_host_alloc.restype = P
     lib.hevcasm_cuda_host_alloc_near.argtypes = [C.c_size_t, C.c_int]
     lib.hevcasm_cuda_host_alloc_near.restype = P
+    lib.hevcasm_cuda_device_numa_node.argtypes = [C.c_int]
+    lib.hevcasm_cuda_device_numa_node.restype = C.c_int
     lib.hevcasm_cuda_host_free.argtypes = [P]
     lib.hevcasm_cuda_host_free.restype = None
     lib.hevcasm_cuda_error_string.argtypes = [C.c_int]

@@ -232,6 +232,7 @@ void HEVCASM_API *hevcasm_cuda_context_stream(hevcasm_cuda_context *ctx);
  * of `device` (falls back to the plain form when the platform does not say which node that is); both are released by hevcasm_cuda_host_free */
 void HEVCASM_API *hevcasm_cuda_host_alloc(size_t bytes);
 void HEVCASM_API *hevcasm_cuda_host_alloc_near(size_t bytes, int device);
+int HEVCASM_API hevcasm_cuda_device_numa_node(int device);   /* the node the _near form binds to, -1 if the platform does not say */
 void HEVCASM_API hevcasm_cuda_host_free(void *p);
 
 /* plane-level host forms: each frame is a tightly described plane {pointer to sample (0,0), stride}; `pad` = the number
