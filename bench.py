@@ -55,6 +55,8 @@ def parse():
     ap.add_argument("--no-kernels", action="store_true", help="skip the per-kernel table")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline legs")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--kernel-launches", type=int, default=200, help="launches per entry of the kernel table (groups of 10; >= 100 for reported numbers, "
+                    "small for an ncu launch list)")
     return ap.parse_args()
 
 
@@ -240,6 +242,13 @@ def time_kernel(torch, fn, groups=20, per_group=10, warm=3):
     """groups x per_group launches on the current stream, one CUDA-event bracket per group: median / best / mean ms per launch"""
     for _ in range(warm):
         fn()
+    # the entry before this one may have left the GPU idle for a second (its CPU baseline): keep launching until ~30 ms of GPU work have
+    # run, so that the timed groups start from ramped clocks and a warm instruction cache
+    t0 = time.perf_counter()
+    while time.perf_counter() - t0 < 0.03:
+        for _ in range(per_group):
+            fn()
+        torch.cuda.synchronize()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(groups)]
     torch.cuda.synchronize()
     for e0, e1 in ev:
@@ -270,7 +279,7 @@ def pu_list(synth, torch, width, height, sizes, nf, bi=False, seed=5):
     return torch.from_numpy(np.stack(cols, -1).astype(np.int16)).cuda(), int((a[:, 2] * a[:, 3]).sum())
 
 
-def kernel_table(torch, lib, synth, stream, hbm_peak, counters, with_cpu):
+def kernel_table(torch, lib, synth, stream, hbm_peak, counters, with_cpu, launches=200):
     """Every other kernel of the path on a 16-frame 4K batch (working set >> L2): CUDA events, 200 launches each (median and best of 20 groups
     of 10), and beside it the reference's C path for the same call on 1-2 frames on all host cores."""
     from oracle.binding import ptr
@@ -306,7 +315,7 @@ def kernel_table(torch, lib, synth, stream, hbm_peak, counters, with_cpu):
 
     def rec(name, fn, samples, bytes_per_sample, bound="hbm", extra=None, cpu_call=None, cpu_samples=None):
         try:
-            t = time_kernel(torch, fn)
+            t = time_kernel(torch, fn, groups=max(1, launches // 10), per_group=min(10, max(1, launches)))
         except Exception as e:  # entry point refused the shape
             out[name] = {"error": str(e)[:100]}
             return
@@ -484,6 +493,11 @@ def timed_steps(torch, lib, step, args, barrier, local, max_over_ranks):
     """W warm-up steps, then exactly K steps between barrier + synchronize, CUDA events on the launching stream; clocks sampled meanwhile"""
     for _ in range(max(args.warmup, 3)):
         step()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    while time.perf_counter() - t0 < 0.05:   # more untimed steps until ~50 ms have passed: clocks ramped before the timed region
+        step()
+        torch.cuda.synchronize()
     barrier()
     launches0 = lib.launch_count()
     with ClockSampler(local) as clocks:
@@ -596,7 +610,7 @@ def run_gpu_4k(args):
         if world == 1 and not args.no_kernels:
             del src_d, ref_d, outs_d
             torch.cuda.empty_cache()
-            line["kernels"] = kernel_table(torch, lib, synth, stream, hbm_peak, counters, with_cpu=not args.no_cpu)
+            line["kernels"] = kernel_table(torch, lib, synth, stream, hbm_peak, counters, with_cpu=not args.no_cpu, launches=args.kernel_launches)
         emit(line)
     if dist is not None:
         dist.barrier()
