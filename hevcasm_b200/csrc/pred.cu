@@ -981,59 +981,112 @@ int launch_uni_stream_tma(const FastParams &fp, const StreamMaps &sm, int mode, 
 
 // ------------------------------------------------------------------------------------------------ PU lists, streaming
 //
-// Prediction-unit lists (per-PU size and quarter / eighth-sample motion vector) with the streaming formulation: a CTA takes
-// 32 descriptors, a warp scan turns their widths into a prefix of 4-column work items, and every thread picks items off that
-// list - so 8x8 PUs fill the CTA as well as 64x64 ones do (the tile kernel spent a 128-thread CTA per PU: 58 Gsamples/s on
-// 8x8 PUs).  Every PU runs the two-pass arithmetic; a zero fraction is the {64} filter, for which the two-pass rounding
-// (sum + 2048) >> 12 reduces exactly to the one-pass (sum + 32) >> 6 and to a copy, so one code path serves all positions
-// without divergence.  Reference rows may have any alignment (a funnel shift per loaded word re-aligns them).
-// descriptors per CTA: 64 PUs of 8x8 are 128 four-column items - one per thread.  (With 32, half of the threads of a CTA had nothing to
-// do on 8x8 lists and three of the four CTAs of a group found no item at all: 438 us per 16 4K frames of 8x8 PUs.)
-constexpr int LIST_G = 64;
-// blockIdx.y slices a group's item list; enough slices that a short list of large PUs (32 groups for a 4K frame of 64x64 PUs, 1024 items each)
+// Prediction-unit lists (per-PU size and quarter / eighth-sample motion vector).  A CTA takes LIST_G descriptors, a warp scan turns
+// their widths into a prefix of work items - one item = a strip of LIST_COLS columns over the whole height of a PU - and every thread
+// picks items off that list, so 8x8 PUs fill the CTA as well as 64x64 ones do (a tile kernel that spent a 128-thread CTA per PU ran 8x8
+// lists at 58 Gsamples/s).  A thread streams its strip top to bottom straight from global memory: per input row it loads the strip's
+// footprint (aligned words + one funnel shift by the row's alignment), runs the HORIZONTAL filter on the bytes (IDP.4A), packs the exact
+// int16 result with the previous row's into a vertical pair and keeps the last TAPS pairs in a register ring; every output row is four
+// (two) IDP.2A per column over that ring.  The first TAPS-1 rows only prime the ring (no vertical work, no tests); after that one input
+// row gives one output row.  Every PU runs the two-pass arithmetic; a zero fraction is the {64} filter, for which the two-pass rounding
+// (sum + 2048) >> 12 reduces exactly to the one-pass (sum + 32) >> 6 and to a copy, so one code path serves all positions without
+// divergence.  Reference rows and strides may have any alignment.
+//   Why not shared-memory staging or TMA: the L1 data stage serves 4 sectors per cycle whatever lines they sit in (ncu on the previous kernel:
+// 16 rows per request = 5.3 wavefronts), so an 8x8 PU's 15 footprint rows cost ~6 cycles of it - less than its arithmetic; a TMA box must start
+// 16-byte aligned (no re-alignment of a motion-compensated source) and the unit retires only one box row per ~1.5 cycles
+// (profiles/r02_tma_box_probe.txt).  What limited the previous kernel (4-column strips, trips of eight rows with the vertical filter run
+// on all of them, 84 warp-instructions per 8x8 PU at 46 % issue utilisation) was instruction count and latency, not the memory path.
+constexpr int LIST_G = 128;   // descriptors per CTA and trip: 128 PUs of 8x8 are 128 eight-column items, one per thread
+// blockIdx.y slices a group's item list; enough slices that a short list of large PUs (16 groups for a 4K frame of 64x64 PUs, 1024 items each)
 // still spreads over the chip, one slice when there are groups enough (empty slices of small-PU groups only cost launches)
-static unsigned list_slices(int n_pu)
+static dim3 list_grid(int n_pu, int ctas_per_sm)
 {
-    const int groups = (n_pu + LIST_G - 1) / LIST_G, want = 4 * sm_count();
-    return (unsigned)std::max(1, std::min(8, (want + groups - 1) / groups));
+    // one CTA per group (the hardware's CTA scheduler balances groups of very different weight - a persistent grid with a fixed stride ran
+    // mixed-size lists 10 % slower); a short list is sliced (blockIdx.y): up to eight CTAs share the items of a group
+    (void)ctas_per_sm;
+    const int groups = (n_pu + LIST_G - 1) / LIST_G;
+    return dim3((unsigned)groups, (unsigned)std::max(1, std::min(8, (4 * sm_count() + groups - 1) / groups)));
 }
-template <int TAPS, bool BI>
-__global__ void __launch_bounds__(NT) pred_list_stream_kernel(PredParams p)
+
+// horizontal filter of COLS adjacent columns from the aligned footprint words A (A[0] byte 0 = first tap of column 0)
+template <int TAPS, int COLS, int NA>
+__device__ __forceinline__ void hrow_cols(const uint32_t (&A)[NA], const int (&cx4)[TAPS / 4], int (&t)[COLS])
 {
-    constexpr int G = LIST_G, NREF = BI ? 2 : 1, DW0 = BI ? 8 : 6, LEFT = TAPS / 2 - 1, FB = TAPS == 8 ? 2 : 3, FM = (1 << FB) - 1;
-    const int DW = DW0 + p.desc_frame;   // a trailing frame index makes one launch cover the PU lists of a whole batch of frames
-    __shared__ int s_prefix[G + 1];
-    __shared__ short s_desc[G][10];
-    const int tid = threadIdx.x, lane = tid & 31, first = blockIdx.x * G;
-    if (tid < 32) {
-        // lane l owns descriptors 2l and 2l+1: inclusive scan over the lanes' pair sums
-        int nq[2] = {0, 0};
 #pragma unroll
-        for (int k = 0; k < 2; ++k) {
-            const int i = 2 * lane + k;
-            if (first + i < p.n_pu) {
-                const int16_t *dsc = p.pus + (size_t)(first + i) * DW;
+    for (int i = 0; i < COLS; ++i) {
+        int acc = 0;
 #pragma unroll
-                for (int j = 0; j < DW0; ++j) s_desc[i][j] = dsc[j];
-                s_desc[i][DW0] = p.desc_frame ? dsc[DW0] : (short)0;
-                const int w = dsc[2], h = dsc[3];
-                if (w > 0 && h > 0 && w <= 64 && h <= 64) nq[k] = (w + 3) >> 2;
-            }
+        for (int g = 0; g < TAPS / 4; ++g) {
+            const int o = i + 4 * g;
+            const uint32_t win = (o & 3) ? shr_bytes(A[o >> 2], A[((o >> 2) + 1) % NA], o & 3) : A[o >> 2];
+            acc = dp4a_us(win, cx4[g], acc);
         }
-        int incl = nq[0] + nq[1];
+        t[i] = acc;
+    }
+}
+
+template <int TAPS, bool BI, int COLS, int MINB>
+__global__ void __launch_bounds__(NT, MINB) pred_list_stream_kernel(PredParams p)
+{
+    constexpr int G = LIST_G, NWARP = NT / 32, NREF = BI ? 2 : 1, DW0 = BI ? 8 : 6, LEFT = TAPS / 2 - 1, FB = TAPS == 8 ? 2 : 3, FM = (1 << FB) - 1;
+    constexpr int NEED = COLS + TAPS - 1;        // footprint bytes of one strip row
+    constexpr int NA = (NEED + 3) / 4;           // aligned words the horizontal filter reads
+    // words loaded per row.  LD8: three aligned 8-byte loads (the footprint starts at any byte of the first; the word it starts in is then
+    // selected) instead of five 4-byte ones: the L1 data stage, 73 % busy with 4-byte loads on 8x8 PU lists, is what these kernels run against
+    constexpr bool LD8 = COLS == 8;
+    constexpr int NW = LD8 ? 6 : (NEED + 3 + 3) / 4;
+    static_assert(!LD8 || NEED + 7 <= 24, "three 8-byte loads must cover the footprint");
+    // rows per load batch; PIPE: the loads of the next batch are in flight while this one is filtered (two buffers - one reference only: with
+    // two the registers do not fit)
+    constexpr int LB = BI ? 2 : TAPS / 2, NB = TAPS / LB;
+    constexpr bool PIPE = !BI;
+    const int DW = DW0 + p.desc_frame;           // a trailing frame index makes one launch cover the PU lists of a whole batch of frames
+    __shared__ int s_prefix[G + 1];
+    __shared__ int s_warp_sum[NWARP];
+    __shared__ short s_desc[G][10];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    // descriptors stream from DRAM and nothing can start before they are here: every CTA asks L2 for the records of the group that the CTA
+    // taking this one's place will read (CTAs start in index order, three per SM at a time)
+    {
+        const size_t ahead = ((size_t)blockIdx.x + 3 * 160) * G * DW * sizeof(int16_t) + (size_t)tid * 128;
+        if (blockIdx.y == 0 && (size_t)tid * 128 < (size_t)G * DW * sizeof(int16_t) && ahead < (size_t)p.n_pu * DW * sizeof(int16_t))
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char *>(p.pus) + ahead));
+    }
+    {
+        // thread t owns descriptor t of the group: inclusive scan of the item counts (warp scans, then the four warp totals)
+        short dreg[DW0 + 1];
+        const long long di = (long long)blockIdx.x * G + tid;
+#pragma unroll
+        for (int j = 0; j <= DW0; ++j) dreg[j] = 0;
+        if (di < p.n_pu) {
+            const int16_t *dsc = p.pus + (size_t)di * DW;
+#pragma unroll
+            for (int j = 0; j < DW0; ++j) dreg[j] = dsc[j];
+            if (p.desc_frame) dreg[DW0] = dsc[DW0];
+        }
+        const int dw = dreg[2], dh = dreg[3];
+        const int nq = (dw > 0 && dh > 0 && dw <= 64 && dh <= 64) ? (dw + COLS - 1) / COLS : 0;   // a zero descriptor (past the end) has no items
+        int incl = nq;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
             const int v = __shfl_up_sync(0xffffffffu, incl, o);
             if (lane >= o) incl += v;
         }
-        s_prefix[2 * lane + 1] = incl - nq[1];
-        s_prefix[2 * lane + 2] = incl;
-        if (lane == 0) s_prefix[0] = 0;
+        if (lane == 31) s_warp_sum[warp] = incl;
+#pragma unroll
+        for (int j = 0; j <= DW0; ++j) s_desc[tid][j] = dreg[j];
+        __syncthreads();
+        int base = 0;
+#pragma unroll
+        for (int k = 0; k < NWARP; ++k)
+            if (k < warp) base += s_warp_sum[k];
+        s_prefix[tid + 1] = base + incl;
+        if (tid == 0) s_prefix[0] = 0;
+        __syncthreads();
     }
-    __syncthreads();
     const int total = s_prefix[G];
-    // blockIdx.y slices the item list, so that 32 large PUs (512 items) spread over four CTAs; for small PUs the extra CTAs find
-    // nothing beyond `total` and leave
+    // blockIdx.y slices the item list, so that a few large PUs spread over several CTAs; for small PUs the extra CTAs find nothing
+    // beyond `total` and go on
     for (int item = tid + NT * blockIdx.y; item < total; item += NT * gridDim.y) {
         int pu = 0;
 #pragma unroll
@@ -1041,14 +1094,14 @@ __global__ void __launch_bounds__(NT) pred_list_stream_kernel(PredParams p)
             if (s_prefix[pu + step] <= item) pu += step;
         const int q = item - s_prefix[pu];
         const int x = s_desc[pu][0], y = s_desc[pu][1], w = s_desc[pu][2], h = s_desc[pu][3];
-        const int nvalid = w - 4 * q, rows_in = h + TAPS - 1, frame = s_desc[pu][DW0];
-        uint8_t *d = p.dst + frame * p.fs_dst + (ptrdiff_t)y * p.sd + x + 4 * q;
-        const uint8_t *src[NREF];
+        const int nvalid = w - COLS * q, frame = s_desc[pu][DW0];
+        uint8_t *d = p.dst + frame * p.fs_dst + (ptrdiff_t)y * p.sd + x + COLS * q;
+        const uint8_t *src[NREF];   // first footprint byte of the strip's first input row
         int cx4[NREF][TAPS / 4], cy2[NREF][TAPS / 2];
 #pragma unroll
         for (int rf = 0; rf < NREF; ++rf) {
             const int mvx = s_desc[pu][4 + 2 * rf], mvy = s_desc[pu][5 + 2 * rf];
-            src[rf] = (rf ? p.ref1 : p.ref0) + frame * p.fs_ref + (ptrdiff_t)(y + (mvy >> FB) - LEFT) * p.sr + x + (mvx >> FB) + 4 * q - 4;
+            src[rf] = (rf ? p.ref1 : p.ref0) + frame * p.fs_ref + (ptrdiff_t)(y + (mvy >> FB) - LEFT) * p.sr + x + (mvx >> FB) + COLS * q - LEFT;
             Coefs<TAPS> c;
             c.load(mvx & FM);
 #pragma unroll
@@ -1057,57 +1110,114 @@ __global__ void __launch_bounds__(NT) pred_list_stream_kernel(PredParams p)
 #pragma unroll
             for (int g = 0; g < TAPS / 2; ++g) cy2[rf][g] = c.p2[g];
         }
-        StreamRef<TAPS> st[NREF];
-#pragma unroll 1
-        for (int r0 = 0; r0 < rows_in; r0 += TAPS) {
-            uint32_t W[NREF][TAPS][3];
+        uint32_t ring[NREF][TAPS][COLS];   // ring[.][r % TAPS] = vertical pairs (row r-1, row r) of the horizontal results
+        int prev[NREF][COLS];
 #pragma unroll
-            for (int k = 0; k < TAPS; ++k)
+        for (int rf = 0; rf < NREF; ++rf)
 #pragma unroll
-                for (int rf = 0; rf < NREF; ++rf) {
-                    const uint8_t *row = src[rf] + (ptrdiff_t)min(r0 + k, rows_in - 1) * p.sr;
-                    const int a = (int)((uintptr_t)row & 3);
-                    const uint32_t *ra = reinterpret_cast<const uint32_t *>(row - a);
-                    const uint32_t l0 = __ldg(ra), l1 = __ldg(ra + 1), l2 = __ldg(ra + 2);
-                    if (a) {
-                        const uint32_t l3 = __ldg(ra + 3);
-                        W[rf][k][0] = __funnelshift_r(l0, l1, 8 * a), W[rf][k][1] = __funnelshift_r(l1, l2, 8 * a), W[rf][k][2] = __funnelshift_r(l2, l3, 8 * a);
-                    } else {
-                        W[rf][k][0] = l0, W[rf][k][1] = l1, W[rf][k][2] = l2;
-                    }
+            for (int i = 0; i < COLS; ++i) prev[rf][i] = 0;
+        // one input row: NW aligned words covering the footprint, and the byte the footprint starts at inside the first
+        const int rows_in = h + TAPS - 1;
+        // one input row: NW aligned words covering the footprint, and the bit the footprint starts at inside the first
+        auto fetch = [&](int rf, int r, uint32_t (&wd)[NW], int &sh8) {
+            const uint8_t *row = src[rf] + (ptrdiff_t)min(r, rows_in - 1) * p.sr;   // batches are whole: rows past the footprint repeat its last one
+            if (LD8) {
+                const int a = (int)((uintptr_t)row & 7);
+                const uint2 *ra = reinterpret_cast<const uint2 *>(row - a);
+#pragma unroll
+                for (int k = 0; k < NW / 2; ++k) {
+                    const uint2 v = __ldg(ra + k);
+                    wd[2 * k] = v.x, wd[2 * k + 1] = v.y;
                 }
+                sh8 = a;
+            } else {
+                const int a = (int)((uintptr_t)row & 3);
+                const uint32_t *ra = reinterpret_cast<const uint32_t *>(row - a);
 #pragma unroll
-            for (int k = 0; k < TAPS; ++k) {
-                int vout[NREF][4];
+                for (int k = 0; k < NW; ++k) wd[k] = __ldg(ra + k);
+                sh8 = 8 * a;
+            }
+        };
+        // horizontal filter of one fetched row; its pairs with the previous row go to a ring slot
+        auto hpack = [&](int rf, const uint32_t (&wd)[NW], int sh8, uint32_t (&slot)[COLS]) {
+            uint32_t A[NA];
+            if (LD8) {
+                uint32_t u[NA + 1];
 #pragma unroll
-                for (int rf = 0; rf < NREF; ++rf) {
-                    int t[4];
-                    hrow4<TAPS>(W[rf][k], cx4[rf], t);
+                for (int j = 0; j < NA + 1; ++j) u[j] = (sh8 & 4) ? wd[(j + 1) % NW] : wd[j];
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        st[rf].ring[k][i] = pack16(st[rf].prev[i], t[i]);
-                        st[rf].prev[i] = t[i];
-                    }
+                for (int j = 0; j < NA; ++j) A[j] = __funnelshift_r(u[j], u[j + 1], 8 * (sh8 & 3));
+            } else {
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        int acc = BI ? 0 : 2048;
+                for (int j = 0; j < NA; ++j) A[j] = __funnelshift_r(wd[j], wd[(j + 1) % NW], sh8);
+            }
+            int t[COLS];
+            hrow_cols<TAPS, COLS, NA>(A, cx4[rf], t);
 #pragma unroll
-                        for (int g = 0; g < TAPS / 2; ++g) acc = dp2a_lo(st[rf].ring[(k + 2 + 2 * g) % TAPS][i], cy2[rf][g], acc);
-                        vout[rf][i] = acc;
-                    }
+            for (int i = 0; i < COLS; ++i) {
+                slot[i] = pack16(prev[rf][i], t[i]);
+                prev[rf][i] = t[i];
+            }
+        };
+        // output row j from the ring; J = j mod TAPS picks the slots: the pairs ending at rows j+1, j+3, ..
+        auto vstore = [&](int J, int j) {
+            int vout[NREF][COLS];
+#pragma unroll
+            for (int rf = 0; rf < NREF; ++rf)
+#pragma unroll
+                for (int i = 0; i < COLS; ++i) {
+                    int acc = BI ? 0 : 2048;
+#pragma unroll
+                    for (int g = 0; g < TAPS / 2; ++g) acc = dp2a_lo(ring[rf][(J + 1 + 2 * g) % TAPS][i], cy2[rf][g], acc);
+                    vout[rf][i] = acc;
                 }
-                const int yo = r0 + k - (TAPS - 1);
-                if (yo < 0 || yo >= h) continue;
-                uint32_t o;
+            uint32_t o[COLS / 4];
+#pragma unroll
+            for (int c = 0; c < COLS / 4; ++c) {
                 if (BI) {
                     int s4[4];
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) s4[i] = ((int)(short)(vout[0][i] >> 6) + (int)(short)(vout[1][i] >> 6) + 64) >> 7;
-                    o = pack_sat_u8(s4[0], s4[1], s4[2], s4[3]);
+                    for (int i = 0; i < 4; ++i) s4[i] = ((int)(short)(vout[0][4 * c + i] >> 6) + (int)(short)(vout[NREF - 1][4 * c + i] >> 6) + 64) >> 7;
+                    o[c] = pack_sat_u8(s4[0], s4[1], s4[2], s4[3]);
                 } else {
-                    o = pack_sat_u8(vout[0][0] >> 12, vout[0][1] >> 12, vout[0][2] >> 12, vout[0][3] >> 12);
+                    o[c] = pack_sat_u8(vout[0][4 * c] >> 12, vout[0][4 * c + 1] >> 12, vout[0][4 * c + 2] >> 12, vout[0][4 * c + 3] >> 12);
                 }
-                store4(d + (ptrdiff_t)yo * p.sd, o, nvalid);
+            }
+            if (COLS == 8)
+                store8(d + (ptrdiff_t)j * p.sd, o[0], o[COLS / 4 - 1], nvalid);
+            else
+                store4(d + (ptrdiff_t)j * p.sd, o[0], nvalid);
+        };
+        // input rows in batches of LB, NB batches per ring period: the ring slots and the buffer a batch sits in are compile-time
+        uint32_t W[PIPE ? 2 : 1][NREF][LB][NW];
+        int sh[PIPE ? 2 : 1][NREF][LB];
+        if (PIPE) {
+#pragma unroll
+            for (int b = 0; b < LB; ++b)
+#pragma unroll
+                for (int rf = 0; rf < NREF; ++rf) fetch(rf, b, W[0][rf][b], sh[0][rf][b]);   // rows 0 .. LB-1 always exist (h >= 1, LB <= TAPS-1)
+        }
+#pragma unroll 1
+        for (int r0 = 0; r0 < rows_in; r0 += TAPS) {
+#pragma unroll
+            for (int bt = 0; bt < NB; ++bt) {
+                const int cur = PIPE ? (bt & 1) : 0, nxt = PIPE ? (cur ^ 1) : 0, ahead = PIPE ? LB : 0;
+                // nothing below is conditional except the output row itself: values defined under a per-row test cost a register move each
+                // (262 IMAD.MOV in 1944 instructions when the loads and the filter of a row were skipped past the footprint)
+                if (r0 + LB * bt >= rows_in) break;                 // whole batches only: nothing left
+                if (r0 + LB * bt + ahead < rows_in) {               // (a batch wholly past the footprint is not requested)
+#pragma unroll
+                    for (int b = 0; b < LB; ++b)
+#pragma unroll
+                        for (int rf = 0; rf < NREF; ++rf) fetch(rf, r0 + LB * bt + ahead + b, W[nxt][rf][b], sh[nxt][rf][b]);
+                }
+#pragma unroll
+                for (int b = 0; b < LB; ++b) {
+                    const int r = r0 + LB * bt + b;   // r mod TAPS = LB * bt + b
+#pragma unroll
+                    for (int rf = 0; rf < NREF; ++rf) hpack(rf, W[cur][rf][b], sh[cur][rf][b], ring[rf][LB * bt + b]);
+                    if (r >= TAPS - 1 && r < rows_in) vstore((LB * bt + b + 1) % TAPS, r - (TAPS - 1));
+                }
             }
         }
     }
@@ -1214,6 +1324,32 @@ static bool stream_ok(const uint8_t *dst, ptrdiff_t sd, ptrdiff_t fs_dst, const 
     if (n_frames > 1) m |= (uintptr_t)fs_dst | (uintptr_t)fs_ref;
     return (m & 3) == 0;
 }
+// columns per work item of the PU-list kernel and CTAs per SM it is compiled for (HEVCASM_LIST_COLS=4 / 8 and HEVCASM_LIST_MINB pin them in
+// the experiments build)
+template <bool BI, int COLS, int MINB>
+static int launch_list_as(int taps, void *stream, const PredParams &p)
+{
+    const dim3 grid = list_grid(p.n_pu, MINB);
+    return taps == 8 ? launch(pred_list_stream_kernel<8, BI, COLS, MINB>, grid, dim3(NT), 0, stream, p)
+                     : launch(pred_list_stream_kernel<4, BI, COLS, MINB>, grid, dim3(NT), 0, stream, p);
+}
+template <bool BI>
+static int launch_list(int taps, void *stream, const PredParams &p)
+{
+#ifdef HEVCASM_EXPERIMENTS
+    const char *pc = tune::knob("HEVCASM_LIST_COLS"), *pb = tune::knob("HEVCASM_LIST_MINB");
+    if (pc || pb) {
+        const int cols = pc ? atoi(pc) : (BI ? 4 : 8), minb = pb ? atoi(pb) : 3;
+        if constexpr (!BI) {
+            if (cols == 8) return minb >= 4 ? launch_list_as<BI, 8, 4>(taps, stream, p) : minb == 3 ? launch_list_as<BI, 8, 3>(taps, stream, p) : launch_list_as<BI, 8, 2>(taps, stream, p);
+        }
+        return minb >= 5 ? launch_list_as<BI, 4, 5>(taps, stream, p) : minb == 4 ? launch_list_as<BI, 4, 4>(taps, stream, p) : launch_list_as<BI, 4, 3>(taps, stream, p);
+    }
+#endif
+    if constexpr (BI) return launch_list_as<true, 4, 4>(taps, stream, p);
+    else return launch_list_as<false, 8, 3>(taps, stream, p);
+}
+
 // PU lists: streaming kernel unless HEVCASM_PRED_PATH=tile / HEVCASM_PRED_GENERIC pins the tile kernel (A/B, and the tile
 // kernel reads exactly the reference's footprint per position while the streaming one always reads the two-pass footprint)
 static bool list_stream_ok()
@@ -1504,8 +1640,7 @@ extern "C" int hevcasm_pred_uni_batch(uint8_t *dst, ptrdiff_t sd, const uint8_t 
     PredParams p{};
     p.dst = dst, p.ref0 = ref, p.sd = sd, p.sr = sr, p.pus = pus, p.n_pu = n_pu;
     if (list_stream_ok()) {
-        const dim3 grid((n_pu + LIST_G - 1) / LIST_G, list_slices(n_pu));
-        return taps == 8 ? launch(pred_list_stream_kernel<8, false>, grid, dim3(NT), 0, stream, p) : launch(pred_list_stream_kernel<4, false>, grid, dim3(NT), 0, stream, p);
+        return launch_list<false>(taps, stream, p);
     }
     return taps == 8 ? launch_pred<8, LTW, LTH, false, RUNTIME>(p, dim3(n_pu), stream) : launch_pred<4, LTW, LTH, false, RUNTIME>(p, dim3(n_pu), stream);
 }
@@ -1518,8 +1653,7 @@ extern "C" int hevcasm_pred_bi_batch(uint8_t *dst, ptrdiff_t sd, const uint8_t *
     PredParams p{};
     p.dst = dst, p.ref0 = ref0, p.ref1 = ref1, p.sd = sd, p.sr = sr, p.pus = pus, p.n_pu = n_pu;
     if (list_stream_ok()) {
-        const dim3 grid((n_pu + LIST_G - 1) / LIST_G, list_slices(n_pu));
-        return taps == 8 ? launch(pred_list_stream_kernel<8, true>, grid, dim3(NT), 0, stream, p) : launch(pred_list_stream_kernel<4, true>, grid, dim3(NT), 0, stream, p);
+        return launch_list<true>(taps, stream, p);
     }
     return taps == 8 ? launch_pred<8, LTW, LTH, true, RUNTIME>(p, dim3(n_pu), stream) : launch_pred<4, LTW, LTH, true, RUNTIME>(p, dim3(n_pu), stream);
 }
@@ -1532,8 +1666,7 @@ extern "C" int hevcasm_pred_uni_list_frames(uint8_t *dst, ptrdiff_t sd, const ui
     if (n_pu == 0) return 0;
     PredParams p{};
     p.dst = dst, p.ref0 = ref, p.sd = sd, p.sr = sr, p.fs_dst = fs_dst, p.fs_ref = fs_ref, p.pus = pus, p.n_pu = n_pu, p.desc_frame = 1;
-    const dim3 grid((n_pu + LIST_G - 1) / LIST_G, list_slices(n_pu));
-    return taps == 8 ? launch(pred_list_stream_kernel<8, false>, grid, dim3(NT), 0, stream, p) : launch(pred_list_stream_kernel<4, false>, grid, dim3(NT), 0, stream, p);
+    return launch_list<false>(taps, stream, p);
 }
 
 extern "C" int hevcasm_pred_bi_list_frames(uint8_t *dst, ptrdiff_t sd, const uint8_t *ref0, const uint8_t *ref1, ptrdiff_t sr, int taps, const int16_t *pus, int n_pu,
@@ -1543,6 +1676,5 @@ extern "C" int hevcasm_pred_bi_list_frames(uint8_t *dst, ptrdiff_t sd, const uin
     if (n_pu == 0) return 0;
     PredParams p{};
     p.dst = dst, p.ref0 = ref0, p.ref1 = ref1, p.sd = sd, p.sr = sr, p.fs_dst = fs_dst, p.fs_ref = fs_ref, p.pus = pus, p.n_pu = n_pu, p.desc_frame = 1;
-    const dim3 grid((n_pu + LIST_G - 1) / LIST_G, list_slices(n_pu));
-    return taps == 8 ? launch(pred_list_stream_kernel<8, true>, grid, dim3(NT), 0, stream, p) : launch(pred_list_stream_kernel<4, true>, grid, dim3(NT), 0, stream, p);
+    return launch_list<true>(taps, stream, p);
 }

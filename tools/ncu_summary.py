@@ -17,6 +17,10 @@ for w in want:
     if w in hdr:
         i = hdr.index(w)
         print(f"{w:72s} {units[i]:10s}", [r[i][:60] for r in rows[2:]])
+if len(sys.argv) > 2:   # every metric whose name matches the regex
+    import re
+    for i, h in enumerate(hdr):
+        if re.search(sys.argv[2], h): print(f"{h:72s} {units[i]:10s}", [r[i][:60] for r in rows[2:]])
 src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "sass"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(src)))
 hdr = rows[1]

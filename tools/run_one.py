@@ -49,15 +49,43 @@ calls = {
 import numpy as np
 def pu_list(sz, bi=False, seed=5):
     xs, ys = np.meshgrid(np.arange(W // sz) * sz, np.arange(H // sz) * sz)
+    if os.environ.get("RUN_ONE_ORDER") == "ctu":   # CTUs (64x64) in raster order, the PUs of a CTU in z-order - the order a codec produces them in
+        def morton(u, v):
+            m = np.zeros_like(u)
+            for bit in range(4):
+                m |= ((u >> bit) & 1) << (2 * bit) | ((v >> bit) & 1) << (2 * bit + 1)
+            return m
+        key = ((ys // 64) * (W // 64 + 1) + xs // 64) * 256 + morton((xs % 64) // sz, (ys % 64) // sz)
+        o = np.argsort(key.reshape(-1), kind="stable")
+        xs, ys = xs.reshape(-1)[o], ys.reshape(-1)[o]
     n = xs.size
     r = synth.splitmix64(seed, 4 * n).astype(np.int64)
-    cols = [xs.reshape(-1), ys.reshape(-1), np.full(n, sz), np.full(n, sz), r[:n] % 129 - 64, r[n:2 * n] % 129 - 64]
+    span = int(os.environ.get("RUN_ONE_MVSPAN", "64"))   # motion vectors in [-span, span] quarter samples; "0" = all zero; "c<N>" = one vector per 64x64 CTU
+    if os.environ.get("RUN_ONE_MVCTU"):
+        ctu = (ys.reshape(-1) // 64) * 64 + xs.reshape(-1) // 64
+        rc = synth.splitmix64(seed + 1, 2 * 4096).astype(np.int64)
+        mvx, mvy = rc[ctu % 4096] % (2 * span + 1) - span, rc[4096 + ctu % 4096] % (2 * span + 1) - span
+    else:
+        mvx, mvy = r[:n] % (2 * span + 1) - span, r[n:2 * n] % (2 * span + 1) - span
+    cols = [xs.reshape(-1), ys.reshape(-1), np.full(n, sz), np.full(n, sz), mvx, mvy]
     if bi:
         cols += [r[2 * n:3 * n] % 129 - 64, r[3 * n:] % 129 - 64]
     return torch.from_numpy(np.stack(cols, -1).astype(np.int16)).cuda()
 for sz in (8, 16, 32, 64):
     calls[f"pred_list{sz}"] = (lambda pl: (lambda: lib.call("pred_uni_batch", d(o8, org), pitch, d(a, org), pitch, 8, d(pl), pl.shape[0])))(pu_list(sz))
     calls[f"pred_bilist{sz}"] = (lambda pl: (lambda: lib.call("pred_bi_batch", d(o8, org), pitch, d(a, org), d(b, org), pitch, 8, d(pl), pl.shape[0])))(pu_list(sz, True))
+def pu_list_frames(sz, bi=False):
+    """the per-frame list of every frame of the batch, each descriptor with its frame index (hevcasm_pred_*_list_frames)"""
+    one = pu_list(sz, bi).cpu().numpy()
+    rows = [np.concatenate([one, np.full((len(one), 1), f, np.int16)], axis=1) for f in range(NF)]
+    return torch.from_numpy(np.ascontiguousarray(np.concatenate(rows))).cuda()
+if name.startswith("pred_listf") or name.startswith("pred_bilistf"):
+    bi = name.startswith("pred_bilistf")
+    plf = pu_list_frames(int(name[len("pred_bilistf" if bi else "pred_listf"):]), bi)
+    if bi:
+        calls[name] = lambda: lib.call("pred_bi_list_frames", d(o8, org), pitch, d(a, org), d(b, org), pitch, 8, d(plf), plf.shape[0], fs, fs)
+    else:
+        calls[name] = lambda: lib.call("pred_uni_list_frames", d(o8, org), pitch, d(a, org), pitch, 8, d(plf), plf.shape[0], fs, fs)
 for _ in range(iters):
     calls[name]()
 torch.cuda.synchronize()
