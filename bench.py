@@ -279,6 +279,31 @@ def pu_list(synth, torch, width, height, sizes, nf, bi=False, seed=5):
     return torch.from_numpy(np.stack(cols, -1).astype(np.int16)).cuda(), int((a[:, 2] * a[:, 3]).sum())
 
 
+def tu_buckets(synth, torch, width, height, nf, seed=9):
+    """a quad-tree-like tiling of `nf` frames into transform units: every 32x32 cell is one 32x32 TU, four 16x16, sixteen 8x8 or sixty-four 4x4
+    (DST / DCT alternating), chosen at random; bucketed by size class as the *_list_frames forms take them: entries {x, y, frame} as int16, counts
+    [4x4 DST, 4x4 DCT, 8x8, 16x16, 32x32]"""
+    cx, cy, ff = np.meshgrid(np.arange(width // 32) * 32, np.arange(height // 32) * 32, np.arange(nf), indexing="ij")
+    cx, cy, ff = cx.reshape(-1), cy.reshape(-1), ff.reshape(-1)
+    kind = synth.splitmix64(seed, len(cx)).astype(np.int64) % 4      # 0: 4x4, 1: 8x8, 2: 16x16, 3: 32x32
+    buckets = [None] * 5
+    for k, nsz in ((0, 4), (1, 8), (2, 16), (3, 32)):
+        sel = kind == k
+        ox, oy = np.meshgrid(np.arange(0, 32, nsz), np.arange(0, 32, nsz))
+        x = (cx[sel, None] + ox.reshape(1, -1)).reshape(-1)
+        y = (cy[sel, None] + oy.reshape(1, -1)).reshape(-1)
+        f = np.repeat(ff[sel], ox.size)
+        e = np.stack([x, y, f], -1).astype(np.int16)
+        if k == 0:
+            dst = ((x // 4 + y // 4) & 1) == 0
+            buckets[0], buckets[1] = e[dst], e[~dst]
+        else:
+            buckets[k + 1] = e
+    counts = np.array([len(b) for b in buckets], np.int32)
+    covered = int(sum(len(b) * (16, 16, 64, 256, 1024)[c] for c, b in enumerate(buckets)))
+    return torch.from_numpy(np.ascontiguousarray(np.concatenate(buckets))).cuda(), counts, covered
+
+
 def kernel_table(torch, lib, synth, stream, hbm_peak, counters, with_cpu, launches=200):
     """Every other kernel of the path on a 16-frame 4K batch (working set >> L2): CUDA events, 200 launches each (median and best of 20 groups
     of 10), and beside it the reference's C path for the same call on 1-2 frames on all host cores."""
@@ -426,6 +451,14 @@ def kernel_table(torch, lib, synth, stream, hbm_peak, counters, with_cpu, launch
             cpu_call=(lambda log2=log2, tr=tr: cpu.drv("inverse_transform_add_frames", ptr(ho, org), pitch, ptr(ha, org), pitch, ptr(hco), W4K, H4K, log2, tr, cnf, fs, fs,
                                                         threads=threads)) if with_cpu else None,
             cpu_samples=(cnf * (W4K // N * N) * (H4K // N * N)) if with_cpu else None)
+    # transform-unit lists over the whole batch in one call (mixed sizes bucketed by class, frame index per TU): up to five launches
+    if hasattr(lib.load(), "hevcasm_inverse_transform_add_list_frames"):
+        from oracle.binding import ptr as hptr
+        tus, counts, covered = tu_buckets(synth, torch, W4K, H4K, NF)
+        rec("fwd_tu_list_mixed_4..32", lambda: lib.call("transform_list_frames", dptr(co2), dptr(res), rp, dptr(tus), hptr(counts), H4K * rp, stream=stream), covered, 4,
+            extra={"tus": int(counts.sum()), "by_class": counts.tolist()})
+        rec("inv_tu_list_mixed_4..32", lambda: lib.call("inverse_transform_add_list_frames", dptr(o8, org), pitch, dptr(a, org), pitch, dptr(co), dptr(tus), hptr(counts),
+                                                        fs, fs, stream=stream), covered, 4, extra={"tus": int(counts.sum()), "by_class": counts.tolist()})
     for log2 in (2, 3, 4, 5):
         N = 1 << log2
         rec(f"quantize_reconstruct_{N}x{N}", lambda log2=log2: lib.call("quantize_reconstruct_frames", dptr(o8, org), pitch, dptr(a, org), pitch, dptr(co), W4K, H4K, log2, NF,

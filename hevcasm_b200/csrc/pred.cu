@@ -981,29 +981,32 @@ int launch_uni_stream_tma(const FastParams &fp, const StreamMaps &sm, int mode, 
 
 // ------------------------------------------------------------------------------------------------ PU lists, streaming
 //
-// Prediction-unit lists (per-PU size and quarter / eighth-sample motion vector).  A CTA takes LIST_G descriptors, a warp scan turns
-// their widths into a prefix of work items - one item = a strip of LIST_COLS columns over the whole height of a PU - and every thread
+// Prediction-unit lists (per-PU size and quarter / eighth-sample motion vector).  A CTA takes LIST_G descriptors, a scan turns their widths
+// into a prefix of work items - one item = a strip of 8 columns (4 with two references) over the whole height of a PU - and every thread
 // picks items off that list, so 8x8 PUs fill the CTA as well as 64x64 ones do (a tile kernel that spent a 128-thread CTA per PU ran 8x8
 // lists at 58 Gsamples/s).  A thread streams its strip top to bottom straight from global memory: per input row it loads the strip's
-// footprint (aligned words + one funnel shift by the row's alignment), runs the HORIZONTAL filter on the bytes (IDP.4A), packs the exact
-// int16 result with the previous row's into a vertical pair and keeps the last TAPS pairs in a register ring; every output row is four
-// (two) IDP.2A per column over that ring.  The first TAPS-1 rows only prime the ring (no vertical work, no tests); after that one input
-// row gives one output row.  Every PU runs the two-pass arithmetic; a zero fraction is the {64} filter, for which the two-pass rounding
-// (sum + 2048) >> 12 reduces exactly to the one-pass (sum + 32) >> 6 and to a copy, so one code path serves all positions without
-// divergence.  Reference rows and strides may have any alignment.
-//   Why not shared-memory staging or TMA: the L1 data stage serves 4 sectors per cycle whatever lines they sit in (ncu on the previous kernel:
-// 16 rows per request = 5.3 wavefronts), so an 8x8 PU's 15 footprint rows cost ~6 cycles of it - less than its arithmetic; a TMA box must start
-// 16-byte aligned (no re-alignment of a motion-compensated source) and the unit retires only one box row per ~1.5 cycles
-// (profiles/r02_tma_box_probe.txt).  What limited the previous kernel (4-column strips, trips of eight rows with the vertical filter run
-// on all of them, 84 warp-instructions per 8x8 PU at 46 % issue utilisation) was instruction count and latency, not the memory path.
+// footprint (aligned 8-byte loads, the start word selected and one funnel shift per word), runs the HORIZONTAL filter on the bytes (IDP.4A),
+// packs the exact int16 result with the previous row's into a vertical pair and keeps the last TAPS pairs in a register ring; every output
+// row is four (two) IDP.2A per column over that ring.  The first TAPS-1 rows only prime the ring; after that one input row gives one
+// output row.  Rows come in batches whose loads are issued one batch ahead (one reference).  Every PU runs the two-pass arithmetic; a zero
+// fraction is the {64} filter, for which the two-pass rounding (sum + 2048) >> 12 reduces exactly to the one-pass (sum + 32) >> 6 and to a
+// copy, so one code path serves all positions without divergence.  Reference rows and strides may have any alignment.
+//   Measured on 16 4K frames of 8x8 / 64x64 PUs with random +-16-sample vectors (profiles/r02_pred.md): 230 / 110 us (round 1's kernel -
+// 4-column strips, trips of eight rows with the vertical filter run on all of them, the group's descriptors fetched through an integer
+// division - 283 / 171 us).  Every thread-row touches its own line, so a warp's load is ~30 sectors in ~30 lines: the L1 data stage is 60-73 %
+// busy and the loads' latency (33 % of the stall samples, 12 warps per SM at 168 registers) is the rest; the list order (raster or CTU
+// z-order) and the vector spread (+-16 samples or none: 197 us) change little.  Tried and dropped: a TMA box per PU (a box must start
+// 16-byte aligned, and the unit retires one box row per ~1.5 cycles: 24 cycles per 8x8 PU, profiles/r02_tma_box_probe.txt); the whole
+// footprint of a small PU requested at once (348 us); 16-byte loads (two per row, but two SELs per word: 275 us); 4-column strips for one
+// reference (271 us at 128 registers); a persistent grid, per CTA (251 / 139 us, mixed sizes 10 % slower: fixed stride, uneven groups) and
+// per warp with the next descriptors prefetched into registers (230 / 168 us: a warp alone on 32 large PUs).
 constexpr int LIST_G = 128;   // descriptors per CTA and trip: 128 PUs of 8x8 are 128 eight-column items, one per thread
 // blockIdx.y slices a group's item list; enough slices that a short list of large PUs (16 groups for a 4K frame of 64x64 PUs, 1024 items each)
 // still spreads over the chip, one slice when there are groups enough (empty slices of small-PU groups only cost launches)
-static dim3 list_grid(int n_pu, int ctas_per_sm)
+static dim3 list_grid(int n_pu)
 {
     // one CTA per group (the hardware's CTA scheduler balances groups of very different weight - a persistent grid with a fixed stride ran
     // mixed-size lists 10 % slower); a short list is sliced (blockIdx.y): up to eight CTAs share the items of a group
-    (void)ctas_per_sm;
     const int groups = (n_pu + LIST_G - 1) / LIST_G;
     return dim3((unsigned)groups, (unsigned)std::max(1, std::min(8, (4 * sm_count() + groups - 1) / groups)));
 }
@@ -1025,17 +1028,17 @@ __device__ __forceinline__ void hrow_cols(const uint32_t (&A)[NA], const int (&c
     }
 }
 
-template <int TAPS, bool BI, int COLS, int MINB>
+template <int TAPS, bool BI, int COLS, int MINB, int LDB>
 __global__ void __launch_bounds__(NT, MINB) pred_list_stream_kernel(PredParams p)
 {
     constexpr int G = LIST_G, NWARP = NT / 32, NREF = BI ? 2 : 1, DW0 = BI ? 8 : 6, LEFT = TAPS / 2 - 1, FB = TAPS == 8 ? 2 : 3, FM = (1 << FB) - 1;
     constexpr int NEED = COLS + TAPS - 1;        // footprint bytes of one strip row
     constexpr int NA = (NEED + 3) / 4;           // aligned words the horizontal filter reads
-    // words loaded per row.  LD8: three aligned 8-byte loads (the footprint starts at any byte of the first; the word it starts in is then
-    // selected) instead of five 4-byte ones: the L1 data stage, 73 % busy with 4-byte loads on 8x8 PU lists, is what these kernels run against
-    constexpr bool LD8 = COLS == 8;
-    constexpr int NW = LD8 ? 6 : (NEED + 3 + 3) / 4;
-    static_assert(!LD8 || NEED + 7 <= 24, "three 8-byte loads must cover the footprint");
+    // words loaded per row, as aligned loads of LDB bytes: the footprint starts at any byte of the first, and the word it starts in is selected
+    // afterwards (one SEL per word and address bit above the word).  Wider loads = fewer requests to the L1 data stage, which 4-byte loads kept
+    // 73 % busy on 8x8 PU lists
+    constexpr int NLD = (NEED + LDB - 1 + LDB - 1) / LDB, NW = NLD * (LDB / 4);
+    static_assert(LDB == 4 || LDB == 8 || LDB == 16, "load width");
     // rows per load batch; PIPE: the loads of the next batch are in flight while this one is filtered (two buffers - one reference only: with
     // two the registers do not fit)
     constexpr int LB = BI ? 2 : TAPS / 2, NB = TAPS / LB;
@@ -1121,36 +1124,46 @@ __global__ void __launch_bounds__(NT, MINB) pred_list_stream_kernel(PredParams p
         // one input row: NW aligned words covering the footprint, and the bit the footprint starts at inside the first
         auto fetch = [&](int rf, int r, uint32_t (&wd)[NW], int &sh8) {
             const uint8_t *row = src[rf] + (ptrdiff_t)min(r, rows_in - 1) * p.sr;   // batches are whole: rows past the footprint repeat its last one
-            if (LD8) {
-                const int a = (int)((uintptr_t)row & 7);
+            const int a = (int)((uintptr_t)row & (LDB - 1));
+            if (LDB == 16) {
+                const uint4 *ra = reinterpret_cast<const uint4 *>(row - a);
+#pragma unroll
+                for (int k = 0; k < NLD; ++k) {
+                    const uint4 v = __ldg(ra + k);
+                    wd[(4 * k) % NW] = v.x, wd[(4 * k + 1) % NW] = v.y, wd[(4 * k + 2) % NW] = v.z, wd[(4 * k + 3) % NW] = v.w;
+                }
+            } else if (LDB == 8) {
                 const uint2 *ra = reinterpret_cast<const uint2 *>(row - a);
 #pragma unroll
-                for (int k = 0; k < NW / 2; ++k) {
+                for (int k = 0; k < NLD; ++k) {
                     const uint2 v = __ldg(ra + k);
-                    wd[2 * k] = v.x, wd[2 * k + 1] = v.y;
+                    wd[(2 * k) % NW] = v.x, wd[(2 * k + 1) % NW] = v.y;
                 }
-                sh8 = a;
             } else {
-                const int a = (int)((uintptr_t)row & 3);
                 const uint32_t *ra = reinterpret_cast<const uint32_t *>(row - a);
 #pragma unroll
                 for (int k = 0; k < NW; ++k) wd[k] = __ldg(ra + k);
-                sh8 = 8 * a;
             }
+            sh8 = a;
         };
         // horizontal filter of one fetched row; its pairs with the previous row go to a ring slot
         auto hpack = [&](int rf, const uint32_t (&wd)[NW], int sh8, uint32_t (&slot)[COLS]) {
-            uint32_t A[NA];
-            if (LD8) {
-                uint32_t u[NA + 1];
+            uint32_t A[NA], u[NA + 1];
+            if (LDB == 16) {
+                uint32_t v[NA + 2];
 #pragma unroll
-                for (int j = 0; j < NA + 1; ++j) u[j] = (sh8 & 4) ? wd[(j + 1) % NW] : wd[j];
+                for (int j = 0; j < NA + 2; ++j) v[j] = (sh8 & 8) ? wd[(j + 2) % NW] : wd[j % NW];
 #pragma unroll
-                for (int j = 0; j < NA; ++j) A[j] = __funnelshift_r(u[j], u[j + 1], 8 * (sh8 & 3));
+                for (int j = 0; j < NA + 1; ++j) u[j] = (sh8 & 4) ? v[j + 1] : v[j];
+            } else if (LDB == 8) {
+#pragma unroll
+                for (int j = 0; j < NA + 1; ++j) u[j] = (sh8 & 4) ? wd[(j + 1) % NW] : wd[j % NW];
             } else {
 #pragma unroll
-                for (int j = 0; j < NA; ++j) A[j] = __funnelshift_r(wd[j], wd[(j + 1) % NW], sh8);
+                for (int j = 0; j < NA + 1; ++j) u[j] = wd[j % NW];
             }
+#pragma unroll
+            for (int j = 0; j < NA; ++j) A[j] = __funnelshift_r(u[j], u[j + 1], 8 * (sh8 & 3));
             int t[COLS];
             hrow_cols<TAPS, COLS, NA>(A, cx4[rf], t);
 #pragma unroll
@@ -1326,28 +1339,27 @@ static bool stream_ok(const uint8_t *dst, ptrdiff_t sd, ptrdiff_t fs_dst, const 
 }
 // columns per work item of the PU-list kernel and CTAs per SM it is compiled for (HEVCASM_LIST_COLS=4 / 8 and HEVCASM_LIST_MINB pin them in
 // the experiments build)
-template <bool BI, int COLS, int MINB>
+template <bool BI, int COLS, int MINB, int LDB>
 static int launch_list_as(int taps, void *stream, const PredParams &p)
 {
-    const dim3 grid = list_grid(p.n_pu, MINB);
-    return taps == 8 ? launch(pred_list_stream_kernel<8, BI, COLS, MINB>, grid, dim3(NT), 0, stream, p)
-                     : launch(pred_list_stream_kernel<4, BI, COLS, MINB>, grid, dim3(NT), 0, stream, p);
+    const dim3 grid = list_grid(p.n_pu);
+    return taps == 8 ? launch(pred_list_stream_kernel<8, BI, COLS, MINB, LDB>, grid, dim3(NT), 0, stream, p)
+                     : launch(pred_list_stream_kernel<4, BI, COLS, MINB, LDB>, grid, dim3(NT), 0, stream, p);
 }
+// one reference: 8-column strips, three CTAs per SM (168 registers), 8-byte loads; two references: 4-column strips, four CTAs per SM.
+// HEVCASM_LIST_LDB = 4 / 8 / 16 pins the load width in the experiments build (A/B)
 template <bool BI>
 static int launch_list(int taps, void *stream, const PredParams &p)
 {
 #ifdef HEVCASM_EXPERIMENTS
-    const char *pc = tune::knob("HEVCASM_LIST_COLS"), *pb = tune::knob("HEVCASM_LIST_MINB");
-    if (pc || pb) {
-        const int cols = pc ? atoi(pc) : (BI ? 4 : 8), minb = pb ? atoi(pb) : 3;
-        if constexpr (!BI) {
-            if (cols == 8) return minb >= 4 ? launch_list_as<BI, 8, 4>(taps, stream, p) : minb == 3 ? launch_list_as<BI, 8, 3>(taps, stream, p) : launch_list_as<BI, 8, 2>(taps, stream, p);
-        }
-        return minb >= 5 ? launch_list_as<BI, 4, 5>(taps, stream, p) : minb == 4 ? launch_list_as<BI, 4, 4>(taps, stream, p) : launch_list_as<BI, 4, 3>(taps, stream, p);
+    if (const char *pl = tune::knob("HEVCASM_LIST_LDB")) {
+        const int ldb = atoi(pl);
+        if constexpr (BI) return ldb == 16 ? launch_list_as<true, 4, 4, 16>(taps, stream, p) : ldb == 8 ? launch_list_as<true, 4, 4, 8>(taps, stream, p) : launch_list_as<true, 4, 4, 4>(taps, stream, p);
+        else return ldb == 16 ? launch_list_as<false, 8, 3, 16>(taps, stream, p) : ldb == 8 ? launch_list_as<false, 8, 3, 8>(taps, stream, p) : launch_list_as<false, 8, 3, 4>(taps, stream, p);
     }
 #endif
-    if constexpr (BI) return launch_list_as<true, 4, 4>(taps, stream, p);
-    else return launch_list_as<false, 8, 3>(taps, stream, p);
+    if constexpr (BI) return launch_list_as<true, 4, 4, 4>(taps, stream, p);
+    else return launch_list_as<false, 8, 3, 8>(taps, stream, p);
 }
 
 // PU lists: streaming kernel unless HEVCASM_PRED_PATH=tile / HEVCASM_PRED_GENERIC pins the tile kernel (A/B, and the tile

@@ -53,6 +53,8 @@ struct BlockGrid {
     long long n;
     FastDiv per_frame, per_row;   // blocks per frame / per block row (regular grids with n < 2^32; finish() fills them)
     bool fast;
+    int desc_w = 2;               // int16 per list entry: (x, y), or (x, y, frame) for the *_list_frames forms
+    bool on_grid = false;         // list entries sit at multiples of the block size (the *_list_frames contract): rows are aligned like a regular grid's
     void finish()
     {
         fast = !blk_xy && n > 0 && n < (1ll << 32) && nbx > 0 && nby > 0;
@@ -61,7 +63,8 @@ struct BlockGrid {
     __device__ __forceinline__ void locate(long long i, int log2, int &x, int &y, int &f) const
     {
         if (blk_xy) {
-            x = blk_xy[2 * i], y = blk_xy[2 * i + 1], f = 0;
+            const int16_t *e = blk_xy + i * desc_w;
+            x = e[0], y = e[1], f = desc_w == 3 ? e[2] : 0;
         } else if (fast) {
             const uint32_t u = (uint32_t)i, fr = per_frame.div(u), r = u - fr * per_frame.d, row = per_row.div(r);
             f = (int)fr, y = (int)(row << log2), x = (int)((r - row * per_row.d) << log2);
@@ -877,7 +880,7 @@ static int launch_fwd(int16_t *coeffs, const int16_t *res, ptrdiff_t stride, ptr
 {
     if (g.n == 0) return 0;
     if (((uintptr_t)coeffs & 15) != 0) return HEVCASM_ERR_ARGUMENT;
-    const bool pa = !g.blk_xy && aligned16(res, stride * 2, fs * 2);
+    const bool pa = (!g.blk_xy || g.on_grid) && aligned16(res, stride * 2, fs * 2);
     const char *pin = tune::knob("HEVCASM_FWD_PATH");
     const bool forced = pin && !strncmp(pin, "umma", 4);
     if ((log2 == 5 || log2 == 4) && !(pin && !strcmp(pin, "butterfly"))) {
@@ -952,7 +955,7 @@ static int launch_inv(uint8_t *dst, ptrdiff_t sd, const uint8_t *pred, ptrdiff_t
 {
     if (g.n == 0) return 0;
     if (((uintptr_t)coeffs & 15) != 0) return HEVCASM_ERR_ARGUMENT;
-    const bool pa = !g.blk_xy && aligned16(dst, sd, fs_dst, pred, sp, fs_pred);
+    const bool pa = (!g.blk_xy || g.on_grid) && aligned16(dst, sd, fs_dst, pred, sp, fs_pred);
 #ifdef HEVCASM_EXPERIMENTS
     // HEVCASM_INV_PATH=hybrid: 16x16 / 32x32 with the second stage on tcgen05 whenever the planes allow it; =hybrid_only: fail instead of
     // falling back (tests)
@@ -997,6 +1000,58 @@ extern "C" int hevcasm_inverse_transform_add_batch(uint8_t *dst, ptrdiff_t sd, c
     BlockGrid g{blk_xy, 0, 0, n};
     g.finish();
     return launch_inv(dst, sd, pred, sp, 0, 0, coeffs, log2size, trType, g, stream);
+}
+
+// Transform-unit lists of a batch of frames, bucketed by size class: entries (x, y, frame), first n_by_class[0] 4x4 DST blocks, then the 4x4,
+// 8x8, 16x16 and 32x32 DCT blocks; the coefficient blocks lie contiguous in the same order.  One launch per class present.
+static const int kClassLog2[5] = {2, 2, 3, 4, 5}, kClassType[5] = {1, 0, 0, 0, 0};
+static bool tu_counts_ok(const int *n_by_class, const int16_t *tus)
+{
+    if (!n_by_class) return false;
+    long long total = 0;
+    for (int c = 0; c < 5; ++c) {
+        if (n_by_class[c] < 0) return false;
+        total += n_by_class[c];
+    }
+    return total == 0 || tus;
+}
+
+extern "C" int hevcasm_transform_list_frames(int16_t *coeffs, const int16_t *residual, ptrdiff_t stride, const int16_t *tus, const int *n_by_class, ptrdiff_t fs,
+                                             void *stream)
+{
+    if (!tu_counts_ok(n_by_class, tus)) return HEVCASM_ERR_ARGUMENT;
+    long long first = 0, coef = 0;
+    for (int c = 0; c < 5; ++c) {
+        const int n = n_by_class[c], log2 = kClassLog2[c];
+        if (n) {
+            BlockGrid g{tus + 3 * first, 0, 0, n};
+            g.desc_w = 3, g.on_grid = true;
+            g.finish();
+            const int e = launch_fwd(coeffs + coef, residual, stride, fs, log2, kClassType[c], g, stream);
+            if (e) return e;
+        }
+        first += n, coef += (long long)n << (2 * log2);
+    }
+    return 0;
+}
+
+extern "C" int hevcasm_inverse_transform_add_list_frames(uint8_t *dst, ptrdiff_t sd, const uint8_t *pred, ptrdiff_t sp, const int16_t *coeffs, const int16_t *tus,
+                                                         const int *n_by_class, ptrdiff_t fs_dst, ptrdiff_t fs_pred, void *stream)
+{
+    if (!tu_counts_ok(n_by_class, tus)) return HEVCASM_ERR_ARGUMENT;
+    long long first = 0, coef = 0;
+    for (int c = 0; c < 5; ++c) {
+        const int n = n_by_class[c], log2 = kClassLog2[c];
+        if (n) {
+            BlockGrid g{tus + 3 * first, 0, 0, n};
+            g.desc_w = 3, g.on_grid = true;
+            g.finish();
+            const int e = launch_inv(dst, sd, pred, sp, fs_dst, fs_pred, coeffs + coef, log2, kClassType[c], g, stream);
+            if (e) return e;
+        }
+        first += n, coef += (long long)n << (2 * log2);
+    }
+    return 0;
 }
 
 extern "C" int hevcasm_inverse_transform_add_frames(uint8_t *dst, ptrdiff_t sd, const uint8_t *pred, ptrdiff_t sp, const int16_t *coeffs, int width,

@@ -102,7 +102,7 @@ __global__ void __launch_bounds__(UMMA_NT, 6) umma_inv_kernel(uint8_t *__restric
         const bool live = blk < grid.n;
         int x0 = 0, y0 = 0, f = 0;
         if (grid.blk_xy) {
-            if (live) x0 = grid.blk_xy[2 * blk], y0 = grid.blk_xy[2 * blk + 1];
+            if (live) x0 = grid.blk_xy[grid.desc_w * blk], y0 = grid.blk_xy[grid.desc_w * blk + 1], f = grid.desc_w == 3 ? grid.blk_xy[grid.desc_w * blk + 2] : 0;
         } else {
             x0 = bx << LOG2, y0 = by << LOG2, f = bf;
             bx += step_x, by += step_y;

@@ -171,6 +171,15 @@ int HEVCASM_API hevcasm_transform_frames(int16_t *coeffs, const int16_t *residua
 int HEVCASM_API hevcasm_inverse_transform_add_batch(uint8_t *dst, ptrdiff_t stride_dst, const uint8_t *pred, ptrdiff_t stride_pred,
                                                     const int16_t *coeffs, int log2size, int trType, const int16_t *blk_xy, int n,
                                                     void *stream);
+/* Transform-unit lists of a batch of frames in one call (a GOP's TUs, bucketed by size class while the lists are built): tus[i] =
+ * {x, y, frame}, x and y multiples of the TU size; the first n_by_class[0] entries are 4x4 DST blocks, then n_by_class[1] 4x4, [2] 8x8, [3] 16x16 and [4] 32x32 DCT
+ * blocks; block i's coefficients follow block i-1's (N*N contiguous int16 each), coeffs 16-byte aligned.  One launch per class present.
+ * Element semantics as hevcasm_transform_batch / hevcasm_inverse_transform_add_batch. */
+int HEVCASM_API hevcasm_transform_list_frames(int16_t *coeffs, const int16_t *residual, ptrdiff_t stride, const int16_t *tus,
+                                              const int *n_by_class, ptrdiff_t frame_stride_residual, void *stream);
+int HEVCASM_API hevcasm_inverse_transform_add_list_frames(uint8_t *dst, ptrdiff_t stride_dst, const uint8_t *pred, ptrdiff_t stride_pred,
+                                                          const int16_t *coeffs, const int16_t *tus, const int *n_by_class,
+                                                          ptrdiff_t frame_stride_dst, ptrdiff_t frame_stride_pred, void *stream);
 int HEVCASM_API hevcasm_inverse_transform_add_frames(uint8_t *dst, ptrdiff_t stride_dst, const uint8_t *pred, ptrdiff_t stride_pred,
                                                      const int16_t *coeffs, int width, int height, int log2size, int trType,
                                                      int n_frames, ptrdiff_t frame_stride_dst, ptrdiff_t frame_stride_pred,

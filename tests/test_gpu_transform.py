@@ -180,3 +180,74 @@ def test_roundtrip_property(log2):
     zero = dev_full(res.buf.shape, np.int16, 0)
     lib.call("transform_frames", dptr(co), dptr(zero, res.origin), res.pitch, width, height, log2, 0, 1, res.frame_stride)
     assert not to_host(co).any()
+
+
+def _tu_buckets(seed, nf, width, height):
+    """a random quad-tree tiling of every frame into 32x32 / 16x16 / 8x8 / 4x4 transform units (4x4: DST or DCT), bucketed by size class in
+    the order the *_list_frames forms take: [4x4 DST, 4x4 DCT, 8x8, 16x16, 32x32], entries (x, y, frame)"""
+    r = synth.splitmix64(seed, nf * (width // 32) * (height // 32) * 2).astype(np.int64)
+    buckets, k = [[] for _ in range(5)], 0
+    for f in range(nf):
+        for cy in range(0, height - 31, 32):
+            for cx in range(0, width - 31, 32):
+                kind, sub = int(r[k] % 5), int(r[k + 1])
+                k += 2
+                if kind == 4:
+                    buckets[4].append((cx, cy, f))
+                    continue
+                n = 4 << max(kind - 1, 0)          # kinds 0 and 1: 4x4 (DST / DCT mixed), 2: 8x8, 3: 16x16
+                for j, y in enumerate(range(cy, cy + 32, n)):
+                    for i, x in enumerate(range(cx, cx + 32, n)):
+                        c = kind if kind >= 2 else ((sub >> ((i + 8 * j) % 60)) & 1)
+                        buckets[c].append((x, y, f))
+    return [np.array(b, np.int16).reshape(-1, 3) for b in buckets]
+
+
+CLASSES = [(1, 2), (0, 2), (0, 3), (0, 4), (0, 5)]   # (trType, log2size) per bucket
+
+
+def test_tu_lists_over_frames(oracle):
+    """hevcasm_inverse_transform_add_list_frames / hevcasm_transform_list_frames: the mixed transform-unit lists of several frames in one call
+    = the oracle's per-size list forms on each frame"""
+    width, height, nf = 352, 288, 3
+    buckets = _tu_buckets(300, nf, width, height)
+    assert all(len(b) > 20 for b in buckets)
+    counts = np.array([len(b) for b in buckets], np.int32)
+    tus = np.ascontiguousarray(np.concatenate(buckets))
+    ncoef = [len(b) << (2 * log2) for b, (_, log2) in zip(buckets, CLASSES)]
+    start = np.concatenate([[0], np.cumsum(ncoef)])
+    # inverse
+    pred = synth.random_planes(301, nf, width, height, 8)
+    co = synth.random_int16(302, int(start[-1]), -3000, 3000)
+    want = synth.random_planes(303, nf, width, height, 8)
+    got = to_dev(want.buf)
+    for c, ((trType, log2), b) in enumerate(zip(CLASSES, buckets)):
+        blk = co[start[c]:start[c + 1]].reshape(len(b), -1)
+        for f in range(nf):
+            sel = b[:, 2] == f
+            xy, cf = np.ascontiguousarray(b[sel, :2]), np.ascontiguousarray(blk[sel])
+            oracle.drv("inverse_transform_add_batch", ptr(want.buf[f], want.origin), want.pitch, ptr(pred.buf[f], pred.origin), pred.pitch, ptr(cf), log2,
+                       trType, ptr(xy), len(xy), threads=4)
+    dp, dc, dt = to_dev(pred.buf), to_dev(co), to_dev(tus)
+    lib.call("inverse_transform_add_list_frames", dptr(got, want.origin), want.pitch, dptr(dp, pred.origin), pred.pitch, dptr(dc), dptr(dt), ptr(counts),
+             want.frame_stride, pred.frame_stride)
+    assert np.array_equal(to_host(got), want.buf)
+    # forward
+    res = _res_planes(304, nf, width, height, -256, 255)
+    want_co = np.zeros(int(start[-1]), np.int16)
+    for c, ((trType, log2), b) in enumerate(zip(CLASSES, buckets)):
+        out = want_co[start[c]:start[c + 1]].reshape(len(b), -1)
+        for f in range(nf):
+            sel = np.flatnonzero(b[:, 2] == f)
+            xy, cf = np.ascontiguousarray(b[sel, :2]), np.zeros((len(sel), out.shape[1]), np.int16)
+            oracle.drv("transform_batch", ptr(cf), ptr(res.buf[f], res.origin), res.pitch, log2, trType, ptr(xy), len(xy), threads=4)
+            out[sel] = cf
+    dres, dco = to_dev(res.buf), dev_full((int(start[-1]),), np.int16, 0)
+    lib.call("transform_list_frames", dptr(dco), dptr(dres, res.origin), res.pitch, dptr(dt), ptr(counts), res.frame_stride)
+    assert np.array_equal(to_host(dco), want_co)
+    # an empty list is a no-op, a negative count an argument error
+    zero = np.zeros(5, np.int32)
+    lib.call("inverse_transform_add_list_frames", dptr(got), want.pitch, dptr(dp), pred.pitch, dptr(dc), None, ptr(zero), 0, 0)
+    bad = np.array([0, -1, 0, 0, 0], np.int32)
+    with pytest.raises(lib.HevcasmError):
+        lib.call("transform_list_frames", dptr(dco), dptr(dres), res.pitch, dptr(dt), ptr(bad), 0)
