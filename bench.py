@@ -280,25 +280,20 @@ def pu_list(synth, torch, width, height, sizes, nf, bi=False, seed=5):
 
 
 def tu_buckets(synth, torch, width, height, nf, seed=9):
-    """a quad-tree-like tiling of `nf` frames into transform units: every 32x32 cell is one 32x32 TU, four 16x16, sixteen 8x8 or sixty-four 4x4
-    (DST / DCT alternating), chosen at random; bucketed by size class as the *_list_frames forms take them: entries {x, y, frame} as int16, counts
-    [4x4 DST, 4x4 DCT, 8x8, 16x16, 32x32]"""
-    cx, cy, ff = np.meshgrid(np.arange(width // 32) * 32, np.arange(height // 32) * 32, np.arange(nf), indexing="ij")
+    """a tiling of `nf` frames into transform units: every 64x64 CTU holds TUs of one size class - 4x4 DST, 4x4, 8x8, 16x16 or 32x32 - chosen at
+    random (the classes of a frame interleave at CTU granularity: a class's blocks are 64-byte row segments scattered over the plane); bucketed by size class as the *_list_frames forms take them: entries
+    {x, y, frame} as int16, counts [4x4 DST, 4x4 DCT, 8x8, 16x16, 32x32]"""
+    cx, cy, ff = np.meshgrid(np.arange(width // 64) * 64, np.arange(height // 64) * 64, np.arange(nf), indexing="ij")
     cx, cy, ff = cx.reshape(-1), cy.reshape(-1), ff.reshape(-1)
-    kind = synth.splitmix64(seed, len(cx)).astype(np.int64) % 4      # 0: 4x4, 1: 8x8, 2: 16x16, 3: 32x32
-    buckets = [None] * 5
-    for k, nsz in ((0, 4), (1, 8), (2, 16), (3, 32)):
+    kind = synth.splitmix64(seed, len(cx)).astype(np.int64) % 5      # the size class of the cell
+    buckets = []
+    for k, nsz in enumerate((4, 4, 8, 16, 32)):
         sel = kind == k
-        ox, oy = np.meshgrid(np.arange(0, 32, nsz), np.arange(0, 32, nsz))
+        ox, oy = np.meshgrid(np.arange(0, 64, nsz), np.arange(0, 64, nsz))
         x = (cx[sel, None] + ox.reshape(1, -1)).reshape(-1)
         y = (cy[sel, None] + oy.reshape(1, -1)).reshape(-1)
         f = np.repeat(ff[sel], ox.size)
-        e = np.stack([x, y, f], -1).astype(np.int16)
-        if k == 0:
-            dst = ((x // 4 + y // 4) & 1) == 0
-            buckets[0], buckets[1] = e[dst], e[~dst]
-        else:
-            buckets[k + 1] = e
+        buckets.append(np.stack([x, y, f], -1).astype(np.int16))
     counts = np.array([len(b) for b in buckets], np.int32)
     covered = int(sum(len(b) * (16, 16, 64, 256, 1024)[c] for c, b in enumerate(buckets)))
     return torch.from_numpy(np.ascontiguousarray(np.concatenate(buckets))).cuda(), counts, covered
