@@ -413,6 +413,16 @@ def kernel_table(torch, lib, synth, stream, hbm_peak, counters, with_cpu, launch
         rec("pred_bi_list_mixed_8..64", lambda: lib.call("pred_bi_list_frames", dptr(o8, org), pitch, dptr(a, org), dptr(b, org), pitch, 8, dptr(pl), pl.shape[0], fs, fs,
                                                          stream=stream), covered, 3, bound="int-pipe (IDP)", extra={"pus": int(pl.shape[0])})
 
+    # SAD of every PU of a mixed list at its own integer vector (the refinement step after the sweep), whole batch in one launch
+    if hasattr(lib.load(), "hevcasm_sad_list_frames"):
+        pl, covered = pu_list(synth, torch, W4K, H4K, (8, 16, 32, 64), NF)
+        sl = pl.clone()
+        sl[:, 4:6] = torch.div(sl[:, 4:6], 4, rounding_mode="floor")
+        sl = sl.contiguous()
+        sad_out = torch.empty((sl.shape[0],), dtype=torch.int32, device="cuda")
+        rec("sad_pu_list_mixed_8..64", lambda: lib.call("sad_list_frames", dptr(a, org), pitch, dptr(b, org), pitch, dptr(sl), sl.shape[0], fs, fs, dptr(sad_out),
+                                                        stream=stream), covered, 2, extra={"pus": int(sl.shape[0])})
+
     # residual path: int16 residual planes
     rp = synth.pitch_for(W4K, 0, 128)
     res = torch.randint(-256, 256, (NF, H4K, rp), dtype=torch.int16, device="cuda", generator=g)

@@ -44,6 +44,8 @@ GPU_ONLY_ABI = {
     "residual_pipeline_frames": [P, PD, P, P, P, PD, P, PD, I, I, I, I, I, I, I, I, I, I, PD, PD, PD],
     "transform_from_planes_frames": [P, P, PD, P, PD, I, I, I, I, I, PD, PD],
     "residual_from_planes_pipeline_frames": [P, PD, P, P, P, PD, P, PD, I, I, I, I, I, I, I, I, I, I, PD, PD, PD],
+    "sad_list_frames": [P, PD, P, PD, P, I, PD, PD, P],
+    "ssd_list_frames": [P, PD, P, PD, P, I, PD, PD, P],
     "transform_list_frames": [P, P, PD, P, P, PD],
     "inverse_transform_add_list_frames": [P, PD, P, PD, P, P, P, PD, PD],
     "pred_uni_list_frames": [P, PD, P, PD, I, P, I, PD, PD],

@@ -855,6 +855,59 @@ static bool rect_ok(uint32_t rect, int &w, int &h)
     return w >= 4 && h >= 4 && w <= 64 && h <= 64 && (w & 3) == 0 && (h & 3) == 0;
 }
 
+// ---- PU lists over a batch of frames: every PU has its own size, integer vector and frame ------------------------------------
+// pus[i] = {x, y, w, h, dx, dy, frame}: out[i] = SAD (or SSD) of the w x h block of `src` at (x, y) and the block of `ref` at (x + dx, y + dy),
+// both in plane `frame`.  One warp per PU.  A descriptor whose w or h is not a multiple of 4 in 4..64 gives -1.
+template <bool SSD>
+__global__ void __launch_bounds__(256) pu_list_cost_kernel(const uint8_t *__restrict__ src, ptrdiff_t ss, ptrdiff_t fs_src, const uint8_t *__restrict__ ref,
+                                                           ptrdiff_t sr, ptrdiff_t fs_ref, const int16_t *__restrict__ pus, int n_pu, int32_t *__restrict__ out)
+{
+    const long long gw = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (gw >= n_pu) return;
+    const int16_t *d = pus + gw * 7;
+    const int x = d[0], y = d[1], w = d[2], h = d[3], dx = d[4], dy = d[5], f = d[6];
+    if (w < 4 || h < 4 || w > 64 || h > 64 || ((w | h) & 3)) {
+        if (lane == 0) out[gw] = -1;
+        return;
+    }
+    const uint8_t *s = src + f * fs_src + (ptrdiff_t)y * ss + x;
+    const uint8_t *r = ref + f * fs_ref + (ptrdiff_t)(y + dy) * sr + (x + dx);
+    const int wpr = w >> 2, total = wpr * h;
+    uint32_t acc = 0;
+    for (int idx = lane; idx < total; idx += 32) {
+        const int row = idx / wpr, k = idx - row * wpr;
+        const uint32_t a = ldg_word_unaligned(s + (ptrdiff_t)row * ss + 4 * k), b = ldg_word_unaligned(r + (ptrdiff_t)row * sr + 4 * k);
+        if (SSD) {
+            const uint32_t df = __vabsdiffu4(a, b);
+            acc = dp4a_uu(df, df, acc);
+        } else {
+            acc = sad4(a, b, acc);
+        }
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) out[gw] = (int32_t)acc;
+}
+
+extern "C" int hevcasm_sad_list_frames(const uint8_t *src, ptrdiff_t ss, const uint8_t *ref, ptrdiff_t sr, const int16_t *pus, int n_pu, ptrdiff_t fs_src,
+                                       ptrdiff_t fs_ref, int32_t *sad, void *stream)
+{
+    if (n_pu < 0 || (n_pu > 0 && (!pus || !sad))) return HEVCASM_ERR_ARGUMENT;
+    if (n_pu == 0) return 0;
+    HV_LAUNCH(pu_list_cost_kernel<false>, (unsigned)((n_pu + 7) / 8), 256, 0, stream, src, ss, fs_src, ref, sr, fs_ref, pus, n_pu, sad);
+    return 0;
+}
+
+extern "C" int hevcasm_ssd_list_frames(const uint8_t *srcA, ptrdiff_t sa, const uint8_t *srcB, ptrdiff_t sb, const int16_t *pus, int n_pu, ptrdiff_t fs_a,
+                                       ptrdiff_t fs_b, int32_t *ssd, void *stream)
+{
+    if (n_pu < 0 || (n_pu > 0 && (!pus || !ssd))) return HEVCASM_ERR_ARGUMENT;
+    if (n_pu == 0) return 0;
+    HV_LAUNCH(pu_list_cost_kernel<true>, (unsigned)((n_pu + 7) / 8), 256, 0, stream, srcA, sa, fs_a, srcB, sb, fs_b, pus, n_pu, ssd);
+    return 0;
+}
+
 extern "C" int hevcasm_sad_multiref_batch(const uint8_t *src, ptrdiff_t ss, const uint8_t *ref, ptrdiff_t sr, uint32_t rect,
                                           const int16_t *pu_xy, int n_pu, const int16_t *cand, int n_cand, int32_t *sad, void *stream)
 {

@@ -56,6 +56,16 @@ int HEVCASM_API hevcasm_sad_multiref_batch(const uint8_t *src, ptrdiff_t stride_
 int HEVCASM_API hevcasm_sad_batch(const uint8_t *src, ptrdiff_t stride_src, const uint8_t *ref, ptrdiff_t stride_ref, uint32_t rect,
                                   const int16_t *pu_xy, const int16_t *mv_xy, int n_pu, int32_t *sad, void *stream);
 
+/* PU lists over a batch of frames in one launch: pus[i] = {x, y, w, h, dx, dy, frame} (int16 x 7; w, h multiples of 4 in 4..64; (dx, dy) an
+ * integer displacement into the reference, 0 0 for a co-located cost).  out[i] = SAD / SSD of src block (x, y) of plane `frame` against
+ * ref block (x + dx, y + dy) of plane `frame`; -1 for a descriptor with an illegal size.  Element semantics: sad.h:50, ssd.h:53. */
+int HEVCASM_API hevcasm_sad_list_frames(const uint8_t *src, ptrdiff_t stride_src, const uint8_t *ref, ptrdiff_t stride_ref,
+                                        const int16_t *pus, int n_pu, ptrdiff_t frame_stride_src, ptrdiff_t frame_stride_ref,
+                                        int32_t *sad, void *stream);
+int HEVCASM_API hevcasm_ssd_list_frames(const uint8_t *srcA, ptrdiff_t stride_srcA, const uint8_t *srcB, ptrdiff_t stride_srcB,
+                                        const int16_t *pus, int n_pu, ptrdiff_t frame_stride_srcA, ptrdiff_t frame_stride_srcB,
+                                        int32_t *ssd, void *stream);
+
 /* Motion-estimation sweep: the floor(width/w) x floor(height/h) non-overlapping PUs of every frame, each against
  * the dense candidate window dx in [dx0, dx0+ncx), dy in [dy0, dy0+ncy).
  * sad[frame][py][px][(dy-dy0)*ncx + (dx-dx0)].  ncx*ncy <= 256. */

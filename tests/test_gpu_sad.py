@@ -236,3 +236,52 @@ def test_pyramid_packed_matches_full(shape):
     for s, a, b in zip((8, 16, 32, 64), full, pk):
         assert np.array_equal(to_host(a), to_host(b).astype(np.int32)), s
     assert int(to_host(pk[1]).max()) == 65280
+
+
+def test_pu_lists_over_frames(oracle):
+    """hevcasm_sad_list_frames / hevcasm_ssd_list_frames: PUs of every partition size, each with its own integer vector and frame index, in one
+    launch = the oracle's per-size list forms on each frame"""
+    width, height, nf = 320, 200, 3
+    src, ref = _frames(nf, width, height, pad=40)
+    ds, dr = to_dev(src.buf), to_dev(ref.buf)
+    rng = synth.splitmix64(78, 8192).astype(np.int64)
+    rows, k = [], 0
+    for rep in range(6):
+        for (w, h) in PARTITIONS:
+            rows.append((rng[k] % (width - w), rng[k + 1] % (height - h), w, h, rng[k + 2] % 65 - 32, rng[k + 3] % 65 - 32, rng[k + 4] % nf))
+            k += 5
+    pus = np.array(rows, np.int16)
+    want = np.zeros(len(pus), np.int32)
+    for (w, h) in PARTITIONS:
+        for f in range(nf):
+            sel = np.flatnonzero((pus[:, 2] == w) & (pus[:, 3] == h) & (pus[:, 6] == f))
+            if not len(sel):
+                continue
+            xy, mv = np.ascontiguousarray(pus[sel, 0:2]), np.ascontiguousarray(pus[sel, 4:6])
+            part = np.zeros(len(sel), np.int32)
+            oracle.drv("sad_batch", ptr(src.buf[f], src.origin), src.pitch, ptr(ref.buf[f], ref.origin), ref.pitch, HEVCASM_RECT(w, h), ptr(xy), ptr(mv),
+                       len(sel), ptr(part))
+            want[sel] = part
+    got = dev_full(want.shape, np.int32, -7)
+    dp = to_dev(pus)
+    lib.call("sad_list_frames", dptr(ds, src.origin), src.pitch, dptr(dr, ref.origin), ref.pitch, dptr(dp), len(pus), src.frame_stride, ref.frame_stride,
+             dptr(got))
+    assert np.array_equal(to_host(got), want)
+    # SSD: square sizes at a zero vector against the oracle's ssd list form; an illegal size gives -1
+    sq = np.array([(rng[k + 5 * i] % (width - 64), rng[k + 5 * i + 1] % (height - 64), 4 << (i % 5), 4 << (i % 5), 0, 0, rng[k + 5 * i + 2] % nf) for i in range(60)]
+                  + [(0, 0, 6, 8, 0, 0, 0)], np.int16)
+    want2 = np.full(len(sq), -1, np.int32)
+    for log2 in range(2, 7):
+        for f in range(nf):
+            sel = np.flatnonzero((sq[:, 2] == 1 << log2) & (sq[:, 6] == f))
+            if not len(sel):
+                continue
+            xy, part = np.ascontiguousarray(sq[sel, 0:2]), np.zeros(len(sel), np.int32)
+            oracle.drv("ssd_batch", ptr(src.buf[f], src.origin), src.pitch, ptr(ref.buf[f], ref.origin), ref.pitch, log2, ptr(xy), len(sel), ptr(part))
+            want2[sel] = part
+    got2 = dev_full(want2.shape, np.int32, -7)
+    dq = to_dev(sq)
+    lib.call("ssd_list_frames", dptr(ds, src.origin), src.pitch, dptr(dr, ref.origin), ref.pitch, dptr(dq), len(sq), src.frame_stride, ref.frame_stride,
+             dptr(got2))
+    assert np.array_equal(to_host(got2), want2)
+    lib.call("sad_list_frames", dptr(ds), src.pitch, dptr(dr), ref.pitch, None, 0, 0, 0, None)   # empty list: no-op
