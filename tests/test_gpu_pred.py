@@ -299,3 +299,39 @@ def test_pu_lists_over_frames(oracle, taps):
             lib.call("pred_uni_list_frames", dptr(got, want.origin), want.pitch, dptr(d0, r0.origin), r0.pitch, taps, dptr(dp), len(mixed), want.frame_stride,
                      r0.frame_stride)
         assert np.array_equal(to_host(got), want.buf), bi
+
+
+@pytest.mark.parametrize("taps", [8, 4])
+def test_pu_lists_odd_strides(oracle, taps):
+    """the PU-list kernels with row strides that are not multiples of 4 (every row of a strip has its own alignment) and odd plane origins"""
+    width, height = 512, 420
+    pus = _pu_list(taps, width, height, 281)
+
+    def odd(planes, extra, shift):
+        """the same planes in a buffer with an odd pitch, origin shifted by `shift` bytes"""
+        nf, rows, pitch = planes.buf.shape
+        flat = np.zeros(nf * rows * (pitch + extra) + 64, np.uint8)
+        view = np.lib.stride_tricks.as_strided(flat[shift:], (nf, rows, pitch), (rows * (pitch + extra), pitch + extra, 1))
+        view[...] = planes.buf
+        return flat, view, shift + planes.pad * (pitch + extra) + planes.pad, pitch + extra, rows * (pitch + extra)
+
+    r0 = _ref_planes(282 + taps, 1, width, height, pad=32)
+    r1 = _ref_planes(283 + taps, 1, width, height, pad=32, kind="smooth")
+    w0 = synth.random_planes(284, 1, width, height, 32)
+    f0, _, o0, p0, _ = odd(r0, 3, 1)
+    f1, _, o1, p1, _ = odd(r1, 3, 1)
+    assert p0 == p1 and o0 == o1
+    for bi in (False, True):
+        fw, vw, ow, pw, _ = odd(w0, 1, 2)
+        d = np.ascontiguousarray(pus if bi else pus[:, :6])
+        if bi:
+            oracle.drv("pred_bi_batch", ptr(fw, ow), pw, ptr(f0, o0), ptr(f1, o1), p0, taps, ptr(d), len(d), threads=4)
+        else:
+            oracle.drv("pred_uni_batch", ptr(fw, ow), pw, ptr(f0, o0), p0, taps, ptr(d), len(d), threads=4)
+        fg = odd(w0, 1, 2)[0]
+        dg, d0, d1, dp = to_dev(fg), to_dev(f0), to_dev(f1), to_dev(d)
+        if bi:
+            lib.call("pred_bi_batch", dptr(dg, ow), pw, dptr(d0, o0), dptr(d1, o1), p0, taps, dptr(dp), len(d))
+        else:
+            lib.call("pred_uni_batch", dptr(dg, ow), pw, dptr(d0, o0), p0, taps, dptr(dp), len(d))
+        assert np.array_equal(to_host(dg), fw), bi
