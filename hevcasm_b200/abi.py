@@ -47,6 +47,7 @@ GPU_ONLY_ABI = {
     "sad_list_frames": [P, PD, P, PD, P, I, PD, PD, P],
     "ssd_list_frames": [P, PD, P, PD, P, I, PD, PD, P],
     "transform_list_frames": [P, P, PD, P, P, PD],
+    "quantize_reconstruct_list_frames": [P, PD, P, PD, P, P, P, PD, PD],
     "inverse_transform_add_list_frames": [P, PD, P, PD, P, P, P, PD, PD],
     "pred_uni_list_frames": [P, PD, P, PD, I, P, I, PD, PD],
     "pred_bi_list_frames": [P, PD, P, P, PD, I, P, I, PD, PD],

@@ -164,6 +164,7 @@ struct ReconParams {
     ptrdiff_t sr, sp, fs_rec, fs_pred;
     int nbx, nby;                // frames form: block grid per frame (blockIdx.y = block row, blockIdx.z = frame)
     const int16_t *blk_xy;       // list form: nbx = number of blocks, nby = 1
+    int desc_w;                  // list form: int16 per entry - (x, y), or (x, y, frame) for the *_list_frames form
 };
 
 // The residual of a block row is one flat run of int16 (blocks are N*N contiguous), so the kernel streams it: unit u is
@@ -192,11 +193,17 @@ __global__ void __launch_bounds__(256) reconstruct_kernel(ReconParams p)
         size_t blk;
         if (N == 4) r = 2 * w, xs = 0;
         else r = w / (N / 8), xs = (w % (N / 8)) * 8;
-        if (p.blk_xy) x = p.blk_xy[2 * bx], y = p.blk_xy[2 * bx + 1], blk = (size_t)bx;
-        else x = bx * N, y = by * N, blk = ((size_t)f * p.nby + by) * p.nbx + bx;
+        int fk = f;
+        if (p.blk_xy) {
+            const int16_t *e = p.blk_xy + (size_t)p.desc_w * bx;
+            x = e[0], y = e[1], blk = (size_t)bx;
+            if (p.desc_w == 3) fk = e[2];
+        } else {
+            x = bx * N, y = by * N, blk = ((size_t)f * p.nby + by) * p.nbx + bx;
+        }
         rv[k] = ldg_stream(reinterpret_cast<const int4 *>(p.res + blk * (N * N)) + w);
-        pp[k] = p.pred + f * p.fs_pred + (ptrdiff_t)(y + r) * p.sp + x + xs;
-        ro[k] = f * p.fs_rec + (ptrdiff_t)(y + r) * p.sr + x + xs;
+        pp[k] = p.pred + fk * p.fs_pred + (ptrdiff_t)(y + r) * p.sp + x + xs;
+        ro[k] = fk * p.fs_rec + (ptrdiff_t)(y + r) * p.sr + x + xs;
         if (N == 4) pv[k] = make_uint2(PA ? __ldg(reinterpret_cast<const uint32_t *>(pp[k])) : ld4(pp[k]),
                                        PA ? __ldg(reinterpret_cast<const uint32_t *>(pp[k] + p.sp)) : ld4(pp[k] + p.sp));
         else pv[k] = PA ? __ldg(reinterpret_cast<const uint2 *>(pp[k])) : make_uint2(ld4(pp[k]), ld4(pp[k] + 4));
@@ -292,8 +299,35 @@ extern "C" int hevcasm_quantize_reconstruct_batch(uint8_t *rec, ptrdiff_t sr, co
     if (n == 0) return 0;
     ReconParams p;
     p.rec = rec, p.pred = pred, p.res = res, p.sr = sr, p.sp = sp, p.fs_rec = 0, p.fs_pred = 0;
-    p.nbx = n, p.nby = 1, p.blk_xy = blk_xy;
+    p.nbx = n, p.nby = 1, p.blk_xy = blk_xy, p.desc_w = 2;
     return launch_reconstruct(p, log2size, 1, stream);
+}
+
+// Transform-unit lists of a batch of frames, bucketed by size: entries (x, y, frame), first the n_by_size[0] 4x4 blocks, then the 8x8, 16x16 and
+// 32x32 ones; the residual blocks lie contiguous in the same order.  One launch per size present.
+extern "C" int hevcasm_quantize_reconstruct_list_frames(uint8_t *rec, ptrdiff_t sr, const uint8_t *pred, ptrdiff_t sp, const int16_t *res, const int16_t *tus,
+                                                        const int *n_by_size, ptrdiff_t fs_rec, ptrdiff_t fs_pred, void *stream)
+{
+    if (!n_by_size || ((uintptr_t)res & 15)) return HEVCASM_ERR_ARGUMENT;
+    long long total = 0;
+    for (int c = 0; c < 4; ++c) {
+        if (n_by_size[c] < 0) return HEVCASM_ERR_ARGUMENT;
+        total += n_by_size[c];
+    }
+    if (total && !tus) return HEVCASM_ERR_ARGUMENT;
+    long long first = 0, off = 0;
+    for (int c = 0; c < 4; ++c) {
+        const int n = n_by_size[c], log2 = 2 + c;
+        if (n) {
+            ReconParams p;
+            p.rec = rec, p.pred = pred, p.res = res + off, p.sr = sr, p.sp = sp, p.fs_rec = fs_rec, p.fs_pred = fs_pred;
+            p.nbx = n, p.nby = 1, p.blk_xy = tus + 3 * first, p.desc_w = 3;
+            const int e = launch_reconstruct(p, log2, 1, stream);
+            if (e) return e;
+        }
+        first += n, off += (long long)n << (2 * log2);
+    }
+    return 0;
 }
 
 extern "C" int hevcasm_quantize_reconstruct_frames(uint8_t *rec, ptrdiff_t sr, const uint8_t *pred, ptrdiff_t sp, const int16_t *res, int width,
@@ -302,7 +336,7 @@ extern "C" int hevcasm_quantize_reconstruct_frames(uint8_t *rec, ptrdiff_t sr, c
     if (log2size < 2 || log2size > 5 || n_frames < 0 || width < 0 || height < 0 || ((uintptr_t)res & 15)) return HEVCASM_ERR_ARGUMENT;
     ReconParams p;
     p.rec = rec, p.pred = pred, p.res = res, p.sr = sr, p.sp = sp, p.fs_rec = fs_rec, p.fs_pred = fs_pred;
-    p.nbx = width >> log2size, p.nby = height >> log2size, p.blk_xy = nullptr;
+    p.nbx = width >> log2size, p.nby = height >> log2size, p.blk_xy = nullptr, p.desc_w = 2;
     if (p.nbx == 0 || p.nby == 0 || n_frames == 0) return 0;
     return launch_reconstruct(p, log2size, n_frames, stream);
 }

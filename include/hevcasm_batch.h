@@ -207,6 +207,11 @@ int HEVCASM_API hevcasm_quantize_inverse_batch(int16_t *dst, const int16_t *src,
                                                void *stream);
 int HEVCASM_API hevcasm_quantize_reconstruct_batch(uint8_t *rec, ptrdiff_t stride_rec, const uint8_t *pred, ptrdiff_t stride_pred,
                                                    const int16_t *res, int log2size, const int16_t *blk_xy, int n, void *stream);
+/* the same over the TU lists of a batch of frames: tus[i] = {x, y, frame}, bucketed by size - n_by_size[0] 4x4 blocks, then the 8x8, 16x16 and
+ * 32x32 ones; block i's residual follows block i-1's.  One launch per size present. */
+int HEVCASM_API hevcasm_quantize_reconstruct_list_frames(uint8_t *rec, ptrdiff_t stride_rec, const uint8_t *pred, ptrdiff_t stride_pred,
+                                                         const int16_t *res, const int16_t *tus, const int *n_by_size,
+                                                         ptrdiff_t frame_stride_rec, ptrdiff_t frame_stride_pred, void *stream);
 int HEVCASM_API hevcasm_quantize_reconstruct_frames(uint8_t *rec, ptrdiff_t stride_rec, const uint8_t *pred, ptrdiff_t stride_pred,
                                                     const int16_t *res, int width, int height, int log2size, int n_frames,
                                                     ptrdiff_t frame_stride_rec, ptrdiff_t frame_stride_pred, void *stream);

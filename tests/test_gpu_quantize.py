@@ -69,3 +69,30 @@ def test_quantize_reconstruct(oracle, log2):
         lib.call("quantize_reconstruct_batch", dptr(got2, want2.origin), want2.pitch, dptr(dp, pred.origin), pred.pitch, dptr(dr), log2,
                  dptr(dxy), len(xy))
         assert np.array_equal(to_host(got2), want2.buf)
+
+
+def test_reconstruct_tu_lists_over_frames(oracle):
+    """hevcasm_quantize_reconstruct_list_frames: mixed-size TU lists of several frames in one call = the oracle's per-size list form per frame"""
+    from test_gpu_transform import _tu_buckets
+    width, height, nf = 352, 288, 3
+    b5 = _tu_buckets(310, nf, width, height)
+    buckets = [np.ascontiguousarray(np.concatenate([b5[0], b5[1]]))] + b5[2:]      # both 4x4 classes are one size here
+    counts = np.array([len(b) for b in buckets], np.int32)
+    tus = np.ascontiguousarray(np.concatenate(buckets))
+    nres = [len(b) << (2 * (2 + c)) for c, b in enumerate(buckets)]
+    start = np.concatenate([[0], np.cumsum(nres)])
+    pred = synth.random_planes(311, nf, width, height, 8)
+    res = synth.random_int16(312, int(start[-1]), -600, 600)
+    want = synth.random_planes(313, nf, width, height, 8)
+    got = to_dev(want.buf)
+    for c, b in enumerate(buckets):
+        blk = res[start[c]:start[c + 1]].reshape(len(b), -1)
+        for f in range(nf):
+            sel = b[:, 2] == f
+            xy, rf = np.ascontiguousarray(b[sel, :2]), np.ascontiguousarray(blk[sel])
+            oracle.drv("quantize_reconstruct_batch", ptr(want.buf[f], want.origin), want.pitch, ptr(pred.buf[f], pred.origin), pred.pitch, ptr(rf), 2 + c,
+                       ptr(xy), len(xy))
+    dp, dr, dt = to_dev(pred.buf), to_dev(res), to_dev(tus)
+    lib.call("quantize_reconstruct_list_frames", dptr(got, want.origin), want.pitch, dptr(dp, pred.origin), pred.pitch, dptr(dr), dptr(dt), ptr(counts),
+             want.frame_stride, pred.frame_stride)
+    assert np.array_equal(to_host(got), want.buf)
