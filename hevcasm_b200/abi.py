@@ -46,6 +46,7 @@ GPU_ONLY_ABI = {
     "residual_from_planes_pipeline_frames": [P, PD, P, P, P, PD, P, PD, I, I, I, I, I, I, I, I, I, I, PD, PD, PD],
     "sad_list_frames": [P, PD, P, PD, P, I, PD, PD, P],
     "ssd_list_frames": [P, PD, P, PD, P, I, PD, PD, P],
+    "hadamard_satd_list_frames": [P, PD, P, PD, P, P, PD, PD, P],
     "transform_list_frames": [P, P, PD, P, P, PD],
     "quantize_reconstruct_list_frames": [P, PD, P, PD, P, P, P, PD, PD],
     "inverse_transform_add_list_frames": [P, PD, P, PD, P, P, P, PD, PD],

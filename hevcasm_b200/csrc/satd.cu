@@ -45,6 +45,7 @@ struct SatdGrid {
     long long n;
     SatdDiv per_frame, per_row;
     bool fast;   // regular grid, n < 2^32: locate by multiply-high
+    int desc_w = 2;   // int16 per list entry: (x, y), or (x, y, frame) for the *_list_frames form
     void finish()
     {
         fast = !blk_xy && n > 0 && n < (1ll << 32) && nbx > 0 && nby > 0;
@@ -54,7 +55,9 @@ struct SatdGrid {
     {
         f = 0;
         if (blk_xy) {
-            x = blk_xy[2 * i], y = blk_xy[2 * i + 1];
+            const int16_t *e = blk_xy + i * desc_w;
+            x = e[0], y = e[1];
+            if (desc_w == 3) f = e[2];
         } else if (fast) {
             const uint32_t u = (uint32_t)i, fr = per_frame.div(u), r = u - fr * per_frame.d, row = per_row.div(r);
             f = (int)fr, y = (int)(row << log2), x = (int)((r - row * per_row.d) << log2);
@@ -285,6 +288,33 @@ extern "C" int hevcasm_hadamard_satd_batch(const uint8_t *a, ptrdiff_t sa, const
     SatdGrid g{blk_xy, 0, 0, n};
     g.finish();
     return launch_satd(a, sa, b, sb, 0, 0, log2size, g, satd, stream);
+}
+
+// Block lists of a batch of frames, bucketed by size: entries (x, y, frame), first the n_by_size[0] 2x2 blocks, then the 4x4 and the 8x8 ones;
+// satd[i] in list order.  One launch per size present.
+extern "C" int hevcasm_hadamard_satd_list_frames(const uint8_t *a, ptrdiff_t sa, const uint8_t *b, ptrdiff_t sb, const int16_t *blks, const int *n_by_size,
+                                                 ptrdiff_t fs_a, ptrdiff_t fs_b, int32_t *satd, void *stream)
+{
+    if (!n_by_size) return HEVCASM_ERR_ARGUMENT;
+    long long total = 0;
+    for (int c = 0; c < 3; ++c) {
+        if (n_by_size[c] < 0) return HEVCASM_ERR_ARGUMENT;
+        total += n_by_size[c];
+    }
+    if (total && (!blks || !satd)) return HEVCASM_ERR_ARGUMENT;
+    long long first = 0;
+    for (int c = 0; c < 3; ++c) {
+        const int n = n_by_size[c];
+        if (n) {
+            SatdGrid g{blks + 3 * first, 0, 0, n};
+            g.desc_w = 3;
+            g.finish();
+            const int e = launch_satd(a, sa, b, sb, fs_a, fs_b, 1 + c, g, satd + first, stream);
+            if (e) return e;
+        }
+        first += n;
+    }
+    return 0;
 }
 
 extern "C" int hevcasm_hadamard_satd_frames(const uint8_t *a, ptrdiff_t sa, const uint8_t *b, ptrdiff_t sb, int width, int height, int log2size, int n_frames,

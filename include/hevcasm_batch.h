@@ -118,6 +118,11 @@ int HEVCASM_API hevcasm_ssd_frames(const uint8_t *srcA, ptrdiff_t stride_srcA, c
  * (hevcasm_ssd_linear over a flat run of `size` samples). */
 int HEVCASM_API hevcasm_hadamard_satd_batch(const uint8_t *srcA, ptrdiff_t stride_srcA, const uint8_t *srcB, ptrdiff_t stride_srcB,
                                             int log2size, const int16_t *blk_xy, int n, int32_t *satd, void *stream);
+/* the same over the block lists of a batch of frames: blks[i] = {x, y, frame}, bucketed by size - n_by_size[0] 2x2 blocks, then the 4x4 and
+ * the 8x8 ones; satd[i] in list order.  One launch per size present. */
+int HEVCASM_API hevcasm_hadamard_satd_list_frames(const uint8_t *srcA, ptrdiff_t stride_srcA, const uint8_t *srcB, ptrdiff_t stride_srcB,
+                                                  const int16_t *blks, const int *n_by_size, ptrdiff_t frame_stride_srcA,
+                                                  ptrdiff_t frame_stride_srcB, int32_t *satd, void *stream);
 /* satd[frame][by][bx] over the regular grid of floor(width/N) x floor(height/N) blocks */
 int HEVCASM_API hevcasm_hadamard_satd_frames(const uint8_t *srcA, ptrdiff_t stride_srcA, const uint8_t *srcB, ptrdiff_t stride_srcB,
                                              int width, int height, int log2size, int n_frames, ptrdiff_t frame_stride_srcA,

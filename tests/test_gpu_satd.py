@@ -83,3 +83,32 @@ def test_ssd_linear(oracle, size):
     got = dev_full((runs,), np.int32, -1)
     lib.call("ssd_linear_batch", dptr(da, 1), stride, dptr(db, 2), stride, size, runs, dptr(got))
     assert np.array_equal(to_host(got), want)
+
+
+def test_satd_lists_over_frames(oracle):
+    """hevcasm_hadamard_satd_list_frames: 2x2 / 4x4 / 8x8 blocks at arbitrary positions of several frames in one call = the oracle's per-size list
+    form per frame"""
+    width, height, nf = 200, 136, 3
+    a = synth.random_planes(511, nf, width, height, 16)
+    b = synth.smooth_planes(512, nf, width, height, 16)
+    rng = synth.splitmix64(513, 4096).astype(np.int64)
+    buckets, k = [], 0
+    for log2 in (1, 2, 3):
+        n = 1 << log2
+        cnt = 90 + 7 * log2
+        buckets.append(np.stack([rng[k:k + cnt] % (width - n), rng[k + cnt:k + 2 * cnt] % (height - n), rng[k + 2 * cnt:k + 3 * cnt] % nf], -1).astype(np.int16))
+        k += 3 * cnt
+    counts = np.array([len(x) for x in buckets], np.int32)
+    blks = np.ascontiguousarray(np.concatenate(buckets))
+    want, first = np.zeros(len(blks), np.int32), 0
+    for c, bk in enumerate(buckets):
+        for f in range(nf):
+            sel = np.flatnonzero(bk[:, 2] == f)
+            xy, part = np.ascontiguousarray(bk[sel, :2]), np.zeros(len(sel), np.int32)
+            oracle.drv("hadamard_satd_batch", ptr(a.buf[f], a.origin), a.pitch, ptr(b.buf[f], b.origin), b.pitch, 1 + c, ptr(xy), len(xy), ptr(part))
+            want[first + sel] = part
+        first += len(bk)
+    da, db, dk = to_dev(a.buf), to_dev(b.buf), to_dev(blks)
+    got = dev_full(want.shape, np.int32, -1)
+    lib.call("hadamard_satd_list_frames", dptr(da, a.origin), a.pitch, dptr(db, b.origin), b.pitch, dptr(dk), ptr(counts), a.frame_stride, b.frame_stride, dptr(got))
+    assert np.array_equal(to_host(got), want)
