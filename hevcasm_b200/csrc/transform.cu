@@ -487,7 +487,7 @@ __device__ __forceinline__ void big_inv_core(uint32_t *tmp, int b, int uw, bool 
 // (A persistent variant with the coefficient blocks prefetched into shared memory by cp.async.bulk, two stages per warp, was measured in
 //  round 2: 165 vs 130 us (32x32) and 136 vs 118 us (16x16) - 128 registers and 16 warps per SM lose more than the prefetch gains; capping
 //  this kernel at 80 registers for 6 CTAs per SM changes nothing either (130.0 us, 20 bytes of spills): it is bound by its pipes.)
-template <int LOG2, bool PA>
+template <int LOG2, bool PA, int GROUPS = 1>
 __global__ void __launch_bounds__(BIG_NT) big_inv_kernel(uint8_t *__restrict__ dst, ptrdiff_t sd, const uint8_t *__restrict__ pred, ptrdiff_t sp,
                                                          ptrdiff_t fs_dst, ptrdiff_t fs_pred, const int16_t *__restrict__ coeffs, BlockGrid g)
 {
@@ -496,17 +496,26 @@ __global__ void __launch_bounds__(BIG_NT) big_inv_kernel(uint8_t *__restrict__ d
     __shared__ __align__(16) uint32_t tmp_all[BIG_NT / 32][G::WARP_WORDS];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int b = lane / HW, uw = lane % HW;
-    const long long gb = ((long long)blockIdx.x * (BIG_NT / 32) + warp) * G::WB + b;
-    const bool valid = gb < g.n;
-    uint32_t W[N];
-    int x = 0, y = 0, f = 0;
-    if (valid) {
-        const uint32_t *cw = reinterpret_cast<const uint32_t *>(coeffs + gb * (N * N)) + uw;
+    // GROUPS block groups per warp: the coefficients of all of them are requested before the first is transformed
+    uint32_t W[GROUPS][N];
+    long long gb[GROUPS];
 #pragma unroll
-        for (int v = 0; v < N; ++v) W[v] = __ldg(cw + v * HW);
-        g.locate(gb, LOG2, x, y, f);
+    for (int k = 0; k < GROUPS; ++k) {
+        gb[k] = (((long long)blockIdx.x * GROUPS + k) * (BIG_NT / 32) + warp) * G::WB + b;
+        if (gb[k] < g.n) {
+            const uint32_t *cw = reinterpret_cast<const uint32_t *>(coeffs + gb[k] * (N * N)) + uw;
+#pragma unroll
+            for (int v = 0; v < N; ++v) W[k][v] = __ldg(cw + v * HW);
+        }
     }
-    big_inv_core<LOG2, PA>(tmp_all[warp], b, uw, valid, W, dst + f * fs_dst + (ptrdiff_t)y * sd + x, sd, pred + f * fs_pred + (ptrdiff_t)y * sp + x, sp);
+#pragma unroll
+    for (int k = 0; k < GROUPS; ++k) {
+        const bool valid = gb[k] < g.n;
+        int x = 0, y = 0, f = 0;
+        if (valid) g.locate(gb[k], LOG2, x, y, f);
+        big_inv_core<LOG2, PA>(tmp_all[warp], b, uw, valid, W[k], dst + f * fs_dst + (ptrdiff_t)y * sd + x, sd, pred + f * fs_pred + (ptrdiff_t)y * sp + x, sp);
+        if (k + 1 < GROUPS) __syncwarp();
+    }
 }
 
 // Forward transform of one block by the HW lanes that own it; on return W[v] = (Y[v][2uw], Y[v][2uw+1]).
@@ -918,7 +927,22 @@ static int launch_inv_t(uint8_t *dst, ptrdiff_t sd, const uint8_t *pred, ptrdiff
         return launch(umma_inv_kernel<5, PA>, blocks, UMMA_NT, 0, stream, dst, sd, pred, sp, fs_dst, fs_pred, coeffs, g);
     }
 #endif
-    if (log2 == 4) return launch(big_inv_kernel<4, PA>, (unsigned)((g.n + 15) / 16), BIG_NT, 0, stream, dst, sd, pred, sp, fs_dst, fs_pred, coeffs, g);
+    if (log2 == 4) {
+        // two block groups per warp, both groups' coefficients requested up front: 115 us per 16 4K frames against 119.5 with one (three: 119, four:
+        // 127; 32x32 with two: 146 against 129 - 128 registers)
+#ifdef HEVCASM_EXPERIMENTS
+        if (const char *k = tune::knob("HEVCASM_INV16_GROUPS")) {
+            const int groups = atoi(k);
+            if (groups == 1) return launch(big_inv_kernel<4, PA, 1>, (unsigned)((g.n + 15) / 16), BIG_NT, 0, stream, dst, sd, pred, sp, fs_dst, fs_pred, coeffs, g);
+            if (groups == 3) return launch(big_inv_kernel<4, PA, 3>, (unsigned)((g.n + 47) / 48), BIG_NT, 0, stream, dst, sd, pred, sp, fs_dst, fs_pred, coeffs, g);
+            if (groups == 4) return launch(big_inv_kernel<4, PA, 4>, (unsigned)((g.n + 63) / 64), BIG_NT, 0, stream, dst, sd, pred, sp, fs_dst, fs_pred, coeffs, g);
+        }
+#endif
+        return launch(big_inv_kernel<4, PA, 2>, (unsigned)((g.n + 31) / 32), BIG_NT, 0, stream, dst, sd, pred, sp, fs_dst, fs_pred, coeffs, g);
+    }
+#ifdef HEVCASM_EXPERIMENTS
+    if (tune::knob("HEVCASM_INV32_GROUPS")) return launch(big_inv_kernel<5, PA, 2>, (unsigned)((g.n + 15) / 16), BIG_NT, 0, stream, dst, sd, pred, sp, fs_dst, fs_pred, coeffs, g);
+#endif
     return launch(big_inv_kernel<5, PA>, (unsigned)((g.n + 7) / 8), BIG_NT, 0, stream, dst, sd, pred, sp, fs_dst, fs_pred, coeffs, g);
 }
 
