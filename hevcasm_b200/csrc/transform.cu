@@ -525,11 +525,22 @@ __device__ __forceinline__ void big_fwd_core(uint32_t *tmp, int b, int uw, bool 
     using G = BigGeom<LOG2>;
     constexpr int N = G::N, HW = G::HW, S1 = fwd_shift1(LOG2), S2 = fwd_shift2(LOG2);
     if (valid) {  // stage 1: rows uw and uw + N/2 of block b, along x
-#pragma unroll 1
+        // 16x16: both rows are requested before the first is transformed (the loop is unrolled); 32x32 keeps one copy of the butterfly code
+        uint32_t Xboth[N == 16 ? 2 : 1][HW];
+        if (N == 16) {
+#pragma unroll
+            for (int h = 0; h < 2; ++h) load_words<HW, PA>(src + (ptrdiff_t)(uw + h * HW) * stride, Xboth[h % (N == 16 ? 2 : 1)]);
+        }
+#pragma unroll(N == 16 ? 2 : 1)
         for (int h = 0; h < 2; ++h) {
             const int r = uw + h * HW;
             uint32_t Xw[HW];
-            load_words<HW, PA>(src + (ptrdiff_t)r * stride, Xw);
+            if (N == 16) {
+#pragma unroll
+                for (int k = 0; k < HW; ++k) Xw[k] = Xboth[h % (N == 16 ? 2 : 1)][k];
+            } else {
+                load_words<HW, PA>(src + (ptrdiff_t)r * stride, Xw);
+            }
             int xv[N], a[N];
             uint32_t range = 0;
 #pragma unroll
