@@ -194,7 +194,7 @@ __global__ void __launch_bounds__(256) reconstruct_kernel(ReconParams p)
         if (N == 4) r = 2 * w, xs = 0;
         else r = w / (N / 8), xs = (w % (N / 8)) * 8;
         int fk = f;
-        if (p.blk_xy) {
+        if (!PA && p.blk_xy) {   // (PA is only ever chosen for regular grids: the list branch folds away there)
             const int16_t *e = p.blk_xy + (size_t)p.desc_w * bx;
             x = e[0], y = e[1], blk = (size_t)bx;
             if (p.desc_w == 3) fk = e[2];
