@@ -51,10 +51,12 @@ struct SatdGrid {
         fast = !blk_xy && n > 0 && n < (1ll << 32) && nbx > 0 && nby > 0;
         if (fast) per_frame = SatdDiv::make((uint32_t)(nbx * nby)), per_row = SatdDiv::make((uint32_t)nbx);
     }
+    // REGULAR: the calling kernel is only ever launched on regular grids, so the list branch folds away
+    template <bool REGULAR = false>
     __device__ __forceinline__ void locate(long long i, int log2, int &x, int &y, int &f) const
     {
         f = 0;
-        if (blk_xy) {
+        if (!REGULAR && blk_xy) {
             const int16_t *e = blk_xy + i * desc_w;
             x = e[0], y = e[1];
             if (desc_w == 3) f = e[2];
@@ -123,7 +125,7 @@ __global__ void __launch_bounds__(128) satd_kernel(const uint8_t *__restrict__ a
     const long long i = (long long)blockIdx.x * 128 + threadIdx.x;
     if (i >= g.n) return;
     int x, y, f;
-    g.locate(i, LOG2, x, y, f);
+    g.template locate<true>(i, LOG2, x, y, f);   // launch_satd picks this kernel for regular grids only
     const uint8_t *pa = a + f * fs_a + (ptrdiff_t)y * sa + x, *pb = b + f * fs_b + (ptrdiff_t)y * sb + x;
     int d[N][N];
 #pragma unroll

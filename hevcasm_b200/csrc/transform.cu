@@ -54,15 +54,16 @@ struct BlockGrid {
     FastDiv per_frame, per_row;   // blocks per frame / per block row (regular grids with n < 2^32; finish() fills them)
     bool fast;
     int desc_w = 2;               // int16 per list entry: (x, y), or (x, y, frame) for the *_list_frames forms
-    bool on_grid = false;         // list entries sit at multiples of the block size (the *_list_frames contract): rows are aligned like a regular grid's
     void finish()
     {
         fast = !blk_xy && n > 0 && n < (1ll << 32) && nbx > 0 && nby > 0;
         if (fast) per_frame = FastDiv::make((uint32_t)(nbx * nby)), per_row = FastDiv::make((uint32_t)nbx);
     }
+    // REGULAR: the caller's kernel variant is only ever launched on regular grids (the plane-aligned variants), so the list branch folds away
+    template <bool REGULAR = false>
     __device__ __forceinline__ void locate(long long i, int log2, int &x, int &y, int &f) const
     {
-        if (blk_xy) {
+        if (!REGULAR && blk_xy) {
             const int16_t *e = blk_xy + i * desc_w;
             x = e[0], y = e[1], f = desc_w == 3 ? e[2] : 0;
         } else if (fast) {
@@ -311,7 +312,7 @@ __global__ void __launch_bounds__(SMALL_NT) small_fwd_kernel(int16_t *__restrict
     uint32_t Yw[N][HW];
     if (i < g.n) {
         int x, y, f;
-        g.locate(i, LOG2, x, y, f);
+        g.template locate<PA>(i, LOG2, x, y, f);
         small_fwd_core<LOG2, DST, PA>(res + f * fs + (ptrdiff_t)y * stride + x, stride, Yw);
     }
     Io::store(coeffs, first, g.n, lane, io[warp], Yw);
@@ -339,7 +340,7 @@ __global__ void __launch_bounds__(SMALL_NT) small_fwd_planes_kernel(int16_t *__r
     uint32_t Yw[N][HW];
     if (i < g.n) {
         int x, y, f;
-        g.locate(i, LOG2, x, y, f);
+        g.template locate<PA>(i, LOG2, x, y, f);
         uint32_t pw[N][N / 4];
         load_pred<N, PA>(pred + f * fs_pred + (ptrdiff_t)y * sp + x, sp, pw);
         small_fwd_core_planes<LOG2, DST, PA>(src + f * fs_src + (ptrdiff_t)y * ss + x, ss, pw, Yw);
@@ -402,7 +403,7 @@ __global__ void __launch_bounds__(SMALL_NT) small_inv_kernel(uint8_t *__restrict
     int x = 0, y = 0, f = 0;
     uint32_t pw[N][N / 4];
     if (valid) {
-        g.locate(i, LOG2, x, y, f);
+        g.template locate<PA>(i, LOG2, x, y, f);
         load_pred<N, PA>(pred + f * fs_pred + (ptrdiff_t)y * sp + x, sp, pw);
     }
     uint32_t Cw[N][HW];
@@ -512,7 +513,7 @@ __global__ void __launch_bounds__(BIG_NT) big_inv_kernel(uint8_t *__restrict__ d
     for (int k = 0; k < GROUPS; ++k) {
         const bool valid = gb[k] < g.n;
         int x = 0, y = 0, f = 0;
-        if (valid) g.locate(gb[k], LOG2, x, y, f);
+        if (valid) g.template locate<PA>(gb[k], LOG2, x, y, f);
         big_inv_core<LOG2, PA>(tmp_all[warp], b, uw, valid, W[k], dst + f * fs_dst + (ptrdiff_t)y * sd + x, sd, pred + f * fs_pred + (ptrdiff_t)y * sp + x, sp);
         if (k + 1 < GROUPS) __syncwarp();
     }
@@ -589,7 +590,7 @@ __global__ void __launch_bounds__(BIG_NT) big_fwd_kernel(int16_t *__restrict__ c
     const long long gb = ((long long)blockIdx.x * (BIG_NT / 32) + warp) * G::WB + b;
     const bool valid = gb < g.n;
     int x = 0, y = 0, f = 0;
-    if (valid) g.locate(gb, LOG2, x, y, f);
+    if (valid) g.template locate<PA>(gb, LOG2, x, y, f);
     uint32_t W[N];
     big_fwd_core<LOG2, PA>(tmp_all[warp], b, uw, valid, res + f * fs + (ptrdiff_t)y * stride + x, stride, W);
     if (valid) {
@@ -801,7 +802,7 @@ __global__ void __launch_bounds__(SMALL_NT) small_pipeline_kernel(PipelineParams
     uint32_t Yw[N][HW], L[N][HW], pw[N][N / 4];
     uint32_t cbf = 0;
     if (valid) {
-        g.locate(i, LOG2, x, y, f);
+        g.template locate<PA>(i, LOG2, x, y, f);
         load_pred<N, PA>(p.pred + f * p.fs_pred + (ptrdiff_t)y * p.s_pred + x, p.s_pred, pw);
         if (PLANES) small_fwd_core_planes<LOG2, DST, PA>(p.src + f * p.fs_src + (ptrdiff_t)y * p.s_src + x, p.s_src, pw, Yw);
         else small_fwd_core<LOG2, DST, PA>(p.res + f * p.fs_res + (ptrdiff_t)y * p.s_res + x, p.s_res, Yw);
@@ -826,7 +827,7 @@ __global__ void __launch_bounds__(BIG_NT) big_pipeline_kernel(PipelineParams p, 
     const long long gb = ((long long)blockIdx.x * (BIG_NT / 32) + warp) * G::WB + b;
     const bool valid = gb < g.n;
     int x = 0, y = 0, f = 0;
-    if (valid) g.locate(gb, LOG2, x, y, f);
+    if (valid) g.template locate<PA>(gb, LOG2, x, y, f);
     uint32_t W[N];
     big_fwd_core<LOG2, PA>(tmp_all[warp], b, uw, valid, p.res + f * p.fs_res + (ptrdiff_t)y * p.s_res + x, p.s_res, W);
     uint32_t cbf = 0;
@@ -900,7 +901,7 @@ static int launch_fwd(int16_t *coeffs, const int16_t *res, ptrdiff_t stride, ptr
 {
     if (g.n == 0) return 0;
     if (((uintptr_t)coeffs & 15) != 0) return HEVCASM_ERR_ARGUMENT;
-    const bool pa = (!g.blk_xy || g.on_grid) && aligned16(res, stride * 2, fs * 2);
+    const bool pa = !g.blk_xy && aligned16(res, stride * 2, fs * 2);
     const char *pin = tune::knob("HEVCASM_FWD_PATH");
     const bool forced = pin && !strncmp(pin, "umma", 4);
     if ((log2 == 5 || log2 == 4) && !(pin && !strcmp(pin, "butterfly"))) {
@@ -990,7 +991,7 @@ static int launch_inv(uint8_t *dst, ptrdiff_t sd, const uint8_t *pred, ptrdiff_t
 {
     if (g.n == 0) return 0;
     if (((uintptr_t)coeffs & 15) != 0) return HEVCASM_ERR_ARGUMENT;
-    const bool pa = (!g.blk_xy || g.on_grid) && aligned16(dst, sd, fs_dst, pred, sp, fs_pred);
+    const bool pa = !g.blk_xy && aligned16(dst, sd, fs_dst, pred, sp, fs_pred);
 #ifdef HEVCASM_EXPERIMENTS
     // HEVCASM_INV_PATH=hybrid: 16x16 / 32x32 with the second stage on tcgen05 whenever the planes allow it; =hybrid_only: fail instead of
     // falling back (tests)
@@ -1060,7 +1061,7 @@ extern "C" int hevcasm_transform_list_frames(int16_t *coeffs, const int16_t *res
         const int n = n_by_class[c], log2 = kClassLog2[c];
         if (n) {
             BlockGrid g{tus + 3 * first, 0, 0, n};
-            g.desc_w = 3, g.on_grid = true;
+            g.desc_w = 3;
             g.finish();
             const int e = launch_fwd(coeffs + coef, residual, stride, fs, log2, kClassType[c], g, stream);
             if (e) return e;
@@ -1079,7 +1080,7 @@ extern "C" int hevcasm_inverse_transform_add_list_frames(uint8_t *dst, ptrdiff_t
         const int n = n_by_class[c], log2 = kClassLog2[c];
         if (n) {
             BlockGrid g{tus + 3 * first, 0, 0, n};
-            g.desc_w = 3, g.on_grid = true;
+            g.desc_w = 3;
             g.finish();
             const int e = launch_inv(dst, sd, pred, sp, fs_dst, fs_pred, coeffs + coef, log2, kClassType[c], g, stream);
             if (e) return e;
