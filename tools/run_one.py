@@ -20,11 +20,13 @@ res = torch.randint(-256, 256, (NF, H, rp), dtype=torch.int16, device="cuda", ge
 co = torch.randint(-600, 600, (n,), dtype=torch.int16, device="cuda", generator=g)
 co2 = torch.empty((n,), dtype=torch.int16, device="cuda")
 cbf = torch.empty((n // 16,), dtype=torch.int32, device="cuda")
+cbf2 = torch.empty((n // 4,), dtype=torch.int32, device="cuda")
 def d(t, off=0): return C.c_void_p(t.data_ptr() + off * t.element_size())
 sad_outs = [torch.empty((NF * (W // s) * (H // s) * 64,), dtype=torch.int32, device="cuda") for s in (8, 16, 32, 64)]
 calls = {
     "sad_pyr": lambda: lib.call("sad_sweep_pyramid_frames", d(a, org), pitch, d(b, org), pitch, W, H, -4, -4, NF, fs, fs, *[d(o) for o in sad_outs]),
     "pred_hv": lambda: lib.call("pred_uni_frames", d(o8, org), pitch, d(a, org), pitch, W, H, 8, 1, 3, NF, fs, fs),
+    "satd2": lambda: lib.call("hadamard_satd_frames", d(a, org), pitch, d(b, org), pitch, W, H, 1, NF, fs, fs, d(cbf2)),
     "satd4": lambda: lib.call("hadamard_satd_frames", d(a, org), pitch, d(b, org), pitch, W, H, 2, NF, fs, fs, d(cbf)),
     "satd8": lambda: lib.call("hadamard_satd_frames", d(a, org), pitch, d(b, org), pitch, W, H, 3, NF, fs, fs, d(cbf)),
     "pred_copy": lambda: lib.call("pred_uni_frames", d(o8, org), pitch, d(a, org), pitch, W, H, 8, 0, 0, NF, fs, fs),
