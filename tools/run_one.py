@@ -45,6 +45,7 @@ calls = {
     "inv8": lambda: lib.call("inverse_transform_add_frames", d(o8, org), pitch, d(a, org), pitch, d(co), W, H, 3, 0, NF, fs, fs),
     "inv16": lambda: lib.call("inverse_transform_add_frames", d(o8, org), pitch, d(a, org), pitch, d(co), W, H, 4, 0, NF, fs, fs),
     "inv32": lambda: lib.call("inverse_transform_add_frames", d(o8, org), pitch, d(a, org), pitch, d(co), W, H, 5, 0, NF, fs, fs),
+    "recon16": lambda: lib.call("quantize_reconstruct_frames", d(o8, org), pitch, d(a, org), pitch, d(co), W, H, 4, NF, fs, fs),
     "recon8": lambda: lib.call("quantize_reconstruct_frames", d(o8, org), pitch, d(a, org), pitch, d(co), W, H, 3, NF, fs, fs),
     "pipe16": lambda: lib.call("residual_pipeline_frames", d(o8, org), pitch, d(co2), d(cbf), d(res), rp, d(a, org), pitch, W, H, 4, 0, 26214, 18, 171 << 7, 18432, 6, NF, fs, H * rp, fs),
     "pipe32": lambda: lib.call("residual_pipeline_frames", d(o8, org), pitch, d(co2), d(cbf), d(res), rp, d(a, org), pitch, W, H, 5, 0, 26214, 18, 171 << 7, 18432, 6, NF, fs, H * rp, fs),
