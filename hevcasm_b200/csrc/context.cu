@@ -99,29 +99,51 @@ int copy_out(const DevPlanes &d, const void *dev, void *h, ptrdiff_t hs, ptrdiff
     return 0;
 }
 
-// Three-stage ring pipeline over chunks of frames.  `slot_bytes(frames)` sizes one slot; stage callbacks enqueue on the
-// stream they are given.
+// Three-stage pipeline over chunks of whole frames; stage callbacks enqueue on the stream they are given.  The arena is a byte ring: a
+// chunk takes the next `frames * per_frame` bytes (wrapping to the start when the tail is too short), and its copy-in first waits for the
+// copy-out of every earlier chunk whose bytes it overlaps.
+//   Chunk sizes: `out_in_ratio` = result bytes / input bytes per frame.  When the results are the larger side (the SAD sweeps), the
+// copy-out stream is the bottleneck and its rate depends on the size of the copies (one B200 of this pool, with a copy-in running beside it:
+// 46.7 GB/s in 128 copies of 6 MB, 50.0 in 32, 51.8 in one; tools/pcie_probe.py) - so chunks GROW slowly: the first is one frame (the
+// pipeline fills in one frame's copy-in) and chunk c has 1 + 0.15 * (frames before c) frames, 14 chunks for 32 frames.  Measured on the 32-frame
+// 4K sweep (packed results), same box: one frame per chunk 15.5-16.0 Gsamples/s, two or four 16.0, growth 0.05 / 0.10 / 0.15 / 0.20 / 0.37:
+// 16.2 / 16.6 / 16.6-16.8 / 15.8 / 15.0 (larger chunks make the copy-out wait for the next chunk's copy-in).  Otherwise chunks are ~32 MB as
+// before (>= 3 in flight).
 template <class In, class Run, class Out>
-int run_pipeline(hevcasm_cuda_context *ctx, int n_frames, size_t bytes_per_frame, In in, Run run, Out out)
+int run_pipeline(hevcasm_cuda_context *ctx, int n_frames, size_t bytes_per_frame, double out_in_ratio, In in, Run run, Out out)
 {
     if (n_frames == 0) return 0;
     HV_CUDA(cudaSetDevice(ctx->device));
     const size_t per_frame = round_up(bytes_per_frame, kAlign) + 16 * kAlign;  // slack for per-piece alignment
     if (per_frame > ctx->arena_bytes) return HEVCASM_ERR_ARGUMENT;               // arena cannot hold even one frame
-    // chunk = whole frames; aim for >= 3 slots so the three stages overlap, and chunks of >= ~32 MB so launches stay large
-    int max_frames_in_arena = (int)std::min<size_t>(ctx->arena_bytes / per_frame, (size_t)n_frames);
-    int chunk = std::max(1, std::min(max_frames_in_arena / 3, std::max(1, (int)((size_t)(32u << 20) / per_frame))));
-    if (max_frames_in_arena < 3) chunk = 1;
-    const int n_slots = std::max(1, std::min(max_frames_in_arena / chunk, 4));
-    const int n_chunks = (n_frames + chunk - 1) / chunk;
-    const size_t slot_bytes = (size_t)chunk * per_frame;
+    const int fit = (int)std::min<size_t>(ctx->arena_bytes / per_frame, (size_t)n_frames);   // frames the arena holds at once
+    const int cap = std::max(1, fit / 3);                                                    // >= 3 chunks in flight so the three stages overlap
+    const int flat = std::max(1, std::min(cap, std::max(1, (int)((size_t)(32u << 20) / per_frame))));
+    const bool grow = out_in_ratio > 1.05;
+    constexpr double kGrowth = 0.15;   // frames(c) = 1 + kGrowth * frames before c
     ctx->next_event = 0;
-    std::vector<cudaEvent_t> done_out(n_chunks, nullptr);
+    struct Busy {
+        size_t begin, end;
+        cudaEvent_t done;
+    };
+    std::vector<Busy> busy;   // chunks whose copy-out may still be reading their bytes, oldest first
+    size_t head = 0;
     auto enqueue = [&]() -> int {
-        for (int c = 0; c < n_chunks; ++c) {
-            const int f0 = c * chunk, nf = std::min(chunk, n_frames - f0);
-            uint8_t *slot = ctx->arena + (size_t)(c % n_slots) * slot_bytes;
-            if (c >= n_slots) HV_CUDA(cudaStreamWaitEvent(ctx->s_in, done_out[c - n_slots], 0));  // slot is free again
+        for (int f0 = 0; f0 < n_frames;) {
+            int nf = grow ? std::min(cap, 1 + (int)(kGrowth * f0)) : flat;
+            nf = std::min(nf, n_frames - f0);
+            const size_t bytes = (size_t)nf * per_frame;
+            if (head + bytes > ctx->arena_bytes) head = 0;
+            const size_t begin = head, end = head + bytes;
+            for (size_t i = 0; i < busy.size();) {
+                if (busy[i].begin < end && begin < busy[i].end) {
+                    HV_CUDA(cudaStreamWaitEvent(ctx->s_in, busy[i].done, 0));   // those bytes are free again once that chunk's results have left
+                    busy.erase(busy.begin() + i);
+                } else {
+                    ++i;
+                }
+            }
+            uint8_t *slot = ctx->arena + begin;
             int e = in(slot, f0, nf, ctx->s_in);
             if (e) return e;
             cudaEvent_t ev_in = ctx->event(), ev_run = ctx->event(), ev_out = ctx->event();
@@ -135,7 +157,9 @@ int run_pipeline(hevcasm_cuda_context *ctx, int n_frames, size_t bytes_per_frame
             e = out(slot, f0, nf, ctx->s_out);
             if (e) return e;
             HV_CUDA(cudaEventRecord(ev_out, ctx->s_out));
-            done_out[c] = ev_out;
+            busy.push_back({begin, end, ev_out});
+            head = end;
+            f0 += nf;
         }
         return 0;
     };
@@ -290,8 +314,9 @@ static int sad_pyramid_host(int mode, hevcasm_cuda_context *ctx, const uint8_t *
         for (int l = 0; l < 4; ++l) s.out[l] = out_bytes[l] ? c.take<uint8_t>(out_bytes[l] * nf) : nullptr;
         return s;
     };
+    const double out_in_ratio = (double)(out_bytes[0] + out_bytes[1] + out_bytes[2] + out_bytes[3]) / (double)(2 * d.frame_elems);
     return run_pipeline(
-        ctx, n_frames, per_frame,
+        ctx, n_frames, per_frame, out_in_ratio,
         [&](uint8_t *slot, int f0, int nf, cudaStream_t s) {
             const Slot k = carve(slot, nf);
             int e = copy_in(d, k.src, src + (ptrdiff_t)f0 * fs_src, ss, fs_src, width, nf, s);
@@ -364,7 +389,7 @@ extern "C" int hevcasm_pred_uni_frames_host(hevcasm_cuda_context *ctx, uint8_t *
         return s;
     };
     return run_pipeline(
-        ctx, n_frames, per_frame,
+        ctx, n_frames, per_frame, 0.0,
         [&](uint8_t *slot, int f0, int nf, cudaStream_t s) { return copy_in(din, carve(slot, nf).ref, ref + (ptrdiff_t)f0 * fs_ref, sr, fs_ref, width, nf, s); },
         [&](uint8_t *slot, int, int nf, cudaStream_t s) {
             const Slot k = carve(slot, nf);
@@ -404,7 +429,7 @@ extern "C" int hevcasm_residual_pipeline_frames_host(hevcasm_cuda_context *ctx, 
         return s;
     };
     return run_pipeline(
-        ctx, n_frames, per_frame,
+        ctx, n_frames, per_frame, 0.0,
         [&](uint8_t *slot, int f0, int nf, cudaStream_t s) {
             const Slot k = carve(slot, nf);
             int e = copy_in(d8, k.pred, pred + (ptrdiff_t)f0 * fs_pred, s_pred, fs_pred, width, nf, s);
