@@ -47,6 +47,16 @@ struct FastDiv {
     }
 };
 
+// (lo16(a >> S), lo16(b >> S)) in one word, the truncating store of the forward transforms.  Written as LEFT shifts by 16 - S and a PRMT of the
+// high halves: ptxas is free to put left shifts on the FMA pipe (IMAD.SHL) - the fused pipelines run against the ALU pipe, which the right
+// shifts (SHF) share with PRMT, IADD3 and the saturating packs.
+template <int S>
+__device__ __forceinline__ uint32_t shr_lolo(int a, int b)
+{
+    static_assert(S >= 0 && S <= 16, "shift");
+    return __byte_perm((uint32_t)a << (16 - S), (uint32_t)b << (16 - S), 0x7632);
+}
+
 struct BlockGrid {
     const int16_t *blk_xy;
     int nbx, nby;
@@ -256,7 +266,7 @@ __device__ __forceinline__ void small_fwd_core(const int16_t *src, ptrdiff_t str
         fwd_matrix<N, DST>(X[r], a0, 1 << (S1 - 1));
         fwd_matrix<N, DST>(X[r + 1], a1, 1 << (S1 - 1));
 #pragma unroll
-        for (int u = 0; u < N; ++u) Aw[u][r / 2] = lolo((uint32_t)(a0[u] >> S1), (uint32_t)(a1[u] >> S1));  // truncating, residual_decode.c:674-682
+        for (int u = 0; u < N; ++u) Aw[u][r / 2] = shr_lolo<S1>(a0[u], a1[u]);  // truncating, residual_decode.c:674-682
     }
     // stage 2 (along y): Y[v][u], emitted as horizontal pairs (Y[v][u], Y[v][u+1]) = the memory order of coeffs[v*N+u]
 #pragma unroll
@@ -265,7 +275,7 @@ __device__ __forceinline__ void small_fwd_core(const int16_t *src, ptrdiff_t str
         fwd_matrix<N, DST>(Aw[u], b0, 1 << (S2 - 1));
         fwd_matrix<N, DST>(Aw[u + 1], b1, 1 << (S2 - 1));
 #pragma unroll
-        for (int v = 0; v < N; ++v) Yw[v][u / 2] = lolo((uint32_t)(b0[v] >> S2), (uint32_t)(b1[v] >> S2));
+        for (int v = 0; v < N; ++v) Yw[v][u / 2] = shr_lolo<S2>(b0[v], b1[v]);
     }
 }
 
@@ -287,7 +297,7 @@ __device__ __forceinline__ void small_fwd_core_planes(const uint8_t *src, ptrdif
         fwd_matrix_bytes<N, DST>(S[r], pw[r], a0, 1 << (S1 - 1));
         fwd_matrix_bytes<N, DST>(S[r + 1], pw[r + 1], a1, 1 << (S1 - 1));
 #pragma unroll
-        for (int u = 0; u < N; ++u) Aw[u][r / 2] = lolo((uint32_t)(a0[u] >> S1), (uint32_t)(a1[u] >> S1));
+        for (int u = 0; u < N; ++u) Aw[u][r / 2] = shr_lolo<S1>(a0[u], a1[u]);
     }
 #pragma unroll
     for (int u = 0; u < N; u += 2) {
@@ -295,7 +305,7 @@ __device__ __forceinline__ void small_fwd_core_planes(const uint8_t *src, ptrdif
         fwd_matrix<N, DST>(Aw[u], b0, 1 << (S2 - 1));
         fwd_matrix<N, DST>(Aw[u + 1], b1, 1 << (S2 - 1));
 #pragma unroll
-        for (int v = 0; v < N; ++v) Yw[v][u / 2] = lolo((uint32_t)(b0[v] >> S2), (uint32_t)(b1[v] >> S2));
+        for (int v = 0; v < N; ++v) Yw[v][u / 2] = shr_lolo<S2>(b0[v], b1[v]);
     }
 }
 
@@ -551,8 +561,8 @@ __device__ __forceinline__ void big_fwd_core(uint32_t *tmp, int b, int uw, bool 
             uint4 *row = reinterpret_cast<uint4 *>(tmp + b * G::BLK_STRIDE + r * G::PITCH);
 #pragma unroll
             for (int k = 0; k < HW / 4; ++k)
-                row[k] = make_uint4(lolo((uint32_t)(a[8 * k] >> S1), (uint32_t)(a[8 * k + 1] >> S1)), lolo((uint32_t)(a[8 * k + 2] >> S1), (uint32_t)(a[8 * k + 3] >> S1)),
-                                    lolo((uint32_t)(a[8 * k + 4] >> S1), (uint32_t)(a[8 * k + 5] >> S1)), lolo((uint32_t)(a[8 * k + 6] >> S1), (uint32_t)(a[8 * k + 7] >> S1)));
+                row[k] = make_uint4(shr_lolo<S1>(a[8 * k], a[8 * k + 1]), shr_lolo<S1>(a[8 * k + 2], a[8 * k + 3]),
+                                    shr_lolo<S1>(a[8 * k + 4], a[8 * k + 5]), shr_lolo<S1>(a[8 * k + 6], a[8 * k + 7]));
         }
     }
     __syncwarp();
@@ -573,7 +583,7 @@ __device__ __forceinline__ void big_fwd_core(uint32_t *tmp, int b, int uw, bool 
         if (packed) FwdBflyPacked<N>::run(x0, c1, 1 << (S2 - 1));
         else FwdBfly<N>::run(x0, c1, 1 << (S2 - 1));
 #pragma unroll
-        for (int v = 0; v < N; ++v) W[v] = lolo((uint32_t)(c0[v] >> S2), (uint32_t)(c1[v] >> S2));
+        for (int v = 0; v < N; ++v) W[v] = shr_lolo<S2>(c0[v], c1[v]);
     }
     __syncwarp();  // tmp may be reused by the caller
 }
