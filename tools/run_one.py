@@ -25,6 +25,10 @@ def d(t, off=0): return C.c_void_p(t.data_ptr() + off * t.element_size())
 sad_outs = [torch.empty((NF * (W // s) * (H // s) * 64,), dtype=torch.int32, device="cuda") for s in (8, 16, 32, 64)]
 calls = {
     "sad_pyr": lambda: lib.call("sad_sweep_pyramid_frames", d(a, org), pitch, d(b, org), pitch, W, H, -4, -4, NF, fs, fs, *[d(o) for o in sad_outs]),
+    "sad_pyr8": lambda: lib.call("sad_sweep_pyramid_frames", d(a, org), pitch, d(b, org), pitch, W, H, -4, -4, NF, fs, fs, d(sad_outs[0]), None, None, None),
+    "sad_sweep8": lambda: lib.call("sad_sweep_frames", d(a, org), pitch, d(b, org), pitch, W, H, (8 << 8) | 8, -4, -4, 8, 8, NF, fs, fs, d(sad_outs[0])),
+    "sad_sweep16": lambda: lib.call("sad_sweep_frames", d(a, org), pitch, d(b, org), pitch, W, H, (16 << 8) | 16, -4, -4, 8, 8, NF, fs, fs, d(sad_outs[1])),
+    "sad_pyr16": lambda: lib.call("sad_sweep_pyramid_frames", d(a, org), pitch, d(b, org), pitch, W, H, -4, -4, NF, fs, fs, None, d(sad_outs[1]), None, None),
     "pred_hv": lambda: lib.call("pred_uni_frames", d(o8, org), pitch, d(a, org), pitch, W, H, 8, 1, 3, NF, fs, fs),
     "satd2": lambda: lib.call("hadamard_satd_frames", d(a, org), pitch, d(b, org), pitch, W, H, 1, NF, fs, fs, d(cbf2)),
     "satd4": lambda: lib.call("hadamard_satd_frames", d(a, org), pitch, d(b, org), pitch, W, H, 2, NF, fs, fs, d(cbf)),
