@@ -1,3 +1,5 @@
+"""Device-to-host copy rate of one GPU as a function of the number of copies, alone and with a host-to-device copy running beside it
+(design input for the chunk sizes of the host forms, csrc/context.cu):  python tools/pcie_probe.py"""
 import torch, time
 n = 768 << 20
 d = torch.empty(n, dtype=torch.uint8, device="cuda"); h = torch.empty(n, dtype=torch.uint8).pin_memory()

@@ -1,5 +1,6 @@
 // How many SMALL TMA boxes per cycle can one SM pull?  (Design input for the prediction-unit list kernels: one box per PU footprint -
-// 15 rows of 15 bytes for an 8x8 luma PU - lands row-aligned in shared memory whatever the alignment of the motion-compensated source.)
+// 15 rows of 15 bytes for an 8x8 luma PU - would land row-aligned in shared memory; but a box must START 16-byte aligned, so the probe
+// rounds its x coordinates down to 16: an unaligned start faults, as tools/tma_probe.cu cases 7, 8 and 12 show.)
 // One CTA per SM, W issuing warps, each keeping two batches of D boxes in flight on two mbarriers; box coordinates walk 8x8 PUs in raster
 // order over 16 4K frames with a pseudo-random +-16 sample displacement, like the bench lists.
 //   nvcc -gencode arch=compute_100a,code=sm_100a -O2 -I hevcasm_b200/csrc -I include -o tools/tma_box_probe tools/tma_box_probe.cu
@@ -11,7 +12,7 @@
 namespace hv { void count_launch() {} }
 using namespace hv;
 
-struct P { CUtensorMap tm; int box_bytes, slot_bytes, depth, iters, per_lane, step, aligned, variant; long long *cycles; unsigned *sink; };
+struct P { CUtensorMap tm; int box_bytes, slot_bytes, depth, iters, per_lane, step; long long *cycles; unsigned *sink; };
 
 __device__ __forceinline__ unsigned mix(unsigned x) { x ^= x >> 16; x *= 0x7feb352du; x ^= x >> 15; x *= 0x846ca68bu; x ^= x >> 16; return x; }
 
@@ -37,15 +38,6 @@ __global__ void __launch_bounds__(1024, 1) probe(const __grid_constant__ P p)
     uint64_t *const mybar = dynbars[warp];
     if (lane == 0) tma::mbar_init(mybar, 1), tma::mbar_init(mybar + 1, 1);
     __syncthreads();
-    if (p.variant == 5) {   // exactly one box, as tools/tma_probe.cu does it
-        if (threadIdx.x == 0) {
-            tma::mbar_expect_tx(mybar, (uint32_t)p.box_bytes);
-            tma::load_box_3d(smem, &p.tm, 64, 64, 0, mybar);
-        }
-        const bool ok = wait_bounded(mybar, 0);
-        if (threadIdx.x == 0) p.cycles[blockIdx.x] = ok ? smem[5] : -1;
-        return;
-    }
     const long long t0 = clock64();
     unsigned acc = 0;
     for (int it = 0; it < p.iters + 2; ++it) {
@@ -56,18 +48,8 @@ __global__ void __launch_bounds__(1024, 1) probe(const __grid_constant__ P p)
         }
         if (it < p.iters) {
             __syncwarp();
-            if (lane == 0) tma::mbar_expect_tx(mybar + half, p.variant == 1 ? 0u : (uint32_t)(p.depth * p.box_bytes));
+            if (lane == 0) tma::mbar_expect_tx(mybar + half, (uint32_t)(p.depth * p.box_bytes));
             __syncwarp();
-            if (p.variant == 1) continue;
-            if (p.variant >= 2) {
-                if (lane == 0)
-                    for (int k = 0; k < p.depth; ++k) {
-                        const unsigned pu = ((blockIdx.x * nw + warp) * p.iters + it) * p.depth + k;
-                        const int r = pu % (480 * 270);
-                        tma::load_box_3d(mine + (size_t)(half * p.depth + (p.variant == 7 ? 0 : k)) * p.slot_bytes, &p.tm, p.variant == 6 ? 64 : 64 + (r % 480) * p.step, p.variant == 6 ? 64 : 64 + (r / 480) * p.step, 0, mybar + half);
-                    }
-                continue;
-            }
             for (int k = p.per_lane ? lane : 0; k < p.depth; k += p.per_lane ? 32 : 1) {
                 if (!p.per_lane && lane) break;
                 const unsigned pu = ((blockIdx.x * nw + warp) * p.iters + it) * p.depth + k;
@@ -97,21 +79,20 @@ int main(int argc, char **argv)
     cudaFuncSetAttribute(probe, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     struct Box { int bx, by, step; } boxes[] = {{32, 16, 8}, {32, 8, 8}, {48, 24, 16}, {64, 40, 32}, {96, 72, 64}, {128, 16, 8}, {16, 16, 8}};
     printf("box_x box_y  warps depth issue     cycles/box/SM   boxes/us/SM   GB/s(chip, box bytes)\n");
-    const int only = argc > 4 ? atoi(argv[4]) : -1;
+    const int only = argc > 3 ? atoi(argv[3]) : -1;   // argv: [max depth] [max iterations] [box index]
     for (const Box &b : boxes) {
         if (only >= 0 && &b != &boxes[only]) continue;
         P p;
         int shift;
-        if (tma::describe_u8(&p.tm, img, pitch, (ptrdiff_t)pitch * rows, (argc > 5 && atoi(argv[5]) == 4) ? pitch - 64 : pitch, rows, NF, b.bx, b.by, &shift)) { printf("describe failed\n"); return 1; }
+        if (tma::describe_u8(&p.tm, img, pitch, (ptrdiff_t)pitch * rows, pitch, rows, NF, b.bx, b.by, &shift)) { printf("describe failed\n"); return 1; }
         p.box_bytes = b.bx * b.by; p.slot_bytes = (p.box_bytes + 127) & ~127; p.step = b.step;
-        p.cycles = cyc; p.sink = sink; p.aligned = argc > 1 ? atoi(argv[1]) : 0; p.variant = argc > 5 ? atoi(argv[5]) : 0;
-        const int max_depth = argc > 2 ? atoi(argv[2]) : 32, max_iters = argc > 3 ? atoi(argv[3]) : 1 << 30;
+        p.cycles = cyc; p.sink = sink;
+        const int max_depth = argc > 1 ? atoi(argv[1]) : 32, max_iters = argc > 2 ? atoi(argv[2]) : 1 << 30;
         for (int nw : {1, 4, 16})
             for (int per_lane : {0, 1}) {
                 int depth = (int)(180 * 1024 / (2 * nw * p.slot_bytes));
                 if (depth > max_depth) depth = max_depth;
                 if (depth < 1) continue;
-                if (per_lane && depth < 32 && depth > 0) { /* fewer lanes issue */ }
                 p.depth = depth; p.per_lane = per_lane;
                 p.iters = std::min(max_iters, 20000 / (nw * depth) + 4);
                 const size_t smem = (size_t)2 * nw * depth * p.slot_bytes + 16 * nw + 1024;
