@@ -858,6 +858,40 @@ __global__ void __launch_bounds__(BIG_NT) big_pipeline_kernel(PipelineParams p, 
                        p.pred + f * p.fs_pred + (ptrdiff_t)y * p.s_pred + x, p.s_pred);
 }
 
+// Second half of the 32x32 pipeline when the first runs on the tensor cores (ft::fwd_umma_kernel<5, true> has written the LEVELS): dequantise,
+// inverse transform, add to the predictor; the coded-block flag is the OR of the level words the kernel reads anyway.
+template <int LOG2, bool PA>
+__global__ void __launch_bounds__(BIG_NT) big_dequant_inv_kernel(PipelineParams p, BlockGrid g)
+{
+    using G = BigGeom<LOG2>;
+    constexpr int N = G::N, HW = G::HW;
+    __shared__ __align__(16) uint32_t tmp_all[BIG_NT / 32][G::WARP_WORDS];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int b = lane / HW, uw = lane % HW;
+    const long long gb = ((long long)blockIdx.x * (BIG_NT / 32) + warp) * G::WB + b;
+    const bool valid = gb < g.n;
+    uint32_t W[N];
+    uint32_t cbf = 0;
+    int x = 0, y = 0, f = 0;
+    if (valid) {
+        const uint32_t *lw = reinterpret_cast<const uint32_t *>(p.levels + gb * (N * N)) + uw;
+#pragma unroll
+        for (int v = 0; v < N; ++v) W[v] = __ldg(lw + v * HW);
+        g.template locate<PA>(gb, LOG2, x, y, f);
+        const int add = 1 << (p.q.iq_shift - 1);
+#pragma unroll
+        for (int v = 0; v < N; ++v) {
+            cbf |= W[v];
+            W[v] = pack_sat_s16((s16lo(W[v]) * p.q.iq_scale + add) >> p.q.iq_shift, (s16hi(W[v]) * p.q.iq_scale + add) >> p.q.iq_shift);
+        }
+    }
+#pragma unroll
+    for (int o = 1; o < HW; o <<= 1) cbf |= __shfl_xor_sync(0xffffffffu, cbf, o);
+    if (valid && uw == 0 && p.cbf) p.cbf[gb] = cbf_fold(cbf);
+    big_inv_core<LOG2, PA>(tmp_all[warp], b, uw, valid, W, p.rec + f * p.fs_rec + (ptrdiff_t)y * p.s_rec + x, p.s_rec,
+                           p.pred + f * p.fs_pred + (ptrdiff_t)y * p.s_pred + x, p.s_pred);
+}
+
 }  // namespace hv
 
 // ================================================================================================ C ABI
@@ -884,7 +918,8 @@ static int launch_fwd_t(int16_t *coeffs, const int16_t *res, ptrdiff_t stride, p
 // 17.1 / 15.0 (1 plane), 24.3 / 25.2 (2), 43.7 / 48.3 (4), 70.5 / 88.8 (8).  HEVCASM_FWD_PATH=umma: whenever the planes allow it;
 // =umma_only: fail instead of falling back (tests); =butterfly: never.
 template <int LOG2>
-static int launch_fwd_umma(int16_t *coeffs, const int16_t *res, ptrdiff_t stride, ptrdiff_t fs, const BlockGrid &g, void *stream, bool forced, bool *taken)
+static int launch_fwd_umma(int16_t *coeffs, const int16_t *res, ptrdiff_t stride, ptrdiff_t fs, const BlockGrid &g, void *stream, bool forced, bool *taken,
+                           const int *quant = nullptr /* {scale, shift, off, offn}: write levels instead of coefficients */)
 {
     *taken = false;
     constexpr int BS = 1 << LOG2, TB = 128 / BS;
@@ -900,11 +935,16 @@ static int launch_fwd_umma(int16_t *coeffs, const int16_t *res, ptrdiff_t stride
     P.n_tiles = (int)tiles;
     if (tma::describe_u8_swizzled(&P.tmres, reinterpret_cast<const uint8_t *>(res), stride * 2, fs * 2, 2ll * BS * g.nbx, (long long)BS * g.nby, n_frames, 128, ft::TROWS))
         return 0;
-    if (ft::ft_tables_init() || set_max_smem(ft::fwd_umma_kernel<LOG2>, ft::SMEM_BYTES)) return (int)cudaErrorInvalidValue;
+    if (ft::ft_tables_init() || set_max_smem(ft::fwd_umma_kernel<LOG2, false>, ft::SMEM_BYTES) || set_max_smem(ft::fwd_umma_kernel<LOG2, true>, ft::SMEM_BYTES))
+        return (int)cudaErrorInvalidValue;
     *taken = true;
     long long grid = std::min<long long>(tiles, (long long)sm_count());   // one persistent CTA per SM
     if (const char *e = tune::knob("HEVCASM_FWD_UMMA_GRID")) grid = std::max(1ll, std::min<long long>(grid, atoll(e)));   // test knob: more tiles per CTA
-    return launch(ft::fwd_umma_kernel<LOG2>, dim3((unsigned)grid), dim3(ft::THREADS), (size_t)ft::SMEM_BYTES, stream, P);
+    if (quant) {
+        P.q_scale = quant[0], P.q_shift = quant[1], P.q_off = quant[2], P.q_offn = quant[3];
+        return launch(ft::fwd_umma_kernel<LOG2, true>, dim3((unsigned)grid), dim3(ft::THREADS), (size_t)ft::SMEM_BYTES, stream, P);
+    }
+    return launch(ft::fwd_umma_kernel<LOG2, false>, dim3((unsigned)grid), dim3(ft::THREADS), (size_t)ft::SMEM_BYTES, stream, P);
 }
 
 static int launch_fwd(int16_t *coeffs, const int16_t *res, ptrdiff_t stride, ptrdiff_t fs, int log2, int trType, const BlockGrid &g, void *stream)
@@ -1139,6 +1179,23 @@ extern "C" int hevcasm_residual_pipeline_frames(uint8_t *rec, ptrdiff_t s_rec, i
     p.s_rec = s_rec, p.s_pred = s_pred, p.s_res = s_res, p.fs_rec = fs_rec, p.fs_pred = fs_pred, p.fs_res = fs_res;
     p.q = make_quant_params(q_scale, q_shift, q_offset, iq_scale, iq_shift);
     const bool pa = aligned16(rec, s_rec, fs_rec, pred, s_pred, fs_pred) && aligned16(residual, s_res * 2, fs_res * 2);
+    // 32x32 on batches that fill the chip: two kernels - the tensor-core forward transform with the quantiser in its epilogue writes the levels,
+    // the butterfly inverse dequantises them on the way in - instead of the one fused CUDA-core kernel (361 us per 16 4K frames).
+    // HEVCASM_PIPE32=fused pins the fused kernel (A/B).
+    if (log2size == 5 && pa && !tune::knob("HEVCASM_PIPE32")) {
+        const int quant[4] = {p.q.q_scale, p.q.q_shift, p.q.q_off, p.q.q_offn};
+        bool taken = false;
+        const int e = launch_fwd_umma<5>(levels, residual, s_res, fs_res, g, stream, false, &taken, quant);
+        if (taken) return e ? e : launch(big_dequant_inv_kernel<5, true>, (unsigned)((g.n + 7) / 8), BIG_NT, 0, stream, p, g);
+    }
+#ifdef HEVCASM_EXPERIMENTS
+    if (log2size == 4 && pa && tune::knob("HEVCASM_PIPE16_SPLIT")) {   // the same split for 16x16 (A/B)
+        const int quant[4] = {p.q.q_scale, p.q.q_shift, p.q.q_off, p.q.q_offn};
+        bool taken = false;
+        const int e = launch_fwd_umma<4>(levels, residual, s_res, fs_res, g, stream, false, &taken, quant);
+        if (taken) return e ? e : launch(big_dequant_inv_kernel<4, true>, (unsigned)((g.n + 15) / 16), BIG_NT, 0, stream, p, g);
+    }
+#endif
     return pa ? launch_pipeline_t<true>(p, g, log2size, trType, stream) : launch_pipeline_t<false>(p, g, log2size, trType, stream);
 }
 

@@ -67,9 +67,11 @@ struct alignas(64) Params {
     int16_t *coeffs;
     int nbx, nby;             // blocks per plane row / column
     int tiles_x, tiles_y, n_tiles;
+    int q_scale, q_shift, q_off, q_offn;   // QUANT: the quantiser of hevcasm_quantize in the form of transform.cu's quant_dequant_word
 };
 
-template <int LOG2>
+// QUANT: the coefficients leave quantised (levels) - the first half of the fused residual pipeline for 32x32 blocks
+template <int LOG2, bool QUANT = false>
 __global__ void __launch_bounds__(THREADS, 1) fwd_umma_kernel(const __grid_constant__ Params P)
 {
     constexpr int BS = 1 << LOG2, TB = 128 / BS, BPT = 32 / BS;   // block size; blocks per tile side; blocks per thread and tile (one below the other)
@@ -217,7 +219,11 @@ __global__ void __launch_bounds__(THREADS, 1) fwd_umma_kernel(const __grid_const
                     FwdBfly<BS>::run(x + h * BS, o, 1 << (S2 - 1));
                     int16_t *out = P.coeffs + (((long long)cf * P.nby + rb) * P.nbx + bcg) * (BS * BS) + k;
 #pragma unroll
-                    for (int v = 0; v < BS; ++v) out[v * BS] = (int16_t)(o[v] >> S2);
+                    for (int v = 0; v < BS; ++v) {
+                        int c = (int)(int16_t)(o[v] >> S2);   // the coefficient as the reference stores it
+                        if (QUANT) c = (c * P.q_scale + (c < 0 ? P.q_offn : P.q_off)) >> P.q_shift;
+                        out[v * BS] = (int16_t)c;
+                    }
                 }
             }
             advance(cx, cy, cf);

@@ -111,3 +111,29 @@ def test_from_planes_forms(oracle, log2, tr, shape):
         lib.call("residual_from_planes_pipeline_frames", dptr(rec, rec_w.origin), rec_w.pitch, dptr(lv), dptr(cbf), dptr(ds, src.origin), src.pitch, dptr(dp, pred.origin),
                  pred.pitch, width, height, log2, tr, *qp, nf, rec_w.frame_stride, src.frame_stride, pred.frame_stride)
         assert np.array_equal(to_host(lv), lv_w) and np.array_equal(to_host(cbf), cbf_w) and np.array_equal(to_host(rec), rec_w.buf), qp
+
+
+@pytest.mark.parametrize("qp", QP[:2])
+def test_pipeline_32x32_two_kernel_path_at_full_size(oracle, qp):
+    """32x32 on a batch that fills the chip (2 x 4K = 1020 tiles >= 6 per SM): the default dispatch runs the tensor-core forward transform with the
+    quantiser in its epilogue, then the dequantising inverse - levels, cbf and reconstruction against the oracle's composition, both the
+    [-256, 255] and the full int16 residual ranges"""
+    width, height, nf, log2 = 3840, 2160, 2, 5
+    for seed, lo, hi in ((330, -256, 255), (331, -32768, 32767)):
+        pitch = synth.pitch_for(width, 0, 128)
+        res = synth.Planes(synth.random_int16(seed, nf * height * pitch, lo, hi).reshape(nf, height, pitch), width, height, 0)
+        pred = synth.random_planes(332, nf, width, height, 16)
+        lv_w, cbf_w, rec_w = oracle_pipeline(oracle, res, pred, width, height, log2, 0, qp, nf)
+        d_res, d_pred = to_dev(res.buf), to_dev(pred.buf)
+        rec_g = to_dev(synth.random_planes(333, nf, width, height, 16).buf)
+        lv_g = dev_full(lv_w.shape, np.int16, 0x5a5a)
+        cbf_g = dev_full((len(cbf_w),), np.int32, -7)
+        lib.call("residual_pipeline_frames", dptr(rec_g, rec_w.origin), rec_w.pitch, dptr(lv_g), dptr(cbf_g), dptr(d_res, res.origin), res.pitch,
+                 dptr(d_pred, pred.origin), pred.pitch, width, height, log2, 0, *qp, nf, rec_w.frame_stride, res.frame_stride, pred.frame_stride)
+        assert np.array_equal(to_host(lv_g), lv_w), (lo, hi)
+        assert np.array_equal(to_host(cbf_g), cbf_w)
+        # the oracle's reconstruction covers the whole-block area; compare there (2160 = 67.5 blocks: the last half row of blocks is not coded)
+        bh = height // 32 * 32
+        got = synth.Planes(to_host(rec_g), width, height, 16)
+        for f in range(nf):
+            assert np.array_equal(got.interior(f)[:bh], rec_w.interior(f)[:bh]), f
