@@ -592,12 +592,17 @@ __global__ void __launch_bounds__(pyr::NT, 5) sad_rect_tma_kernel(const __grid_c
         const int pu = i >> 4, g = i & 15, ppx = pu & ((1 << lpx) - 1), ppy = pu >> lpx;
         const int gx = pu_x0 + ppx, gy = pu_y0 + ppy;
         if (gx >= p.npx || gy >= p.npy) continue;
-        int4 v = make_int4(0, 0, 0, 0);
-        for (int b = 0; b < my; ++b)
-            for (int a = 0; a < mx; ++a) {
-                const int c = ((ppy << p.lmy) + b) * CX + (ppx << p.lmx) + a;
-                v = add4(v, cb[cb_index(c, g)]);
-            }
+        int4 v;
+        if (mx == 1 && my == 1) {   // 8x8 PUs: a PU is one cell (uniform branch: no composition loops)
+            v = cb[cb_index(ppy * CX + ppx, g)];
+        } else {
+            v = make_int4(0, 0, 0, 0);
+            for (int b = 0; b < my; ++b)
+                for (int a = 0; a < mx; ++a) {
+                    const int c = ((ppy << p.lmy) + b) * CX + (ppx << p.lmx) + a;
+                    v = add4(v, cb[cb_index(c, g)]);
+                }
+        }
         const int dyi = g >> 1, dxi = (g & 1) * 4;
         if (dyi >= p.nvy) continue;
         int32_t *o = p.out + (((size_t)f * p.npy + gy) * p.npx + gx) * p.nc + (p.wy + dyi) * p.ncx + p.wx + dxi;
